@@ -1,0 +1,154 @@
+/* psnerf_b200 — C ABI of the B200-native PS-NeRF render / shading hot path.
+ *
+ * The reference (ywq/psnerf) has no FFI on this path: its boundary is the Python nn.Module surface
+ * (SURVEY.md §8b).  This header is the C-ABI a maintainer binds underneath those modules; every
+ * entry point names the reference code it replaces (paths relative to /root/reference).
+ *
+ * Conventions
+ *  - All tensors are contiguous fp32 DEVICE pointers unless marked "host".  The caller owns every
+ *    input / output / workspace buffer; the library owns only psn_mlp handles.
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, no implicit sync.
+ *  - Return 0 on success, <0 on error (PSN_ERR_*); psn_last_error() gives the message (thread local).
+ *  - `precision`: PSN_PREC_FP32 = fp32 FFMA kernels; PSN_PREC_TC = tcgen05 tensor-core kernels with
+ *    error-compensated fp16 split operands (hi+lo, 3 MMAs per product), fp32 accumulate in TMEM.
+ *  - No CPU fallback exists: every entry point fails with PSN_ERR_CUDA without a sm_100 device.
+ */
+#ifndef PSNERF_B200_H
+#define PSNERF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSN_OK 0
+#define PSN_ERR_ARG (-1)
+#define PSN_ERR_SHAPE (-2)
+#define PSN_ERR_CUDA (-3)
+#define PSN_ERR_WORKSPACE (-4)
+
+#define PSN_PREC_FP32 0
+#define PSN_PREC_TC 1
+
+#define PSN_NET_GEO 0 /* stage1/model/network.py:37-66 lin0..lin8 (softplus beta=100, skip concat /sqrt2) */
+#define PSN_NET_APP 1 /* stage1/model/network.py:71-79 lina0..lina4 (ReLU, tanh*0.5+0.5)               */
+#define PSN_NET_S2 2  /* stage2/model/renderer.py:17-49 Network / Normal_Network (ReLU, cat[y,x] skip)   */
+
+#define PSN_OUT_ALPHA 0     /* sigmoid(-10*logit)  network.py:124-125 */
+#define PSN_OUT_NEG_LOGIT 1 /* -logit              network.py:137-138 */
+#define PSN_OUT_LOGIT 2     /* raw logit (infer_occ[...,0]) */
+
+typedef struct psn_mlp psn_mlp;
+
+typedef struct {
+  int kind;      /* PSN_NET_* */
+  int n_layers;  /* number of Linear layers */
+  int octaves;   /* GEO: octaves_pe of the point encoding; APP: octaves_pe_views; S2: unused */
+  int skip;      /* GEO: index of the layer whose INPUT is cat[x, pe]/sqrt(2) (network.py:90-91), -1 = none.
+                    S2: index of the layer AFTER whose output cat[y, x0] is formed (renderer.py:30-31), -1 = none */
+  int final_act; /* S2: 0 = linear output (Normal_Network), 1 = sigmoid (Network) */
+  float rescale; /* GEO: points are divided by this before encoding (network.py:86) */
+} psn_mlp_desc;
+
+int psn_version(void);
+const char* psn_last_error(void);
+/* Device probe: fails with PSN_ERR_CUDA unless a compute-capability-10.x GPU is current. */
+int psn_device_check(int* sm_count);
+
+/* Pack one network.  W[l] is the EFFECTIVE weight [out_dims[l], in_dims[l]] row-major (weight-norm already
+ * folded: W = g*v/||v||, network.py:64,77), b[l] is [out_dims[l]].  Builds the fp32 k-major copies, the
+ * transposed copies for the analytic-normal reverse pass and the swizzled fp16 hi/lo tiles for tcgen05. */
+int psn_mlp_create(const psn_mlp_desc* desc, const int* in_dims, const int* out_dims,
+                   const float* const* W, const float* const* b, void* stream, psn_mlp** out);
+int psn_mlp_free(psn_mlp* net);
+
+/* Workspace (bytes) needed by the calls below for the given problem size; query once, allocate, pass in. */
+int64_t psn_workspace_bytes(const char* op, int64_t n_rays, int64_t n_samples, int64_t n_lights);
+
+/* NeuralNetwork.forward(p, only_occupancy=True) / (return_logits=True): network.py:122-125,137-138. */
+int psn_occupancy(const psn_mlp* geo, const float* pts /*[M,3]*/, int64_t M, int out_kind, float* out /*[M]*/,
+                  int precision, void* stream);
+/* NeuralNetwork.infer_occ: network.py:85-95.  out is [M, 1+feat]: logit then feature vector. */
+int psn_infer_occ(const psn_mlp* geo, const float* pts, int64_t M, float* out, int precision, void* stream);
+/* NeuralNetwork.gradient (d logit / d p, un-normalised): network.py:108-120, evaluated analytically. */
+int psn_gradient(const psn_mlp* geo, const float* pts, int64_t M, float* grad /*[M,3]*/, void* ws, int64_t ws_bytes,
+                 int precision, void* stream);
+/* NeuralNetwork.forward(p, ray_d, return_addocc=True): network.py:126-134 -> rgb [M,3], alpha [M]. */
+int psn_radiance(const psn_mlp* geo, const psn_mlp* app, const float* pts, const float* view_dirs /*[M,3]*/,
+                 int64_t M, float* rgb, float* alpha, void* ws, int64_t ws_bytes, int precision, void* stream);
+
+/* image_points_to_ray + origin_to_world + normalise: stage1/model/common.py:205-226, rendering.py:67-71.
+ * cam (host, 16 floats) = R row-major[9], origin[3], fx, fy, cx, cy.  Stage 1 passes fy = fx (common.py:220).
+ * pixels are float (x, y).  With normalize_like_stage2 != 0 it is get_camera_params/lift of
+ * stage2/utils/rend_util.py:90-147 (F.normalize, separate fx/fy). */
+int psn_rays_from_pixels(const float* pixels /*[N,2]*/, int64_t N, const float* cam /*host[16]*/,
+                         int normalize_like_stage2, float* dirs /*[N,3]*/, void* stream);
+
+/* Renderer.ray_marching + secant: rendering.py:410-555.  depth[N]: +inf = no surface, 0 = first proposal
+ * occupied, else the refined depth.  Sphere far depth from get_sphere_intersection (rendering.py:576-596). */
+int psn_raymarch(const psn_mlp* geo, const float* origin /*host[3]*/, const float* dirs /*[N,3]*/, int64_t N,
+                 float near, float radius, int n_steps, int n_secant, float tau, float* depth /*[N]*/,
+                 void* ws, int64_t ws_bytes, int precision, void* stream);
+
+typedef struct {
+  float near_, radius, delta, tau;
+  int march_steps, secant_steps;
+  int steps_in;  /* num_points_in  (samples inside the surface interval) */
+  int steps_out; /* num_points_out, or 0 when the reference uses full_steps == steps (rendering.py:124-127) */
+  int white_background;
+} psn_unisurf_params;
+
+/* Renderer.unisurf (eval path, optional externally supplied jitter): rendering.py:50-226.
+ * noise: nullable [N, steps_in+steps_out] uniform(0,1) samples replacing torch.rand (rendering.py:139,163).
+ * Outputs: rgb[N,3], acc[N], normal[N,3] (g/(|g|+1e-5) on hit rays, 0 elsewhere), mask[N] (uint8),
+ * depth[N] (raw ray_marching result), sample_depth (nullable) [N, steps_in+steps_out]. */
+int psn_render_unisurf(const psn_mlp* geo, const psn_mlp* app, const float* origin /*host[3]*/,
+                       const float* dirs /*[N,3]*/, int64_t N, const psn_unisurf_params* prm,
+                       const float* noise, float* rgb, float* acc, float* normal, uint8_t* mask, float* depth,
+                       float* sample_depth, void* ws, int64_t ws_bytes, int precision, void* stream);
+
+/* Renderer.light_visibility: rendering.py:378-408.  vis[L, Ns] light-major = 1 - sum_i a_i prod_{j<i}(1-a_j+1e-6),
+ * occupancy zeroed outside the [-box, box]^3 cube. */
+int psn_shadow_visibility(const psn_mlp* geo, const float* surf /*[Ns,3]*/, const float* lights /*[L,3]*/,
+                          int64_t Ns, int L, float lnear, float lfar, int n_steps, float box, float* vis,
+                          void* ws, int64_t ws_bytes, int precision, void* stream);
+
+typedef struct {
+  int n_freqs_xyz;    /* brdf.net.n_freqs_xyz (embedder.py:39-54) */
+  int n_freqs_normal; /* normal.net.n_freqs_xyz */
+  int nbasis;         /* lobes per channel (sgbasis.py:7-14) */
+  int specular_rgb;   /* train.specular_rgb: weights are [3, nbasis] */
+  int intensity_kind; /* 0 scalar, 1 per-light [L,1], 2 per-light rgb [L,3] (renderer.py:188-190) */
+  float intensity;    /* scalar intensity when intensity_kind == 0 */
+} psn_shade_params;
+
+/* PSNetwork.forward, eval path: stage2/model/renderer.py:110-266 with sgbasis.py:16-32, embedder.py:36.
+ * Inputs are per SURFACE point (already gathered by surface_mask): pts, view (= -ray_dir), normal_in
+ * (used when normal_net is NULL), pix[Ns] = pixel index of the point in [0,N).
+ * Outputs are image shaped and fully written by the library, non-surface pixels pre-filled exactly as the
+ * reference does (1.0; sg weights 0: renderer.py:145-152):
+ *   rgb[L,N,3], spec[L,N,3], vis[L,N,3] (nullable when vis_net is NULL), normal[N,3], albedo[N,3], sgw[N,nbt]. */
+int psn_shade_stage2(const psn_mlp* normal_net, const psn_mlp* albedo_net, const psn_mlp* rough_net,
+                     const psn_mlp* vis_net, const float* lobe, const psn_shade_params* prm,
+                     const float* pts, const float* view, const float* normal_in, const int32_t* pix,
+                     int64_t Ns, int64_t N, const float* lights /*[L,3]*/, int L, const float* intensity,
+                     float* rgb, float* spec, float* vis, float* normal, float* albedo, float* sgw,
+                     void* ws, int64_t ws_bytes, int precision, void* stream);
+
+/* Per-point stage-2 nets only (albedo / rough evaluated at jittered points, renderer.py:211-231): outputs are
+ * per surface point: albedo[Ns,3] (sigmoid), weights[Ns,nbt] (relu). */
+int psn_s2_point_nets(const psn_mlp* albedo_net, const psn_mlp* rough_net, int n_freqs, const float* pts,
+                      int64_t Ns, float* albedo, float* weights, int nbt, int precision, void* stream);
+/* visibility_net over (light, point) pairs, light-major [L, Ns] raw (unclamped) outputs (renderer.py:193, :251-262). */
+int psn_s2_visibility(const psn_mlp* vis_net, int n_freqs, const float* pts, int64_t Ns, const float* lights, int L,
+                      float* vis /*[L,Ns]*/, void* ws, int64_t ws_bytes, int precision, void* stream);
+
+/* alpha compositing of per-sample (rgb, alpha): rendering.py:196-197,214-216. */
+int psn_composite(const float* rgb_s /*[N,S,3]*/, const float* alpha /*[N,S]*/, int64_t N, int S,
+                  int white_background, float* rgb /*[N,3]*/, float* acc /*[N]*/, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSNERF_B200_H */

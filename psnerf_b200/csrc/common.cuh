@@ -1,0 +1,74 @@
+// Shared declarations for the psnerf_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/psnerf_b200.h"
+
+namespace psn {
+
+void set_error(const char* fmt, ...);
+
+#define PSN_CUDA_CHECK(expr)                                                                  \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      psn::set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__, cudaGetErrorString(_e)); \
+      return PSN_ERR_CUDA;                                                                    \
+    }                                                                                         \
+  } while (0)
+
+#define PSN_REQUIRE(cond, code, ...)                                                          \
+  do {                                                                                        \
+    if (!(cond)) {                                                                            \
+      psn::set_error(__VA_ARGS__);                                                            \
+      return (code);                                                                          \
+    }                                                                                         \
+  } while (0)
+
+inline int pad_to(int x, int m) { return (x + m - 1) / m * m; }
+
+// One Linear layer packed for the SIMT fp32 path: wt is [K_pad][N_pad] (k-major, i.e. the transpose of
+// torch's [out,in] weight), zero padded; bias is [N_pad].
+struct SimtLayer {
+  const float* wt;
+  const float* bias;
+  int K, N, K_pad, N_pad;
+};
+
+constexpr int kMaxLayers = 12;
+
+// Packed tcgen05 layer: fp16 hi/lo weight tiles, pre-swizzled (see tc_mlp.cuh).
+struct TcLayer {
+  const __half* tiles;  // [n_kblk][2 (hi,lo)][N_TILE rows][64] swizzled-128B images, 32 KB per (kblk,part) at N=256
+  const float* bias;    // [N_pad]
+  int K, N, K_pad, N_pad, n_kblk;
+};
+
+}  // namespace psn
+
+// Opaque handle behind the C ABI.  kind: 0 = stage-1 geo, 1 = stage-1 app, 2 = stage-2 MLP.
+struct psn_mlp {
+  int kind;
+  psn_mlp_desc desc;
+  int n_layers;
+  int in_dims[psn::kMaxLayers], out_dims[psn::kMaxLayers];
+  // forward layers (SIMT).  For kind 0 the last Linear is split: fwd[n_layers-1] = feature head
+  // (rows 1..feat), logit_head = row 0.
+  psn::SimtLayer fwd[psn::kMaxLayers];
+  psn::SimtLayer logit_head;
+  // reverse layers (kind 0 only): rev[l].wt is W_l in its native [out][in] layout, zero padded.
+  psn::SimtLayer rev[psn::kMaxLayers];
+  const float* w_logit_row;  // [hidden] row 0 of the last geo layer (d logit / d x_last)
+  float b_logit;
+  // tcgen05 packs (filled when the shape is one the tensor path supports)
+  int tc_ok;
+  psn::TcLayer tc_fwd[psn::kMaxLayers];
+  psn::TcLayer tc_rev[psn::kMaxLayers];
+  // stage-2 visibility restructuring: columns of layer 0 / skip layer split into point / light parts
+  void* device_blob;  // single allocation that owns every packed array
+  size_t blob_bytes;
+};

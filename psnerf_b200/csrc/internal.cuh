@@ -1,0 +1,53 @@
+// Cross-translation-unit declarations (host side).
+#pragma once
+#include "stage1_simt.cuh"
+
+namespace psn {
+
+struct SecantState {
+  int* count;    // number of active (masked) rays
+  int* ray;      // [N] ray id per slot
+  float *d_low, *d_high, *f_low, *f_high, *d_pred;  // [N] per slot
+};
+struct SurfList { int* count; int* ray; float* depth; };
+
+// stage1_simt.cu
+int simt_occupancy(const psn_mlp* geo, const PointGen& gen, long long M, const int* M_dev, int out_kind, float* out,
+                   int with_feat, cudaStream_t st);
+int simt_gradient(const psn_mlp* geo, const PointGen& gen, long long M, const int* M_dev, float* grad, void* stash,
+                  cudaStream_t st);
+int simt_radiance(const psn_mlp* geo, const psn_mlp* app, const PointGen& gen, long long M, float* rgb, float* alpha,
+                  void* stash, cudaStream_t st);
+size_t simt_stash_bytes();
+int make_geo_dev(const psn_mlp* net, GeoDev* g);
+
+// tc_*.cu (tcgen05 path)
+int tc_occupancy(const psn_mlp* geo, const PointGen& gen, long long M, const int* M_dev, int out_kind, float* out,
+                 cudaStream_t st);
+int tc_infer_occ(const psn_mlp* geo, const PointGen& gen, long long M, float* out, cudaStream_t st);
+int tc_gradient(const psn_mlp* geo, const PointGen& gen, long long M, const int* M_dev, float* grad, void* stash,
+                cudaStream_t st);
+int tc_radiance(const psn_mlp* geo, const psn_mlp* app, const PointGen& gen, long long M, float* rgb, float* alpha,
+                void* stash, cudaStream_t st);
+int tc_shadow(const psn_mlp* geo, const PointGen& gen, long long pairs, float box, float* vis, cudaStream_t st);
+size_t tc_stash_bytes();
+
+// stage1_aux.cu
+int launch_rays(const float* pix, long long N, const float* cam, int stage2, float* dirs, cudaStream_t st);
+int launch_sphere_far(const float* dirs, long long N, const float* o, float r, float* far, cudaStream_t st);
+int launch_march_scan(const float* occ, const float* far, long long N, int S, float near_, float tau, SecantState s,
+                      float* depth, cudaStream_t st);
+int launch_secant_update(SecantState s, const float* occ_mid, float tau, long long N, cudaStream_t st);
+int launch_march_finalize(SecantState s, float* depth, long long N, cudaStream_t st);
+int launch_sample_plan(const float* d_i, const float* far, long long N, const psn_unisurf_params& prm, const float* noise,
+                       float* sample_depth, uint8_t* mask, SurfList sl, cudaStream_t st);
+int launch_composite(const float* rgb_s, const float* alpha, long long N, int S, int white, float* rgb, float* acc,
+                     cudaStream_t st);
+int launch_shadow_composite(const float* occ, const float* surf, const float* lights, long long Ns, long long pairs, int S,
+                            float lnear, float lfar, float box, float* vis, cudaStream_t st);
+int launch_scatter_normals(const float* grad, SurfList sl, float* normal, long long N, cudaStream_t st);
+
+// stage2_simt.cu
+size_t s2_workspace_bytes(long long Ns, long long L);
+
+}  // namespace psn

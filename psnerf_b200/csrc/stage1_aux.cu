@@ -1,0 +1,340 @@
+// Stage-1 non-MLP kernels: ray generation, sphere test, first-sign-change scan, secant bookkeeping, interval
+// sampling plan, alpha compositing, shadow transmittance.  All are HBM-/latency-bound streaming kernels
+// (coalesced loads, warp shuffles); the MLP work between them lives in stage1_simt.cu / tc_*.cu.
+#include <math_constants.h>
+
+#include "stage1_simt.cuh"
+#include "launch.cuh"
+#include "internal.cuh"
+
+namespace psn {
+
+// ---- rays ------------------------------------------------------------------------------------------------
+// cam = R[9] row-major, origin[3], fx, fy, cx, cy.
+struct CamDev { float v[16]; };
+
+__global__ void k_rays_from_pixels(const float* __restrict__ pix, long long N, CamDev cam, int stage2, float* __restrict__ dirs) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const float* R = cam.v;
+  const float fx = cam.v[12], fy = cam.v[13], cx = cam.v[14], cy = cam.v[15];
+  const float x = __fdiv_rn(__fsub_rn(pix[i * 2 + 0], cx), fx);
+  const float y = __fdiv_rn(__fsub_rn(pix[i * 2 + 1], cy), fy);
+  float d[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) d[r] = R[r * 3 + 0] * x + R[r * 3 + 1] * y + R[r * 3 + 2];
+  float n = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+  if (stage2) n = fmaxf(n, 1e-12f);  // F.normalize eps (rend_util.py:118)
+  dirs[i * 3 + 0] = d[0] / n; dirs[i * 3 + 1] = d[1] / n; dirs[i * 3 + 2] = d[2] / n;
+}
+
+// get_sphere_intersection far depth, clamped at 0, 0 for misses (rendering.py:576-596)
+__global__ void k_sphere_far(const float* __restrict__ dirs, long long N, float ox, float oy, float oz, float r,
+                             float* __restrict__ far) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const float rc = dirs[i * 3 + 0] * ox + dirs[i * 3 + 1] * oy + dirs[i * 3 + 2] * oz;
+  const float cn = sqrtf(ox * ox + oy * oy + oz * oz);
+  const float under = __fsub_rn(__fmul_rn(rc, rc), __fsub_rn(__fmul_rn(cn, cn), __fmul_rn(r, r)));
+  float f = 0.f;
+  if (under > 0.f) f = fmaxf(__fsub_rn(sqrtf(under), rc), 0.f);
+  far[i] = f;
+}
+
+// ---- ray marching: first sign change + secant state ---------------------------------------------------------
+__device__ __forceinline__ float secant_estimate(float f_low, float f_high, float d_low, float d_high) {
+  // - f_low * (d_high - d_low) / (f_high - f_low) + d_low   (rendering.py:538,554)
+  return __fadd_rn(__fdiv_rn(__fmul_rn(-f_low, __fsub_rn(d_high, d_low)), __fsub_rn(f_high, f_low)), d_low);
+}
+
+// One warp per ray.  occ is [N, S] occupancy probabilities; val = occ - tau (rendering.py:457-462).
+__global__ void k_march_scan(const float* __restrict__ occ, const float* __restrict__ far, long long N, int S, float near_,
+                             float tau, SecantState st, float* __restrict__ depth) {
+  const long long ray = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (ray >= N) return;
+  const float* v = occ + ray * S;
+  int idx = -1;
+  for (int b = 0; b < S && idx < 0; b += 32) {
+    const int s = b + lane;
+    const float cur = (s < S) ? v[s] - tau : 0.f;
+    float nxt = __shfl_down_sync(0xffffffffu, cur, 1);
+    if (lane == 31) nxt = (s + 1 < S) ? v[s + 1] - tau : 0.f;
+    const bool flag = (s + 1 < S) && (cur * nxt < 0.f);
+    const unsigned m = __ballot_sync(0xffffffffu, flag);
+    if (m) idx = b + __ffs(m) - 1;
+  }
+  if (lane != 0) return;
+  const float v0 = v[0] - tau;
+  const bool first_free = v0 < 0.f;
+  bool mask = false;
+  if (idx >= 0) {
+    const float f_low = v[idx] - tau;
+    mask = first_free && (f_low < 0.f);
+    if (mask) {
+      const int i2 = min(idx + 1, S - 1);
+      const float f_high = v[i2] - tau;
+      const float fr = far[ray];
+      const float d_low = lerp_depth(near_, fr, linspace01(idx, S));
+      const float d_high = lerp_depth(near_, fr, linspace01(i2, S));
+      const int slot = atomicAdd(st.count, 1);
+      st.ray[slot] = (int)ray;
+      st.d_low[slot] = d_low; st.d_high[slot] = d_high; st.f_low[slot] = f_low; st.f_high[slot] = f_high;
+      st.d_pred[slot] = secant_estimate(f_low, f_high, d_low, d_high);
+    }
+  }
+  depth[ray] = first_free ? CUDART_INF_F : 0.f;  // masked rays are overwritten by k_march_finalize
+}
+
+__global__ void k_secant_update(SecantState st, const float* __restrict__ occ_mid, float tau) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= *st.count) return;
+  const float f_mid = occ_mid[slot] - tau;
+  float d_low = st.d_low[slot], d_high = st.d_high[slot], f_low = st.f_low[slot], f_high = st.f_high[slot];
+  const float d_pred = st.d_pred[slot];
+  if (f_mid < 0.f) { d_low = d_pred; f_low = f_mid; } else { d_high = d_pred; f_high = f_mid; }
+  st.d_low[slot] = d_low; st.d_high[slot] = d_high; st.f_low[slot] = f_low; st.f_high[slot] = f_high;
+  st.d_pred[slot] = secant_estimate(f_low, f_high, d_low, d_high);
+}
+
+__global__ void k_march_finalize(SecantState st, float* __restrict__ depth) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= *st.count) return;
+  depth[st.ray[slot]] = st.d_pred[slot];
+}
+
+// ---- unisurf sampling plan (rendering.py:88-168) -----------------------------------------------------------
+// One warp per ray.  Writes sample_depth[N, S] (S = steps_in + steps_out), mask[N], and appends object rays to
+// the surface list (ray id + surface depth) used for the normal pass.
+
+constexpr int PLAN_MAX_S = 256;
+
+__global__ void __launch_bounds__(128)
+k_sample_plan(const float* __restrict__ d_i, const float* __restrict__ far, long long N, psn_unisurf_params prm,
+              const float* __restrict__ noise, float* __restrict__ sample_depth, uint8_t* __restrict__ mask,
+              SurfList sl) {
+  __shared__ float sv[4][PLAN_MAX_S];
+  __shared__ float so[4][PLAN_MAX_S];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long ray = (long long)blockIdx.x * 4 + w;
+  if (ray >= N) return;
+  const int S_in = prm.steps_in, S_out = prm.steps_out, S = S_in + S_out;
+  const float d = d_i[ray];
+  const bool obj = (fabsf(d) != CUDART_INF_F) && !(d != d) && (d != 0.f);
+  const float fr = far[ray];
+  float* out = sample_depth + ray * S;
+  float* v = sv[w];
+  float* o = so[w];
+  if (!obj) {
+    for (int s = lane; s < S; s += 32) o[s] = lerp_depth(prm.near_, fr, linspace01(s, S));
+  } else {
+    float dnp = __fsub_rn(d, prm.delta), dfp = __fadd_rn(d, prm.delta);
+    if (dnp < prm.near_) dnp = prm.near_;
+    if (dfp > fr) dfp = fr;
+    for (int s = lane; s < S; s += 32) {
+      v[s] = (s < S_out) ? lerp_depth(prm.near_, dnp, linspace01(s, S_out))
+                         : lerp_depth(dnp, dfp, linspace01(s - S_out, S_in));
+    }
+    __syncwarp();
+    if (S_out > 0) {  // torch.sort(cat[d_binterval, d_interval]) (rendering.py:155): stable rank sort
+      for (int s = lane; s < S; s += 32) {
+        const float x = v[s];
+        int rank = 0;
+        for (int t = 0; t < S; ++t) {
+          const float y = v[t];
+          rank += (y < x) || (y == x && t < s);
+        }
+        o[rank] = x;
+      }
+    } else {
+      for (int s = lane; s < S; s += 32) o[s] = v[s];
+    }
+  }
+  __syncwarp();
+  if (noise) {  // stratified jitter with caller-supplied uniforms (rendering.py:135-140,159-164)
+    for (int s = lane; s < S; s += 32) {
+      const float lo = (s == 0) ? o[0] : __fmul_rn(0.5f, __fadd_rn(o[s], o[s - 1]));
+      const float hi = (s == S - 1) ? o[S - 1] : __fmul_rn(0.5f, __fadd_rn(o[s + 1], o[s]));
+      out[s] = __fadd_rn(lo, __fmul_rn(__fsub_rn(hi, lo), noise[ray * S + s]));
+    }
+  } else {
+    for (int s = lane; s < S; s += 32) out[s] = o[s];
+  }
+  if (lane == 0) {
+    mask[ray] = obj ? 1 : 0;
+    if (obj) {
+      const int slot = atomicAdd(sl.count, 1);
+      sl.ray[slot] = (int)ray;
+      sl.depth[slot] = d;
+    }
+  }
+}
+
+// ---- alpha compositing (rendering.py:196-197, 214-216) ----------------------------------------------------
+// One warp per ray; exclusive product scan of (1 - a + 1e-6) by shuffles, carried across 32-sample blocks.
+__global__ void k_composite(const float* __restrict__ rgb_s, const float* __restrict__ alpha, long long N, int S, int white,
+                            float* __restrict__ rgb, float* __restrict__ acc) {
+  const long long ray = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (ray >= N) return;
+  float carry = 1.f, sr = 0.f, sg = 0.f, sb = 0.f, sw = 0.f;
+  for (int b = 0; b < S; b += 32) {
+    const int s = b + lane;
+    const float a = (s < S) ? alpha[ray * S + s] : 0.f;
+    float t = (s < S) ? __fadd_rn(__fsub_rn(1.f, a), 1e-6f) : 1.f;
+    float incl = t;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const float u = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl *= u;
+    }
+    float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = 1.f;
+    const float wgt = a * (carry * excl);
+    if (s < S) {
+      const float* c = rgb_s + (ray * S + s) * 3;
+      sr += wgt * c[0]; sg += wgt * c[1]; sb += wgt * c[2]; sw += wgt;
+    }
+    carry *= __shfl_sync(0xffffffffu, incl, 31);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    sr += __shfl_xor_sync(0xffffffffu, sr, off);
+    sg += __shfl_xor_sync(0xffffffffu, sg, off);
+    sb += __shfl_xor_sync(0xffffffffu, sb, off);
+    sw += __shfl_xor_sync(0xffffffffu, sw, off);
+  }
+  if (lane == 0) {
+    if (white) { const float bg = 1.f - sw; sr += bg; sg += bg; sb += bg; }
+    rgb[ray * 3 + 0] = sr; rgb[ray * 3 + 1] = sg; rgb[ray * 3 + 2] = sb;
+    acc[ray] = sw;
+  }
+}
+
+// ---- shadow transmittance (rendering.py:402-408) ------------------------------------------------------------
+// One warp per (light, point) pair of the current light chunk; occ is [pairs, S].
+__global__ void k_shadow_composite(const float* __restrict__ occ, const float* __restrict__ surf, const float* __restrict__ lights,
+                                   long long Ns, long long pairs, int S, float lnear, float lfar, float box,
+                                   float* __restrict__ vis) {
+  const long long pair = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (pair >= pairs) return;
+  const long long l = pair / Ns, n = pair - l * Ns;
+  const float p0[3] = {surf[n * 3], surf[n * 3 + 1], surf[n * 3 + 2]};
+  const float ld[3] = {lights[l * 3], lights[l * 3 + 1], lights[l * 3 + 2]};
+  float carry = 1.f, sw = 0.f;
+  for (int b = 0; b < S; b += 32) {
+    const int s = b + lane;
+    float a = 0.f;
+    if (s < S) {
+      const float dd = lerp_depth(lnear, lfar, linspace01(s, S));
+      bool inside = true;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float pc = madd_rn(p0[c], ld[c], dd);
+        inside = inside && (pc <= box) && (pc >= -box);
+      }
+      a = inside ? occ[pair * S + s] : 0.f;
+    }
+    const float t = (s < S) ? __fadd_rn(__fsub_rn(1.f, a), 1e-6f) : 1.f;
+    float incl = t;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const float u = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl *= u;
+    }
+    float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = 1.f;
+    sw += a * (carry * excl);
+    carry *= __shfl_sync(0xffffffffu, incl, 31);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) sw += __shfl_xor_sync(0xffffffffu, sw, off);
+  if (lane == 0) vis[pair] = 1.f - sw;
+}
+
+// ---- surface normals (rendering.py:208-211) -----------------------------------------------------------------
+__global__ void k_scatter_normals(const float* __restrict__ grad, SurfList sl, float* __restrict__ normal) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= *sl.count) return;
+  const float gx = grad[slot * 3], gy = grad[slot * 3 + 1], gz = grad[slot * 3 + 2];
+  const float n = sqrtf(gx * gx + gy * gy + gz * gz) + 1e-5f;
+  const long long r = sl.ray[slot];
+  normal[r * 3] = gx / n; normal[r * 3 + 1] = gy / n; normal[r * 3 + 2] = gz / n;
+}
+
+// ---- host wrappers --------------------------------------------------------------------------------------------
+static int g_num_ctas = 0;
+int num_ctas() {
+  if (g_num_ctas == 0) {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+      g_num_ctas = sms;
+    else
+      g_num_ctas = 148;
+  }
+  return g_num_ctas;
+}
+
+int launch_rays(const float* pix, long long N, const float* cam, int stage2, float* dirs, cudaStream_t st) {
+  if (N == 0) return PSN_OK;
+  CamDev c;
+  memcpy(c.v, cam, sizeof(c.v));
+  k_rays_from_pixels<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(pix, N, c, stage2, dirs);
+  PSN_CUDA_CHECK(cudaGetLastError());
+  return PSN_OK;
+}
+int launch_sphere_far(const float* dirs, long long N, const float* o, float r, float* far, cudaStream_t st) {
+  if (N == 0) return PSN_OK;
+  k_sphere_far<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(dirs, N, o[0], o[1], o[2], r, far);
+  PSN_CUDA_CHECK(cudaGetLastError());
+  return PSN_OK;
+}
+int launch_march_scan(const float* occ, const float* far, long long N, int S, float near_, float tau, SecantState s,
+                      float* depth, cudaStream_t st) {
+  k_march_scan<<<(unsigned)((N * 32 + 255) / 256), 256, 0, st>>>(occ, far, N, S, near_, tau, s, depth);
+  PSN_CUDA_CHECK(cudaGetLastError());
+  return PSN_OK;
+}
+int launch_secant_update(SecantState s, const float* occ_mid, float tau, long long N, cudaStream_t st) {
+  k_secant_update<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(s, occ_mid, tau);
+  PSN_CUDA_CHECK(cudaGetLastError());
+  return PSN_OK;
+}
+int launch_march_finalize(SecantState s, float* depth, long long N, cudaStream_t st) {
+  k_march_finalize<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(s, depth);
+  PSN_CUDA_CHECK(cudaGetLastError());
+  return PSN_OK;
+}
+int launch_sample_plan(const float* d_i, const float* far, long long N, const psn_unisurf_params& prm, const float* noise,
+                       float* sample_depth, uint8_t* mask, SurfList sl, cudaStream_t st) {
+  PSN_REQUIRE(prm.steps_in + prm.steps_out <= PLAN_MAX_S && prm.steps_in >= 2 && prm.steps_out != 1, PSN_ERR_SHAPE,
+              "unisurf: steps_in=%d steps_out=%d unsupported (need 2 <= total <= %d)", prm.steps_in, prm.steps_out,
+              PLAN_MAX_S);
+  k_sample_plan<<<(unsigned)((N + 3) / 4), 128, 0, st>>>(d_i, far, N, prm, noise, sample_depth, mask, sl);
+  PSN_CUDA_CHECK(cudaGetLastError());
+  return PSN_OK;
+}
+int launch_composite(const float* rgb_s, const float* alpha, long long N, int S, int white, float* rgb, float* acc,
+                     cudaStream_t st) {
+  if (N == 0) return PSN_OK;
+  k_composite<<<(unsigned)((N * 32 + 255) / 256), 256, 0, st>>>(rgb_s, alpha, N, S, white, rgb, acc);
+  PSN_CUDA_CHECK(cudaGetLastError());
+  return PSN_OK;
+}
+int launch_shadow_composite(const float* occ, const float* surf, const float* lights, long long Ns, long long pairs, int S,
+                            float lnear, float lfar, float box, float* vis, cudaStream_t st) {
+  if (pairs == 0) return PSN_OK;
+  k_shadow_composite<<<(unsigned)((pairs * 32 + 255) / 256), 256, 0, st>>>(occ, surf, lights, Ns, pairs, S, lnear, lfar,
+                                                                            box, vis);
+  PSN_CUDA_CHECK(cudaGetLastError());
+  return PSN_OK;
+}
+int launch_scatter_normals(const float* grad, SurfList sl, float* normal, long long N, cudaStream_t st) {
+  k_scatter_normals<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(grad, sl, normal);
+  PSN_CUDA_CHECK(cudaGetLastError());
+  return PSN_OK;
+}
+
+}  // namespace psn

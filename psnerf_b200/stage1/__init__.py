@@ -1,0 +1,3 @@
+from .network import NeuralNetwork  # noqa: F401
+from .rendering import Renderer  # noqa: F401
+from .common import arange_pixels  # noqa: F401

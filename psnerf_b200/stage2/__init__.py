@@ -1,0 +1,2 @@
+from .renderer import PSNetwork, Network, Normal_Network, SGBasis  # noqa: F401
+from .general import split_input, merge_output  # noqa: F401

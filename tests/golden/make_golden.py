@@ -1,0 +1,148 @@
+"""Generate golden fixtures by running the REAL reference (/root/reference) on CPU.
+
+Run in the authoring container only:   python tests/golden/make_golden.py
+Writes tests/golden/{stage1_net,stage1_render,stage2_shade}.npz.  Weights are NOT stored: both the reference
+constructors and the drop-in constructors are deterministic under torch.manual_seed, so fixtures carry weight
+checksums instead and the tests rebuild the weights (tests/test_host.py checks the checksums).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+import ref_loader  # noqa: E402
+from psnerf_b200 import synth  # noqa: E402
+
+torch.set_num_threads(8)
+
+
+def checksum(sd):
+    return np.array([[float(v.double().sum()), float(v.double().abs().sum())] for _, v in sorted(sd.items())])
+
+
+def np_(t):
+    return t.detach().cpu().numpy()
+
+
+def stage1_variants(net_mod):
+    cfg = synth.stage1_cfg()
+    torch.manual_seed(0)
+    model = net_mod.NeuralNetwork(cfg)
+    sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+    sd1 = synth.perturb_state_dict(sd0, rel=0.1, seed=1)
+    return cfg, model, {"init": sd0, "trained": sd1}
+
+
+def make_stage1_net():
+    net_mod, rend_mod, _ = ref_loader.load_stage1()
+    cfg, model, variants = stage1_variants(net_mod)
+    g = torch.Generator().manual_seed(11)
+    pts = (torch.rand(96, 3, generator=g) * 2.4 - 1.2)
+    views = torch.randn(96, 3, generator=g)
+    views = views / views.norm(dim=-1, keepdim=True)
+    out = {"pts": np_(pts), "views": np_(views)}
+    for name, sd in variants.items():
+        model.load_state_dict(sd)
+        with torch.no_grad():
+            out[name + "_infer_occ"] = np_(model.infer_occ(pts.clone()))
+            out[name + "_alpha"] = np_(model(pts.clone(), only_occupancy=True))
+            out[name + "_neg_logit"] = np_(model(pts.clone(), return_logits=True))
+        out[name + "_grad"] = np_(model.gradient(pts.clone(), tflag=False))
+        rgb, a = model(pts.clone(), views.clone(), return_addocc=True)
+        out[name + "_rgb"] = np_(rgb)
+        out[name + "_rgb_alpha"] = np_(a)
+        out[name + "_checksum"] = checksum(sd)
+    np.savez_compressed(os.path.join(HERE, "stage1_net.npz"), **out)
+    print("stage1_net", {k: v.shape for k, v in out.items()})
+
+
+def make_stage1_render():
+    net_mod, rend_mod, common = ref_loader.load_stage1()
+    _, model, variants = stage1_variants(net_mod)
+    out = {}
+    cases = {
+        # name: (h, w, num_points_in, num_points_out, march steps, it)
+        "cfg1small": (24, 24, 32, 0, 256, 100000),     # BASELINE config 1 shape at 24x24
+        "inout": (20, 20, 16, 8, 128, 100000),         # interval + outside samples, sorted (rendering.py:150-155)
+        "early": (16, 16, 16, 8, 64, 1000),            # it <= 5000: full_steps == steps, wide delta
+    }
+    pose = synth.look_at_pose(25.0, 15.0)
+    for vname, sd in variants.items():
+        model.load_state_dict(sd)
+        for cname, (h, w, s_in, s_out, msteps, it) in cases.items():
+            cfg = synth.stage1_cfg(num_points_in=s_in, num_points_out=s_out, ray_marching_steps=msteps)
+            rend = rend_mod.Renderer(model, cfg, device=torch.device("cpu"))
+            pix = synth.pixel_grid_xmajor(h, w)
+            K = synth.intrinsics(h, w)
+            with torch.no_grad():
+                res = rend(pix, K, pose, torch.eye(4)[None], "unisurf", add_noise=False, eval_=True, it=it)
+                ray0 = common.origin_to_world(pix.shape[1], K, pose, None)
+                rayd = common.image_points_to_ray(pix, K, pose)
+                rayd = rayd / rayd.norm(2, 2).unsqueeze(-1)
+                d_i = rend.ray_marching(ray0, rayd, model, n_secant_steps=8, n_steps=[msteps, msteps + 1], rad=cfg["rendering"]["radius"],
+                                        depth_range=rend.depth_range)
+            key = "%s_%s_" % (vname, cname)
+            out[key + "rgb"] = np_(res["rgb"])
+            out[key + "normal"] = np_(res["normal_pred"])
+            out[key + "acc"] = np_(res["acc_map"])
+            out[key + "mask"] = np_(res["mask_pred"])
+            out[key + "d_i"] = np_(d_i)
+            out[key + "dirs"] = np_(rayd)
+            print(key, "hit rays", int(res["mask_pred"].sum()), "/", h * w)
+        # shape_extract + shadow visibility (rendering.py:297-408)
+        cfg = synth.stage1_cfg()
+        rend = rend_mod.Renderer(model, cfg, device=torch.device("cpu"))
+        h = w = 14
+        pix = synth.pixel_grid_xmajor(h, w)
+        lights = synth.lights(3, seed=5, axis=tuple((-pose[0, :3, 2]).tolist()))
+        res = rend(pix, synth.intrinsics(h, w), pose, torch.eye(4)[None], "shape_extract", visibility=True, light_dir=lights)
+        key = "%s_extract_" % vname
+        for k in ("mask", "normal", "points", "visibility"):
+            out[key + k] = np_(res[k])
+        out[key + "lights"] = np_(lights)
+        print(key, "surface", int(res["mask"].sum()), "vis range", float(res["visibility"].min()), float(res["visibility"].max()))
+    out["pose"] = np_(pose)
+    np.savez_compressed(os.path.join(HERE, "stage1_render.npz"), **out)
+
+
+def make_stage2():
+    m2 = ref_loader.load_stage2()
+    conf = synth.stage2_conf()
+    torch.manual_seed(0)
+    model = m2.PSNetwork(ref_loader.DictConf(conf))
+    sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+    sd1 = synth.perturb_state_dict(sd0, rel=0.5, seed=1)
+    out = {}
+    for vname, sd in {"init": sd0, "trained": sd1}.items():
+        model.load_state_dict(sd)
+        for cname, (h, w, L, all_surf) in {"multi": (16, 16, 4, False), "single": (12, 12, 1, False), "full": (8, 8, 3, True)}.items():
+            inp = synth.stage2_input(h, w, L, all_surface=all_surf)
+            if cname == "multi":
+                inp["light_intensity"] = torch.tensor([[1.0], [2.0], [0.5], [3.0]])
+                inp["light_vis_train"] = synth.lights(2, seed=9)
+            if cname == "full":
+                inp["light_intensity"] = torch.tensor([[1.0, 2.0, 0.5], [3.0, 1.0, 1.0], [0.3, 0.6, 2.0]])
+            torch.manual_seed(123)  # the jitter branch draws torch.normal (renderer.py:212); its outputs are not compared
+            with torch.no_grad():
+                res = model(inp)
+            key = "%s_%s_" % (vname, cname)
+            for k in ("sg_rgb_values", "sg_specular_rgb_values", "visibility", "normal_pred", "sg_diffuse_albedo_values",
+                      "sg_weight", "vis_train"):
+                if k in res:
+                    out[key + k] = np_(res[k])
+            print(key, {k: tuple(v.shape) for k, v in res.items() if torch.is_tensor(v)})
+        out[vname + "_checksum"] = checksum(sd)
+    np.savez_compressed(os.path.join(HERE, "stage2_shade.npz"), **out)
+
+
+if __name__ == "__main__":
+    make_stage1_net()
+    make_stage1_render()
+    make_stage2()
+    for f in ("stage1_net", "stage1_render", "stage2_shade"):
+        print(f, os.path.getsize(os.path.join(HERE, f + ".npz")) // 1024, "KB")

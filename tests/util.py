@@ -1,0 +1,66 @@
+"""Shared test helpers: golden loading, deterministic weights, error metrics."""
+import os
+
+import numpy as np
+import torch
+
+from psnerf_b200 import synth
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden(name):
+    return np.load(os.path.join(GOLD, name + ".npz"))
+
+
+def stage1_state_dicts():
+    """Reference-constructor weights (seed 0) and the perturbed 'trained-like' variant, on CPU."""
+    from psnerf_b200.stage1.network import NeuralNetwork
+    cfg = synth.stage1_cfg()
+    torch.manual_seed(0)
+    sd0 = {k: v.detach().clone() for k, v in NeuralNetwork(cfg).state_dict().items()}
+    return cfg, {"init": sd0, "trained": synth.perturb_state_dict(sd0, rel=0.1, seed=1)}
+
+
+def stage2_state_dicts():
+    from psnerf_b200.stage2 import PSNetwork
+    conf = synth.stage2_conf()
+    torch.manual_seed(0)
+    sd0 = {k: v.detach().clone() for k, v in PSNetwork(conf).state_dict().items()}
+    return conf, {"init": sd0, "trained": synth.perturb_state_dict(sd0, rel=0.5, seed=1)}
+
+
+def checksum(sd):
+    return np.array([[float(v.double().sum()), float(v.double().abs().sum())] for _, v in sorted(sd.items())])
+
+
+def rel_l2(a, b):
+    a = torch.as_tensor(np.asarray(a)).double().reshape(-1)
+    b = torch.as_tensor(np.asarray(b)).double().reshape(-1)
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def max_abs(a, b):
+    a = torch.as_tensor(np.asarray(a)).double()
+    b = torch.as_tensor(np.asarray(b)).double()
+    return float((a - b).abs().max()) if a.numel() else 0.0
+
+
+STAGE1_CASES = {
+    # name: (h, w, num_points_in, num_points_out, march steps, it)  -- must match tests/golden/make_golden.py
+    "cfg1small": (24, 24, 32, 0, 256, 100000),
+    "inout": (20, 20, 16, 8, 128, 100000),
+    "early": (16, 16, 16, 8, 64, 1000),
+}
+STAGE2_CASES = {"multi": (16, 16, 4, False), "single": (12, 12, 1, False), "full": (8, 8, 3, True)}
+
+
+def stage2_case_input(cname):
+    h, w, L, all_surf = STAGE2_CASES[cname]
+    inp = synth.stage2_input(h, w, L, all_surface=all_surf)
+    if cname == "multi":
+        inp["light_intensity"] = torch.tensor([[1.0], [2.0], [0.5], [3.0]])
+        inp["light_vis_train"] = synth.lights(2, seed=9)
+    if cname == "full":
+        inp["light_intensity"] = torch.tensor([[1.0, 2.0, 0.5], [3.0, 1.0, 1.0], [0.3, 0.6, 2.0]])
+    return inp
