@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the PS-NeRF render hot path on B200 (contract: see DESIGN.md §Measurement).
+
+One "step" = one full Renderer.unisurf pass over a 512x512 view at 128 samples/ray (BASELINE.json configs[1]):
+ray generation, 256-step surface march + 8 secant refinements, interval sampling plan, 33.5 M radiance samples
+(geo MLP + analytic normal + appearance MLP), alpha compositing and surface normals.
+metric: Msamples/s = rays x samples (x lights, 1 for the stage-1 render) / second.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--precision tc|fp32] [--impl reference]
+
+N > 1 (torchrun): every rank renders the ray shard [rank::N] of N views per step (weak scaling: one view's worth
+of rays per GPU) and one NCCL all_gather of the rendered pixels closes the step.
+--impl reference: the CPU oracle port of the reference path on a bounded crop of the same workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H = W = 512
+S_IN, S_OUT, MARCH = 96, 32, 256  # 128 samples/ray, bear.yaml ray_marching_steps
+MFLOP_OCC = 0.918016      # occupancy sample, logit row only (2 * 459,008 MAC): what the occupancy kernels compute
+MFLOP_RAD = 2.509824      # radiance sample: fwd 524,544 + reverse 459,008 + app 271,360 MAC
+PROF_TAGS = ["occ_march", "occ_secant", "radiance", "gradient", "shadow", "s2_vis", "s2_point", "occ_other"]
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"tflops": d.get("bf16_tflops_sustained", 1400.0), "tflops_burst": d.get("bf16_tflops", 1590.0),
+                "hbm_gbs": d.get("hbm_gbs", 6650.0), "src": "measured (MEASURED_PEAKS.json, sustained bf16)"}
+    return {"tflops": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(int(float(r[0])) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def scene(device, view):
+    from psnerf_b200 import synth
+    pose = synth.look_at_pose(20.0 + 37.0 * view, 10.0 + 3.0 * (view % 5))
+    return synth.intrinsics(H, W), pose
+
+
+def build_model(device, precision):
+    from psnerf_b200 import synth
+    from psnerf_b200.stage1 import NeuralNetwork, Renderer
+    cfg = synth.stage1_cfg(num_points_in=S_IN, num_points_out=S_OUT, ray_marching_steps=MARCH)
+    torch.manual_seed(0)
+    net = NeuralNetwork(cfg)  # geometric init: sphere-like occupancy, ~17 % of the rays hit the surface
+    net.precision = precision
+    return cfg, net, Renderer(net, cfg, device=device)
+
+
+def run_reference(args):
+    """CPU arm: the oracle port of the reference path (oracle/psnerf_oracle.py) on a bounded crop, all host threads."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import psnerf_oracle as O
+    from psnerf_b200 import synth
+    from psnerf_b200.stage1 import NeuralNetwork
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = synth.stage1_cfg(num_points_in=S_IN, num_points_out=S_OUT, ray_marching_steps=MARCH)
+    torch.manual_seed(0)
+    sd = {k: v.detach().clone() for k, v in NeuralNetwork(cfg).state_dict().items()}
+    crop = args.ref_crop  # crop x crop pixels from the centre of the 512x512 view (rays are independent)
+    K, pose = synth.intrinsics(H, W), synth.look_at_pose(20.0, 10.0)
+    gx, gy = torch.meshgrid(torch.arange(W // 2 - crop // 2, W // 2 + crop // 2), torch.arange(H // 2 - crop // 2, H // 2 + crop // 2),
+                            indexing="ij")
+    pix = torch.stack([gx, gy], -1).long().view(1, -1, 2)
+    units = pix.shape[1] * (S_IN + S_OUT)
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        O.unisurf_render(sd, cfg, pix, K, pose, it=100000)
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    ms = 1e3 * sum(times) / len(times)
+    val = units / (ms / 1e3) / 1e6
+    sample = "%dx%d centre crop of the 512x512 view (all rays hit the sphere-init surface region more often than the full view)" % (crop, crop)
+    line = {"impl": "reference", "metric": "Msamples/sec (rays x samples x lights)", "value": val, "unit": "Msamples/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "stage1-unisurf-render 512x512x128spp (BASELINE configs[1]), CPU oracle port of the reference path",
+                       "sample": sample},
+            "cpu_baseline": {"value": val, "unit": "Msamples/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def cpu_baseline_quick():
+    """Oracle port on a 16x16 crop (about 10-20 s of CPU work) for the cpu_baseline object of the main line."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import psnerf_oracle as O
+    from psnerf_b200 import synth
+    from psnerf_b200.stage1 import NeuralNetwork
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = synth.stage1_cfg(num_points_in=S_IN, num_points_out=S_OUT, ray_marching_steps=MARCH)
+    torch.manual_seed(0)
+    sd = {k: v.detach().clone() for k, v in NeuralNetwork(cfg).state_dict().items()}
+    crop = 16
+    K, pose = synth.intrinsics(H, W), synth.look_at_pose(20.0, 10.0)
+    gx, gy = torch.meshgrid(torch.arange(W // 2 - crop // 2, W // 2 + crop // 2), torch.arange(H // 2 - crop // 2, H // 2 + crop // 2),
+                            indexing="ij")
+    pix = torch.stack([gx, gy], -1).long().view(1, -1, 2)
+    O.unisurf_render(sd, cfg, pix[:, :64], K, pose, it=100000)  # warm-up
+    t0 = time.perf_counter()
+    O.unisurf_render(sd, cfg, pix, K, pose, it=100000)
+    dt = time.perf_counter() - t0
+    return {"value": pix.shape[1] * (S_IN + S_OUT) / dt / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "port",
+            "sample": "16x16 centre crop of the 512x512x128spp view, 1 pass, oracle port (torch CPU fp32, %d threads)" % cores}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--precision", default="auto", choices=["auto", "tc", "fp32"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ref-crop", type=int, default=24)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    from psnerf_b200 import _binding as B, engine, synth
+    if not os.path.exists(B.LIB_PATH):
+        import __graft_entry__ as ge
+        ge.build()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = world > 1
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if dist:
+        import torch.distributed as td
+        td.init_process_group("nccl", device_id=dev)
+    lib = B.load()
+    precision = args.precision
+    if precision == "auto":
+        precision = "tc" if engine.tc_available() else "fp32"
+    cfg, net, rend = build_model(dev, precision)
+    N = H * W
+    S = S_IN + S_OUT
+    pix_host = synth.pixel_grid_xmajor(H, W).pin_memory()      # long [1,N,2]
+    n_views = world                                            # weak scaling: one view's worth of rays per GPU
+    views = [scene(dev, v) for v in range(n_views)]
+    shard = torch.arange(rank, N, world)                       # this rank's rays of every view
+    pix_dev = pix_host[:, shard].to(dev)
+    n_local = pix_dev.shape[1]
+    gather_buf = torch.empty(world, n_views * n_local, 7, device=dev) if dist else None
+    out_host = torch.empty(n_views * n_local, 7, dtype=torch.float32).pin_memory()
+    pix_host_shard = pix_host[:, shard].contiguous().pin_memory()
+
+    def step(e2e=False):
+        outs = []
+        for (K, pose) in views:
+            p = pix_host_shard.to(dev, non_blocking=True) if e2e else pix_dev
+            o = rend(p, K, pose, None, "unisurf", add_noise=False, eval_=True, it=100000)
+            outs.append(torch.cat([o["rgb"][0], o["normal_pred"][0], o["acc_map"][0].unsqueeze(-1)], -1))
+        res = torch.cat(outs, 0)
+        if dist:
+            td.all_gather_into_tensor(gather_buf.view(-1), res.view(-1))  # the single NCCL pixel gather
+        if e2e:
+            out_host.copy_(res, non_blocking=True)
+        return res
+
+    def timed(e2e, steps):
+        if dist:
+            td.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            step(e2e)
+        b.record()
+        torch.cuda.synchronize()
+        if dist:
+            td.barrier()
+        ms = a.elapsed_time(b) / steps
+        if dist:
+            t = torch.tensor([ms], device=dev)
+            td.all_reduce(t, op=td.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    for _ in range(args.warmup):
+        step(False)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # device-resident timing, with per-kernel CUDA-event profiling of the same steps
+    lib.psn_profile_enable(1)
+    l0 = lib.psn_launch_count()
+    ms = timed(False, args.steps)
+    launches = (lib.psn_launch_count() - l0) / args.steps
+    nt = len(PROF_TAGS)
+    pl, pms, prow = (C.c_int64 * nt)(), (C.c_double * nt)(), (C.c_double * nt)()
+    lib.psn_profile_collect(nt, pl, pms, prow)
+    lib.psn_profile_enable(0)
+    step(True)
+    ms_e2e = timed(True, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    units = n_views * n_local * S * world  # whole job per step
+    value = units / (ms / 1e3) / 1e6
+    if rank == 0:
+        peaks = load_peaks()
+        kern = {}
+        for i, t in enumerate(PROF_TAGS):
+            if pl[i]:
+                kern[t] = {"launches_per_step": pl[i] / args.steps, "ms_per_launch": pms[i] / pl[i], "rows_per_launch": prow[i] / pl[i]}
+        rad = kern.get("radiance")
+        roof = None
+        if rad:
+            tf = rad["rows_per_launch"] * MFLOP_RAD * 1e6 / (rad["ms_per_launch"] * 1e-3) / 1e12
+            roof = {"bound": "tensor", "kernel": "radiance (geo fwd + analytic normal + app MLP), %s path" % precision,
+                    "achieved": tf, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": tf / peaks["tflops"], "traffic": None,
+                    "peak_source": peaks["src"], "flops_per_row": MFLOP_RAD * 1e6,
+                    "issued_frac": (3.0 * tf / peaks["tflops"]) if precision == "tc" else None}
+            occ = kern.get("occ_march")
+            if occ:
+                tfo = occ["rows_per_launch"] * MFLOP_OCC * 1e6 / (occ["ms_per_launch"] * 1e-3) / 1e12
+                roof["second_kernel"] = {"kernel": "occ_march", "achieved": tfo, "frac": tfo / peaks["tflops"], "flops_per_row": MFLOP_OCC * 1e6}
+        line = {"metric": "Msamples/sec (rays x samples x lights)", "value": value, "unit": "Msamples/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f16x3-split operands, f32 accumulate" if precision == "tc" else "f32", "data": "synthetic",
+                "config": {"workload": "stage1-unisurf-render 512x512x128spp (BASELINE configs[1]): %d march steps + 8 secant, %d+%d samples/ray, "
+                                       "lights=1" % (MARCH, S_IN, S_OUT),
+                           "views_per_step": n_views, "rays_per_gpu_per_step": n_views * n_local, "parallelism": "ray-shard x%d" % world,
+                           "precision": precision, "l2": "per-step working set (>=400 MB of samples / occupancies) exceeds the 126 MB L2",
+                           "weights": "reference constructors, torch.manual_seed(0) (geometric init)"},
+                "gpu_launches": launches, "clocks": clocks,
+                "e2e": {"value": units / (ms_e2e / 1e3) / 1e6, "unit": "Msamples/s", "ms_per_step": ms_e2e,
+                        "h2d_bytes_per_step": n_views * n_local * 2 * 8, "d2h_bytes_per_step": n_views * n_local * 7 * 4},
+                "roofline": roof, "kernels": kern}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_quick()
+        print(json.dumps(line))
+    if dist:
+        td.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

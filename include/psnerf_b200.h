@@ -53,6 +53,23 @@ typedef struct {
 
 int psn_version(void);
 const char* psn_last_error(void);
+/* Number of CUDA kernels this library has launched in this process (bench.py reports the per-step delta). */
+int64_t psn_launch_count(void);
+/* Per-kernel timing (CUDA events on the launching stream) for bench.py's roofline numbers. Tags: */
+#define PSN_PROF_OCC_MARCH 0  /* occupancy MLP over ray-march proposals (rendering.py:457-462) */
+#define PSN_PROF_OCC_SECANT 1 /* occupancy MLP inside the secant loop (rendering.py:540-546)     */
+#define PSN_PROF_RADIANCE 2   /* geo fwd + analytic normal + app MLP per sample (network.py:122-136) */
+#define PSN_PROF_GRADIENT 3   /* surface normals (rendering.py:208)                                */
+#define PSN_PROF_SHADOW 4     /* shadow-ray occupancy (+ transmittance) (rendering.py:391-408)      */
+#define PSN_PROF_S2_VIS 5     /* stage-2 visibility MLP over (light, point) pairs (renderer.py:193)  */
+#define PSN_PROF_S2_POINT 6   /* stage-2 per-point MLPs (renderer.py:130,166,169)                   */
+#define PSN_PROF_OCC_OTHER 7  /* explicit-point occupancy / infer_occ calls                          */
+#define PSN_PROF_NTAGS 8
+int psn_profile_enable(int on); /* clears previous records */
+/* Sums per tag since enable: launches, elapsed ms, rows (samples) processed; waits for the recorded events. */
+int psn_profile_collect(int n_tags, int64_t* launches, double* ms, double* rows);
+/* 1 when this build contains the tcgen05 (PSN_PREC_TC) kernels. */
+int psn_has_tensor_path(void);
 /* Device probe: fails with PSN_ERR_CUDA unless a compute-capability-10.x GPU is current. */
 int psn_device_check(int* sm_count);
 

@@ -58,6 +58,9 @@ def load():
     vp, i64, i32, f32 = C.c_void_p, C.c_int64, C.c_int, C.c_float
     lib.psn_version.restype = C.c_int
     lib.psn_last_error.restype = C.c_char_p
+    lib.psn_launch_count.restype = i64
+    lib.psn_profile_enable.argtypes = [i32]
+    lib.psn_profile_collect.argtypes = [i32, C.POINTER(i64), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.psn_device_check.argtypes = [C.POINTER(C.c_int)]
     lib.psn_mlp_create.argtypes = [C.POINTER(MlpDesc), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(vp),
                                    C.POINTER(vp), vp, C.POINTER(vp)]

@@ -2,6 +2,7 @@
 #include "stage1_simt.cuh"
 #include "launch.cuh"
 #include "internal.cuh"
+#include "prof.cuh"
 
 using namespace psn;
 
@@ -10,16 +11,21 @@ namespace psn {
 // Evaluate occupancy probabilities for generated points with the requested arithmetic.
 static int occupancy_any(const psn_mlp* geo, const PointGen& gen, long long M, const int* M_dev, int out_kind, float* out,
                          int precision, cudaStream_t st) {
+  const int tag = gen.kind == GEN_MARCH ? PSN_PROF_OCC_MARCH : gen.kind == GEN_INDEXED_DEPTH ? PSN_PROF_OCC_SECANT
+                : gen.kind == GEN_SHADOW ? PSN_PROF_SHADOW : PSN_PROF_OCC_OTHER;
+  ProfScope prof(tag, M, st);
   if (precision == PSN_PREC_TC) return tc_occupancy(geo, gen, M, M_dev, out_kind, out, st);
   return simt_occupancy(geo, gen, M, M_dev, out_kind, out, 0, st);
 }
 static int gradient_any(const psn_mlp* geo, const PointGen& gen, long long M, const int* M_dev, float* grad, void* stash,
                         int precision, cudaStream_t st) {
+  ProfScope prof(PSN_PROF_GRADIENT, M, st);
   if (precision == PSN_PREC_TC) return tc_gradient(geo, gen, M, M_dev, grad, stash, st);
   return simt_gradient(geo, gen, M, M_dev, grad, stash, st);
 }
 static int radiance_any(const psn_mlp* geo, const psn_mlp* app, const PointGen& gen, long long M, float* rgb, float* alpha,
                         void* stash, int precision, cudaStream_t st) {
+  ProfScope prof(PSN_PROF_RADIANCE, M, st);
   if (precision == PSN_PREC_TC) return tc_radiance(geo, app, gen, M, rgb, alpha, stash, st);
   return simt_radiance(geo, app, gen, M, rgb, alpha, stash, st);
 }
@@ -244,6 +250,7 @@ extern "C" int psn_shadow_visibility(const psn_mlp* geo, const float* surf, cons
     gen.lfar = lfar;
     int rc;
     if (precision == PSN_PREC_TC) {
+      ProfScope prof(PSN_PROF_SHADOW, nl * Ns * n_steps, st);
       rc = tc_shadow(geo, gen, nl * Ns, box, vis + l0 * Ns, st);  // fused march + transmittance, no HBM round trip
       if (rc) return rc;
       continue;

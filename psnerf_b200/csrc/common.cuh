@@ -11,6 +11,7 @@
 namespace psn {
 
 void set_error(const char* fmt, ...);
+void count_launch();  // every kernel launch of this library is counted (psn_launch_count)
 
 #define PSN_CUDA_CHECK(expr)                                                                  \
   do {                                                                                        \

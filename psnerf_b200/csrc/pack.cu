@@ -1,5 +1,6 @@
 // Library state, error reporting and network packing (psn_mlp_create / psn_mlp_free).
 #include <stdarg.h>
+#include <atomic>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -7,6 +8,8 @@
 namespace psn {
 
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -49,6 +52,7 @@ using namespace psn;
 
 extern "C" int psn_version(void) { return 100; }
 extern "C" const char* psn_last_error(void) { return g_err; }
+extern "C" int64_t psn_launch_count(void) { return (int64_t)g_launches.load(); }
 
 extern "C" int psn_device_check(int* sm_count) {
   int dev = 0;
@@ -134,16 +138,21 @@ extern "C" int psn_mlp_create(const psn_mlp_desc* desc, const int* in_dims, cons
     SimtLayer& L = net->fwd[l];
     const int row0 = (geo && l == nl - 1) ? 1 : 0;
     const int tot = L.K_pad * L.N_pad;
+    psn::count_launch();
     pack_kmajor<<<(tot + 255) / 256, 256, 0, st>>>(W[l], in_dims[l], row0, L.N, L.K_pad, L.N_pad, base + off_wt[l]);
+    psn::count_launch();
     pack_vec<<<(L.N_pad + 255) / 256, 256, 0, st>>>(b[l], row0, L.N, L.N_pad, base + off_b[l]);
     L.wt = base + off_wt[l];
     L.bias = base + off_b[l];
   }
   if (geo) {
     SimtLayer& H = net->logit_head;
+    psn::count_launch();
     pack_kmajor<<<(H.K_pad * 32 + 255) / 256, 256, 0, st>>>(W[nl - 1], in_dims[nl - 1], 0, 1, H.K_pad, 32,
                                                              base + off_logit_w);
+    psn::count_launch();
     pack_vec<<<1, 256, 0, st>>>(b[nl - 1], 0, 1, 32, base + off_logit_b);
+    psn::count_launch();
     pack_vec<<<(H.K_pad + 255) / 256, 256, 0, st>>>(W[nl - 1], 0, in_dims[nl - 1], H.K_pad, base + off_row);
     H.wt = base + off_logit_w;
     H.bias = base + off_logit_b;
@@ -151,6 +160,7 @@ extern "C" int psn_mlp_create(const psn_mlp_desc* desc, const int* in_dims, cons
     for (int l = 0; l < nl - 1; ++l) {
       SimtLayer& R = net->rev[l];
       const int tot = R.K_pad * R.N_pad;
+      psn::count_launch();
       pack_native<<<(tot + 255) / 256, 256, 0, st>>>(W[l], out_dims[l], in_dims[l], R.K_pad, R.N_pad, base + off_rev[l]);
       R.wt = base + off_rev[l];
       R.bias = nullptr;

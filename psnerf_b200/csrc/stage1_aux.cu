@@ -281,28 +281,33 @@ int launch_rays(const float* pix, long long N, const float* cam, int stage2, flo
   if (N == 0) return PSN_OK;
   CamDev c;
   memcpy(c.v, cam, sizeof(c.v));
+  psn::count_launch();
   k_rays_from_pixels<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(pix, N, c, stage2, dirs);
   PSN_CUDA_CHECK(cudaGetLastError());
   return PSN_OK;
 }
 int launch_sphere_far(const float* dirs, long long N, const float* o, float r, float* far, cudaStream_t st) {
   if (N == 0) return PSN_OK;
+  psn::count_launch();
   k_sphere_far<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(dirs, N, o[0], o[1], o[2], r, far);
   PSN_CUDA_CHECK(cudaGetLastError());
   return PSN_OK;
 }
 int launch_march_scan(const float* occ, const float* far, long long N, int S, float near_, float tau, SecantState s,
                       float* depth, cudaStream_t st) {
+  psn::count_launch();
   k_march_scan<<<(unsigned)((N * 32 + 255) / 256), 256, 0, st>>>(occ, far, N, S, near_, tau, s, depth);
   PSN_CUDA_CHECK(cudaGetLastError());
   return PSN_OK;
 }
 int launch_secant_update(SecantState s, const float* occ_mid, float tau, long long N, cudaStream_t st) {
+  psn::count_launch();
   k_secant_update<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(s, occ_mid, tau);
   PSN_CUDA_CHECK(cudaGetLastError());
   return PSN_OK;
 }
 int launch_march_finalize(SecantState s, float* depth, long long N, cudaStream_t st) {
+  psn::count_launch();
   k_march_finalize<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(s, depth);
   PSN_CUDA_CHECK(cudaGetLastError());
   return PSN_OK;
@@ -312,6 +317,7 @@ int launch_sample_plan(const float* d_i, const float* far, long long N, const ps
   PSN_REQUIRE(prm.steps_in + prm.steps_out <= PLAN_MAX_S && prm.steps_in >= 2 && prm.steps_out != 1, PSN_ERR_SHAPE,
               "unisurf: steps_in=%d steps_out=%d unsupported (need 2 <= total <= %d)", prm.steps_in, prm.steps_out,
               PLAN_MAX_S);
+  psn::count_launch();
   k_sample_plan<<<(unsigned)((N + 3) / 4), 128, 0, st>>>(d_i, far, N, prm, noise, sample_depth, mask, sl);
   PSN_CUDA_CHECK(cudaGetLastError());
   return PSN_OK;
@@ -319,6 +325,7 @@ int launch_sample_plan(const float* d_i, const float* far, long long N, const ps
 int launch_composite(const float* rgb_s, const float* alpha, long long N, int S, int white, float* rgb, float* acc,
                      cudaStream_t st) {
   if (N == 0) return PSN_OK;
+  psn::count_launch();
   k_composite<<<(unsigned)((N * 32 + 255) / 256), 256, 0, st>>>(rgb_s, alpha, N, S, white, rgb, acc);
   PSN_CUDA_CHECK(cudaGetLastError());
   return PSN_OK;
@@ -326,12 +333,14 @@ int launch_composite(const float* rgb_s, const float* alpha, long long N, int S,
 int launch_shadow_composite(const float* occ, const float* surf, const float* lights, long long Ns, long long pairs, int S,
                             float lnear, float lfar, float box, float* vis, cudaStream_t st) {
   if (pairs == 0) return PSN_OK;
+  psn::count_launch();
   k_shadow_composite<<<(unsigned)((pairs * 32 + 255) / 256), 256, 0, st>>>(occ, surf, lights, Ns, pairs, S, lnear, lfar,
                                                                             box, vis);
   PSN_CUDA_CHECK(cudaGetLastError());
   return PSN_OK;
 }
 int launch_scatter_normals(const float* grad, SurfList sl, float* normal, long long N, cudaStream_t st) {
+  psn::count_launch();
   k_scatter_normals<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(grad, sl, normal);
   PSN_CUDA_CHECK(cudaGetLastError());
   return PSN_OK;

@@ -278,6 +278,7 @@ int simt_occupancy(const psn_mlp* geo, const PointGen& gen, long long M, const i
   PSN_CUDA_CHECK(cudaFuncSetAttribute(k_geo_occ, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_occ()));
   const long long tiles = M_dev ? (long long)num_ctas() : (M + TM - 1) / TM;
   const int grid = (int)(tiles < num_ctas() ? tiles : num_ctas());
+  psn::count_launch();
   k_geo_occ<<<grid, NT, smem_occ(), st>>>(g, gen, M, M_dev, out_kind, out, with_feat);
   PSN_CUDA_CHECK(cudaGetLastError());
   return PSN_OK;
@@ -292,6 +293,7 @@ int simt_gradient(const psn_mlp* geo, const PointGen& gen, long long M, const in
   PSN_CUDA_CHECK(cudaFuncSetAttribute(k_geo_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_grad()));
   const long long tiles = M_dev ? (long long)num_ctas() : (M + TM - 1) / TM;
   const int grid = (int)(tiles < num_ctas() ? tiles : num_ctas());
+  psn::count_launch();
   k_geo_grad<<<grid, NT, smem_grad(), st>>>(g, gen, M, M_dev, grad, (float4*)stash);
   PSN_CUDA_CHECK(cudaGetLastError());
   return PSN_OK;
@@ -309,6 +311,7 @@ int simt_radiance(const psn_mlp* geo, const psn_mlp* app, const PointGen& gen, l
   PSN_CUDA_CHECK(cudaFuncSetAttribute(k_radiance, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rad()));
   const long long tiles = (M + TM - 1) / TM;
   const int grid = (int)(tiles < num_ctas() ? tiles : num_ctas());
+  psn::count_launch();
   k_radiance<<<grid, NT, smem_rad(), st>>>(g, a, gen, M, nullptr, rgb, alpha, (float4*)stash);
   PSN_CUDA_CHECK(cudaGetLastError());
   return PSN_OK;

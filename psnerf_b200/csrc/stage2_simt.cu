@@ -4,6 +4,7 @@
 #include "simt_mlp.cuh"
 #include "launch.cuh"
 #include "internal.cuh"
+#include "prof.cuh"
 
 namespace psn {
 
@@ -301,6 +302,7 @@ int s2_point_nets(const psn_mlp* normal_net, int nf_n, const psn_mlp* albedo_net
   PSN_CUDA_CHECK(cudaFuncSetAttribute(k_s2_point, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long tiles = (Ns + TM - 1) / TM;
   const int grid = (int)(tiles < num_ctas() ? tiles : num_ctas());
+  psn::count_launch();
   k_s2_point<<<grid, NT, smem, st>>>(pn, pts, Ns, normal, albedo, weights, nbt, k_rows);
   PSN_CUDA_CHECK(cudaGetLastError());
   return PSN_OK;
@@ -321,6 +323,7 @@ int s2_visibility_simt(const psn_mlp* vis_net, int nf, const float* pts, long lo
   PSN_CUDA_CHECK(cudaFuncSetAttribute(k_s2_vis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long tiles = (pairs + TM - 1) / TM;
   const int grid = (int)(tiles < num_ctas() ? tiles : num_ctas());
+  psn::count_launch();
   k_s2_vis<<<grid, NT, smem, st>>>(d, nf, pts, Ns, lights, pairs, vis);
   PSN_CUDA_CHECK(cudaGetLastError());
   return PSN_OK;
@@ -374,10 +377,14 @@ extern "C" int psn_shade_stage2(const psn_mlp* normal_net, const psn_mlp* albedo
   PSN_REQUIRE(w.ok, PSN_ERR_WORKSPACE, "psn_shade_stage2: workspace too small (need %zu bytes, have %lld)", w.used,
               (long long)ws_bytes);
   int rc;
-  if ((rc = s2_point_nets(normal_net, prm->n_freqs_normal, albedo_net, rough_net, prm->n_freqs_xyz, pts, Ns, n_s, a_s, w_s, nbt,
-                          st)))
-    return rc;
+  {
+    ProfScope prof(PSN_PROF_S2_POINT, Ns, st);
+    if ((rc = s2_point_nets(normal_net, prm->n_freqs_normal, albedo_net, rough_net, prm->n_freqs_xyz, pts, Ns, n_s, a_s, w_s,
+                            nbt, st)))
+      return rc;
+  }
   if (vis_net) {
+    ProfScope prof(PSN_PROF_S2_VIS, (long long)Ns * L, st);
     if (precision == PSN_PREC_TC) {
       const size_t off = (w.used + 255) / 256 * 256;
       rc = tc_s2_visibility(vis_net, prm->n_freqs_xyz, pts, Ns, lights, L, v_s, (char*)ws + off,
@@ -387,8 +394,9 @@ extern "C" int psn_shade_stage2(const psn_mlp* normal_net, const psn_mlp* albedo
     }
     if (rc) return rc;
   }
+  psn::count_launch();
   k_fill_int<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(sop, N, -1);
-  if (Ns > 0) k_slot_of_pixel<<<(unsigned)((Ns + 255) / 256), 256, 0, st>>>(pix, Ns, sop);
+  if (Ns > 0) { psn::count_launch(); k_slot_of_pixel<<<(unsigned)((Ns + 255) / 256), 256, 0, st>>>(pix, Ns, sop); }
   ShadeArgs a;
   memset(&a, 0, sizeof(a));
   a.normal = normal_net ? n_s : normal_in;
@@ -398,6 +406,7 @@ extern "C" int psn_shade_stage2(const psn_mlp* normal_net, const psn_mlp* albedo
   a.N = N; a.Ns = Ns; a.L = L; a.nbasis = prm->nbasis; a.specular_rgb = prm->specular_rgb; a.nbt = nbt;
   a.intensity_kind = prm->intensity_kind; a.intensity_scalar = prm->intensity; a.write_normal = normal_net ? 1 : 0;
   dim3 grid((unsigned)((N + 255) / 256), (unsigned)(L + 1));
+  psn::count_launch();
   k_s2_shade<<<grid, 256, 0, st>>>(a);
   PSN_CUDA_CHECK(cudaGetLastError());
   return PSN_OK;

@@ -1,5 +1,6 @@
 // Placeholder for the tcgen05 path while it is being brought up: every entry reports "unavailable".
 #include "internal.cuh"
+extern "C" int psn_has_tensor_path(void) { return 0; }
 namespace psn {
 static int na() { set_error("tensor-core (PSN_PREC_TC) path is not available in this build"); return PSN_ERR_SHAPE; }
 int tc_pack_bytes(const psn_mlp*) { return 0; }

@@ -15,6 +15,10 @@ def set_default_precision(name):
     _DEFAULT_PRECISION[0] = {"fp32": B.PREC_FP32, "tc": B.PREC_TC}[name]
 
 
+def tc_available():
+    return bool(B.load().psn_has_tensor_path())
+
+
 def default_precision():
     return _DEFAULT_PRECISION[0]
 

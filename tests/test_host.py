@@ -1,0 +1,82 @@
+"""CPU-only checks of the host side: drop-in constructors / state-dict layout, C-ABI symbol export, loud failure
+without a GPU."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import util
+from psnerf_b200 import synth
+
+
+def test_stage1_state_dict_layout():
+    from psnerf_b200.stage1 import NeuralNetwork
+    m = NeuralNetwork(synth.stage1_cfg())
+    sd = m.state_dict()
+    assert sum(v.numel() for v in sd.values()) == 802490
+    for l in range(9):
+        assert sd["lin%d.weight_g" % l].shape[1] == 1
+        assert sd["lin%d.weight_v" % l].shape[0] == sd["lin%d.bias" % l].shape[0]
+    assert sd["lin3.weight_v"].shape == (217, 256) and sd["lin4.weight_v"].shape == (256, 256)
+    assert sd["lin8.weight_v"].shape == (257, 256) and sd["lina0.weight_v"].shape == (256, 289)
+    # weight_g initialised to the row norms of weight_v, like torch.nn.utils.weight_norm
+    assert torch.allclose(sd["lin2.weight_g"], sd["lin2.weight_v"].norm(2, dim=1, keepdim=True))
+
+
+def test_stage2_state_dict_layout():
+    from psnerf_b200.stage2 import PSNetwork
+    m = PSNetwork(synth.stage2_conf())
+    sd = m.state_dict()
+    assert sum(v.numel() for v in sd.values()) == 667947
+    assert sd["visibility_net.linears.5.weight"].shape == (256, 382)
+    assert sd["albedo_net.linears.3.weight"].shape == (128, 191)
+    assert sd["rough_net.linears.2.weight"].shape == (27, 64)
+    assert not m.sgbasis.lobe.requires_grad
+    assert np.allclose(sd["sgbasis.lobe"].numpy(), np.exp(np.arange(2, 11)), rtol=1e-6)
+
+
+def test_constructor_weights_equal_reference():
+    g1, g2 = util.golden("stage1_net"), util.golden("stage2_shade")
+    _, s1 = util.stage1_state_dicts()
+    _, s2 = util.stage2_state_dicts()
+    np.testing.assert_array_equal(util.checksum(s1["init"]), g1["init_checksum"])
+    np.testing.assert_array_equal(util.checksum(s2["init"]), g2["init_checksum"])
+
+
+def test_abi_exports_every_declared_symbol(lib_built):
+    from psnerf_b200 import _binding
+    names = _binding.declared_symbols()
+    assert len(names) >= 17 and "psn_render_unisurf" in names and "psn_shade_stage2" in names
+    for n in names:
+        assert hasattr(lib_built, n), n
+    assert lib_built.psn_version() >= 100
+
+
+def test_abi_rejects_bad_arguments_without_gpu(lib_built):
+    assert lib_built.psn_workspace_bytes(b"no-such-op", 1, 1, 1) < 0
+    assert b"unknown op" in lib_built.psn_last_error()
+    assert lib_built.psn_workspace_bytes(b"unisurf", 1024, 256, 1) > 1024 * 256 * 4
+    rc = lib_built.psn_occupancy(None, None, 0, 0, None, 0, None)
+    assert rc == -1 and b"null" in lib_built.psn_last_error()
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")
+def test_no_cpu_fallback():
+    from psnerf_b200.stage1 import NeuralNetwork
+    from psnerf_b200.stage2 import PSNetwork
+    m = NeuralNetwork(synth.stage1_cfg())
+    with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
+        m(torch.zeros(4, 3), only_occupancy=True)
+    p = PSNetwork(synth.stage2_conf())
+    with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
+        p(synth.stage2_input(4, 4, 2))
+
+
+def test_arange_pixels_is_xmajor():
+    from psnerf_b200.stage1 import arange_pixels
+    import psnerf_oracle as O
+    loc, sc = arange_pixels((3, 5))
+    assert loc.shape == (1, 15, 2) and loc[0, 1].tolist() == [0, 1] and loc[0, 3].tolist() == [1, 0]
+    lo, so = O.arange_pixels((3, 5))
+    assert torch.equal(loc, lo) and torch.equal(sc, so)
