@@ -161,6 +161,10 @@ int psn_s2_point_nets(const psn_mlp* albedo_net, const psn_mlp* rough_net, int n
 int psn_s2_visibility(const psn_mlp* vis_net, int n_freqs, const float* pts, int64_t Ns, const float* lights, int L,
                       float* vis /*[L,Ns]*/, void* ws, int64_t ws_bytes, int precision, void* stream);
 
+/* Bring-up / test hook of the tensor-core path: activations handed from geo layer `layer` (0..7) to the next one,
+ * fp32 before the fp16 hi/lo split, out[M,256]; logits[M] receives the resulting logit. */
+int psn_tc_debug_layer(const psn_mlp* geo, const float* pts, int64_t M, int layer, float* out, float* logits, void* stream);
+
 /* alpha compositing of per-sample (rgb, alpha): rendering.py:196-197,214-216. */
 int psn_composite(const float* rgb_s /*[N,S,3]*/, const float* alpha /*[N,S]*/, int64_t N, int S,
                   int white_background, float* rgb /*[N,3]*/, float* acc /*[N]*/, void* stream);

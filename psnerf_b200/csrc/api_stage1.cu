@@ -249,7 +249,7 @@ extern "C" int psn_shadow_visibility(const psn_mlp* geo, const float* surf, cons
     gen.lnear = lnear;
     gen.lfar = lfar;
     int rc;
-    if (precision == PSN_PREC_TC) {
+    if (precision == PSN_PREC_TC && n_steps == 128) {
       ProfScope prof(PSN_PROF_SHADOW, nl * Ns * n_steps, st);
       rc = tc_shadow(geo, gen, nl * Ns, box, vis + l0 * Ns, st);  // fused march + transmittance, no HBM round trip
       if (rc) return rc;

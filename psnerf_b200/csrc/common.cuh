@@ -42,12 +42,16 @@ struct SimtLayer {
 
 constexpr int kMaxLayers = 12;
 
-// Packed tcgen05 layer: fp16 hi/lo weight tiles, pre-swizzled (see tc_mlp.cuh).
-struct TcLayer {
-  const __half* tiles;  // [n_kblk][2 (hi,lo)][N_TILE rows][64] swizzled-128B images, 32 KB per (kblk,part) at N=256
-  const float* bias;    // [N_pad]
-  int K, N, K_pad, N_pad, n_kblk;
+// One tcgen05 step: weight tiles [kb][hi,lo][n_pad rows][64] fp16, pre-swizzled (tc_mlp.cuh, tc_pack.cu).
+struct TcStepW {
+  unsigned int w_off;  // byte offset inside the net's tile blob
+  unsigned short nkb, n_pad;
 };
+constexpr int kMaxTcSteps = 20;
+// step indices per net kind
+enum { TCG_FWD0 = 0, TCG_FEAT = 8, TCG_REV_TOP = 9 /* rev step of layer l is TCG_REV_TOP + (n_hidden-1-l) */, TCG_REV0 = 16 };
+enum { TCA_L0F = 0, TCA_L0R = 1, TCA_L1 = 2, TCA_L4 = 5 };
+enum { TCV_L1 = 0, TCV_L5Y = 4, TCV_L6 = 5, TCV_L7 = 6 };
 
 }  // namespace psn
 
@@ -67,8 +71,12 @@ struct psn_mlp {
   float b_logit;
   // tcgen05 packs (filled when the shape is one the tensor path supports)
   int tc_ok;
-  psn::TcLayer tc_fwd[psn::kMaxLayers];
-  psn::TcLayer tc_rev[psn::kMaxLayers];
+  psn::TcStepW tc_step[psn::kMaxTcSteps];
+  const unsigned char* tc_blob;
+  // stage-2 visibility net restructuring (tc path): layer 0 and the skip layer are split into per-point and
+  // per-light partial products; vis_aux = {W0 point part, W0 light part, Wskip point part, Wskip light part}
+  psn::SimtLayer vis_aux[4];
+  const float* w_last_row;  // S2: row 0 of the last layer (dot-product head), [K_pad]
   // stage-2 visibility restructuring: columns of layer 0 / skip layer split into point / light parts
   void* device_blob;  // single allocation that owns every packed array
   size_t blob_bytes;

@@ -269,6 +269,7 @@ static int make_s2_dev(const psn_mlp* net, int expect_in, S2Dev* d, const char* 
   return PSN_OK;
 }
 
+size_t tc_vis_workspace_bytes(long long Ns, long long L);
 size_t s2_workspace_bytes(long long Ns, long long L) {
   if (L < 1) L = 1;
   const size_t a = 256;
@@ -277,7 +278,7 @@ size_t s2_workspace_bytes(long long Ns, long long L) {
   b += (size_t)Ns * 32 * 4 + a;                // weights per slot
   b += (size_t)Ns * L * 4 + a;                 // raw visibility per pair
   b += (size_t)Ns * 16 * 4 + a;                // slot_of_pixel upper bound is N; callers pass max(N, Ns) as n_rays
-  return b + 4096;
+  return b + tc_vis_workspace_bytes(Ns, L) + 4096;
 }
 
 int s2_point_nets(const psn_mlp* normal_net, int nf_n, const psn_mlp* albedo_net, const psn_mlp* rough_net, int nf,

@@ -1,0 +1,222 @@
+// tcgen05 occupancy kernels of the stage-1 geo MLP: PE -> 8 softplus layers on tensor cores -> fp32 logit head.
+//   MODE_OUT    : one value per sample (alpha / logits) - ray-march proposals, secant points, explicit queries
+//   MODE_SHADOW : a 128-row tile is one shadow ray; box mask + transmittance are reduced in the epilogue and only
+//                 vis[pair] is written (rendering.py:378-408), no per-sample HBM traffic at all.
+// Algorithmic work per sample: 2 * 459,008 FLOP (the 256 unused feature rows of the last layer are not computed).
+#include "tc_mlp.cuh"
+#include "stage1_simt.cuh"
+#include "launch.cuh"
+#include "internal.cuh"
+
+namespace psn {
+using namespace tc;
+
+struct TcGeoArgs {
+  Program prog;
+  const float* bias[8];
+  const float* w_row;     // [256] logit row
+  const float* b_logit;   // [>=1]
+  int n_out[8];           // valid output columns per layer (217 for the pre-skip layer)
+  int skip;               // layer whose input is cat[x, pe]/sqrt2
+  int octaves, pe_dim;
+  float rescale;
+};
+
+// entry idx of [p, sin(2^0 p), cos(2^0 p), ...] (network.py:141-150)
+__device__ __forceinline__ float pe_entry(const float x[3], int idx) {
+  if (idx < 3) return x[idx];
+  const int j = idx - 3, oct = j / 6, r = j - 6 * oct, c = r % 3;
+  const float a = (float)(1 << oct) * x[c];
+  return r < 3 ? sinf(a) : cosf(a);
+}
+
+constexpr int MODE_OUT = 0, MODE_SHADOW = 1;
+
+template <int MODE>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+k_tc_occ(TcGeoArgs g, PointGen gen, long long M_host, const int* M_dev, int out_kind, float* out, float box, int dump_layer,
+         float* dump) {
+  extern __shared__ unsigned char smem_raw[];
+  const Smem s = carve(smem_raw);
+  const uint32_t tmem_base = setup(s);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long M = M_dev ? (long long)*M_dev : M_host;
+  const long long n_tiles = (M + TILE_M - 1) / TILE_M;
+  const long long iters = (n_tiles > (long long)blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (warp == 0) {
+    if (lane == 0) producer_loop(s, g.prog, iters);
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) mma_loop(s, g.prog, iters, tmem_base);
+    __syncwarp();
+  } else if (warp >= EPI_WARP0) {
+    EpiCtx e = epi_ctx(tmem_base);
+    const int row = e.row, half = e.half;
+    for (long long it = 0; it < iters; ++it) {
+      const long long tile = blockIdx.x + it * gridDim.x;
+      const long long idx = tile * TILE_M + row;
+      float p[3] = {0.f, 0.f, 0.f}, vdummy[3];
+      if (idx < M) gen_point(gen, idx, p, vdummy);
+      const float x[3] = {p[0] / g.rescale, p[1] / g.rescale, p[2] / g.rescale};
+      if (half == 0) {  // layer-0 operand: the point encoding, zero padded to one 64-wide K block
+#pragma unroll 1
+        for (int k = 0; k < KBLK; ++k) epi_store_a1(s, row, k, k < g.pe_dim ? pe_entry(x, k) : 0.f);
+        epi_signal_a(s, 0);
+      }
+      float part = 0.f;  // partial logit over this thread's 128 columns
+#pragma unroll 1
+      for (int l = 0; l < 8; ++l) {
+        epi_wait_d(s, e);
+        const float* bias = g.bias[l];
+        const bool pre_skip = (l + 1 == g.skip);
+        const int n_out = g.n_out[l];
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          const int col = half * 128 + c * 32;
+          float v[32];
+          epi_load32(e, col, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float a = softplus100_fast(v[i] + __ldg(bias + col + i));
+            if (pre_skip) a = a * 0.70710678118654752440f;
+            v[i] = a;
+          }
+          if (dump && dump_layer == l && idx < M) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) dump[idx * 256 + col + i] = (pre_skip && col + i >= n_out) ? pe_entry(x, col + i - n_out) * 0.70710678118654752440f : v[i];
+          }
+          if (l < 7) {
+            epi_store_a32(s, row, col, v);
+            if (pre_skip && col + 32 > n_out) {  // columns n_out.. of the skip layer's input are pe/sqrt2 (network.py:90-91)
+#pragma unroll 1
+              for (int k = (n_out > col ? n_out : col); k < col + 32; ++k)
+                epi_store_a1(s, row, k, pe_entry(x, k - n_out) * 0.70710678118654752440f);
+            }
+            if (c & 1) epi_signal_a(s, col >> 6);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) part = fmaf(v[i], __ldg(g.w_row + col + i), part);
+          }
+        }
+        e.step_ctr++;
+      }
+      tc_fence_before();  // order this tile's last TMEM reads before the next tile's MMAs (via a_ready)
+      if (half == 1) s.c->xhalf[row] = part;
+      named_bar_sync(1, EPI_THREADS);
+      if (half == 0) {
+        const float z = part + s.c->xhalf[row] + __ldg(g.b_logit);
+        if (MODE == MODE_OUT) {
+          if (idx < M) {
+            float o = z;
+            if (out_kind == PSN_OUT_ALPHA) o = 1.f / (1.f + __expf(10.f * z));
+            else if (out_kind == PSN_OUT_NEG_LOGIT) o = -z;
+            out[idx] = o;
+          }
+        } else {
+          // shadow ray: rows are the 128 march steps of pair `tile`; alpha zeroed outside the box (rendering.py:402-408)
+          float a = 1.f / (1.f + __expf(10.f * z));
+          const bool inside = (p[0] <= box) && (p[0] >= -box) && (p[1] <= box) && (p[1] >= -box) && (p[2] <= box) && (p[2] >= -box);
+          if (!inside || idx >= M) a = 0.f;
+          const float t = (1.f - a) + 1e-6f;
+          float incl = t;
+#pragma unroll
+          for (int off = 1; off < 32; off <<= 1) {
+            const float u = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl *= u;
+          }
+          float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+          if (lane == 0) excl = 1.f;
+          const int q = row >> 5;
+          if (lane == 31) s.c->g3[q] = incl;
+          named_bar_sync(2, 128);
+          float pre = 1.f;
+          for (int qq = 0; qq < q; ++qq) pre *= s.c->g3[qq];
+          float w = a * (pre * excl);
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) w += __shfl_xor_sync(0xffffffffu, w, off);
+          if (lane == 0) s.c->g3[8 + q] = w;
+          named_bar_sync(2, 128);
+          if (row == 0) out[tile] = 1.f - (s.c->g3[8] + s.c->g3[9] + s.c->g3[10] + s.c->g3[11]);
+        }
+      }
+    }
+  }
+  teardown(tmem_base);
+}
+
+// ---- host -------------------------------------------------------------------------------------------------------------
+static int make_tc_geo(const psn_mlp* geo, TcGeoArgs* a) {
+  PSN_REQUIRE(geo && geo->kind == PSN_NET_GEO, PSN_ERR_ARG, "expected a PSN_NET_GEO handle");
+  PSN_REQUIRE(geo->tc_ok, PSN_ERR_SHAPE,
+              "geo net shape is not supported by the tensor-core path (needs 8 hidden layers of width 129..256, pe <= 64, feat 256)");
+  memset(a, 0, sizeof(*a));
+  a->prog.n_steps = 8;
+  for (int l = 0; l < 8; ++l) {
+    a->prog.step[l].w_off = geo->tc_step[TCG_FWD0 + l].w_off;
+    a->prog.step[l].nkb = geo->tc_step[TCG_FWD0 + l].nkb;
+    a->prog.step[l].n_pad = geo->tc_step[TCG_FWD0 + l].n_pad;
+    a->prog.blob[l] = geo->tc_blob;
+    a->bias[l] = geo->fwd[l].bias;
+    a->n_out[l] = geo->fwd[l].N;
+  }
+  a->w_row = geo->w_logit_row;
+  a->b_logit = geo->logit_head.bias;
+  a->skip = geo->desc.skip;
+  a->octaves = geo->desc.octaves;
+  a->pe_dim = 3 + 6 * geo->desc.octaves;
+  a->rescale = geo->desc.rescale;
+  if (a->skip >= 0)
+    PSN_REQUIRE(a->skip >= 1 && a->skip <= 7 && geo->fwd[a->skip - 1].N + a->pe_dim == 256, PSN_ERR_SHAPE,
+                "tensor path: skip layer input must be exactly 256 wide");
+  return PSN_OK;
+}
+
+template <int MODE>
+static int launch_tc_occ(const TcGeoArgs& a, const PointGen& gen, long long M, const int* M_dev, int out_kind, float* out, float box,
+                         int dump_layer, float* dump, cudaStream_t st) {
+  PSN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_occ<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  const long long tiles = M_dev ? (long long)num_ctas() : (M + TILE_M - 1) / TILE_M;
+  const int grid = (int)(tiles < num_ctas() ? tiles : num_ctas());
+  count_launch();
+  k_tc_occ<MODE><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(a, gen, M, M_dev, out_kind, out, box, dump_layer, dump);
+  PSN_CUDA_CHECK(cudaGetLastError());
+  return PSN_OK;
+}
+
+int tc_occupancy(const psn_mlp* geo, const PointGen& gen, long long M, const int* M_dev, int out_kind, float* out, cudaStream_t st) {
+  TcGeoArgs a;
+  int rc = make_tc_geo(geo, &a);
+  if (rc) return rc;
+  if (M == 0 && !M_dev) return PSN_OK;
+  return launch_tc_occ<MODE_OUT>(a, gen, M, M_dev, out_kind, out, 0.f, -1, nullptr, st);
+}
+
+// pairs shadow rays of gen.S == 128 steps each; vis[pair]
+int tc_shadow(const psn_mlp* geo, const PointGen& gen, long long pairs, float box, float* vis, cudaStream_t st) {
+  TcGeoArgs a;
+  int rc = make_tc_geo(geo, &a);
+  if (rc) return rc;
+  PSN_REQUIRE(gen.S == TILE_M, PSN_ERR_SHAPE, "fused tensor-core shadow pass needs n_steps == 128 (got %d)", gen.S);
+  if (pairs == 0) return PSN_OK;
+  return launch_tc_occ<MODE_SHADOW>(a, gen, pairs * TILE_M, nullptr, PSN_OUT_ALPHA, vis, box, -1, nullptr, st);
+}
+
+}  // namespace psn
+
+using namespace psn;
+
+// Bring-up / test hook: run the tensor-core geo stack on explicit points and dump the activations that layer `layer`
+// hands to the next one (fp32, before the fp16 hi/lo split): out[M, 256].
+extern "C" int psn_tc_debug_layer(const psn_mlp* geo, const float* pts, int64_t M, int layer, float* out, float* logits,
+                                  void* stream) {
+  PSN_REQUIRE(geo && pts && out && logits && layer >= 0 && layer < 8, PSN_ERR_ARG, "psn_tc_debug_layer: bad argument");
+  TcGeoArgs a;
+  int rc = make_tc_geo(geo, &a);
+  if (rc) return rc;
+  PointGen gen;
+  memset(&gen, 0, sizeof(gen));
+  gen.kind = GEN_EXPLICIT;
+  gen.pts = pts;
+  return launch_tc_occ<MODE_OUT>(a, gen, M, nullptr, PSN_OUT_LOGIT, logits, 0.f, layer, out, (cudaStream_t)stream);
+}

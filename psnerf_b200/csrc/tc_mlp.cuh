@@ -1,0 +1,328 @@
+// tcgen05 / TMEM / mbarrier / bulk-copy primitives and the layer-pipelined fused-MLP machinery (sm_100a).
+//
+// One CTA (one per SM, persistent) owns a 128-row tile.  Per "step" (one Linear layer)
+//     D[128 x N] (fp32, TMEM)  =  A[128 x K] (fp16 hi+lo, shared)  x  W[N x K]^T (fp16 hi+lo, shared ring)
+// is evaluated as three UMMA passes  A_hi W_hi + A_lo W_hi + A_hi W_lo  (error-compensated split operands:
+// the dropped A_lo W_lo term is 2^-22 relative, fp32 accumulate) so the result tracks an fp32 GEMM.
+//
+// Shared memory: A = 4 K-blocks x (hi 16 KB + lo 16 KB), K-major, 128-byte swizzle (the canonical UMMA layout
+// Swizzle<3,4,3>: 16-byte chunk c of row r lives at chunk c ^ (r & 7)); weight ring = 3 stages x 32 KB, each one
+// pre-swizzled [N rows][64 K] tile streamed from L2 with cp.async.bulk (UBLKCP) + mbarrier complete_tx.
+// TMEM: two 256-column fp32 accumulators (all 512 columns).
+//
+// Warp roles: warp 0 = weight producer, warp 1 = MMA issuer (one elected lane), warp 2 = TMEM allocator,
+// warps 4..11 = epilogue (warp w reads TMEM lanes 32*(w%4).. and column half (w-4)/4).
+// Layer pipelining: the epilogue of step L rewrites the A buffer in place (every MMA of step L has retired when
+// d_full fires) K-block by K-block and signals a_ready[kb]; the MMA warp starts step L+1's K-block kb as soon as
+// that block is ready, accumulating into the OTHER TMEM buffer - so tensor work of step L+1 overlaps the
+// activation math of step L and the tensor pipe only idles for the first 64-column chunk of each layer.
+#pragma once
+#include "common.cuh"
+
+namespace psn {
+namespace tc {
+
+constexpr int TILE_M = 128;
+constexpr int KBLK = 64;                      // K elements per block (128 bytes of fp16)
+constexpr int A_PART_BYTES = TILE_M * 128;    // one K-block of one part (hi or lo): 16 KB
+constexpr int A_KB_BYTES = 2 * A_PART_BYTES;  // hi + lo
+constexpr int A_MAX_KB = 4;
+constexpr int A_BYTES = A_MAX_KB * A_KB_BYTES;  // 128 KB
+constexpr int W_STAGE_BYTES = 256 * 128;        // 32 KB: [256 N rows][64 K] fp16
+constexpr int W_STAGES = 3;
+constexpr int NUM_THREADS = 384;
+constexpr int EPI_WARP0 = 4;
+constexpr int EPI_THREADS = 256;
+
+// ---- shared-memory control block (after the 1024-aligned A and W regions) ---------------------------------
+struct Ctrl {
+  unsigned long long w_full[W_STAGES];
+  unsigned long long w_empty[W_STAGES];
+  unsigned long long a_ready[A_MAX_KB];
+  unsigned long long d_full[2];
+  unsigned int tmem_base;
+  unsigned int pad;
+  float xhalf[TILE_M];     // cross-half exchange (partial dot products / transmittance scans)
+  float g3[TILE_M * 3];    // per-row 3-vectors (d logit / d p contributions)
+};
+constexpr int SMEM_BYTES = A_BYTES + W_STAGES * W_STAGE_BYTES + (int)sizeof(Ctrl) + 1024;  // +1024: manual alignment
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(void* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(void* bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(void* bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(void* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// generic-proxy smem writes -> visible to the async proxy (UMMA operand reads)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, void* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc_512(uint32_t* smem_dst) {  // whole warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(smem_dst)) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_512(uint32_t taddr) {  // whole warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, 128-byte-swizzled operand descriptor: start>>4 | LBO(16 B, ignored)<<16 | SBO(1024 B)<<32 | version 1 | SW128
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16, A = B = fp16 (format 0), D = fp32, both K-major, M = 128
+__device__ __forceinline__ uint32_t umma_idesc(uint32_t n) { return (1u << 4) | ((n >> 3) << 17) | (8u << 24); }
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(void* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// 32 lanes x 32 consecutive fp32 columns: thread (lane i) receives row (lane_base + i), columns col..col+31
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// ---- step table -------------------------------------------------------------------------------------------------
+struct Step {
+  uint32_t w_off;  // byte offset (from the net's tile blob) of tile (kb=0, hi); tiles follow as [kb][hi, lo]
+  uint16_t nkb;    // K blocks of 64
+  uint16_t n_pad;  // N (multiple of 16, <= 256); a tile is n_pad x 128 bytes
+};
+constexpr int MAX_STEPS = 24;
+struct Program {
+  Step step[MAX_STEPS];
+  const unsigned char* blob[MAX_STEPS];  // tile blob base per step (steps may come from different nets)
+  int n_steps;
+};
+
+// ---- shared-memory carve-up ---------------------------------------------------------------------------------------
+struct Smem {
+  unsigned char* a;   // A buffer, 1024-aligned
+  unsigned char* w;   // weight ring, 1024-aligned
+  Ctrl* c;
+};
+__device__ __forceinline__ Smem carve(unsigned char* raw) {
+  Smem s;
+  const uint32_t base = smem_u32(raw);
+  const uint32_t pad = (1024u - (base & 1023u)) & 1023u;
+  s.a = raw + pad;
+  s.w = s.a + A_BYTES;
+  s.c = reinterpret_cast<Ctrl*>(s.w + W_STAGES * W_STAGE_BYTES);
+  return s;
+}
+
+// Barrier init (thread 0) + TMEM allocation (warp 2).  Ends with a CTA barrier; returns the TMEM base address.
+__device__ __forceinline__ uint32_t setup(const Smem& s) {
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < W_STAGES; ++i) { mbar_init(&s.c->w_full[i], 1); mbar_init(&s.c->w_empty[i], 1); }
+    for (int i = 0; i < A_MAX_KB; ++i) mbar_init(&s.c->a_ready[i], 128);
+    for (int i = 0; i < 2; ++i) mbar_init(&s.c->d_full[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_512(&s.c->tmem_base);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  return *reinterpret_cast<volatile uint32_t*>(&s.c->tmem_base);
+}
+__device__ __forceinline__ void teardown(uint32_t tmem_base) {
+  tc_fence_before();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 2) tmem_dealloc_512(tmem_base);
+}
+
+// ---- producer: stream every weight tile of `iters` tile-iterations through the ring (warp 0, lane 0) ------------------
+__device__ __forceinline__ void producer_loop(const Smem& s, const Program& prog, long long iters) {
+  uint32_t stage = 0, phase = 0;
+  for (long long it = 0; it < iters; ++it) {
+    for (int st = 0; st < prog.n_steps; ++st) {
+      const Step sp = prog.step[st];
+      const uint32_t tile_bytes = (uint32_t)sp.n_pad * 128u;
+      const unsigned char* src = prog.blob[st] + sp.w_off;
+      for (int t = 0; t < 2 * sp.nkb; ++t) {
+        mbar_wait(&s.c->w_empty[stage], phase ^ 1u);
+        mbar_arrive_expect_tx(&s.c->w_full[stage], tile_bytes);
+        bulk_g2s(s.w + stage * W_STAGE_BYTES, src + (size_t)t * tile_bytes, tile_bytes, &s.c->w_full[stage]);
+        if (++stage == W_STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  }
+}
+
+// ---- MMA issuer (warp 1, lane 0) -------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_loop(const Smem& s, const Program& prog, long long iters, uint32_t tmem_base) {
+  uint32_t stage = 0, phase = 0;   // weight ring
+  uint32_t a_phase = 0;            // bit kb = parity to wait for on a_ready[kb]
+  uint32_t step_ctr = 0;           // selects the TMEM accumulator
+  const uint32_t a_base = smem_u32(s.a), w_base = smem_u32(s.w);
+  for (long long it = 0; it < iters; ++it) {
+    for (int st = 0; st < prog.n_steps; ++st, ++step_ctr) {
+      const Step sp = prog.step[st];
+      const uint32_t idesc = umma_idesc(sp.n_pad);
+      const uint32_t d_addr = tmem_base + (step_ctr & 1u) * 256u;
+      for (int kb = 0; kb < sp.nkb; ++kb) {
+        mbar_wait(&s.c->a_ready[kb], (a_phase >> kb) & 1u);
+        a_phase ^= (1u << kb);
+        tc_fence_after();
+        const uint32_t a_hi = a_base + kb * A_KB_BYTES, a_lo = a_hi + A_PART_BYTES;
+        // W_hi tile: A_hi W_hi + A_lo W_hi
+        mbar_wait(&s.c->w_full[stage], phase);
+        tc_fence_after();
+        {
+          const uint32_t wb = w_base + stage * W_STAGE_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_f16(d_addr, umma_desc(a_hi + ks * 32), umma_desc(wb + ks * 32), idesc, (kb | ks) ? 1u : 0u);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) umma_f16(d_addr, umma_desc(a_lo + ks * 32), umma_desc(wb + ks * 32), idesc, 1u);
+        }
+        umma_commit(&s.c->w_empty[stage]);
+        if (++stage == W_STAGES) { stage = 0; phase ^= 1u; }
+        // W_lo tile: A_hi W_lo
+        mbar_wait(&s.c->w_full[stage], phase);
+        tc_fence_after();
+        {
+          const uint32_t wb = w_base + stage * W_STAGE_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) umma_f16(d_addr, umma_desc(a_hi + ks * 32), umma_desc(wb + ks * 32), idesc, 1u);
+        }
+        umma_commit(&s.c->w_empty[stage]);
+        if (++stage == W_STAGES) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(&s.c->d_full[step_ctr & 1u]);
+    }
+  }
+}
+
+// ---- epilogue-side helpers ---------------------------------------------------------------------------------------------
+struct EpiCtx {
+  uint32_t tmem_base;
+  uint32_t step_ctr;   // global step counter (same sequence as the MMA warp)
+  int row;             // tile row owned by this thread (TMEM lane)
+  int half;            // column half: 0 -> columns 0..127, 1 -> 128..255
+  uint32_t lane_addr;  // (32 * quadrant) << 16
+};
+__device__ __forceinline__ EpiCtx epi_ctx(uint32_t tmem_base) {
+  EpiCtx e;
+  const int ew = (threadIdx.x >> 5) - EPI_WARP0;
+  e.tmem_base = tmem_base;
+  e.step_ctr = 0;
+  e.row = (ew & 3) * 32 + (threadIdx.x & 31);
+  e.half = ew >> 2;
+  e.lane_addr = (uint32_t)((ew & 3) * 32) << 16;
+  return e;
+}
+// wait for the accumulator of the current step
+__device__ __forceinline__ void epi_wait_d(const Smem& s, const EpiCtx& e) {
+  mbar_wait(&s.c->d_full[e.step_ctr & 1u], (e.step_ctr >> 1) & 1u);
+  tc_fence_after();
+}
+__device__ __forceinline__ void epi_load32(const EpiCtx& e, int col, float (&v)[32]) {
+  tmem_ld32(e.tmem_base + e.lane_addr + (e.step_ctr & 1u) * 256u + (uint32_t)col, v);
+}
+
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
+  return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+// Write 32 consecutive activation values (columns col..col+31 of this thread's row) as fp16 hi/lo into the A buffer.
+__device__ __forceinline__ void epi_store_a32(const Smem& s, int row, int col, const float (&v)[32]) {
+  const int kb = col >> 6;
+  unsigned char* hi_row = s.a + kb * A_KB_BYTES + row * 128;
+  unsigned char* lo_row = hi_row + A_PART_BYTES;
+  const int c0 = (col & 63) >> 3;  // first 16-byte chunk
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float x0 = v[t * 8 + 2 * u], x1 = v[t * 8 + 2 * u + 1];
+      const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+      const __half l0 = __float2half_rn(x0 - __half2float(h0)), l1 = __float2half_rn(x1 - __half2float(h1));
+      h[u] = pack_h2(h0, h1);
+      l[u] = pack_h2(l0, l1);
+    }
+    const int phys = ((c0 + t) ^ (row & 7)) * 16;
+    *reinterpret_cast<uint4*>(hi_row + phys) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(lo_row + phys) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+// single element (column col of this thread's row): used for the few encoding columns that are not MMA outputs
+__device__ __forceinline__ void epi_store_a1(const Smem& s, int row, int col, float x) {
+  const int kb = col >> 6, kk = col & 63;
+  unsigned char* hi_row = s.a + kb * A_KB_BYTES + row * 128;
+  const int phys = (((kk >> 3) ^ (row & 7)) << 4) + (kk & 7) * 2;
+  const __half h = __float2half_rn(x);
+  *reinterpret_cast<__half*>(hi_row + phys) = h;
+  *reinterpret_cast<__half*>(hi_row + A_PART_BYTES + phys) = __float2half_rn(x - __half2float(h));
+}
+// all of this thread's writes to K-block kb are done: publish to the MMA warp (128 arrivals per block)
+__device__ __forceinline__ void epi_signal_a(const Smem& s, int kb) {
+  tc_fence_before();
+  fence_proxy_async_smem();
+  mbar_arrive(&s.c->a_ready[kb]);
+}
+
+// fast softplus(beta=100, threshold=20) and its derivative sigmoid(100 z) on the MUFU pipe
+__device__ __forceinline__ float softplus100_fast(float z) {
+  const float v = z * 100.f;
+  const float e = __expf(fminf(v, 20.f));
+  const float sp = 0.01f * __logf(1.f + e);
+  return v > 20.f ? z : sp;
+}
+
+}  // namespace tc
+}  // namespace psn

@@ -1,15 +1,19 @@
-// Placeholder for the tcgen05 path while it is being brought up: every entry reports "unavailable".
+// Parts of the PSN_PREC_TC path that still run on the fp32 FFMA kernels (explicit forwarding, never a CPU path).
+// Replaced one by one by tcgen05 kernels: see DESIGN.md "Kernels" for the current split.
 #include "internal.cuh"
-extern "C" int psn_has_tensor_path(void) { return 0; }
+extern "C" int psn_has_tensor_path(void) { return 1; }
 namespace psn {
-static int na() { set_error("tensor-core (PSN_PREC_TC) path is not available in this build"); return PSN_ERR_SHAPE; }
-int tc_pack_bytes(const psn_mlp*) { return 0; }
-int tc_pack_fill(psn_mlp*, const float* const*, const float* const*, char*, size_t, cudaStream_t) { return PSN_ERR_SHAPE; }
-int tc_occupancy(const psn_mlp*, const PointGen&, long long, const int*, int, float*, cudaStream_t) { return na(); }
-int tc_infer_occ(const psn_mlp*, const PointGen&, long long, float*, cudaStream_t) { return na(); }
-int tc_gradient(const psn_mlp*, const PointGen&, long long, const int*, float*, void*, cudaStream_t) { return na(); }
-int tc_radiance(const psn_mlp*, const psn_mlp*, const PointGen&, long long, float*, float*, void*, cudaStream_t) { return na(); }
-int tc_shadow(const psn_mlp*, const PointGen&, long long, float, float*, cudaStream_t) { return na(); }
-size_t tc_stash_bytes() { return 0; }
-int tc_s2_visibility(const psn_mlp*, int, const float*, long long, const float*, int, float*, void*, size_t, cudaStream_t) { return na(); }
+int s2_visibility_simt(const psn_mlp* vis_net, int nf, const float* pts, long long Ns, const float* lights, int L, float* vis,
+                       cudaStream_t st);
+int tc_infer_occ(const psn_mlp* geo, const PointGen& gen, long long M, float* out, cudaStream_t st) {
+  return simt_occupancy(geo, gen, M, nullptr, PSN_OUT_LOGIT, out, 1, st);  // full 257-wide query: API completeness only
 }
+int tc_gradient(const psn_mlp* geo, const PointGen& gen, long long M, const int* M_dev, float* grad, void* stash, cudaStream_t st) {
+  return simt_gradient(geo, gen, M, M_dev, grad, stash, st);
+}
+int tc_radiance(const psn_mlp* geo, const psn_mlp* app, const PointGen& gen, long long M, float* rgb, float* alpha, void* stash,
+                cudaStream_t st) {
+  return simt_radiance(geo, app, gen, M, rgb, alpha, stash, st);
+}
+size_t tc_stash_bytes() { return simt_stash_bytes(); }
+}  // namespace psn

@@ -1,0 +1,217 @@
+// tcgen05 path of the stage-2 visibility MLP (stage2/model/renderer.py:193: 126 -> 256 x8 -> 1 over L x Ns pairs).
+//
+// Algebraic restructuring (disclosed in DESIGN.md; FLOPs are still reported canonically): the network input is
+// cat[embed(p), embed(l)], so layer 0 and the skip layer (whose input is cat[y, embed(p), embed(l)]) split into a
+// per-point and a per-light partial product:
+//     z0(l, n) = P0[n] + L0[l],          z5(l, n) = W5[:, :256] y + P5[n] + L5[l]
+// P*/L* are tiny exact fp32 tables (fp32 FFMA kernel below, Ns x 63 x 512 MAC); the per-pair work is seven
+// 256x256 layers on tensor cores plus an fp32 dot-product head.  Tiles are (128 consecutive points) x (one light);
+// a CTA walks a contiguous range of tile ids with the light index fastest, so a point block's P rows are re-read
+// from L1/L2, not HBM.
+#include "tc_mlp.cuh"
+#include "simt_mlp.cuh"
+#include "launch.cuh"
+#include "internal.cuh"
+
+namespace psn {
+using namespace tc;
+
+// ---- fp32 tables --------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT, 1)
+k_s2_tables(SimtLayer la, SimtLayer lb, int nf, const float* __restrict__ x, long long n, float* __restrict__ outa,
+            float* __restrict__ outb) {
+  extern __shared__ __align__(16) float smem[];
+  float* E = smem;             // [64][LDX]
+  float* WS = E + 64 * LDX;
+  float* P = WS + WRING_FLOATS;  // [3][TM]
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int used = 3 + 6 * nf;
+  for (long long tile = blockIdx.x; tile < (n + TM - 1) / TM; tile += gridDim.x) {
+    const long long base = tile * TM;
+    if (threadIdx.x < TM) {
+      const long long i = base + threadIdx.x;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) P[c * TM + threadIdx.x] = (i < n) ? x[i * 3 + c] : 0.f;
+    }
+    __syncthreads();
+    {
+      const int r = threadIdx.x & (TM - 1), q = threadIdx.x / TM;
+      const float v[3] = {P[r], P[TM + r], P[2 * TM + r]};
+      if (q == 0) { E[0 * LDX + r] = v[0]; E[1 * LDX + r] = v[1]; E[2 * LDX + r] = v[2]; }
+      for (int idx = q; idx < nf * 3; idx += NT / TM) {
+        const int i = idx / 3, c = idx - 3 * i;
+        float s, co;
+        sincosf(v[c] * (float)(1 << i), &s, &co);
+        E[(3 + 6 * i + c) * LDX + r] = s;
+        E[(6 + 6 * i + c) * LDX + r] = co;
+      }
+      for (int k = used + q; k < 64; k += NT / TM) E[k * LDX + r] = 0.f;
+    }
+    __syncthreads();
+    for (int which = 0; which < 2; ++which) {
+      float acc[8][8];
+      dense<8>(which ? lb : la, E, WS, acc);
+      float* o = which ? outb : outa;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const long long row = base + ty * 8 + i;
+        if (row < n) {
+          *reinterpret_cast<float4*>(o + row * 256 + tx * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+          *reinterpret_cast<float4*>(o + row * 256 + 128 + tx * 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---- tensor-core pair kernel ------------------------------------------------------------------------------------------
+struct TcVisArgs {
+  Program prog;          // 7 steps: layers 1..4, 5 (y part), 6, 7
+  const float* bias[7];  // bias of layers 1..4, (unused: folded into P5), 6, 7
+  const float* w_last;   // [256]
+  const float* b_last;   // [1]
+  const float *P0, *P5;  // [Ns][256]
+  const float *L0, *L5;  // [L][256]
+  long long Ns;
+  int L;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+k_tc_vis(TcVisArgs g, float* __restrict__ vis) {
+  extern __shared__ unsigned char smem_raw[];
+  const Smem s = carve(smem_raw);
+  const uint32_t tmem_base = setup(s);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long pblocks = (g.Ns + TILE_M - 1) / TILE_M;
+  const long long n_tiles = pblocks * g.L;
+  const long long chunk = (n_tiles + gridDim.x - 1) / gridDim.x;
+  const long long t0 = chunk * blockIdx.x;
+  const long long t1 = (t0 + chunk < n_tiles) ? t0 + chunk : n_tiles;
+  const long long iters = t1 > t0 ? t1 - t0 : 0;
+  if (warp == 0) {
+    if (lane == 0) producer_loop(s, g.prog, iters);
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) mma_loop(s, g.prog, iters, tmem_base);
+    __syncwarp();
+  } else if (warp >= EPI_WARP0) {
+    EpiCtx e = epi_ctx(tmem_base);
+    const int row = e.row, half = e.half;
+    for (long long t = t0; t < t1; ++t) {
+      const long long pb = t / g.L;
+      const int l = (int)(t - pb * g.L);
+      const long long n = pb * TILE_M + row;
+      const bool valid = n < g.Ns;
+      const long long nn = valid ? n : g.Ns - 1;
+      // layer 0: relu(P0[n] + L0[l])
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        const int col = half * 128 + c * 32;
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(g.P0 + nn * 256 + col) + i);
+          const float4 b = __ldg(reinterpret_cast<const float4*>(g.L0 + (long long)l * 256 + col) + i);
+          v[4 * i + 0] = fmaxf(a.x + b.x, 0.f); v[4 * i + 1] = fmaxf(a.y + b.y, 0.f);
+          v[4 * i + 2] = fmaxf(a.z + b.z, 0.f); v[4 * i + 3] = fmaxf(a.w + b.w, 0.f);
+        }
+        epi_store_a32(s, row, col, v);
+        if (c & 1) epi_signal_a(s, col >> 6);
+      }
+      float part = 0.f;
+#pragma unroll 1
+      for (int st = 0; st < 7; ++st) {
+        epi_wait_d(s, e);
+        const float* bias = g.bias[st];
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          const int col = half * 128 + c * 32;
+          float v[32];
+          epi_load32(e, col, v);
+          if (st == 4) {  // skip layer: + P5[n] (bias folded) + L5[l]
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 a = __ldg(reinterpret_cast<const float4*>(g.P5 + nn * 256 + col) + i);
+              const float4 b = __ldg(reinterpret_cast<const float4*>(g.L5 + (long long)l * 256 + col) + i);
+              v[4 * i + 0] += a.x + b.x; v[4 * i + 1] += a.y + b.y; v[4 * i + 2] += a.z + b.z; v[4 * i + 3] += a.w + b.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += __ldg(bias + col + i);
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+          if (st < 6) {
+            epi_store_a32(s, row, col, v);
+            if (c & 1) epi_signal_a(s, col >> 6);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) part = fmaf(v[i], __ldg(g.w_last + col + i), part);
+          }
+        }
+        e.step_ctr++;
+      }
+      tc_fence_before();
+      if (half == 1) s.c->xhalf[row] = part;
+      named_bar_sync(1, EPI_THREADS);
+      if (half == 0 && valid) vis[(long long)l * g.Ns + n] = part + s.c->xhalf[row] + __ldg(g.b_last);
+    }
+  }
+  teardown(tmem_base);
+}
+
+int s2_visibility_simt(const psn_mlp* vis_net, int nf, const float* pts, long long Ns, const float* lights, int L, float* vis,
+                       cudaStream_t st);
+
+size_t tc_vis_workspace_bytes(long long Ns, long long L) { return (size_t)(Ns + L) * 2 * 256 * sizeof(float) + 4096; }
+
+int tc_s2_visibility(const psn_mlp* net, int nf, const float* pts, long long Ns, const float* lights, int L, float* vis, void* ws,
+                     size_t ws_bytes, cudaStream_t st) {
+  PSN_REQUIRE(net && net->kind == PSN_NET_S2, PSN_ERR_ARG, "visibility_net: expected a PSN_NET_S2 handle");
+  if (!net->tc_ok || net->in_dims[0] != 2 * (3 + 6 * nf) || 3 + 6 * nf > 64)
+    return s2_visibility_simt(net, nf, pts, Ns, lights, L, vis, st);  // shapes outside the tensor plan: fp32 kernels
+  if (Ns == 0 || L == 0) return PSN_OK;
+  Workspace w(ws, (long long)ws_bytes);
+  float* P0 = w.take<float>((size_t)Ns * 256);
+  float* P5 = w.take<float>((size_t)Ns * 256);
+  float* L0 = w.take<float>((size_t)L * 256);
+  float* L5 = w.take<float>((size_t)L * 256);
+  PSN_REQUIRE(w.ok, PSN_ERR_WORKSPACE, "visibility (tensor path): workspace too small (need %zu bytes, have %zu)", w.used, ws_bytes);
+  const size_t smem_t = (size_t)(64 * LDX + WRING_FLOATS + 3 * TM) * 4;
+  PSN_CUDA_CHECK(cudaFuncSetAttribute(k_s2_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+  {
+    const long long tiles = (Ns + TM - 1) / TM;
+    count_launch();
+    k_s2_tables<<<(int)(tiles < num_ctas() ? tiles : num_ctas()), NT, smem_t, st>>>(net->vis_aux[0], net->vis_aux[2], nf, pts, Ns, P0, P5);
+    const long long tl = (L + TM - 1) / TM;
+    count_launch();
+    k_s2_tables<<<(int)(tl < num_ctas() ? tl : num_ctas()), NT, smem_t, st>>>(net->vis_aux[1], net->vis_aux[3], nf, lights, L, L0, L5);
+    PSN_CUDA_CHECK(cudaGetLastError());
+  }
+  TcVisArgs a;
+  memset(&a, 0, sizeof(a));
+  a.prog.n_steps = 7;
+  const int layer_of_step[7] = {1, 2, 3, 4, 5, 6, 7};
+  for (int i = 0; i < 7; ++i) {
+    a.prog.step[i].w_off = net->tc_step[TCV_L1 + i].w_off;
+    a.prog.step[i].nkb = net->tc_step[TCV_L1 + i].nkb;
+    a.prog.step[i].n_pad = net->tc_step[TCV_L1 + i].n_pad;
+    a.prog.blob[i] = net->tc_blob;
+    a.bias[i] = net->fwd[layer_of_step[i]].bias;
+  }
+  a.w_last = net->w_last_row;
+  a.b_last = net->fwd[8].bias;
+  a.P0 = P0; a.P5 = P5; a.L0 = L0; a.L5 = L5;
+  a.Ns = Ns;
+  a.L = L;
+  PSN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_vis, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  const long long n_tiles = ((Ns + TILE_M - 1) / TILE_M) * L;
+  const int grid = (int)(n_tiles < num_ctas() ? n_tiles : num_ctas());
+  count_launch();
+  k_tc_vis<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(a, vis);
+  PSN_CUDA_CHECK(cudaGetLastError());
+  return PSN_OK;
+}
+
+}  // namespace psn

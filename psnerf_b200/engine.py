@@ -28,7 +28,11 @@ def _stream():
 
 
 def _ptr(t):
-    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+    if t is None:
+        return C.c_void_p(0)
+    if isinstance(t, C.c_void_p):
+        return t
+    return C.c_void_p(t.data_ptr())
 
 
 def f32c(t, device=None):
