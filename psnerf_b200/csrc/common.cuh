@@ -17,6 +17,7 @@ void count_launch();  // every kernel launch of this library is counted (psn_lau
   do {                                                                                        \
     cudaError_t _e = (expr);                                                                  \
     if (_e != cudaSuccess) {                                                                  \
+      (void)cudaGetLastError(); /* do not leave a stale error for the caller's runtime (torch) */ \
       psn::set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__, cudaGetErrorString(_e)); \
       return PSN_ERR_CUDA;                                                                    \
     }                                                                                         \

@@ -36,7 +36,7 @@ template <int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_tc_occ(TcGeoArgs g, PointGen gen, long long M_host, const int* M_dev, int out_kind, float* out, float box, int dump_layer,
          float* dump) {
-  extern __shared__ unsigned char smem_raw[];
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
   const Smem s = carve(smem_raw);
   const uint32_t tmem_base = setup(s);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

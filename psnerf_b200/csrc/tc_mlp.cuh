@@ -45,7 +45,8 @@ struct Ctrl {
   float xhalf[TILE_M];     // cross-half exchange (partial dot products / transmittance scans)
   float g3[TILE_M * 3];    // per-row 3-vectors (d logit / d p contributions)
 };
-constexpr int SMEM_BYTES = A_BYTES + W_STAGES * W_STAGE_BYTES + (int)sizeof(Ctrl) + 1024;  // +1024: manual alignment
+constexpr int SMEM_BYTES = A_BYTES + W_STAGES * W_STAGE_BYTES + (int)sizeof(Ctrl);  // dynamic smem is declared __align__(1024)
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory of sm_100");
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -156,9 +157,8 @@ struct Smem {
 };
 __device__ __forceinline__ Smem carve(unsigned char* raw) {
   Smem s;
-  const uint32_t base = smem_u32(raw);
-  const uint32_t pad = (1024u - (base & 1023u)) & 1023u;
-  s.a = raw + pad;
+  if (smem_u32(raw) & 1023u) __trap();  // SWIZZLE_128B operands need 1024-byte alignment
+  s.a = raw;
   s.w = s.a + A_BYTES;
   s.c = reinterpret_cast<Ctrl*>(s.w + W_STAGES * W_STAGE_BYTES);
   return s;

@@ -1,0 +1,402 @@
+// tcgen05 radiance-sample kernel (stage1/model/network.py:122-136): per 128-sample tile, 23 layer-pipelined steps
+//   s0..s7   geo layers 0..7 (softplus; sigma'(z) = sigmoid(100 z) of every unit stashed to an L2-resident scratch)
+//   s8       feature head (rows 1..256 of the last geo layer, no activation)
+//   s9       appearance layer 0, feature part (columns 33.. of lina0): partial pre-activation parked in the scratch
+//   s10..s16 reverse pass through layers 7..1:  dx = dz W_l ;  dz_{l-1} = dx * sigma'(z_{l-1})   (analytic normal)
+//   s17      reverse layer 0 -> d logit / d pe -> J_pe^T -> gradient; assembles [p, PE(view), gradient] for s18
+//   s18      appearance layer 0, remaining 33 inputs (+ parked partial + bias, ReLU)
+//   s19..s21 appearance layers 1..3 (ReLU);   s22 appearance layer 4 (N = 3) -> tanh * 0.5 + 0.5
+// plus the fp32 logit head (alpha) folded into s7's epilogue.  The same kernel with only s0..s7, s10..s17 is the
+// gradient (surface normal) kernel.  Algorithmic work: 2,509,824 FLOP per sample.
+#include "tc_mlp.cuh"
+#include "stage1_simt.cuh"
+#include "launch.cuh"
+#include "internal.cuh"
+
+namespace psn {
+using namespace tc;
+
+constexpr int SCR_STASH_F4 = 8 * 64 * TILE_M;        // float4 elements: [layer][col/4][row]
+constexpr int SCR_PART_F4 = 64 * TILE_M;             // [col/4][row]
+constexpr int SCR_F4_PER_CTA = SCR_STASH_F4 + SCR_PART_F4;
+
+struct TcRadArgs {
+  Program prog;
+  const float* gbias[8];
+  const float* bias_feat;
+  const float* w_row;
+  const float* b_logit;
+  int n_out[8];
+  int skip, octaves, pe_dim;
+  float rescale;
+  const float* abias[5];
+  int octaves_view, pe_view_dim;
+  float4* scratch;
+  int with_app;  // 1: radiance (23 steps), 0: gradient only (16 steps)
+};
+
+__device__ __forceinline__ float pe_entry_r(const float x[3], int idx) {
+  if (idx < 3) return x[idx];
+  const int j = idx - 3, oct = j / 6, r = j - 6 * oct, c = r % 3;
+  const float a = (float)(1 << oct) * x[c];
+  return r < 3 ? sinf(a) : cosf(a);
+}
+// d pe[idx] / d x[c]  (0 unless idx belongs to coordinate c)
+__device__ __forceinline__ float pe_jac(const float x[3], int idx, int* coord) {
+  if (idx < 3) { *coord = idx; return 1.f; }
+  const int j = idx - 3, oct = j / 6, r = j - 6 * oct, c = r % 3;
+  const float f = (float)(1 << oct), a = f * x[c];
+  *coord = c;
+  return r < 3 ? f * cosf(a) : -f * sinf(a);
+}
+
+#define PSN_INV_SQRT2 0.70710678118654752440f
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* __restrict__ rgb, float* __restrict__ alpha,
+         float* __restrict__ grad_out) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const Smem s = carve(smem_raw);
+  const uint32_t tmem_base = setup(s);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long M = M_dev ? (long long)*M_dev : M_host;
+  const long long n_tiles = (M + TILE_M - 1) / TILE_M;
+  const long long iters = (n_tiles > (long long)blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (warp == 0) {
+    if (lane == 0) producer_loop(s, g.prog, iters);
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) mma_loop(s, g.prog, iters, tmem_base);
+    __syncwarp();
+  } else if (warp >= EPI_WARP0) {
+    EpiCtx e = epi_ctx(tmem_base);
+    const int row = e.row, half = e.half;
+    float4* stash = g.scratch + (size_t)blockIdx.x * SCR_F4_PER_CTA;
+    float4* parked = stash + SCR_STASH_F4;
+    for (long long it = 0; it < iters; ++it) {
+      const long long tile = blockIdx.x + it * gridDim.x;
+      const long long idx = tile * TILE_M + row;
+      float p[3] = {0.f, 0.f, 0.f}, vd[3] = {0.f, 0.f, 1.f};
+      if (idx < M) gen_point(gen, idx, p, vd);
+      const float x[3] = {p[0] / g.rescale, p[1] / g.rescale, p[2] / g.rescale};
+      if (half == 0) {
+#pragma unroll 1
+        for (int k = 0; k < KBLK; ++k) epi_store_a1(s, row, k, k < g.pe_dim ? pe_entry_r(x, k) : 0.f);
+        epi_signal_a(s, 0);
+      }
+      // ---- s0..s7: geo forward --------------------------------------------------------------------------------------
+      float part = 0.f;
+#pragma unroll 1
+      for (int l = 0; l < 8; ++l) {
+        epi_wait_d(s, e);
+        const float* bias = g.gbias[l];
+        const bool pre_skip = (l + 1 == g.skip);
+        const int n_out = g.n_out[l];
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          const int col = half * 128 + c * 32;
+          float v[32];
+          epi_load32(e, col, v);
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            float sg[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int i = 4 * t + u;
+              const float z = v[i] + __ldg(bias + col + i);
+              const float vv = z * 100.f;
+              const float ex = __expf(fminf(vv, 20.f));
+              const float sp = 0.01f * __logf(1.f + ex);
+              float a = vv > 20.f ? z : sp;
+              sg[u] = __fdividef(ex, 1.f + ex);
+              if (pre_skip) a *= PSN_INV_SQRT2;
+              if (l == 7 && !g.with_app) a = __ldg(g.w_row + col + i) * sg[u];  // gradient only: seed dz_7 directly
+              v[i] = a;
+            }
+            stash[(size_t)(l * 64 + (col >> 2) + t) * TILE_M + row] = make_float4(sg[0], sg[1], sg[2], sg[3]);
+          }
+          epi_store_a32(s, row, col, v);
+          if (pre_skip && col + 32 > n_out) {
+#pragma unroll 1
+            for (int k = (n_out > col ? n_out : col); k < col + 32; ++k)
+              epi_store_a1(s, row, k, pe_entry_r(x, k - n_out) * PSN_INV_SQRT2);
+          }
+          if (l == 7 && g.with_app) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) part = fmaf(v[i], __ldg(g.w_row + col + i), part);
+          }
+          if (c & 1) epi_signal_a(s, col >> 6);
+        }
+        e.step_ctr++;
+      }
+      if (half == 1) s.c->xhalf[row] = part;
+      float g_acc[3] = {0.f, 0.f, 0.f};  // this thread's share of J_pe^T (d logit / d pe)
+      if (g.with_app) {
+        // ---- s8: feature head -> A (no activation) ---------------------------------------------------------------------
+        epi_wait_d(s, e);
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          const int col = half * 128 + c * 32;
+          float v[32];
+          epi_load32(e, col, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += __ldg(g.bias_feat + col + i);
+          epi_store_a32(s, row, col, v);
+          if (c & 1) epi_signal_a(s, col >> 6);
+        }
+        e.step_ctr++;
+        // ---- s9: appearance layer 0, feature part -> parked -------------------------------------------------------------
+        epi_wait_d(s, e);
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          const int col = half * 128 + c * 32;
+          float v[32];
+          epi_load32(e, col, v);
+#pragma unroll
+          for (int t = 0; t < 8; ++t)
+            parked[(size_t)((col >> 2) + t) * TILE_M + row] = make_float4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
+        }
+        e.step_ctr++;
+      }
+      // ---- reverse seed: dz_7 = W_last[0,:] * sigma'(z_7) -> A  (gradient-only mode wrote it in s7) ---------------------
+#pragma unroll 1
+      for (int c = 0; c < (g.with_app ? 4 : 0); ++c) {
+        const int col = half * 128 + c * 32;
+        float v[32];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const float4 sg = stash[(size_t)(7 * 64 + (col >> 2) + t) * TILE_M + row];
+          const float4 w = __ldg(reinterpret_cast<const float4*>(g.w_row + col) + t);
+          v[4 * t] = w.x * sg.x; v[4 * t + 1] = w.y * sg.y; v[4 * t + 2] = w.z * sg.z; v[4 * t + 3] = w.w * sg.w;
+        }
+        epi_store_a32(s, row, col, v);
+        if (c & 1) epi_signal_a(s, col >> 6);
+      }
+      // ---- s10..s16: reverse through layers 7..1 -----------------------------------------------------------------------------
+#pragma unroll 1
+      for (int l = 7; l >= 1; --l) {
+        epi_wait_d(s, e);
+        const bool is_skip = (l == g.skip);
+        const int nprev = g.n_out[l - 1];
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          const int col = half * 128 + c * 32;
+          float v[32];
+          epi_load32(e, col, v);
+          if (is_skip) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] *= PSN_INV_SQRT2;
+            if (col + 32 > nprev) {  // encoding part of the skip input: contributes J_pe^T directly
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const int k = col + i - nprev;
+                if (k >= 0 && k < g.pe_dim) {
+                  int cc;
+                  const float jv = pe_jac(x, k, &cc);
+                  const float t = jv * v[i];
+                  g_acc[0] += cc == 0 ? t : 0.f; g_acc[1] += cc == 1 ? t : 0.f; g_acc[2] += cc == 2 ? t : 0.f;
+                }
+              }
+            }
+          }
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const float4 sg = stash[(size_t)((l - 1) * 64 + (col >> 2) + t) * TILE_M + row];
+            v[4 * t] *= sg.x; v[4 * t + 1] *= sg.y; v[4 * t + 2] *= sg.z; v[4 * t + 3] *= sg.w;
+          }
+          if (col + 32 > nprev) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (col + i >= nprev) v[i] = 0.f;
+          }
+          epi_store_a32(s, row, col, v);
+          if (c & 1) epi_signal_a(s, col >> 6);
+        }
+        e.step_ctr++;
+      }
+      // ---- s17: reverse layer 0 -> gradient ------------------------------------------------------------------------------
+      epi_wait_d(s, e);
+      if (half == 1) {
+        s.c->g3[row * 3 + 0] = g_acc[0]; s.c->g3[row * 3 + 1] = g_acc[1]; s.c->g3[row * 3 + 2] = g_acc[2];
+      }
+      named_bar_sync(1, EPI_THREADS);
+      float gr[3] = {0.f, 0.f, 0.f};
+      float logit = 0.f;
+      if (half == 0) {
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          float v[32];
+          epi_load32(e, c * 32, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int k = c * 32 + i;
+            if (k < g.pe_dim) {
+              int cc;
+              const float jv = pe_jac(x, k, &cc);
+              const float t = jv * v[i];
+              g_acc[0] += cc == 0 ? t : 0.f; g_acc[1] += cc == 1 ? t : 0.f; g_acc[2] += cc == 2 ? t : 0.f;
+            }
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) gr[c] = (g_acc[c] + s.c->g3[row * 3 + c]) / g.rescale;
+        logit = part + s.c->xhalf[row] + __ldg(g.b_logit);
+        if (grad_out && idx < M) { grad_out[idx * 3] = gr[0]; grad_out[idx * 3 + 1] = gr[1]; grad_out[idx * 3 + 2] = gr[2]; }
+      }
+      e.step_ctr++;
+      tc_fence_before();
+      if (g.with_app) {
+        if (half == 0) {  // [p, PE(view/|view|), gradient] -> K block 0 (network.py:98,127-132)
+          const float nv = sqrtf(vd[0] * vd[0] + vd[1] * vd[1] + vd[2] * vd[2]);
+          const float vn[3] = {vd[0] / nv, vd[1] / nv, vd[2] / nv};
+          const int o_g = 3 + g.pe_view_dim;
+#pragma unroll 1
+          for (int k = 0; k < KBLK; ++k) {
+            float val = 0.f;
+            if (k < 3) val = p[k];
+            else if (k < o_g) val = pe_entry_r(vn, k - 3);
+            else if (k < o_g + 3) val = gr[k - o_g];
+            epi_store_a1(s, row, k, val);
+          }
+          epi_signal_a(s, 0);
+        }
+        // ---- s18: appearance layer 0 (rest) + parked + bias, ReLU ------------------------------------------------------------
+        epi_wait_d(s, e);
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          const int col = half * 128 + c * 32;
+          float v[32];
+          epi_load32(e, col, v);
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const float4 pk = parked[(size_t)((col >> 2) + t) * TILE_M + row];
+            v[4 * t] += pk.x; v[4 * t + 1] += pk.y; v[4 * t + 2] += pk.z; v[4 * t + 3] += pk.w;
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + __ldg(g.abias[0] + col + i), 0.f);
+          epi_store_a32(s, row, col, v);
+          if (c & 1) epi_signal_a(s, col >> 6);
+        }
+        e.step_ctr++;
+        // ---- s19..s21: appearance layers 1..3 -------------------------------------------------------------------------------
+#pragma unroll 1
+        for (int l = 1; l <= 3; ++l) {
+          epi_wait_d(s, e);
+          const float* bias = g.abias[l];
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            const int col = half * 128 + c * 32;
+            float v[32];
+            epi_load32(e, col, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + __ldg(bias + col + i), 0.f);
+            epi_store_a32(s, row, col, v);
+            if (c & 1) epi_signal_a(s, col >> 6);
+          }
+          e.step_ctr++;
+        }
+        // ---- s22: appearance layer 4 -> rgb ------------------------------------------------------------------------------------
+        epi_wait_d(s, e);
+        if (half == 0) {
+          float v[32];
+          epi_load32(e, 0, v);
+          if (idx < M) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) rgb[idx * 3 + c] = tanhf(v[c] + __ldg(g.abias[4] + c)) * 0.5f + 0.5f;
+            alpha[idx] = 1.f / (1.f + __expf(10.f * logit));
+          }
+        }
+        e.step_ctr++;
+        tc_fence_before();
+      }
+      named_bar_sync(1, EPI_THREADS);  // xhalf / g3 are rewritten by the next tile
+    }
+  }
+  teardown(tmem_base);
+}
+
+// ---- host ---------------------------------------------------------------------------------------------------------------------
+static void put_step(Program& p, int i, const psn_mlp* net, int idx) {
+  p.step[i].w_off = net->tc_step[idx].w_off;
+  p.step[i].nkb = net->tc_step[idx].nkb;
+  p.step[i].n_pad = net->tc_step[idx].n_pad;
+  p.blob[i] = net->tc_blob;
+}
+
+static int make_tc_rad(const psn_mlp* geo, const psn_mlp* app, void* scratch, TcRadArgs* a) {
+  PSN_REQUIRE(geo && geo->kind == PSN_NET_GEO && geo->tc_ok, PSN_ERR_SHAPE, "geo net is not packed for the tensor-core path");
+  memset(a, 0, sizeof(*a));
+  int n = 0;
+  for (int l = 0; l < 8; ++l) {
+    put_step(a->prog, n++, geo, TCG_FWD0 + l);
+    a->gbias[l] = geo->fwd[l].bias;
+    a->n_out[l] = geo->fwd[l].N;
+  }
+  a->with_app = app ? 1 : 0;
+  if (app) {
+    PSN_REQUIRE(app->kind == PSN_NET_APP && app->tc_ok, PSN_ERR_SHAPE, "app net is not packed for the tensor-core path");
+    put_step(a->prog, n++, geo, TCG_FEAT);
+    put_step(a->prog, n++, app, TCA_L0F);
+  }
+  for (int l = 7; l >= 1; --l) put_step(a->prog, n++, geo, TCG_REV_TOP + (7 - l));
+  put_step(a->prog, n++, geo, TCG_REV0);
+  if (app) {
+    put_step(a->prog, n++, app, TCA_L0R);
+    for (int l = 1; l <= 3; ++l) put_step(a->prog, n++, app, TCA_L1 + (l - 1));
+    put_step(a->prog, n++, app, TCA_L4);
+    for (int l = 0; l < 5; ++l) a->abias[l] = app->fwd[l].bias;
+    a->octaves_view = app->desc.octaves;
+    a->pe_view_dim = 3 + 6 * app->desc.octaves;
+    PSN_REQUIRE(3 + a->pe_view_dim + 3 + 256 == app->in_dims[0], PSN_ERR_SHAPE, "app net input layout mismatch");
+  }
+  a->prog.n_steps = n;
+  a->bias_feat = geo->fwd[8].bias;
+  a->w_row = geo->w_logit_row;
+  a->b_logit = geo->logit_head.bias;
+  a->skip = geo->desc.skip;
+  a->octaves = geo->desc.octaves;
+  a->pe_dim = 3 + 6 * geo->desc.octaves;
+  a->rescale = geo->desc.rescale;
+  a->scratch = (float4*)scratch;
+  PSN_REQUIRE(a->skip >= 2 && a->skip <= 7 && geo->fwd[a->skip - 1].N + a->pe_dim == 256, PSN_ERR_SHAPE,
+              "tensor path: the skip layer input must be exactly 256 wide");
+  return PSN_OK;
+}
+
+size_t tc_stash_bytes() {
+  const size_t tc = (size_t)num_ctas() * SCR_F4_PER_CTA * sizeof(float4);
+  const size_t si = simt_stash_bytes();
+  return tc > si ? tc : si;
+}
+
+static int launch_tc_rad(const TcRadArgs& a, const PointGen& gen, long long M, const int* M_dev, float* rgb, float* alpha,
+                         float* grad, cudaStream_t st) {
+  PSN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_rad, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  const long long tiles = M_dev ? (long long)num_ctas() : (M + TILE_M - 1) / TILE_M;
+  const int grid = (int)(tiles < num_ctas() ? tiles : num_ctas());
+  count_launch();
+  k_tc_rad<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(a, gen, M, M_dev, rgb, alpha, grad);
+  PSN_CUDA_CHECK(cudaGetLastError());
+  return PSN_OK;
+}
+
+int tc_radiance(const psn_mlp* geo, const psn_mlp* app, const PointGen& gen, long long M, float* rgb, float* alpha, void* stash,
+                cudaStream_t st) {
+  PSN_REQUIRE(app, PSN_ERR_ARG, "tc_radiance: app net is null");
+  TcRadArgs a;
+  int rc = make_tc_rad(geo, app, stash, &a);
+  if (rc) return rc;
+  if (M == 0) return PSN_OK;
+  return launch_tc_rad(a, gen, M, nullptr, rgb, alpha, nullptr, st);
+}
+
+int tc_gradient(const psn_mlp* geo, const PointGen& gen, long long M, const int* M_dev, float* grad, void* stash, cudaStream_t st) {
+  TcRadArgs a;
+  int rc = make_tc_rad(geo, nullptr, stash, &a);
+  if (rc) return rc;
+  if (M == 0 && !M_dev) return PSN_OK;
+  return launch_tc_rad(a, gen, M, M_dev, nullptr, nullptr, grad, st);
+}
+
+}  // namespace psn

@@ -8,12 +8,4 @@ int s2_visibility_simt(const psn_mlp* vis_net, int nf, const float* pts, long lo
 int tc_infer_occ(const psn_mlp* geo, const PointGen& gen, long long M, float* out, cudaStream_t st) {
   return simt_occupancy(geo, gen, M, nullptr, PSN_OUT_LOGIT, out, 1, st);  // full 257-wide query: API completeness only
 }
-int tc_gradient(const psn_mlp* geo, const PointGen& gen, long long M, const int* M_dev, float* grad, void* stash, cudaStream_t st) {
-  return simt_gradient(geo, gen, M, M_dev, grad, stash, st);
-}
-int tc_radiance(const psn_mlp* geo, const psn_mlp* app, const PointGen& gen, long long M, float* rgb, float* alpha, void* stash,
-                cudaStream_t st) {
-  return simt_radiance(geo, app, gen, M, rgb, alpha, stash, st);
-}
-size_t tc_stash_bytes() { return simt_stash_bytes(); }
 }  // namespace psn

@@ -79,7 +79,7 @@ struct TcVisArgs {
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_tc_vis(TcVisArgs g, float* __restrict__ vis) {
-  extern __shared__ unsigned char smem_raw[];
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
   const Smem s = carve(smem_raw);
   const uint32_t tmem_base = setup(s);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -1,0 +1,37 @@
+"""Ray sharding across the GPUs of one box + the single pixel gather that closes a render.
+
+Every ray / pixel / (point, light) pair is independent and the weights (<= 3.2 MB) are replicated, so the data path
+needs no collective; the only exchange is one all_gather of the rendered pixel shards.  Backend-agnostic
+(`nccl` on GPUs, `gloo` in the CPU tests)."""
+import torch
+import torch.distributed as dist
+
+
+def shard_indices(n_rays, rank, world, tile=128):
+    """Ray ids owned by `rank`: tiles of `tile` consecutive rays dealt round-robin (balances sparse masks)."""
+    ids = torch.arange(n_rays)
+    t = ids // tile
+    return ids[(t % world) == rank]
+
+
+def shard_counts(n_rays, world, tile=128):
+    return [int(shard_indices(n_rays, r, world, tile).numel()) for r in range(world)]
+
+
+def gather_pixels(local, n_rays, rank, world, tile=128, group=None):
+    """local: [n_local, C] rendered values of this rank's rays -> full [n_rays, C] image on every rank.
+    One collective (all_gather on equally padded shards), then an index scatter to undo the tile interleave."""
+    if world == 1:
+        return local
+    counts = shard_counts(n_rays, world, tile)
+    pad = max(counts)
+    C = local.shape[1]
+    buf = local.new_zeros(pad, C)
+    buf[: local.shape[0]] = local
+    out = local.new_empty(world * pad, C)
+    dist.all_gather_into_tensor(out, buf, group=group)
+    full = local.new_empty(n_rays, C)
+    for r in range(world):
+        idx = shard_indices(n_rays, r, world, tile).to(local.device)
+        full[idx] = out[r * pad: r * pad + counts[r]]
+    return full

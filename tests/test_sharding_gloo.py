@@ -1,0 +1,58 @@
+"""world_size-2 gloo test of the multi-GPU host logic: ray sharding + the single pixel gather (CPU only)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from psnerf_b200 import sharding
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_rays, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    idx = sharding.shard_indices(n_rays, rank, world)
+    # a fake "render": pixel value = f(ray id); every rank must end up with the identical full image
+    local = torch.stack([idx.float() * 2.0, idx.float() + 0.5, -idx.float()], -1)
+    full = sharding.gather_pixels(local, n_rays, rank, world)
+    q.put((rank, full))
+    dist.destroy_process_group()
+
+
+def test_shards_partition_the_rays():
+    for n, w in [(1000, 2), (262144, 8), (129, 4), (5, 8)]:
+        parts = [sharding.shard_indices(n, r, w) for r in range(w)]
+        allidx = torch.cat(parts).sort().values
+        assert torch.equal(allidx, torch.arange(n))
+        assert sum(sharding.shard_counts(n, w)) == n
+        if n >= 128 * w * 8:
+            c = sharding.shard_counts(n, w)
+            assert max(c) - min(c) <= 128
+
+
+def test_gather_pixels_world2_gloo():
+    n_rays, world = 1000, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_rays, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ids = torch.arange(n_rays).float()
+    want = torch.stack([ids * 2.0, ids + 0.5, -ids], -1)
+    for r in range(world):
+        assert torch.equal(res[r], want)
