@@ -217,9 +217,12 @@ __global__ void k_s2_shade(ShadeArgs a) {
   const float* nn = a.normal + (long long)slot * 3;
   const float* vv = a.view + (long long)slot * 3;
   const float* ll = a.lights + (long long)l * 3;
-  const float hx = ll[0] + vv[0], hy = ll[1] + vv[1], hz = ll[2] + vv[2];
-  const float hn = fmaxf(sqrtf(hx * hx + hy * hy + hz * hz), 1e-12f);
-  const float hdn = ((hx / hn) * nn[0] + (hy / hn) * nn[1] + (hz / hn) * nn[2]) - 1.f;
+  // h = F.normalize(l + v); (h*n).sum(-1) - 1 with torch's separate roundings (sgbasis.py:24-25): the lobe sharpness
+  // lambda <= e^10 amplifies every ulp of this dot product 2e4 times, so no FMA contraction here.
+  const float hx = __fadd_rn(ll[0], vv[0]), hy = __fadd_rn(ll[1], vv[1]), hz = __fadd_rn(ll[2], vv[2]);
+  const float hn = fmaxf(sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(hx, hx), __fmul_rn(hy, hy)), __fmul_rn(hz, hz))), 1e-12f);
+  const float hdn = __fsub_rn(__fadd_rn(__fadd_rn(__fmul_rn(__fdiv_rn(hx, hn), nn[0]), __fmul_rn(__fdiv_rn(hy, hn), nn[1])),
+                                        __fmul_rn(__fdiv_rn(hz, hn), nn[2])), 1.f);
   float spec[3] = {0.f, 0.f, 0.f};
   const float* w = a.weights + (long long)slot * a.nbt;
   for (int k = 0; k < a.nbasis; ++k) {
