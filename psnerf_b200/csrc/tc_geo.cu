@@ -24,9 +24,9 @@ struct TcGeoArgs {
 
 // entry idx of [p, sin(2^0 p), cos(2^0 p), ...] (network.py:141-150)
 __device__ __forceinline__ float pe_entry(const float x[3], int idx) {
-  if (idx < 3) return x[idx];
+  if (idx < 3) return idx == 0 ? x[0] : (idx == 1 ? x[1] : x[2]);  // selects, not a dynamically indexed local array
   const int j = idx - 3, oct = j / 6, r = j - 6 * oct, c = r % 3;
-  const float a = (float)(1 << oct) * x[c];
+  const float a = (float)(1 << oct) * (c == 0 ? x[0] : (c == 1 ? x[1] : x[2]));
   return r < 3 ? sinf(a) : cosf(a);
 }
 
@@ -44,13 +44,13 @@ k_tc_occ(TcGeoArgs g, PointGen gen, long long M_host, const int* M_dev, int out_
   const long long n_tiles = (M + TILE_M - 1) / TILE_M;
   const long long iters = (n_tiles > (long long)blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-  if (warp == 0) {
-    if (lane == 0) producer_loop(s, g.prog, iters);
+  if (warp < EPI_WARP0) {
+    regs_shrink_control();
+    if (warp == 0 && lane == 0) producer_loop(s, g.prog, iters);
+    if (warp == 1 && lane == 0) mma_loop(s, g.prog, iters, tmem_base);
     __syncwarp();
-  } else if (warp == 1) {
-    if (lane == 0) mma_loop(s, g.prog, iters, tmem_base);
-    __syncwarp();
-  } else if (warp >= EPI_WARP0) {
+  } else {
+    regs_grow_epilogue();
     EpiCtx e = epi_ctx(tmem_base);
     const int row = e.row, half = e.half;
     for (long long it = 0; it < iters; ++it) {
@@ -59,26 +59,24 @@ k_tc_occ(TcGeoArgs g, PointGen gen, long long M_host, const int* M_dev, int out_
       float p[3] = {0.f, 0.f, 0.f}, vdummy[3];
       if (idx < M) gen_point(gen, idx, p, vdummy);
       const float x[3] = {p[0] / g.rescale, p[1] / g.rescale, p[2] / g.rescale};
-      if (half == 0) {  // layer-0 operand: the point encoding, zero padded to one 64-wide K block
+      if (MODE == MODE_SHADOW) { p[0] = p[1] = p[2] = 0.f; }
+      {  // layer-0 operand: the point encoding, zero padded to one 64-wide K block (each half writes 32 columns)
 #pragma unroll 1
-        for (int k = 0; k < KBLK; ++k) epi_store_a1(s, row, k, k < g.pe_dim ? pe_entry(x, k) : 0.f);
+        for (int k = half * 32; k < half * 32 + 32; ++k) epi_store_a1(s, row, k, k < g.pe_dim ? pe_entry(x, k) : 0.f);
         epi_signal_a(s, 0);
       }
-      float part = 0.f;  // partial logit over this thread's 128 columns
+      float part = 0.f;  // partial logit over this thread's 128 columns (4 interleaved chunks)
 #pragma unroll 1
       for (int l = 0; l < 8; ++l) {
         epi_wait_d(s, e);
         const float* bias = g.bias[l];
         const bool pre_skip = (l + 1 == g.skip);
         const int n_out = g.n_out[l];
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          const int col = half * 128 + c * 32;
-          float v[32];
-          epi_load32(e, col, v);
+        epi_for_chunks(e, 4, [&](int c, int col, float (&v)[32]) {
+          add_bias32(v, bias, col);
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            float a = softplus100_fast(v[i] + __ldg(bias + col + i));
+            float a = softplus100_fast(v[i]);
             if (pre_skip) a = a * 0.70710678118654752440f;
             v[i] = a;
           }
@@ -93,12 +91,17 @@ k_tc_occ(TcGeoArgs g, PointGen gen, long long M_host, const int* M_dev, int out_
               for (int k = (n_out > col ? n_out : col); k < col + 32; ++k)
                 epi_store_a1(s, row, k, pe_entry(x, k - n_out) * 0.70710678118654752440f);
             }
-            if (c & 1) epi_signal_a(s, col >> 6);
+            epi_signal_a(s, c);
           } else {
+            const float4* w4 = reinterpret_cast<const float4*>(g.w_row + col);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) part = fmaf(v[i], __ldg(g.w_row + col + i), part);
+            for (int t = 0; t < 8; ++t) {
+              const float4 w = __ldg(w4 + t);
+              part = fmaf(v[4 * t], w.x, part); part = fmaf(v[4 * t + 1], w.y, part);
+              part = fmaf(v[4 * t + 2], w.z, part); part = fmaf(v[4 * t + 3], w.w, part);
+            }
           }
-        }
+        });
         e.step_ctr++;
       }
       tc_fence_before();  // order this tile's last TMEM reads before the next tile's MMAs (via a_ready)
@@ -116,6 +119,7 @@ k_tc_occ(TcGeoArgs g, PointGen gen, long long M_host, const int* M_dev, int out_
         } else {
           // shadow ray: rows are the 128 march steps of pair `tile`; alpha zeroed outside the box (rendering.py:402-408)
           float a = 1.f / (1.f + __expf(10.f * z));
+          if (idx < M) gen_point(gen, idx, p, vdummy);  // regenerate the sample position instead of keeping it live
           const bool inside = (p[0] <= box) && (p[0] >= -box) && (p[1] <= box) && (p[1] >= -box) && (p[2] <= box) && (p[2] >= -box);
           if (!inside || idx >= M) a = 0.f;
           const float t = (1.f - a) + 1e-6f;

@@ -10,8 +10,10 @@
 // pre-swizzled [N rows][64 K] tile streamed from L2 with cp.async.bulk (UBLKCP) + mbarrier complete_tx.
 // TMEM: two 256-column fp32 accumulators (all 512 columns).
 //
-// Warp roles: warp 0 = weight producer, warp 1 = MMA issuer (one elected lane), warp 2 = TMEM allocator,
-// warps 4..11 = epilogue (warp w reads TMEM lanes 32*(w%4).. and column half (w-4)/4).
+// Warp roles: warp 0 = TMEM allocator + weight producer (one lane), warp 1 = MMA issuer (one lane), warps 2-3 idle
+// (the control warpgroup releases registers with setmaxnreg.dec), warps 4..11 = epilogue (setmaxnreg.inc) (warp w reads TMEM lanes 32*(w%4)..; the two warps sharing a lane quadrant interleave over
+// 32-column chunks: half h = (w-4)/4 owns columns [(2c+h)*32, (2c+h)*32+32), c = 0..3, so K block c of the next layer is
+// complete after chunk c of BOTH halves).
 // Layer pipelining: the epilogue of step L rewrites the A buffer in place (every MMA of step L has retired when
 // d_full fires) K-block by K-block and signals a_ready[kb]; the MMA warp starts step L+1's K-block kb as soon as
 // that block is ready, accumulating into the OTHER TMEM buffer - so tensor work of step L+1 overlaps the
@@ -30,7 +32,7 @@ constexpr int A_MAX_KB = 4;
 constexpr int A_BYTES = A_MAX_KB * A_KB_BYTES;  // 128 KB
 constexpr int W_STAGE_BYTES = 256 * 128;        // 32 KB: [256 N rows][64 K] fp16
 constexpr int W_STAGES = 3;
-constexpr int NUM_THREADS = 384;
+constexpr int NUM_THREADS = 384;  // warpgroup 0 = control (setmaxnreg 48), warpgroups 1-2 = epilogue (setmaxnreg 224)
 constexpr int EPI_WARP0 = 4;
 constexpr int EPI_THREADS = 256;
 
@@ -77,6 +79,10 @@ __device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// for waits that are not on the critical path (weight producer): sleep between polls instead of burning issue slots
+__device__ __forceinline__ void mbar_wait_relaxed(void* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(64);
+}
 // generic-proxy smem writes -> visible to the async proxy (UMMA operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -116,9 +122,10 @@ __device__ __forceinline__ void umma_commit(void* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// 32 lanes x 32 consecutive fp32 columns: thread (lane i) receives row (lane_base + i), columns col..col+31
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
+// 32 lanes x 32 consecutive fp32 columns: thread (lane i) receives row (lane_base + i), columns col..col+31.
+// Issue and wait are separate so that the next chunk's load overlaps the current chunk's math; the wait names every
+// destination register as read-write so the compiler cannot consume (or move) them before the load has landed.
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -129,10 +136,27 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
         "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld32_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                 "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  tmem_ld32_issue(taddr, r);
+  tmem_ld32_wait(r);
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+
+// register re-allocation between warpgroups (all 4 warps of a warpgroup must execute it)
+__device__ __forceinline__ void regs_shrink_control() { asm volatile("setmaxnreg.dec.sync.aligned.u32 48;" ::: "memory"); }
+__device__ __forceinline__ void regs_grow_epilogue() { asm volatile("setmaxnreg.inc.sync.aligned.u32 224;" ::: "memory"); }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
@@ -164,16 +188,16 @@ __device__ __forceinline__ Smem carve(unsigned char* raw) {
   return s;
 }
 
-// Barrier init (thread 0) + TMEM allocation (warp 2).  Ends with a CTA barrier; returns the TMEM base address.
+// Barrier init (thread 0) + TMEM allocation (warp 0).  Ends with a CTA barrier; returns the TMEM base address.
 __device__ __forceinline__ uint32_t setup(const Smem& s) {
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     for (int i = 0; i < W_STAGES; ++i) { mbar_init(&s.c->w_full[i], 1); mbar_init(&s.c->w_empty[i], 1); }
-    for (int i = 0; i < A_MAX_KB; ++i) mbar_init(&s.c->a_ready[i], 128);
+    for (int i = 0; i < A_MAX_KB; ++i) mbar_init(&s.c->a_ready[i], EPI_THREADS);
     for (int i = 0; i < 2; ++i) mbar_init(&s.c->d_full[i], 1);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc_512(&s.c->tmem_base);
+  if (warp == 0) tmem_alloc_512(&s.c->tmem_base);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -182,7 +206,7 @@ __device__ __forceinline__ uint32_t setup(const Smem& s) {
 __device__ __forceinline__ void teardown(uint32_t tmem_base) {
   tc_fence_before();
   __syncthreads();
-  if ((threadIdx.x >> 5) == 2) tmem_dealloc_512(tmem_base);
+  if ((threadIdx.x >> 5) == 0) tmem_dealloc_512(tmem_base);
 }
 
 // ---- producer: stream every weight tile of `iters` tile-iterations through the ring (warp 0, lane 0) ------------------
@@ -194,7 +218,7 @@ __device__ __forceinline__ void producer_loop(const Smem& s, const Program& prog
       const uint32_t tile_bytes = (uint32_t)sp.n_pad * 128u;
       const unsigned char* src = prog.blob[st] + sp.w_off;
       for (int t = 0; t < 2 * sp.nkb; ++t) {
-        mbar_wait(&s.c->w_empty[stage], phase ^ 1u);
+        mbar_wait_relaxed(&s.c->w_empty[stage], phase ^ 1u);
         mbar_arrive_expect_tx(&s.c->w_full[stage], tile_bytes);
         bulk_g2s(s.w + stage * W_STAGE_BYTES, src + (size_t)t * tile_bytes, tile_bytes, &s.c->w_full[stage]);
         if (++stage == W_STAGES) { stage = 0; phase ^= 1u; }
@@ -253,17 +277,18 @@ struct EpiCtx {
   uint32_t tmem_base;
   uint32_t step_ctr;   // global step counter (same sequence as the MMA warp)
   int row;             // tile row owned by this thread (TMEM lane)
-  int half;            // column half: 0 -> columns 0..127, 1 -> 128..255
+  int half;            // which of the two interleaved column sets: chunk c covers columns (2c + half) * 32 ...
   uint32_t lane_addr;  // (32 * quadrant) << 16
 };
 __device__ __forceinline__ EpiCtx epi_ctx(uint32_t tmem_base) {
   EpiCtx e;
-  const int ew = (threadIdx.x >> 5) - EPI_WARP0;
+  const int warp = threadIdx.x >> 5;
+  const int q = warp & 3;  // a warp may only touch TMEM lanes 32*(warp%4) .. +31
   e.tmem_base = tmem_base;
   e.step_ctr = 0;
-  e.row = (ew & 3) * 32 + (threadIdx.x & 31);
-  e.half = ew >> 2;
-  e.lane_addr = (uint32_t)((ew & 3) * 32) << 16;
+  e.row = q * 32 + (threadIdx.x & 31);
+  e.half = (warp - EPI_WARP0) >> 2;
+  e.lane_addr = (uint32_t)(q * 32) << 16;
   return e;
 }
 // wait for the accumulator of the current step
@@ -273,6 +298,43 @@ __device__ __forceinline__ void epi_wait_d(const Smem& s, const EpiCtx& e) {
 }
 __device__ __forceinline__ void epi_load32(const EpiCtx& e, int col, float (&v)[32]) {
   tmem_ld32(e.tmem_base + e.lane_addr + (e.step_ctr & 1u) * 256u + (uint32_t)col, v);
+}
+
+// Visit the four 32-column chunks this thread owns in the current accumulator: f(c, col, v[32]).  The TMEM load of chunk
+// c+1 is in flight while chunk c is processed.
+template <class F>
+__device__ __forceinline__ void epi_for_chunks(const EpiCtx& e, int n_chunks, F&& f) {
+  uint32_t ra[32], rb[32];
+  const uint32_t base = e.tmem_base + e.lane_addr + (e.step_ctr & 1u) * 256u;
+  tmem_ld32_issue(base + (uint32_t)(e.half * 32), ra);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    if (c < n_chunks) {
+      const int col = (2 * c + e.half) * 32;
+      float v[32];
+      if (c & 1) {
+        tmem_ld32_wait(rb);
+        if (c + 1 < n_chunks) tmem_ld32_issue(base + (uint32_t)((2 * (c + 1) + e.half) * 32), ra);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rb[i]);
+      } else {
+        tmem_ld32_wait(ra);
+        if (c + 1 < n_chunks) tmem_ld32_issue(base + (uint32_t)((2 * (c + 1) + e.half) * 32), rb);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(ra[i]);
+      }
+      f(c, col, v);
+    }
+  }
+}
+// v[i] += bias[col + i] with 128-bit loads
+__device__ __forceinline__ void add_bias32(float (&v)[32], const float* __restrict__ bias, int col) {
+  const float4* b4 = reinterpret_cast<const float4*>(bias + col);
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    const float4 b = __ldg(b4 + t);
+    v[4 * t] += b.x; v[4 * t + 1] += b.y; v[4 * t + 2] += b.z; v[4 * t + 3] += b.w;
+  }
 }
 
 __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
@@ -288,12 +350,13 @@ __device__ __forceinline__ void epi_store_a32(const Smem& s, int row, int col, c
   for (int t = 0; t < 4; ++t) {
     uint32_t h[4], l[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 4; ++u) {  // packed cvt.rn.f16x2.f32 (F2FP, ALU pipe) - scalar F2F would queue on the XU pipe with the MUFUs
       const float x0 = v[t * 8 + 2 * u], x1 = v[t * 8 + 2 * u + 1];
-      const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
-      const __half l0 = __float2half_rn(x0 - __half2float(h0)), l1 = __float2half_rn(x1 - __half2float(h1));
-      h[u] = pack_h2(h0, h1);
-      l[u] = pack_h2(l0, l1);
+      const __half2 hh = __floats2half2_rn(x0, x1);
+      const float2 hf = __half22float2(hh);
+      const __half2 ll = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+      h[u] = *reinterpret_cast<const uint32_t*>(&hh);
+      l[u] = *reinterpret_cast<const uint32_t*>(&ll);
     }
     const int phys = ((c0 + t) ^ (row & 7)) * 16;
     *reinterpret_cast<uint4*>(hi_row + phys) = make_uint4(h[0], h[1], h[2], h[3]);
@@ -309,7 +372,7 @@ __device__ __forceinline__ void epi_store_a1(const Smem& s, int row, int col, fl
   *reinterpret_cast<__half*>(hi_row + phys) = h;
   *reinterpret_cast<__half*>(hi_row + A_PART_BYTES + phys) = __float2half_rn(x - __half2float(h));
 }
-// all of this thread's writes to K-block kb are done: publish to the MMA warp (128 arrivals per block)
+// this thread's contribution to K-block kb is written: publish to the MMA warp (256 arrivals per block)
 __device__ __forceinline__ void epi_signal_a(const Smem& s, int kb) {
   tc_fence_before();
   fence_proxy_async_smem();

@@ -36,16 +36,16 @@ struct TcRadArgs {
 };
 
 __device__ __forceinline__ float pe_entry_r(const float x[3], int idx) {
-  if (idx < 3) return x[idx];
+  if (idx < 3) return idx == 0 ? x[0] : (idx == 1 ? x[1] : x[2]);  // selects, not a dynamically indexed local array
   const int j = idx - 3, oct = j / 6, r = j - 6 * oct, c = r % 3;
-  const float a = (float)(1 << oct) * x[c];
+  const float a = (float)(1 << oct) * (c == 0 ? x[0] : (c == 1 ? x[1] : x[2]));
   return r < 3 ? sinf(a) : cosf(a);
 }
 // d pe[idx] / d x[c]  (0 unless idx belongs to coordinate c)
 __device__ __forceinline__ float pe_jac(const float x[3], int idx, int* coord) {
   if (idx < 3) { *coord = idx; return 1.f; }
   const int j = idx - 3, oct = j / 6, r = j - 6 * oct, c = r % 3;
-  const float f = (float)(1 << oct), a = f * x[c];
+  const float f = (float)(1 << oct), a = f * (c == 0 ? x[0] : (c == 1 ? x[1] : x[2]));
   *coord = c;
   return r < 3 ? f * cosf(a) : -f * sinf(a);
 }
@@ -63,13 +63,13 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
   const long long n_tiles = (M + TILE_M - 1) / TILE_M;
   const long long iters = (n_tiles > (long long)blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-  if (warp == 0) {
-    if (lane == 0) producer_loop(s, g.prog, iters);
+  if (warp < EPI_WARP0) {
+    regs_shrink_control();
+    if (warp == 0 && lane == 0) producer_loop(s, g.prog, iters);
+    if (warp == 1 && lane == 0) mma_loop(s, g.prog, iters, tmem_base);
     __syncwarp();
-  } else if (warp == 1) {
-    if (lane == 0) mma_loop(s, g.prog, iters, tmem_base);
-    __syncwarp();
-  } else if (warp >= EPI_WARP0) {
+  } else {
+    regs_grow_epilogue();
     EpiCtx e = epi_ctx(tmem_base);
     const int row = e.row, half = e.half;
     float4* stash = g.scratch + (size_t)blockIdx.x * SCR_F4_PER_CTA;
@@ -80,9 +80,9 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
       float p[3] = {0.f, 0.f, 0.f}, vd[3] = {0.f, 0.f, 1.f};
       if (idx < M) gen_point(gen, idx, p, vd);
       const float x[3] = {p[0] / g.rescale, p[1] / g.rescale, p[2] / g.rescale};
-      if (half == 0) {
+      {
 #pragma unroll 1
-        for (int k = 0; k < KBLK; ++k) epi_store_a1(s, row, k, k < g.pe_dim ? pe_entry_r(x, k) : 0.f);
+        for (int k = half * 32; k < half * 32 + 32; ++k) epi_store_a1(s, row, k, k < g.pe_dim ? pe_entry_r(x, k) : 0.f);
         epi_signal_a(s, 0);
       }
       // ---- s0..s7: geo forward --------------------------------------------------------------------------------------
@@ -95,7 +95,7 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
         const int n_out = g.n_out[l];
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
-          const int col = half * 128 + c * 32;
+          const int col = (2 * c + half) * 32;
           float v[32];
           epi_load32(e, col, v);
 #pragma unroll
@@ -126,7 +126,7 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
 #pragma unroll
             for (int i = 0; i < 32; ++i) part = fmaf(v[i], __ldg(g.w_row + col + i), part);
           }
-          if (c & 1) epi_signal_a(s, col >> 6);
+          epi_signal_a(s, c);
         }
         e.step_ctr++;
       }
@@ -137,20 +137,20 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
         epi_wait_d(s, e);
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
-          const int col = half * 128 + c * 32;
+          const int col = (2 * c + half) * 32;
           float v[32];
           epi_load32(e, col, v);
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] += __ldg(g.bias_feat + col + i);
           epi_store_a32(s, row, col, v);
-          if (c & 1) epi_signal_a(s, col >> 6);
+          epi_signal_a(s, c);
         }
         e.step_ctr++;
         // ---- s9: appearance layer 0, feature part -> parked -------------------------------------------------------------
         epi_wait_d(s, e);
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
-          const int col = half * 128 + c * 32;
+          const int col = (2 * c + half) * 32;
           float v[32];
           epi_load32(e, col, v);
 #pragma unroll
@@ -162,7 +162,7 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
       // ---- reverse seed: dz_7 = W_last[0,:] * sigma'(z_7) -> A  (gradient-only mode wrote it in s7) ---------------------
 #pragma unroll 1
       for (int c = 0; c < (g.with_app ? 4 : 0); ++c) {
-        const int col = half * 128 + c * 32;
+        const int col = (2 * c + half) * 32;
         float v[32];
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
@@ -171,7 +171,7 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
           v[4 * t] = w.x * sg.x; v[4 * t + 1] = w.y * sg.y; v[4 * t + 2] = w.z * sg.z; v[4 * t + 3] = w.w * sg.w;
         }
         epi_store_a32(s, row, col, v);
-        if (c & 1) epi_signal_a(s, col >> 6);
+        epi_signal_a(s, c);
       }
       // ---- s10..s16: reverse through layers 7..1 -----------------------------------------------------------------------------
 #pragma unroll 1
@@ -181,7 +181,7 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
         const int nprev = g.n_out[l - 1];
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
-          const int col = half * 128 + c * 32;
+          const int col = (2 * c + half) * 32;
           float v[32];
           epi_load32(e, col, v);
           if (is_skip) {
@@ -211,34 +211,33 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
               if (col + i >= nprev) v[i] = 0.f;
           }
           epi_store_a32(s, row, col, v);
-          if (c & 1) epi_signal_a(s, col >> 6);
+          epi_signal_a(s, c);
         }
         e.step_ctr++;
       }
       // ---- s17: reverse layer 0 -> gradient ------------------------------------------------------------------------------
       epi_wait_d(s, e);
+      float gr[3] = {0.f, 0.f, 0.f};
+      float logit = 0.f;
+      {  // d logit / d pe: columns 0..pe_dim-1 of this step (half 0: 0..31, half 1: 32..63)
+        float v[32];
+        epi_load32(e, half * 32, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int k = half * 32 + i;
+          if (k < g.pe_dim) {
+            int cc;
+            const float jv = pe_jac(x, k, &cc);
+            const float t = jv * v[i];
+            g_acc[0] += cc == 0 ? t : 0.f; g_acc[1] += cc == 1 ? t : 0.f; g_acc[2] += cc == 2 ? t : 0.f;
+          }
+        }
+      }
       if (half == 1) {
         s.c->g3[row * 3 + 0] = g_acc[0]; s.c->g3[row * 3 + 1] = g_acc[1]; s.c->g3[row * 3 + 2] = g_acc[2];
       }
       named_bar_sync(1, EPI_THREADS);
-      float gr[3] = {0.f, 0.f, 0.f};
-      float logit = 0.f;
       if (half == 0) {
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-          float v[32];
-          epi_load32(e, c * 32, v);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int k = c * 32 + i;
-            if (k < g.pe_dim) {
-              int cc;
-              const float jv = pe_jac(x, k, &cc);
-              const float t = jv * v[i];
-              g_acc[0] += cc == 0 ? t : 0.f; g_acc[1] += cc == 1 ? t : 0.f; g_acc[2] += cc == 2 ? t : 0.f;
-            }
-          }
-        }
 #pragma unroll
         for (int c = 0; c < 3; ++c) gr[c] = (g_acc[c] + s.c->g3[row * 3 + c]) / g.rescale;
         logit = part + s.c->xhalf[row] + __ldg(g.b_logit);
@@ -260,12 +259,14 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
             epi_store_a1(s, row, k, val);
           }
           epi_signal_a(s, 0);
+        } else {
+          epi_signal_a(s, 0);  // half 1 contributes nothing to this 64-column block
         }
         // ---- s18: appearance layer 0 (rest) + parked + bias, ReLU ------------------------------------------------------------
         epi_wait_d(s, e);
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
-          const int col = half * 128 + c * 32;
+          const int col = (2 * c + half) * 32;
           float v[32];
           epi_load32(e, col, v);
 #pragma unroll
@@ -276,7 +277,7 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + __ldg(g.abias[0] + col + i), 0.f);
           epi_store_a32(s, row, col, v);
-          if (c & 1) epi_signal_a(s, col >> 6);
+          epi_signal_a(s, c);
         }
         e.step_ctr++;
         // ---- s19..s21: appearance layers 1..3 -------------------------------------------------------------------------------
@@ -286,13 +287,13 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
           const float* bias = g.abias[l];
 #pragma unroll 1
           for (int c = 0; c < 4; ++c) {
-            const int col = half * 128 + c * 32;
+            const int col = (2 * c + half) * 32;
             float v[32];
             epi_load32(e, col, v);
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + __ldg(bias + col + i), 0.f);
             epi_store_a32(s, row, col, v);
-            if (c & 1) epi_signal_a(s, col >> 6);
+            epi_signal_a(s, c);
           }
           e.step_ctr++;
         }

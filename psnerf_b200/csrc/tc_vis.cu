@@ -89,13 +89,13 @@ k_tc_vis(TcVisArgs g, float* __restrict__ vis) {
   const long long t0 = chunk * blockIdx.x;
   const long long t1 = (t0 + chunk < n_tiles) ? t0 + chunk : n_tiles;
   const long long iters = t1 > t0 ? t1 - t0 : 0;
-  if (warp == 0) {
-    if (lane == 0) producer_loop(s, g.prog, iters);
+  if (warp < EPI_WARP0) {
+    regs_shrink_control();
+    if (warp == 0 && lane == 0) producer_loop(s, g.prog, iters);
+    if (warp == 1 && lane == 0) mma_loop(s, g.prog, iters, tmem_base);
     __syncwarp();
-  } else if (warp == 1) {
-    if (lane == 0) mma_loop(s, g.prog, iters, tmem_base);
-    __syncwarp();
-  } else if (warp >= EPI_WARP0) {
+  } else {
+    regs_grow_epilogue();
     EpiCtx e = epi_ctx(tmem_base);
     const int row = e.row, half = e.half;
     for (long long t = t0; t < t1; ++t) {
@@ -107,7 +107,7 @@ k_tc_vis(TcVisArgs g, float* __restrict__ vis) {
       // layer 0: relu(P0[n] + L0[l])
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
-        const int col = half * 128 + c * 32;
+        const int col = (2 * c + half) * 32;
         float v[32];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -117,18 +117,14 @@ k_tc_vis(TcVisArgs g, float* __restrict__ vis) {
           v[4 * i + 2] = fmaxf(a.z + b.z, 0.f); v[4 * i + 3] = fmaxf(a.w + b.w, 0.f);
         }
         epi_store_a32(s, row, col, v);
-        if (c & 1) epi_signal_a(s, col >> 6);
+        epi_signal_a(s, c);
       }
       float part = 0.f;
 #pragma unroll 1
       for (int st = 0; st < 7; ++st) {
         epi_wait_d(s, e);
         const float* bias = g.bias[st];
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          const int col = half * 128 + c * 32;
-          float v[32];
-          epi_load32(e, col, v);
+        epi_for_chunks(e, 4, [&](int c, int col, float (&v)[32]) {
           if (st == 4) {  // skip layer: + P5[n] (bias folded) + L5[l]
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -137,19 +133,23 @@ k_tc_vis(TcVisArgs g, float* __restrict__ vis) {
               v[4 * i + 0] += a.x + b.x; v[4 * i + 1] += a.y + b.y; v[4 * i + 2] += a.z + b.z; v[4 * i + 3] += a.w + b.w;
             }
           } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] += __ldg(bias + col + i);
+            add_bias32(v, bias, col);
           }
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
           if (st < 6) {
             epi_store_a32(s, row, col, v);
-            if (c & 1) epi_signal_a(s, col >> 6);
+            epi_signal_a(s, c);
           } else {
+            const float4* w4 = reinterpret_cast<const float4*>(g.w_last + col);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) part = fmaf(v[i], __ldg(g.w_last + col + i), part);
+            for (int t = 0; t < 8; ++t) {
+              const float4 w = __ldg(w4 + t);
+              part = fmaf(v[4 * t], w.x, part); part = fmaf(v[4 * t + 1], w.y, part);
+              part = fmaf(v[4 * t + 2], w.z, part); part = fmaf(v[4 * t + 3], w.w, part);
+            }
           }
-        }
+        });
         e.step_ctr++;
       }
       tc_fence_before();
