@@ -74,12 +74,9 @@ k_tc_occ(TcGeoArgs g, PointGen gen, long long M_host, const int* M_dev, int out_
         const int n_out = g.n_out[l];
         epi_for_chunks(e, 4, [&](int c, int col, float (&v)[32]) {
           add_bias32(v, bias, col);
+          const float cc = pre_skip ? PSN_SOFTPLUS_C * 0.70710678118654752440f : PSN_SOFTPLUS_C;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float a = softplus100_fast(v[i]);
-            if (pre_skip) a = a * 0.70710678118654752440f;
-            v[i] = a;
-          }
+          for (int i = 0; i < 32; ++i) v[i] = softplus_scaled(v[i], cc);
           if (dump && dump_layer == l && idx < M) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) dump[idx * 256 + col + i] = (pre_skip && col + i >= n_out) ? pe_entry(x, col + i - n_out) * 0.70710678118654752440f : v[i];
@@ -161,7 +158,7 @@ static int make_tc_geo(const psn_mlp* geo, TcGeoArgs* a) {
     a->prog.step[l].nkb = geo->tc_step[TCG_FWD0 + l].nkb;
     a->prog.step[l].n_pad = geo->tc_step[TCG_FWD0 + l].n_pad;
     a->prog.blob[l] = geo->tc_blob;
-    a->bias[l] = geo->fwd[l].bias;
+    a->bias[l] = geo->tc_bias_scaled[l];
     a->n_out[l] = geo->fwd[l].N;
   }
   a->w_row = geo->w_logit_row;

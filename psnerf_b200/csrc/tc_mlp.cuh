@@ -68,10 +68,10 @@ __device__ __forceinline__ bool mbar_try_wait(void* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(2000u)  // suspend-time hint (ns): sleep in hardware instead of spinning
       : "memory");
   return ok != 0;
 }
@@ -379,12 +379,23 @@ __device__ __forceinline__ void epi_signal_a(const Smem& s, int kb) {
   mbar_arrive(&s.c->a_ready[kb]);
 }
 
-// fast softplus(beta=100, threshold=20) and its derivative sigmoid(100 z) on the MUFU pipe
-__device__ __forceinline__ float softplus100_fast(float z) {
-  const float v = z * 100.f;
-  const float e = __expf(fminf(v, 20.f));
-  const float sp = 0.01f * __logf(1.f + e);
-  return v > 20.f ? z : sp;
+// softplus(beta=100) on pre-scaled accumulators: zs = 100*log2(e)*z  ->  softplus(z) = c * max(zs, lg2(1 + 2^min(zs,40))),
+// c = ln2/100 (times any layer constant).  2 MUFU + 4 ALU ops; for zs > ~25 the lg2 term equals zs in fp32, so the max
+// reproduces PyTorch's linear branch (threshold 20) to <1e-9 without a compare/select.
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+#define PSN_SOFTPLUS_C 0.0069314718055994531f  /* ln2 / 100 */
+__device__ __forceinline__ float softplus_scaled(float zs, float c) {
+  const float e = ex2_approx(fminf(zs, 40.f));
+  return c * fmaxf(zs, lg2_approx(1.f + e));
+}
+// same, also returning sigma'(z) = sigmoid(100 z) = e / (1 + e)
+__device__ __forceinline__ float softplus_scaled_d(float zs, float c, float* dsig) {
+  const float e = ex2_approx(fminf(zs, 40.f));
+  const float t = 1.f + e;
+  *dsig = e * rcp_approx(t);
+  return c * fmaxf(zs, lg2_approx(t));
 }
 
 }  // namespace tc

@@ -93,24 +93,16 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
         const float* bias = g.gbias[l];
         const bool pre_skip = (l + 1 == g.skip);
         const int n_out = g.n_out[l];
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          const int col = (2 * c + half) * 32;
-          float v[32];
-          epi_load32(e, col, v);
+        epi_for_chunks(e, 4, [&](int c, int col, float (&v)[32]) {
+          add_bias32(v, bias, col);
+          const float cc = pre_skip ? PSN_SOFTPLUS_C * PSN_INV_SQRT2 : PSN_SOFTPLUS_C;
 #pragma unroll
           for (int t = 0; t < 8; ++t) {
             float sg[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               const int i = 4 * t + u;
-              const float z = v[i] + __ldg(bias + col + i);
-              const float vv = z * 100.f;
-              const float ex = __expf(fminf(vv, 20.f));
-              const float sp = 0.01f * __logf(1.f + ex);
-              float a = vv > 20.f ? z : sp;
-              sg[u] = __fdividef(ex, 1.f + ex);
-              if (pre_skip) a *= PSN_INV_SQRT2;
+              float a = softplus_scaled_d(v[i], cc, &sg[u]);
               if (l == 7 && !g.with_app) a = __ldg(g.w_row + col + i) * sg[u];  // gradient only: seed dz_7 directly
               v[i] = a;
             }
@@ -127,7 +119,7 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
             for (int i = 0; i < 32; ++i) part = fmaf(v[i], __ldg(g.w_row + col + i), part);
           }
           epi_signal_a(s, c);
-        }
+                });
         e.step_ctr++;
       }
       if (half == 1) s.c->xhalf[row] = part;
@@ -135,28 +127,20 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
       if (g.with_app) {
         // ---- s8: feature head -> A (no activation) ---------------------------------------------------------------------
         epi_wait_d(s, e);
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          const int col = (2 * c + half) * 32;
-          float v[32];
-          epi_load32(e, col, v);
+        epi_for_chunks(e, 4, [&](int c, int col, float (&v)[32]) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] += __ldg(g.bias_feat + col + i);
           epi_store_a32(s, row, col, v);
           epi_signal_a(s, c);
-        }
+                });
         e.step_ctr++;
         // ---- s9: appearance layer 0, feature part -> parked -------------------------------------------------------------
         epi_wait_d(s, e);
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          const int col = (2 * c + half) * 32;
-          float v[32];
-          epi_load32(e, col, v);
+        epi_for_chunks(e, 4, [&](int c, int col, float (&v)[32]) {
 #pragma unroll
           for (int t = 0; t < 8; ++t)
             parked[(size_t)((col >> 2) + t) * TILE_M + row] = make_float4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
-        }
+                });
         e.step_ctr++;
       }
       // ---- reverse seed: dz_7 = W_last[0,:] * sigma'(z_7) -> A  (gradient-only mode wrote it in s7) ---------------------
@@ -179,11 +163,7 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
         epi_wait_d(s, e);
         const bool is_skip = (l == g.skip);
         const int nprev = g.n_out[l - 1];
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          const int col = (2 * c + half) * 32;
-          float v[32];
-          epi_load32(e, col, v);
+        epi_for_chunks(e, 4, [&](int c, int col, float (&v)[32]) {
           if (is_skip) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] *= PSN_INV_SQRT2;
@@ -212,7 +192,7 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
           }
           epi_store_a32(s, row, col, v);
           epi_signal_a(s, c);
-        }
+                });
         e.step_ctr++;
       }
       // ---- s17: reverse layer 0 -> gradient ------------------------------------------------------------------------------
@@ -264,11 +244,7 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
         }
         // ---- s18: appearance layer 0 (rest) + parked + bias, ReLU ------------------------------------------------------------
         epi_wait_d(s, e);
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          const int col = (2 * c + half) * 32;
-          float v[32];
-          epi_load32(e, col, v);
+        epi_for_chunks(e, 4, [&](int c, int col, float (&v)[32]) {
 #pragma unroll
           for (int t = 0; t < 8; ++t) {
             const float4 pk = parked[(size_t)((col >> 2) + t) * TILE_M + row];
@@ -278,23 +254,19 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
           for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + __ldg(g.abias[0] + col + i), 0.f);
           epi_store_a32(s, row, col, v);
           epi_signal_a(s, c);
-        }
+                });
         e.step_ctr++;
         // ---- s19..s21: appearance layers 1..3 -------------------------------------------------------------------------------
 #pragma unroll 1
         for (int l = 1; l <= 3; ++l) {
           epi_wait_d(s, e);
           const float* bias = g.abias[l];
-#pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
-            const int col = (2 * c + half) * 32;
-            float v[32];
-            epi_load32(e, col, v);
+          epi_for_chunks(e, 4, [&](int c, int col, float (&v)[32]) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + __ldg(bias + col + i), 0.f);
             epi_store_a32(s, row, col, v);
             epi_signal_a(s, c);
-          }
+                    });
           e.step_ctr++;
         }
         // ---- s22: appearance layer 4 -> rgb ------------------------------------------------------------------------------------
@@ -331,7 +303,7 @@ static int make_tc_rad(const psn_mlp* geo, const psn_mlp* app, void* scratch, Tc
   int n = 0;
   for (int l = 0; l < 8; ++l) {
     put_step(a->prog, n++, geo, TCG_FWD0 + l);
-    a->gbias[l] = geo->fwd[l].bias;
+    a->gbias[l] = geo->tc_bias_scaled[l];
     a->n_out[l] = geo->fwd[l].N;
   }
   a->with_app = app ? 1 : 0;
