@@ -159,6 +159,51 @@ def cpu_baseline_quick():
             "sample": "16x16 centre crop of the 512x512x128spp view, 1 pass, oracle port (torch CPU fp32, %d threads)" % cores}
 
 
+def _time_cuda(fn, reps=2):
+    fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+def extra_workloads(dev, precision, rend, view, peaks):
+    """The other BASELINE configurations, timed once each (device-resident inputs, CUDA events; not the headline value):
+    configs[2] stage-2 shading 512x512 x 96 lights (all-surface synthetic points) and the 96-light shadow-ray pass
+    (rays x 128 samples x lights) on the surface found by the stage-1 render of the bench view."""
+    from psnerf_b200 import synth, engine
+    from psnerf_b200.stage2 import PSNetwork
+    out = {}
+    conf = synth.stage2_conf()
+    torch.manual_seed(0)
+    ps = PSNetwork(conf).to(dev)
+    ps.precision = precision
+    inp = synth.stage2_input(H, W, 96, all_surface=True)
+    inp = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in inp.items()}
+    ms = _time_cuda(lambda: ps(inp))
+    pairs = H * W * 96
+    tf = (pairs * 1.04704 + H * W * 0.282368) * 1e6 / (ms * 1e-3) / 1e12
+    out["stage2_shade_512x512x96L"] = {"ms": ms, "Mpairs_per_s": pairs / ms / 1e3, "algorithmic_TFLOPs": tf, "frac_of_peak": tf / peaks["tflops"],
+                                       "hbm_output_GBps": 3 * pairs * 3 * 4 / (ms * 1e-3) / 1e9}
+    K, pose = view
+    g, _ = rend._geo_app()
+    origin, dirs = rend._rays(synth.pixel_grid_xmajor(H, W).to(dev), K, pose)
+    d = engine.raymarch(g, origin, dirs, 2.0, 2.0, 512, 8, 0.5, rend.model._prec())
+    obj, pts = rend._surface(d, origin, dirs)
+    surf = pts[obj].contiguous()
+    lights = synth.lights(96, axis=tuple((-pose[0, :3, 2]).tolist())).to(dev)
+    ms2 = _time_cuda(lambda: engine.shadow_visibility(g, surf, lights, precision=rend.model._prec()), reps=1)
+    samples = surf.shape[0] * 96 * 128
+    tf2 = samples * MFLOP_OCC * 1e6 / (ms2 * 1e-3) / 1e12
+    out["shadow_visibility_96L_x128"] = {"surface_points": int(surf.shape[0]), "ms": ms2, "Msamples_per_s": samples / ms2 / 1e3,
+                                         "algorithmic_TFLOPs": tf2, "frac_of_peak": tf2 / peaks["tflops"]}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -168,6 +213,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ref-crop", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
     if args.impl == "reference":
@@ -196,7 +242,8 @@ def main():
     pix_host = synth.pixel_grid_xmajor(H, W).pin_memory()      # long [1,N,2]
     n_views = world                                            # weak scaling: one view's worth of rays per GPU
     views = [scene(dev, v) for v in range(n_views)]
-    shard = torch.arange(rank, N, world)                       # this rank's rays of every view
+    from psnerf_b200 import sharding
+    shard = sharding.shard_indices(N, rank, world)             # this rank's 128-ray tiles of every view (round-robin)
     pix_dev = pix_host[:, shard].to(dev)
     n_local = pix_dev.shape[1]
     gather_buf = torch.empty(world, n_views * n_local, 7, device=dev) if dist else None
@@ -285,6 +332,8 @@ def main():
                 "e2e": {"value": units / (ms_e2e / 1e3) / 1e6, "unit": "Msamples/s", "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": n_views * n_local * 2 * 8, "d2h_bytes_per_step": n_views * n_local * 7 * 4},
                 "roofline": roof, "kernels": kern}
+        if world == 1 and not args.no_extras:
+            line["other_workloads"] = extra_workloads(dev, precision, rend, views[0], peaks)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_quick()
         print(json.dumps(line))

@@ -52,29 +52,30 @@ k_tc_occ(TcGeoArgs g, PointGen gen, long long M_host, const int* M_dev, int out_
   } else {
     regs_grow_epilogue();
     EpiCtx e = epi_ctx(tmem_base);
-    const int row = e.row, half = e.half;
+    const int row = e.row, sub = e.sub;
     for (long long it = 0; it < iters; ++it) {
       const long long tile = blockIdx.x + it * gridDim.x;
       const long long idx = tile * TILE_M + row;
       float p[3] = {0.f, 0.f, 0.f}, vdummy[3];
       if (idx < M) gen_point(gen, idx, p, vdummy);
       const float x[3] = {p[0] / g.rescale, p[1] / g.rescale, p[2] / g.rescale};
-      if (MODE == MODE_SHADOW) { p[0] = p[1] = p[2] = 0.f; }
-      {  // layer-0 operand: the point encoding, zero padded to one 64-wide K block (each half writes 32 columns)
+      if (sub == 0) s.c->xsum[row] = 0.f;
+      if (sub < 2) {  // layer-0 operand: the point encoding, zero padded to one 64-wide K block (subs 0, 1: 32 columns each)
 #pragma unroll 1
-        for (int k = half * 32; k < half * 32 + 32; ++k) epi_store_a1(s, row, k, k < g.pe_dim ? pe_entry(x, k) : 0.f);
+        for (int k = sub * 32; k < sub * 32 + 32; ++k) epi_store_a1(s, row, k, k < g.pe_dim ? pe_entry(x, k) : 0.f);
         epi_signal_a(s, 0);
       }
-      float part = 0.f;  // partial logit over this thread's 128 columns (4 interleaved chunks)
+      named_bar_sync(1, EPI_THREADS);  // xsum zeroed before any sub accumulates into it
+      float part = 0.f;  // partial logit over this thread's 64 columns
 #pragma unroll 1
       for (int l = 0; l < 8; ++l) {
         epi_wait_d(s, e);
         const float* bias = g.bias[l];
         const bool pre_skip = (l + 1 == g.skip);
         const int n_out = g.n_out[l];
-        epi_for_chunks(e, 4, [&](int c, int col, float (&v)[32]) {
+        const float cc = pre_skip ? PSN_SOFTPLUS_C * 0.70710678118654752440f : PSN_SOFTPLUS_C;
+        epi_for_chunks(e, 8, [&](int chunk, int col, float (&v)[32]) {
           add_bias32(v, bias, col);
-          const float cc = pre_skip ? PSN_SOFTPLUS_C * 0.70710678118654752440f : PSN_SOFTPLUS_C;
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = softplus_scaled(v[i], cc);
           if (dump && dump_layer == l && idx < M) {
@@ -88,7 +89,7 @@ k_tc_occ(TcGeoArgs g, PointGen gen, long long M_host, const int* M_dev, int out_
               for (int k = (n_out > col ? n_out : col); k < col + 32; ++k)
                 epi_store_a1(s, row, k, pe_entry(x, k - n_out) * 0.70710678118654752440f);
             }
-            epi_signal_a(s, c);
+            epi_signal_a(s, chunk >> 1);
           } else {
             const float4* w4 = reinterpret_cast<const float4*>(g.w_row + col);
 #pragma unroll
@@ -102,10 +103,10 @@ k_tc_occ(TcGeoArgs g, PointGen gen, long long M_host, const int* M_dev, int out_
         e.step_ctr++;
       }
       tc_fence_before();  // order this tile's last TMEM reads before the next tile's MMAs (via a_ready)
-      if (half == 1) s.c->xhalf[row] = part;
+      atomicAdd(&s.c->xsum[row], part);
       named_bar_sync(1, EPI_THREADS);
-      if (half == 0) {
-        const float z = part + s.c->xhalf[row] + __ldg(g.b_logit);
+      if (sub == 0) {
+        const float z = s.c->xsum[row] + __ldg(g.b_logit);
         if (MODE == MODE_OUT) {
           if (idx < M) {
             float o = z;
@@ -116,7 +117,6 @@ k_tc_occ(TcGeoArgs g, PointGen gen, long long M_host, const int* M_dev, int out_
         } else {
           // shadow ray: rows are the 128 march steps of pair `tile`; alpha zeroed outside the box (rendering.py:402-408)
           float a = 1.f / (1.f + __expf(10.f * z));
-          if (idx < M) gen_point(gen, idx, p, vdummy);  // regenerate the sample position instead of keeping it live
           const bool inside = (p[0] <= box) && (p[0] >= -box) && (p[1] <= box) && (p[1] >= -box) && (p[2] <= box) && (p[2] >= -box);
           if (!inside || idx >= M) a = 0.f;
           const float t = (1.f - a) + 1e-6f;
@@ -141,6 +141,7 @@ k_tc_occ(TcGeoArgs g, PointGen gen, long long M_host, const int* M_dev, int out_
           if (row == 0) out[tile] = 1.f - (s.c->g3[8] + s.c->g3[9] + s.c->g3[10] + s.c->g3[11]);
         }
       }
+      named_bar_sync(1, EPI_THREADS);  // xsum / g3 are reused by the next tile
     }
   }
   teardown(tmem_base);

@@ -10,10 +10,12 @@
 // pre-swizzled [N rows][64 K] tile streamed from L2 with cp.async.bulk (UBLKCP) + mbarrier complete_tx.
 // TMEM: two 256-column fp32 accumulators (all 512 columns).
 //
-// Warp roles: warp 0 = TMEM allocator + weight producer (one lane), warp 1 = MMA issuer (one lane), warps 2-3 idle
-// (the control warpgroup releases registers with setmaxnreg.dec), warps 4..11 = epilogue (setmaxnreg.inc) (warp w reads TMEM lanes 32*(w%4)..; the two warps sharing a lane quadrant interleave over
-// 32-column chunks: half h = (w-4)/4 owns columns [(2c+h)*32, (2c+h)*32+32), c = 0..3, so K block c of the next layer is
-// complete after chunk c of BOTH halves).
+// Warp roles: warp 0 = TMEM allocator + weight producer (one lane), warp 1 = MMA issuer (one lane), warps 2-3 idle (the
+// control warpgroup releases registers with setmaxnreg.dec);
+// warps 4..19 = epilogue: warp w reads TMEM lanes 32*(w%4).. and is "sub" s = (w-4)/4 of its lane quadrant; sub s owns the
+// 32-column chunks s and s+4 of every accumulator, so after ONE chunk time K blocks 0 and 1 of the next layer are complete
+// and the MMA warp can restart.  Four epilogue warps per scheduler hide the MUFU / TMEM / L2 latencies that two could not
+// (ncu: issue slots 34 % busy, tensor pipe waiting); registers are rebalanced with setmaxnreg (control 40, epilogue 112).
 // Layer pipelining: the epilogue of step L rewrites the A buffer in place (every MMA of step L has retired when
 // d_full fires) K-block by K-block and signals a_ready[kb]; the MMA warp starts step L+1's K-block kb as soon as
 // that block is ready, accumulating into the OTHER TMEM buffer - so tensor work of step L+1 overlaps the
@@ -32,9 +34,11 @@ constexpr int A_MAX_KB = 4;
 constexpr int A_BYTES = A_MAX_KB * A_KB_BYTES;  // 128 KB
 constexpr int W_STAGE_BYTES = 256 * 128;        // 32 KB: [256 N rows][64 K] fp16
 constexpr int W_STAGES = 3;
-constexpr int NUM_THREADS = 384;  // warpgroup 0 = control (setmaxnreg 48), warpgroups 1-2 = epilogue (setmaxnreg 224)
+constexpr int NUM_THREADS = 640;  // warpgroup 0 = control (setmaxnreg 40), warpgroups 1-4 = epilogue (setmaxnreg 112)
 constexpr int EPI_WARP0 = 4;
-constexpr int EPI_THREADS = 256;
+constexpr int EPI_THREADS = 512;
+constexpr int EPI_SUBS = 4;       // epilogue warps per TMEM lane quadrant; sub s owns 32-column chunks s and s+4
+constexpr int A_READY_ARRIVALS = 256;  // a K block (2 chunks) is written by 2 subs x 128 rows
 
 // ---- shared-memory control block (after the 1024-aligned A and W regions) ---------------------------------
 struct Ctrl {
@@ -44,8 +48,8 @@ struct Ctrl {
   unsigned long long d_full[2];
   unsigned int tmem_base;
   unsigned int pad;
-  float xhalf[TILE_M];     // cross-half exchange (partial dot products / transmittance scans)
-  float g3[TILE_M * 3];    // per-row 3-vectors (d logit / d p contributions)
+  float xsum[TILE_M];      // per-row sums accumulated across the 4 subs (shared-memory atomics): logit / head dot product
+  float g3[TILE_M * 3];    // per-row 3-vectors accumulated across subs (d logit / d p), also scratch of the shadow scan
 };
 constexpr int SMEM_BYTES = A_BYTES + W_STAGES * W_STAGE_BYTES + (int)sizeof(Ctrl);  // dynamic smem is declared __align__(1024)
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory of sm_100");
@@ -155,8 +159,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 }
 
 // register re-allocation between warpgroups (all 4 warps of a warpgroup must execute it)
-__device__ __forceinline__ void regs_shrink_control() { asm volatile("setmaxnreg.dec.sync.aligned.u32 48;" ::: "memory"); }
-__device__ __forceinline__ void regs_grow_epilogue() { asm volatile("setmaxnreg.inc.sync.aligned.u32 224;" ::: "memory"); }
+__device__ __forceinline__ void regs_shrink_control() { asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory"); }
+__device__ __forceinline__ void regs_grow_epilogue() { asm volatile("setmaxnreg.inc.sync.aligned.u32 112;" ::: "memory"); }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
@@ -193,7 +197,7 @@ __device__ __forceinline__ uint32_t setup(const Smem& s) {
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     for (int i = 0; i < W_STAGES; ++i) { mbar_init(&s.c->w_full[i], 1); mbar_init(&s.c->w_empty[i], 1); }
-    for (int i = 0; i < A_MAX_KB; ++i) mbar_init(&s.c->a_ready[i], EPI_THREADS);
+    for (int i = 0; i < A_MAX_KB; ++i) mbar_init(&s.c->a_ready[i], A_READY_ARRIVALS);
     for (int i = 0; i < 2; ++i) mbar_init(&s.c->d_full[i], 1);
     fence_barrier_init();
   }
@@ -277,7 +281,7 @@ struct EpiCtx {
   uint32_t tmem_base;
   uint32_t step_ctr;   // global step counter (same sequence as the MMA warp)
   int row;             // tile row owned by this thread (TMEM lane)
-  int half;            // which of the two interleaved column sets: chunk c covers columns (2c + half) * 32 ...
+  int sub;             // 0..3: owns chunks sub and sub + 4 (columns 32*sub.. and 32*(sub+4)..)
   uint32_t lane_addr;  // (32 * quadrant) << 16
 };
 __device__ __forceinline__ EpiCtx epi_ctx(uint32_t tmem_base) {
@@ -287,7 +291,7 @@ __device__ __forceinline__ EpiCtx epi_ctx(uint32_t tmem_base) {
   e.tmem_base = tmem_base;
   e.step_ctr = 0;
   e.row = q * 32 + (threadIdx.x & 31);
-  e.half = (warp - EPI_WARP0) >> 2;
+  e.sub = (warp - EPI_WARP0) >> 2;
   e.lane_addr = (uint32_t)(q * 32) << 16;
   return e;
 }
@@ -300,30 +304,19 @@ __device__ __forceinline__ void epi_load32(const EpiCtx& e, int col, float (&v)[
   tmem_ld32(e.tmem_base + e.lane_addr + (e.step_ctr & 1u) * 256u + (uint32_t)col, v);
 }
 
-// Visit the four 32-column chunks this thread owns in the current accumulator: f(c, col, v[32]).  The TMEM load of chunk
-// c+1 is in flight while chunk c is processed.
+// Visit the 32-column chunks this thread owns in the current accumulator: f(chunk, col, v[32]); chunk = sub, sub + 4
+// (only chunks < n_chunks exist for narrow steps).  Not unrolled: the bodies are large and the kernels are I-cache bound
+// otherwise; latency is hidden by the other three epilogue warps of the scheduler.
 template <class F>
 __device__ __forceinline__ void epi_for_chunks(const EpiCtx& e, int n_chunks, F&& f) {
-  uint32_t ra[32], rb[32];
   const uint32_t base = e.tmem_base + e.lane_addr + (e.step_ctr & 1u) * 256u;
-  tmem_ld32_issue(base + (uint32_t)(e.half * 32), ra);
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    if (c < n_chunks) {
-      const int col = (2 * c + e.half) * 32;
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    const int chunk = e.sub + 4 * pass;
+    if (chunk < n_chunks) {
       float v[32];
-      if (c & 1) {
-        tmem_ld32_wait(rb);
-        if (c + 1 < n_chunks) tmem_ld32_issue(base + (uint32_t)((2 * (c + 1) + e.half) * 32), ra);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rb[i]);
-      } else {
-        tmem_ld32_wait(ra);
-        if (c + 1 < n_chunks) tmem_ld32_issue(base + (uint32_t)((2 * (c + 1) + e.half) * 32), rb);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(ra[i]);
-      }
-      f(c, col, v);
+      tmem_ld32(base + (uint32_t)(chunk * 32), v);
+      f(chunk, chunk * 32, v);
     }
   }
 }
@@ -372,7 +365,7 @@ __device__ __forceinline__ void epi_store_a1(const Smem& s, int row, int col, fl
   *reinterpret_cast<__half*>(hi_row + phys) = h;
   *reinterpret_cast<__half*>(hi_row + A_PART_BYTES + phys) = __float2half_rn(x - __half2float(h));
 }
-// this thread's contribution to K-block kb is written: publish to the MMA warp (256 arrivals per block)
+// this thread's 32 columns of K-block kb are written: publish to the MMA warp (2 subs x 128 rows = 256 arrivals per block)
 __device__ __forceinline__ void epi_signal_a(const Smem& s, int kb) {
   tc_fence_before();
   fence_proxy_async_smem();

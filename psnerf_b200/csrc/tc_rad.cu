@@ -71,7 +71,7 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
   } else {
     regs_grow_epilogue();
     EpiCtx e = epi_ctx(tmem_base);
-    const int row = e.row, half = e.half;
+    const int row = e.row, sub = e.sub;
     float4* stash = g.scratch + (size_t)blockIdx.x * SCR_F4_PER_CTA;
     float4* parked = stash + SCR_STASH_F4;
     for (long long it = 0; it < iters; ++it) {
@@ -80,11 +80,16 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
       float p[3] = {0.f, 0.f, 0.f}, vd[3] = {0.f, 0.f, 1.f};
       if (idx < M) gen_point(gen, idx, p, vd);
       const float x[3] = {p[0] / g.rescale, p[1] / g.rescale, p[2] / g.rescale};
-      {
+      if (sub == 0) {
+        s.c->xsum[row] = 0.f;
+        s.c->g3[row * 3] = 0.f; s.c->g3[row * 3 + 1] = 0.f; s.c->g3[row * 3 + 2] = 0.f;
+      }
+      if (sub < 2) {
 #pragma unroll 1
-        for (int k = half * 32; k < half * 32 + 32; ++k) epi_store_a1(s, row, k, k < g.pe_dim ? pe_entry_r(x, k) : 0.f);
+        for (int k = sub * 32; k < sub * 32 + 32; ++k) epi_store_a1(s, row, k, k < g.pe_dim ? pe_entry_r(x, k) : 0.f);
         epi_signal_a(s, 0);
       }
+      named_bar_sync(1, EPI_THREADS);  // xsum / g3 zeroed before any sub accumulates into them
       // ---- s0..s7: geo forward --------------------------------------------------------------------------------------
       float part = 0.f;
 #pragma unroll 1
@@ -93,20 +98,28 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
         const float* bias = g.gbias[l];
         const bool pre_skip = (l + 1 == g.skip);
         const int n_out = g.n_out[l];
-        epi_for_chunks(e, 4, [&](int c, int col, float (&v)[32]) {
+        const float cc = pre_skip ? PSN_SOFTPLUS_C * PSN_INV_SQRT2 : PSN_SOFTPLUS_C;
+        epi_for_chunks(e, 8, [&](int chunk, int col, float (&v)[32]) {
           add_bias32(v, bias, col);
-          const float cc = pre_skip ? PSN_SOFTPLUS_C * PSN_INV_SQRT2 : PSN_SOFTPLUS_C;
 #pragma unroll
           for (int t = 0; t < 8; ++t) {
             float sg[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int i = 4 * t + u;
-              float a = softplus_scaled_d(v[i], cc, &sg[u]);
-              if (l == 7 && !g.with_app) a = __ldg(g.w_row + col + i) * sg[u];  // gradient only: seed dz_7 directly
-              v[i] = a;
-            }
+            for (int u = 0; u < 4; ++u) v[4 * t + u] = softplus_scaled_d(v[4 * t + u], cc, &sg[u]);
             stash[(size_t)(l * 64 + (col >> 2) + t) * TILE_M + row] = make_float4(sg[0], sg[1], sg[2], sg[3]);
+            if (l == 7 && !g.with_app) {  // gradient only: seed dz_7 = W_last[0,:] * sigma'(z_7) directly
+              const float4 w = __ldg(reinterpret_cast<const float4*>(g.w_row + col) + t);
+              v[4 * t] = w.x * sg[0]; v[4 * t + 1] = w.y * sg[1]; v[4 * t + 2] = w.z * sg[2]; v[4 * t + 3] = w.w * sg[3];
+            }
+          }
+          if (l == 7 && g.with_app) {
+            const float4* w4 = reinterpret_cast<const float4*>(g.w_row + col);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+              const float4 w = __ldg(w4 + t);
+              part = fmaf(v[4 * t], w.x, part); part = fmaf(v[4 * t + 1], w.y, part);
+              part = fmaf(v[4 * t + 2], w.z, part); part = fmaf(v[4 * t + 3], w.w, part);
+            }
           }
           epi_store_a32(s, row, col, v);
           if (pre_skip && col + 32 > n_out) {
@@ -114,48 +127,37 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
             for (int k = (n_out > col ? n_out : col); k < col + 32; ++k)
               epi_store_a1(s, row, k, pe_entry_r(x, k - n_out) * PSN_INV_SQRT2);
           }
-          if (l == 7 && g.with_app) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) part = fmaf(v[i], __ldg(g.w_row + col + i), part);
-          }
-          epi_signal_a(s, c);
-                });
+          epi_signal_a(s, chunk >> 1);
+        });
         e.step_ctr++;
       }
-      if (half == 1) s.c->xhalf[row] = part;
+      if (g.with_app) atomicAdd(&s.c->xsum[row], part);
       float g_acc[3] = {0.f, 0.f, 0.f};  // this thread's share of J_pe^T (d logit / d pe)
       if (g.with_app) {
         // ---- s8: feature head -> A (no activation) ---------------------------------------------------------------------
         epi_wait_d(s, e);
-        epi_for_chunks(e, 4, [&](int c, int col, float (&v)[32]) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] += __ldg(g.bias_feat + col + i);
+        epi_for_chunks(e, 8, [&](int chunk, int col, float (&v)[32]) {
+          add_bias32(v, g.bias_feat, col);
           epi_store_a32(s, row, col, v);
-          epi_signal_a(s, c);
-                });
+          epi_signal_a(s, chunk >> 1);
+        });
         e.step_ctr++;
-        // ---- s9: appearance layer 0, feature part -> parked -------------------------------------------------------------
+        // ---- s9: appearance layer 0, feature part -> parked; then the reverse seed dz_7 -> A -------------------------------
         epi_wait_d(s, e);
-        epi_for_chunks(e, 4, [&](int c, int col, float (&v)[32]) {
+        epi_for_chunks(e, 8, [&](int chunk, int col, float (&v)[32]) {
 #pragma unroll
           for (int t = 0; t < 8; ++t)
             parked[(size_t)((col >> 2) + t) * TILE_M + row] = make_float4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
-                });
-        e.step_ctr++;
-      }
-      // ---- reverse seed: dz_7 = W_last[0,:] * sigma'(z_7) -> A  (gradient-only mode wrote it in s7) ---------------------
-#pragma unroll 1
-      for (int c = 0; c < (g.with_app ? 4 : 0); ++c) {
-        const int col = (2 * c + half) * 32;
-        float v[32];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          const float4 sg = stash[(size_t)(7 * 64 + (col >> 2) + t) * TILE_M + row];
-          const float4 w = __ldg(reinterpret_cast<const float4*>(g.w_row + col) + t);
-          v[4 * t] = w.x * sg.x; v[4 * t + 1] = w.y * sg.y; v[4 * t + 2] = w.z * sg.z; v[4 * t + 3] = w.w * sg.w;
-        }
-        epi_store_a32(s, row, col, v);
-        epi_signal_a(s, c);
+          for (int t = 0; t < 8; ++t) {
+            const float4 sg = stash[(size_t)(7 * 64 + (col >> 2) + t) * TILE_M + row];
+            const float4 w = __ldg(reinterpret_cast<const float4*>(g.w_row + col) + t);
+            v[4 * t] = w.x * sg.x; v[4 * t + 1] = w.y * sg.y; v[4 * t + 2] = w.z * sg.z; v[4 * t + 3] = w.w * sg.w;
+          }
+          epi_store_a32(s, row, col, v);
+          epi_signal_a(s, chunk >> 1);
+        });
+        e.step_ctr++;
       }
       // ---- s10..s16: reverse through layers 7..1 -----------------------------------------------------------------------------
 #pragma unroll 1
@@ -163,27 +165,30 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
         epi_wait_d(s, e);
         const bool is_skip = (l == g.skip);
         const int nprev = g.n_out[l - 1];
-        epi_for_chunks(e, 4, [&](int c, int col, float (&v)[32]) {
+        epi_for_chunks(e, 8, [&](int chunk, int col, float (&v)[32]) {
           if (is_skip) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] *= PSN_INV_SQRT2;
             if (col + 32 > nprev) {  // encoding part of the skip input: contributes J_pe^T directly
-#pragma unroll
+#pragma unroll 1
               for (int i = 0; i < 32; ++i) {
                 const int k = col + i - nprev;
                 if (k >= 0 && k < g.pe_dim) {
                   int cc;
                   const float jv = pe_jac(x, k, &cc);
-                  const float t = jv * v[i];
+                  float vi = 0.f;
+#pragma unroll
+                  for (int u = 0; u < 32; ++u) vi = (u == i) ? v[u] : vi;
+                  const float t = jv * vi;
                   g_acc[0] += cc == 0 ? t : 0.f; g_acc[1] += cc == 1 ? t : 0.f; g_acc[2] += cc == 2 ? t : 0.f;
                 }
               }
             }
           }
 #pragma unroll
-          for (int t = 0; t < 8; ++t) {
-            const float4 sg = stash[(size_t)((l - 1) * 64 + (col >> 2) + t) * TILE_M + row];
-            v[4 * t] *= sg.x; v[4 * t + 1] *= sg.y; v[4 * t + 2] *= sg.z; v[4 * t + 3] *= sg.w;
+          for (int t = 0; t < 8; ++t) {  // the L2 latency of the stash is covered by the other epilogue warps of the scheduler
+            const float4 q = stash[(size_t)((l - 1) * 64 + (col >> 2) + t) * TILE_M + row];
+            v[4 * t] *= q.x; v[4 * t + 1] *= q.y; v[4 * t + 2] *= q.z; v[4 * t + 3] *= q.w;
           }
           if (col + 32 > nprev) {
 #pragma unroll
@@ -191,99 +196,105 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
               if (col + i >= nprev) v[i] = 0.f;
           }
           epi_store_a32(s, row, col, v);
-          epi_signal_a(s, c);
-                });
+          epi_signal_a(s, chunk >> 1);
+        });
         e.step_ctr++;
       }
       // ---- s17: reverse layer 0 -> gradient ------------------------------------------------------------------------------
       epi_wait_d(s, e);
-      float gr[3] = {0.f, 0.f, 0.f};
-      float logit = 0.f;
-      {  // d logit / d pe: columns 0..pe_dim-1 of this step (half 0: 0..31, half 1: 32..63)
+      if (sub < 2) {  // d logit / d pe: columns 0..pe_dim-1 of this step (sub 0: 0..31, sub 1: 32..63)
         float v[32];
-        epi_load32(e, half * 32, v);
-#pragma unroll
+        epi_load32(e, sub * 32, v);
+#pragma unroll 1
         for (int i = 0; i < 32; ++i) {
-          const int k = half * 32 + i;
+          const int k = sub * 32 + i;
           if (k < g.pe_dim) {
             int cc;
             const float jv = pe_jac(x, k, &cc);
-            const float t = jv * v[i];
+            float vi = 0.f;
+#pragma unroll
+            for (int u = 0; u < 32; ++u) vi = (u == i) ? v[u] : vi;
+            const float t = jv * vi;
             g_acc[0] += cc == 0 ? t : 0.f; g_acc[1] += cc == 1 ? t : 0.f; g_acc[2] += cc == 2 ? t : 0.f;
           }
         }
       }
-      if (half == 1) {
-        s.c->g3[row * 3 + 0] = g_acc[0]; s.c->g3[row * 3 + 1] = g_acc[1]; s.c->g3[row * 3 + 2] = g_acc[2];
-      }
-      named_bar_sync(1, EPI_THREADS);
-      if (half == 0) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) gr[c] = (g_acc[c] + s.c->g3[row * 3 + c]) / g.rescale;
-        logit = part + s.c->xhalf[row] + __ldg(g.b_logit);
-        if (grad_out && idx < M) { grad_out[idx * 3] = gr[0]; grad_out[idx * 3 + 1] = gr[1]; grad_out[idx * 3 + 2] = gr[2]; }
+      if (g_acc[0] != 0.f || g_acc[1] != 0.f || g_acc[2] != 0.f) {
+        atomicAdd(&s.c->g3[row * 3], g_acc[0]); atomicAdd(&s.c->g3[row * 3 + 1], g_acc[1]); atomicAdd(&s.c->g3[row * 3 + 2], g_acc[2]);
       }
       e.step_ctr++;
       tc_fence_before();
+      named_bar_sync(1, EPI_THREADS);
+      float gr[3] = {0.f, 0.f, 0.f};
+      float logit = 0.f;
+      if (sub == 0) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) gr[c] = s.c->g3[row * 3 + c] / g.rescale;
+        logit = s.c->xsum[row] + __ldg(g.b_logit);
+        if (grad_out && idx < M) { grad_out[idx * 3] = gr[0]; grad_out[idx * 3 + 1] = gr[1]; grad_out[idx * 3 + 2] = gr[2]; }
+      }
       if (g.with_app) {
-        if (half == 0) {  // [p, PE(view/|view|), gradient] -> K block 0 (network.py:98,127-132)
+        if (sub == 0) {  // [p, PE(view/|view|), gradient] -> K block 0 (network.py:98,127-132)
           const float nv = sqrtf(vd[0] * vd[0] + vd[1] * vd[1] + vd[2] * vd[2]);
           const float vn[3] = {vd[0] / nv, vd[1] / nv, vd[2] / nv};
           const int o_g = 3 + g.pe_view_dim;
 #pragma unroll 1
           for (int k = 0; k < KBLK; ++k) {
             float val = 0.f;
-            if (k < 3) val = p[k];
+            if (k < 3) val = (k == 0 ? p[0] : (k == 1 ? p[1] : p[2]));
             else if (k < o_g) val = pe_entry_r(vn, k - 3);
-            else if (k < o_g + 3) val = gr[k - o_g];
+            else if (k < o_g + 3) val = (k == o_g ? gr[0] : (k == o_g + 1 ? gr[1] : gr[2]));
             epi_store_a1(s, row, k, val);
           }
           epi_signal_a(s, 0);
-        } else {
-          epi_signal_a(s, 0);  // half 1 contributes nothing to this 64-column block
+        } else if (sub == 1) {
+          epi_signal_a(s, 0);  // second of the two arrival groups of K block 0 (sub 0 wrote all 64 columns)
         }
         // ---- s18: appearance layer 0 (rest) + parked + bias, ReLU ------------------------------------------------------------
         epi_wait_d(s, e);
-        epi_for_chunks(e, 4, [&](int c, int col, float (&v)[32]) {
+        epi_for_chunks(e, 8, [&](int chunk, int col, float (&v)[32]) {
 #pragma unroll
           for (int t = 0; t < 8; ++t) {
             const float4 pk = parked[(size_t)((col >> 2) + t) * TILE_M + row];
             v[4 * t] += pk.x; v[4 * t + 1] += pk.y; v[4 * t + 2] += pk.z; v[4 * t + 3] += pk.w;
           }
+          add_bias32(v, g.abias[0], col);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + __ldg(g.abias[0] + col + i), 0.f);
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
           epi_store_a32(s, row, col, v);
-          epi_signal_a(s, c);
-                });
+          epi_signal_a(s, chunk >> 1);
+        });
         e.step_ctr++;
         // ---- s19..s21: appearance layers 1..3 -------------------------------------------------------------------------------
 #pragma unroll 1
         for (int l = 1; l <= 3; ++l) {
           epi_wait_d(s, e);
           const float* bias = g.abias[l];
-          epi_for_chunks(e, 4, [&](int c, int col, float (&v)[32]) {
+          epi_for_chunks(e, 8, [&](int chunk, int col, float (&v)[32]) {
+            add_bias32(v, bias, col);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + __ldg(bias + col + i), 0.f);
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
             epi_store_a32(s, row, col, v);
-            epi_signal_a(s, c);
-                    });
+            epi_signal_a(s, chunk >> 1);
+          });
           e.step_ctr++;
         }
         // ---- s22: appearance layer 4 -> rgb ------------------------------------------------------------------------------------
         epi_wait_d(s, e);
-        if (half == 0) {
+        if (sub == 0) {
           float v[32];
           epi_load32(e, 0, v);
           if (idx < M) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) rgb[idx * 3 + c] = tanhf(v[c] + __ldg(g.abias[4] + c)) * 0.5f + 0.5f;
+            rgb[idx * 3 + 0] = tanhf(v[0] + __ldg(g.abias[4] + 0)) * 0.5f + 0.5f;
+            rgb[idx * 3 + 1] = tanhf(v[1] + __ldg(g.abias[4] + 1)) * 0.5f + 0.5f;
+            rgb[idx * 3 + 2] = tanhf(v[2] + __ldg(g.abias[4] + 2)) * 0.5f + 0.5f;
             alpha[idx] = 1.f / (1.f + __expf(10.f * logit));
           }
         }
         e.step_ctr++;
         tc_fence_before();
       }
-      named_bar_sync(1, EPI_THREADS);  // xhalf / g3 are rewritten by the next tile
+      named_bar_sync(1, EPI_THREADS);  // xsum / g3 are rewritten by the next tile
     }
   }
   teardown(tmem_base);

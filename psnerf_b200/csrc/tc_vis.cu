@@ -97,17 +97,18 @@ k_tc_vis(TcVisArgs g, float* __restrict__ vis) {
   } else {
     regs_grow_epilogue();
     EpiCtx e = epi_ctx(tmem_base);
-    const int row = e.row, half = e.half;
+    const int row = e.row, sub = e.sub;
     for (long long t = t0; t < t1; ++t) {
       const long long pb = t / g.L;
       const int l = (int)(t - pb * g.L);
       const long long n = pb * TILE_M + row;
       const bool valid = n < g.Ns;
       const long long nn = valid ? n : g.Ns - 1;
-      // layer 0: relu(P0[n] + L0[l])
+      if (sub == 0) s.c->xsum[row] = 0.f;
+      // layer 0: relu(P0[n] + L0[l]) for this thread's two 32-column chunks
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        const int col = (2 * c + half) * 32;
+      for (int pass = 0; pass < 2; ++pass) {
+        const int chunk = sub + 4 * pass, col = chunk * 32;
         float v[32];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -117,14 +118,15 @@ k_tc_vis(TcVisArgs g, float* __restrict__ vis) {
           v[4 * i + 2] = fmaxf(a.z + b.z, 0.f); v[4 * i + 3] = fmaxf(a.w + b.w, 0.f);
         }
         epi_store_a32(s, row, col, v);
-        epi_signal_a(s, c);
+        epi_signal_a(s, chunk >> 1);
       }
+      named_bar_sync(1, EPI_THREADS);  // xsum zeroed before any sub accumulates into it
       float part = 0.f;
 #pragma unroll 1
       for (int st = 0; st < 7; ++st) {
         epi_wait_d(s, e);
         const float* bias = g.bias[st];
-        epi_for_chunks(e, 4, [&](int c, int col, float (&v)[32]) {
+        epi_for_chunks(e, 8, [&](int chunk, int col, float (&v)[32]) {
           if (st == 4) {  // skip layer: + P5[n] (bias folded) + L5[l]
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -139,7 +141,7 @@ k_tc_vis(TcVisArgs g, float* __restrict__ vis) {
           for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
           if (st < 6) {
             epi_store_a32(s, row, col, v);
-            epi_signal_a(s, c);
+            epi_signal_a(s, chunk >> 1);
           } else {
             const float4* w4 = reinterpret_cast<const float4*>(g.w_last + col);
 #pragma unroll
@@ -153,9 +155,10 @@ k_tc_vis(TcVisArgs g, float* __restrict__ vis) {
         e.step_ctr++;
       }
       tc_fence_before();
-      if (half == 1) s.c->xhalf[row] = part;
+      atomicAdd(&s.c->xsum[row], part);
       named_bar_sync(1, EPI_THREADS);
-      if (half == 0 && valid) vis[(long long)l * g.Ns + n] = part + s.c->xhalf[row] + __ldg(g.b_last);
+      if (sub == 0 && valid) vis[(long long)l * g.Ns + n] = s.c->xsum[row] + __ldg(g.b_last);
+      named_bar_sync(1, EPI_THREADS);
     }
   }
   teardown(tmem_base);

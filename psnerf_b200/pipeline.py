@@ -1,0 +1,79 @@
+"""Entry-point loops of the reference kept as thin host code over the CUDA path:
+
+  render_stage1_view   <- stage1/eval.py:82-119          (one library call per view instead of 256 x 1024-ray chunks)
+  extract_shape        <- stage1/shape_extract.py:103-165 (points / normals / mask / per-light visibility of a view)
+  render_stage2_view   <- stage2/eval.py:314-417          (all light batches of a view)
+  extract_and_shade    <- SURVEY.md §8f-1: stage-1 surface extraction feeding stage-2 shading directly, no .npy hand-off
+  *_sharded            <- SURVEY.md §8e: rays of a view dealt over the ranks, one all_gather of pixels at the end
+
+All functions take / return torch tensors; `view` dicts carry the camera: stage 1 {camera_mat, world_mat}, stage 2
+{intrinsics, pose}.  The pixel order conventions of the reference are preserved (stage 1: x-major, undone by to_hw;
+stage 2: row-major uv)."""
+import torch
+
+from . import sharding
+from .stage1.common import arange_pixels, to_hw
+
+
+@torch.no_grad()
+def render_stage1_view(renderer, h, w, camera_mat, world_mat, it=100000, pixels=None):
+    """rgb [h,w,3], normal [h,w,3], acc [h,w], mask [h,w] exactly as stage1/eval.py assembles them."""
+    dev = next(renderer.model.parameters()).device
+    p_loc = arange_pixels((h, w))[0].to(dev) if pixels is None else pixels
+    out = renderer(p_loc, camera_mat, world_mat, None, "unisurf", add_noise=False, eval_=True, it=it)
+    if pixels is not None:
+        return out
+    return {"rgb": to_hw(out["rgb"][0], h, w), "normal": to_hw(out["normal_pred"][0], h, w),
+            "acc": to_hw(out["acc_map"][0], h, w)[..., 0], "mask": to_hw(out["mask_pred"].float(), h, w)[..., 0] > 0.5}
+
+
+@torch.no_grad()
+def extract_shape(renderer, h, w, camera_mat, world_mat, light_dir=None):
+    """points/normal/mask (+ visibility [L, h*w]) of one view in x-major pixel order (shape_extract.py:133-163)."""
+    dev = next(renderer.model.parameters()).device
+    p_loc = arange_pixels((h, w))[0].to(dev)
+    return renderer(p_loc, camera_mat, world_mat, None, "shape_extract", visibility=light_dir is not None, light_dir=light_dir)
+
+
+@torch.no_grad()
+def render_stage2_view(model, model_input, light_dirs, light_batch=96, light_intensity=None):
+    """Loop over light batches (stage2/eval.py:345-365) and concatenate along the light axis."""
+    outs = []
+    for s in range(0, light_dirs.shape[0], light_batch):
+        inp = dict(model_input)
+        inp["light_direction"] = light_dirs[s:s + light_batch]
+        if light_intensity is not None:
+            inp["light_intensity"] = light_intensity[s:s + light_batch]
+        outs.append(model(inp))
+    res = dict(outs[-1])
+    for k in ("sg_rgb_values", "sg_specular_rgb_values", "visibility"):
+        if k in res:
+            res[k] = torch.cat([o[k] for o in outs], 0)
+    return res
+
+
+@torch.no_grad()
+def extract_and_shade(renderer, ps_model, h, w, camera_mat, world_mat, light_dirs, light_batch=96):
+    """Stage-1 surface search + analytic normals feeding stage-2 shading in one pass (no points/normal/mask .npy files).
+    Stage-1 pixel order is x-major while stage 2 consumes uv pairs explicitly, so no re-ordering is needed."""
+    dev = next(renderer.model.parameters()).device
+    shp = extract_shape(renderer, h, w, camera_mat, world_mat)
+    p_loc = arange_pixels((h, w))[0].to(dev)
+    K = torch.eye(4).unsqueeze(0)
+    cm = camera_mat.detach().float().cpu()
+    K[0, 0, 0] = K[0, 1, 1] = cm[0, 0, 0]  # stage 1 uses fx for both axes (common.py:220)
+    K[0, 0, 2], K[0, 1, 2] = cm[0, 0, 2], cm[0, 1, 2]
+    inp = {"intrinsics": K, "uv": p_loc.float(), "pose": world_mat, "object_mask": shp["mask"], "surface_mask": shp["mask"],
+           "points": shp["points"], "normal": shp["normal"]}
+    return shp, render_stage2_view(ps_model, inp, light_dirs.to(dev), light_batch)
+
+
+@torch.no_grad()
+def render_stage1_view_sharded(renderer, h, w, camera_mat, world_mat, rank, world, it=100000):
+    """Every rank renders its tiles of rays; ONE all_gather returns the full [h*w, 7] (rgb, normal, acc) image."""
+    dev = next(renderer.model.parameters()).device
+    p_all = arange_pixels((h, w))[0]
+    idx = sharding.shard_indices(h * w, rank, world)
+    out = renderer(p_all[:, idx].to(dev), camera_mat, world_mat, None, "unisurf", add_noise=False, eval_=True, it=it)
+    local = torch.cat([out["rgb"][0], out["normal_pred"][0], out["acc_map"][0].unsqueeze(-1)], -1)
+    return sharding.gather_pixels(local, h * w, rank, world)
