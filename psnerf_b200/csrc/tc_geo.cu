@@ -59,13 +59,11 @@ k_tc_occ(TcGeoArgs g, PointGen gen, long long M_host, const int* M_dev, int out_
       float p[3] = {0.f, 0.f, 0.f}, vdummy[3];
       if (idx < M) gen_point(gen, idx, p, vdummy);
       const float x[3] = {p[0] / g.rescale, p[1] / g.rescale, p[2] / g.rescale};
-      if (sub == 0) s.c->xsum[row] = 0.f;
       if (sub < 2) {  // layer-0 operand: the point encoding, zero padded to one 64-wide K block (subs 0, 1: 32 columns each)
 #pragma unroll 1
         for (int k = sub * 32; k < sub * 32 + 32; ++k) epi_store_a1(s, row, k, k < g.pe_dim ? pe_entry(x, k) : 0.f);
         epi_signal_a(s, 0);
       }
-      named_bar_sync(1, EPI_THREADS);  // xsum zeroed before any sub accumulates into it
       float part = 0.f;  // partial logit over this thread's 64 columns
 #pragma unroll 1
       for (int l = 0; l < 8; ++l) {
@@ -103,10 +101,11 @@ k_tc_occ(TcGeoArgs g, PointGen gen, long long M_host, const int* M_dev, int out_
         e.step_ctr++;
       }
       tc_fence_before();  // order this tile's last TMEM reads before the next tile's MMAs (via a_ready)
-      atomicAdd(&s.c->xsum[row], part);
+      float* stage = epi_stage(s);  // [4 subs][128 rows]
+      stage[sub * TILE_M + row] = part;
       named_bar_sync(1, EPI_THREADS);
       if (sub == 0) {
-        const float z = s.c->xsum[row] + __ldg(g.b_logit);
+        const float z = ((stage[row] + stage[TILE_M + row]) + (stage[2 * TILE_M + row] + stage[3 * TILE_M + row])) + __ldg(g.b_logit);
         if (MODE == MODE_OUT) {
           if (idx < M) {
             float o = z;
@@ -141,7 +140,7 @@ k_tc_occ(TcGeoArgs g, PointGen gen, long long M_host, const int* M_dev, int out_
           if (row == 0) out[tile] = 1.f - (s.c->g3[8] + s.c->g3[9] + s.c->g3[10] + s.c->g3[11]);
         }
       }
-      named_bar_sync(1, EPI_THREADS);  // xsum / g3 are reused by the next tile
+      named_bar_sync(1, EPI_THREADS);  // the staging area (A buffer) and g3 are reused by the next tile
     }
   }
   teardown(tmem_base);

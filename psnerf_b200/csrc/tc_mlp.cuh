@@ -15,7 +15,7 @@
 // warps 4..19 = epilogue: warp w reads TMEM lanes 32*(w%4).. and is "sub" s = (w-4)/4 of its lane quadrant; sub s owns the
 // 32-column chunks s and s+4 of every accumulator, so after ONE chunk time K blocks 0 and 1 of the next layer are complete
 // and the MMA warp can restart.  Four epilogue warps per scheduler hide the MUFU / TMEM / L2 latencies that two could not
-// (ncu: issue slots 34 % busy, tensor pipe waiting); registers are rebalanced with setmaxnreg (control 40, epilogue 112).
+// (ncu: issue slots 34 % busy, tensor pipe waiting); registers are rebalanced with setmaxnreg (control 32, epilogue 112).
 // Layer pipelining: the epilogue of step L rewrites the A buffer in place (every MMA of step L has retired when
 // d_full fires) K-block by K-block and signals a_ready[kb]; the MMA warp starts step L+1's K-block kb as soon as
 // that block is ready, accumulating into the OTHER TMEM buffer - so tensor work of step L+1 overlaps the
@@ -34,7 +34,7 @@ constexpr int A_MAX_KB = 4;
 constexpr int A_BYTES = A_MAX_KB * A_KB_BYTES;  // 128 KB
 constexpr int W_STAGE_BYTES = 256 * 128;        // 32 KB: [256 N rows][64 K] fp16
 constexpr int W_STAGES = 3;
-constexpr int NUM_THREADS = 640;  // warpgroup 0 = control (setmaxnreg 40), warpgroups 1-4 = epilogue (setmaxnreg 112)
+constexpr int NUM_THREADS = 640;  // warpgroup 0 = control (setmaxnreg 32), warpgroups 1-4 = epilogue (setmaxnreg 112)
 constexpr int EPI_WARP0 = 4;
 constexpr int EPI_THREADS = 512;
 constexpr int EPI_SUBS = 4;       // epilogue warps per TMEM lane quadrant; sub s owns 32-column chunks s and s+4
@@ -48,8 +48,7 @@ struct Ctrl {
   unsigned long long d_full[2];
   unsigned int tmem_base;
   unsigned int pad;
-  float xsum[TILE_M];      // per-row sums accumulated across the 4 subs (shared-memory atomics): logit / head dot product
-  float g3[TILE_M * 3];    // per-row 3-vectors accumulated across subs (d logit / d p), also scratch of the shadow scan
+  float g3[64];            // scratch of the shadow-ray transmittance scan
 };
 constexpr int SMEM_BYTES = A_BYTES + W_STAGES * W_STAGE_BYTES + (int)sizeof(Ctrl);  // dynamic smem is declared __align__(1024)
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory of sm_100");
@@ -159,7 +158,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 }
 
 // register re-allocation between warpgroups (all 4 warps of a warpgroup must execute it)
-__device__ __forceinline__ void regs_shrink_control() { asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory"); }
+// The CTA's register pool is what it was launched with (ptxas: 96 regs x 640 threads); setmaxnreg.inc BLOCKS until the pool
+// has room, so the budget must close exactly: 4 control warps x 32 + 16 epilogue warps x 112 = 96 x 20 warps.
+constexpr int LAUNCH_REGS = 96, CONTROL_REGS = 32, EPILOGUE_REGS = 112;
+static_assert(CONTROL_REGS * 4 + EPILOGUE_REGS * 16 <= LAUNCH_REGS * 20, "setmaxnreg budget exceeds the CTA register pool (deadlock)");
+__device__ __forceinline__ void regs_shrink_control() { asm volatile("setmaxnreg.dec.sync.aligned.u32 32;" ::: "memory"); }
 __device__ __forceinline__ void regs_grow_epilogue() { asm volatile("setmaxnreg.inc.sync.aligned.u32 112;" ::: "memory"); }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
@@ -356,6 +359,10 @@ __device__ __forceinline__ void epi_store_a32(const Smem& s, int row, int col, c
     *reinterpret_cast<uint4*>(lo_row + phys) = make_uint4(l[0], l[1], l[2], l[3]);
   }
 }
+// Cross-sub reductions (fixed order => bit-reproducible): every sub parks its per-row partials in the LAST K block of the A
+// buffer, which is dead whenever this is used (after the accumulator wait of a step whose epilogue does not rewrite it).
+__device__ __forceinline__ float* epi_stage(const Smem& s) { return reinterpret_cast<float*>(s.a + 3 * A_KB_BYTES); }
+
 // single element (column col of this thread's row): used for the few encoding columns that are not MMA outputs
 __device__ __forceinline__ void epi_store_a1(const Smem& s, int row, int col, float x) {
   const int kb = col >> 6, kk = col & 63;

@@ -80,16 +80,11 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
       float p[3] = {0.f, 0.f, 0.f}, vd[3] = {0.f, 0.f, 1.f};
       if (idx < M) gen_point(gen, idx, p, vd);
       const float x[3] = {p[0] / g.rescale, p[1] / g.rescale, p[2] / g.rescale};
-      if (sub == 0) {
-        s.c->xsum[row] = 0.f;
-        s.c->g3[row * 3] = 0.f; s.c->g3[row * 3 + 1] = 0.f; s.c->g3[row * 3 + 2] = 0.f;
-      }
       if (sub < 2) {
 #pragma unroll 1
         for (int k = sub * 32; k < sub * 32 + 32; ++k) epi_store_a1(s, row, k, k < g.pe_dim ? pe_entry_r(x, k) : 0.f);
         epi_signal_a(s, 0);
       }
-      named_bar_sync(1, EPI_THREADS);  // xsum / g3 zeroed before any sub accumulates into them
       // ---- s0..s7: geo forward --------------------------------------------------------------------------------------
       float part = 0.f;
 #pragma unroll 1
@@ -131,7 +126,6 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
         });
         e.step_ctr++;
       }
-      if (g.with_app) atomicAdd(&s.c->xsum[row], part);
       float g_acc[3] = {0.f, 0.f, 0.f};  // this thread's share of J_pe^T (d logit / d pe)
       if (g.with_app) {
         // ---- s8: feature head -> A (no activation) ---------------------------------------------------------------------
@@ -219,20 +213,22 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
           }
         }
       }
-      if (g_acc[0] != 0.f || g_acc[1] != 0.f || g_acc[2] != 0.f) {
-        atomicAdd(&s.c->g3[row * 3], g_acc[0]); atomicAdd(&s.c->g3[row * 3 + 1], g_acc[1]); atomicAdd(&s.c->g3[row * 3 + 2], g_acc[2]);
-      }
       e.step_ctr++;
       tc_fence_before();
+      float4* stage = reinterpret_cast<float4*>(epi_stage(s));  // [4 subs][128 rows] (g_acc.xyz, logit partial)
+      stage[sub * TILE_M + row] = make_float4(g_acc[0], g_acc[1], g_acc[2], part);
       named_bar_sync(1, EPI_THREADS);
       float gr[3] = {0.f, 0.f, 0.f};
       float logit = 0.f;
       if (sub == 0) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) gr[c] = s.c->g3[row * 3 + c] / g.rescale;
-        logit = s.c->xsum[row] + __ldg(g.b_logit);
+        const float4 a0 = stage[row], a1 = stage[TILE_M + row], a2 = stage[2 * TILE_M + row], a3 = stage[3 * TILE_M + row];
+        gr[0] = ((a0.x + a1.x) + (a2.x + a3.x)) / g.rescale;
+        gr[1] = ((a0.y + a1.y) + (a2.y + a3.y)) / g.rescale;
+        gr[2] = ((a0.z + a1.z) + (a2.z + a3.z)) / g.rescale;
+        logit = ((a0.w + a1.w) + (a2.w + a3.w)) + __ldg(g.b_logit);
         if (grad_out && idx < M) { grad_out[idx * 3] = gr[0]; grad_out[idx * 3 + 1] = gr[1]; grad_out[idx * 3 + 2] = gr[2]; }
       }
+      named_bar_sync(1, EPI_THREADS);  // staging area read before anybody rewrites the A buffer
       if (g.with_app) {
         if (sub == 0) {  // [p, PE(view/|view|), gradient] -> K block 0 (network.py:98,127-132)
           const float nv = sqrtf(vd[0] * vd[0] + vd[1] * vd[1] + vd[2] * vd[2]);
@@ -294,7 +290,6 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
         e.step_ctr++;
         tc_fence_before();
       }
-      named_bar_sync(1, EPI_THREADS);  // xsum / g3 are rewritten by the next tile
     }
   }
   teardown(tmem_base);

@@ -104,7 +104,6 @@ k_tc_vis(TcVisArgs g, float* __restrict__ vis) {
       const long long n = pb * TILE_M + row;
       const bool valid = n < g.Ns;
       const long long nn = valid ? n : g.Ns - 1;
-      if (sub == 0) s.c->xsum[row] = 0.f;
       // layer 0: relu(P0[n] + L0[l]) for this thread's two 32-column chunks
 #pragma unroll 1
       for (int pass = 0; pass < 2; ++pass) {
@@ -120,7 +119,6 @@ k_tc_vis(TcVisArgs g, float* __restrict__ vis) {
         epi_store_a32(s, row, col, v);
         epi_signal_a(s, chunk >> 1);
       }
-      named_bar_sync(1, EPI_THREADS);  // xsum zeroed before any sub accumulates into it
       float part = 0.f;
 #pragma unroll 1
       for (int st = 0; st < 7; ++st) {
@@ -155,9 +153,11 @@ k_tc_vis(TcVisArgs g, float* __restrict__ vis) {
         e.step_ctr++;
       }
       tc_fence_before();
-      atomicAdd(&s.c->xsum[row], part);
+      float* stage = epi_stage(s);  // [4 subs][128 rows]
+      stage[sub * TILE_M + row] = part;
       named_bar_sync(1, EPI_THREADS);
-      if (sub == 0 && valid) vis[(long long)l * g.Ns + n] = s.c->xsum[row] + __ldg(g.b_last);
+      if (sub == 0 && valid)
+        vis[(long long)l * g.Ns + n] = ((stage[row] + stage[TILE_M + row]) + (stage[2 * TILE_M + row] + stage[3 * TILE_M + row])) + __ldg(g.b_last);
       named_bar_sync(1, EPI_THREADS);
     }
   }
