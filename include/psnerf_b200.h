@@ -165,6 +165,9 @@ int psn_s2_visibility(const psn_mlp* vis_net, int n_freqs, const float* pts, int
  * fp32 before the fp16 hi/lo split, out[M,256]; logits[M] receives the resulting logit. */
 int psn_tc_debug_layer(const psn_mlp* geo, const float* pts, int64_t M, int layer, float* out, float* logits, void* stream);
 
+/* Bring-up tool: clock64() timeline of one tile of the tensor-core occupancy kernel; trace is int64[256] on the device. */
+int psn_tc_debug_trace(const psn_mlp* geo, const float* pts, int64_t M, float* out, long long* trace, void* stream);
+
 /* alpha compositing of per-sample (rgb, alpha): rendering.py:196-197,214-216. */
 int psn_composite(const float* rgb_s /*[N,S,3]*/, const float* alpha /*[N,S]*/, int64_t N, int S,
                   int white_background, float* rgb /*[N,3]*/, float* acc /*[N]*/, void* stream);

@@ -81,6 +81,7 @@ def load():
     lib.psn_s2_point_nets.argtypes = [vp, vp, i32, vp, i64, vp, vp, i32, i32, vp]
     lib.psn_s2_visibility.argtypes = [vp, i32, vp, i64, vp, i32, vp, vp, i64, i32, vp]
     lib.psn_tc_debug_layer.argtypes = [vp, vp, i64, i32, vp, vp, vp]
+    lib.psn_tc_debug_trace.argtypes = [vp, vp, i64, vp, vp, vp]
     lib.psn_composite.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp]
     _lib = lib
     return lib

@@ -30,12 +30,12 @@ __device__ __forceinline__ float pe_entry(const float x[3], int idx) {
   return r < 3 ? sinf(a) : cosf(a);
 }
 
-constexpr int MODE_OUT = 0, MODE_SHADOW = 1;
+constexpr int MODE_OUT = 0, MODE_SHADOW = 1, MODE_DEBUG = 2;  // MODE_DEBUG = MODE_OUT + layer dump / clock64 trace hooks
 
 template <int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_tc_occ(TcGeoArgs g, PointGen gen, long long M_host, const int* M_dev, int out_kind, float* out, float box, int dump_layer,
-         float* dump) {
+         float* dump, long long* trace) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const Smem s = carve(smem_raw);
   const uint32_t tmem_base = setup(s);
@@ -47,7 +47,7 @@ k_tc_occ(TcGeoArgs g, PointGen gen, long long M_host, const int* M_dev, int out_
   if (warp < EPI_WARP0) {
     regs_shrink_control();
     if (warp == 0 && lane == 0) producer_loop(s, g.prog, iters);
-    if (warp == 1 && lane == 0) mma_loop(s, g.prog, iters, tmem_base);
+    if (warp == 1 && lane == 0) mma_loop(s, g.prog, iters, tmem_base, MODE == MODE_DEBUG ? trace : nullptr);
     __syncwarp();
   } else {
     regs_grow_epilogue();
@@ -59,39 +59,44 @@ k_tc_occ(TcGeoArgs g, PointGen gen, long long M_host, const int* M_dev, int out_
       float p[3] = {0.f, 0.f, 0.f}, vdummy[3];
       if (idx < M) gen_point(gen, idx, p, vdummy);
       const float x[3] = {p[0] / g.rescale, p[1] / g.rescale, p[2] / g.rescale};
-      if (sub < 2) {  // layer-0 operand: the point encoding, zero padded to one 64-wide K block (subs 0, 1: 32 columns each)
+      {  // layer-0 operand: the point encoding, zero padded to one 64-wide K block (16 columns per sub)
 #pragma unroll 1
-        for (int k = sub * 32; k < sub * 32 + 32; ++k) epi_store_a1(s, row, k, k < g.pe_dim ? pe_entry(x, k) : 0.f);
+        for (int k = sub * CW; k < sub * CW + CW; ++k) epi_store_a1(s, row, k, k < g.pe_dim ? pe_entry(x, k) : 0.f);
         epi_signal_a(s, 0);
       }
       float part = 0.f;  // partial logit over this thread's 64 columns
 #pragma unroll 1
       for (int l = 0; l < 8; ++l) {
         epi_wait_d(s, e);
+        const bool tr = (MODE == MODE_DEBUG) && trace && it == TRACE_ITER && blockIdx.x == 0 && row == 0;
+        if (tr) trace[64 + sub * 40 + l * 5] = clock64();
         const float* bias = g.bias[l];
         const bool pre_skip = (l + 1 == g.skip);
         const int n_out = g.n_out[l];
         const float cc = pre_skip ? PSN_SOFTPLUS_C * 0.70710678118654752440f : PSN_SOFTPLUS_C;
-        epi_for_chunks(e, 8, [&](int chunk, int col, float (&v)[32]) {
-          add_bias32(v, bias, col);
+        epi_for_chunks(e, 256, [&](int pass, int col, float (&v)[CW]) {
+          add_bias16(v, bias, col);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = softplus_scaled(v[i], cc);
-          if (dump && dump_layer == l && idx < M) {
+          for (int i = 0; i < CW; ++i) v[i] = softplus_scaled(v[i], cc);
+          if (MODE == MODE_DEBUG) {
+            if (dump && dump_layer == l && idx < M) {  // bring-up hook: the MMA-produced columns only
 #pragma unroll
-            for (int i = 0; i < 32; ++i) dump[idx * 256 + col + i] = (pre_skip && col + i >= n_out) ? pe_entry(x, col + i - n_out) * 0.70710678118654752440f : v[i];
+              for (int i = 0; i < CW; ++i) dump[idx * 256 + col + i] = v[i];
+            }
           }
           if (l < 7) {
-            epi_store_a32(s, row, col, v);
-            if (pre_skip && col + 32 > n_out) {  // columns n_out.. of the skip layer's input are pe/sqrt2 (network.py:90-91)
+            epi_store_a16(s, row, col, v);
+            if (pre_skip && col + CW > n_out) {  // columns n_out.. of the skip layer's input are pe/sqrt2 (network.py:90-91)
 #pragma unroll 1
-              for (int k = (n_out > col ? n_out : col); k < col + 32; ++k)
+              for (int k = (n_out > col ? n_out : col); k < col + CW; ++k)
                 epi_store_a1(s, row, k, pe_entry(x, k - n_out) * 0.70710678118654752440f);
             }
-            epi_signal_a(s, chunk >> 1);
+            epi_signal_a(s, pass);
+            if (tr) trace[64 + sub * 40 + l * 5 + 1 + pass] = clock64();
           } else {
             const float4* w4 = reinterpret_cast<const float4*>(g.w_row + col);
 #pragma unroll
-            for (int t = 0; t < 8; ++t) {
+            for (int t = 0; t < 4; ++t) {
               const float4 w = __ldg(w4 + t);
               part = fmaf(v[4 * t], w.x, part); part = fmaf(v[4 * t + 1], w.y, part);
               part = fmaf(v[4 * t + 2], w.z, part); part = fmaf(v[4 * t + 3], w.w, part);
@@ -106,7 +111,7 @@ k_tc_occ(TcGeoArgs g, PointGen gen, long long M_host, const int* M_dev, int out_
       named_bar_sync(1, EPI_THREADS);
       if (sub == 0) {
         const float z = ((stage[row] + stage[TILE_M + row]) + (stage[2 * TILE_M + row] + stage[3 * TILE_M + row])) + __ldg(g.b_logit);
-        if (MODE == MODE_OUT) {
+        if (MODE != MODE_SHADOW) {
           if (idx < M) {
             float o = z;
             if (out_kind == PSN_OUT_ALPHA) o = 1.f / (1.f + __expf(10.f * z));
@@ -175,12 +180,16 @@ static int make_tc_geo(const psn_mlp* geo, TcGeoArgs* a) {
 
 template <int MODE>
 static int launch_tc_occ(const TcGeoArgs& a, const PointGen& gen, long long M, const int* M_dev, int out_kind, float* out, float box,
-                         int dump_layer, float* dump, cudaStream_t st) {
+                         int dump_layer, float* dump, cudaStream_t st, long long* trace = nullptr) {
   PSN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_occ<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  {
+    const int rcr = check_launch_regs((const void*)k_tc_occ<MODE>, "k_tc_occ");
+    if (rcr) return rcr;
+  }
   const long long tiles = M_dev ? (long long)num_ctas() : (M + TILE_M - 1) / TILE_M;
   const int grid = (int)(tiles < num_ctas() ? tiles : num_ctas());
   count_launch();
-  k_tc_occ<MODE><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(a, gen, M, M_dev, out_kind, out, box, dump_layer, dump);
+  k_tc_occ<MODE><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(a, gen, M, M_dev, out_kind, out, box, dump_layer, dump, trace);
   PSN_CUDA_CHECK(cudaGetLastError());
   return PSN_OK;
 }
@@ -219,5 +228,18 @@ extern "C" int psn_tc_debug_layer(const psn_mlp* geo, const float* pts, int64_t 
   memset(&gen, 0, sizeof(gen));
   gen.kind = GEN_EXPLICIT;
   gen.pts = pts;
-  return launch_tc_occ<MODE_OUT>(a, gen, M, nullptr, PSN_OUT_LOGIT, logits, 0.f, layer, out, (cudaStream_t)stream);
+  return launch_tc_occ<MODE_DEBUG>(a, gen, M, nullptr, PSN_OUT_LOGIT, logits, 0.f, layer, out, (cudaStream_t)stream);
+}
+
+// Bring-up tool: clock64() timeline of one tile of the occupancy kernel (see TRACE_ITER in tc_mlp.cuh): trace[256] int64 device.
+extern "C" int psn_tc_debug_trace(const psn_mlp* geo, const float* pts, int64_t M, float* out, long long* trace, void* stream) {
+  PSN_REQUIRE(geo && pts && out && trace, PSN_ERR_ARG, "psn_tc_debug_trace: bad argument");
+  TcGeoArgs a;
+  int rc = make_tc_geo(geo, &a);
+  if (rc) return rc;
+  PointGen gen;
+  memset(&gen, 0, sizeof(gen));
+  gen.kind = GEN_EXPLICIT;
+  gen.pts = pts;
+  return launch_tc_occ<MODE_DEBUG>(a, gen, M, nullptr, PSN_OUT_ALPHA, out, 0.f, -1, nullptr, (cudaStream_t)stream, trace);
 }

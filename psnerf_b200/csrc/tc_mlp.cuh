@@ -12,9 +12,8 @@
 //
 // Warp roles: warp 0 = TMEM allocator + weight producer (one lane), warp 1 = MMA issuer (one lane), warps 2-3 idle (the
 // control warpgroup releases registers with setmaxnreg.dec);
-// warps 4..19 = epilogue: warp w reads TMEM lanes 32*(w%4).. and is "sub" s = (w-4)/4 of its lane quadrant; sub s owns the
-// 32-column chunks s and s+4 of every accumulator, so after ONE chunk time K blocks 0 and 1 of the next layer are complete
-// and the MMA warp can restart.  Four epilogue warps per scheduler hide the MUFU / TMEM / L2 latencies that two could not
+// warps 4..19 = epilogue: warp w reads TMEM lanes 32*(w%4).. and is "sub" s = (w-4)/4 of its lane quadrant; in pass p sub s
+// owns columns [64p + 16s, +16), so every pass completes one K block of the next layer and the MMA warp restarts early.  Four epilogue warps per scheduler hide the MUFU / TMEM / L2 latencies that two could not
 // (ncu: issue slots 34 % busy, tensor pipe waiting); registers are rebalanced with setmaxnreg (control 32, epilogue 112).
 // Layer pipelining: the epilogue of step L rewrites the A buffer in place (every MMA of step L has retired when
 // d_full fires) K-block by K-block and signals a_ready[kb]; the MMA warp starts step L+1's K-block kb as soon as
@@ -37,8 +36,9 @@ constexpr int W_STAGES = 3;
 constexpr int NUM_THREADS = 640;  // warpgroup 0 = control (setmaxnreg 32), warpgroups 1-4 = epilogue (setmaxnreg 112)
 constexpr int EPI_WARP0 = 4;
 constexpr int EPI_THREADS = 512;
-constexpr int EPI_SUBS = 4;       // epilogue warps per TMEM lane quadrant; sub s owns 32-column chunks s and s+4
-constexpr int A_READY_ARRIVALS = 256;  // a K block (2 chunks) is written by 2 subs x 128 rows
+constexpr int EPI_SUBS = 4;       // epilogue warps per TMEM lane quadrant
+constexpr int CW = 16;            // columns per epilogue chunk: in pass p sub s owns columns [64 p + 16 s, +16)
+constexpr int A_READY_ARRIVALS = 512;  // a K block (64 columns) is written by 4 subs x 128 rows in ONE pass
 
 // ---- shared-memory control block (after the 1024-aligned A and W regions) ---------------------------------
 struct Ctrl {
@@ -149,6 +149,23 @@ __device__ __forceinline__ void tmem_ld32_wait(uint32_t (&r)[32]) {
                :
                : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
   tmem_ld32_issue(taddr, r);
@@ -160,12 +177,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 // register re-allocation between warpgroups (all 4 warps of a warpgroup must execute it)
 // The CTA's register pool is what it was launched with (ptxas: 96 regs x 640 threads); setmaxnreg.inc BLOCKS until the pool
 // has room, so the budget must close exactly: 4 control warps x 32 + 16 epilogue warps x 112 = 96 x 20 warps.
-constexpr int LAUNCH_REGS = 96, CONTROL_REGS = 32, EPILOGUE_REGS = 112;
+constexpr int LAUNCH_REGS = 96, CONTROL_REGS = 32, EPILOGUE_REGS = 112;  // LAUNCH_REGS is verified at launch (check_launch_regs)
 static_assert(CONTROL_REGS * 4 + EPILOGUE_REGS * 16 <= LAUNCH_REGS * 20, "setmaxnreg budget exceeds the CTA register pool (deadlock)");
 __device__ __forceinline__ void regs_shrink_control() { asm volatile("setmaxnreg.dec.sync.aligned.u32 32;" ::: "memory"); }
 __device__ __forceinline__ void regs_grow_epilogue() { asm volatile("setmaxnreg.inc.sync.aligned.u32 112;" ::: "memory"); }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// Host-side guard: setmaxnreg.inc deadlocks if the kernel was compiled to fewer launch registers than the budget assumes.
+inline int check_launch_regs(const void* kernel, const char* name) {
+  cudaFuncAttributes at;
+  PSN_CUDA_CHECK(cudaFuncGetAttributes(&at, kernel));
+  PSN_REQUIRE(at.numRegs >= 96 && at.numRegs <= 102, PSN_ERR_CUDA,
+              "%s was compiled with %d registers/thread; the setmaxnreg budget (tc_mlp.cuh) assumes 96", name, at.numRegs);
+  return PSN_OK;
+}
 
 // ---- step table -------------------------------------------------------------------------------------------------
 struct Step {
@@ -235,7 +261,11 @@ __device__ __forceinline__ void producer_loop(const Smem& s, const Program& prog
 }
 
 // ---- MMA issuer (warp 1, lane 0) -------------------------------------------------------------------------------------
-__device__ __forceinline__ void mma_loop(const Smem& s, const Program& prog, long long iters, uint32_t tmem_base) {
+// trace (optional, bring-up tool): for CTA 0, tile iteration TRACE_ITER the MMA lane stores clock64() after every a_ready wait
+// (slot st*8 + kb) and after the step's last commit (slot st*8 + 7).
+constexpr int TRACE_ITER = 3;
+__device__ __forceinline__ void mma_loop(const Smem& s, const Program& prog, long long iters, uint32_t tmem_base,
+                                         long long* trace = nullptr) {
   uint32_t stage = 0, phase = 0;   // weight ring
   uint32_t a_phase = 0;            // bit kb = parity to wait for on a_ready[kb]
   uint32_t step_ctr = 0;           // selects the TMEM accumulator
@@ -249,6 +279,7 @@ __device__ __forceinline__ void mma_loop(const Smem& s, const Program& prog, lon
         mbar_wait(&s.c->a_ready[kb], (a_phase >> kb) & 1u);
         a_phase ^= (1u << kb);
         tc_fence_after();
+        if (trace && it == TRACE_ITER && blockIdx.x == 0) trace[st * 8 + kb] = clock64();
         const uint32_t a_hi = a_base + kb * A_KB_BYTES, a_lo = a_hi + A_PART_BYTES;
         // W_hi tile: A_hi W_hi + A_lo W_hi
         mbar_wait(&s.c->w_full[stage], phase);
@@ -275,6 +306,7 @@ __device__ __forceinline__ void mma_loop(const Smem& s, const Program& prog, lon
         if (++stage == W_STAGES) { stage = 0; phase ^= 1u; }
       }
       umma_commit(&s.c->d_full[step_ctr & 1u]);
+      if (trace && it == TRACE_ITER && blockIdx.x == 0) trace[st * 8 + 7] = clock64();
     }
   }
 }
@@ -284,7 +316,7 @@ struct EpiCtx {
   uint32_t tmem_base;
   uint32_t step_ctr;   // global step counter (same sequence as the MMA warp)
   int row;             // tile row owned by this thread (TMEM lane)
-  int sub;             // 0..3: owns chunks sub and sub + 4 (columns 32*sub.. and 32*(sub+4)..)
+  int sub;             // 0..3: owns columns [64 p + 16 sub, +16) in pass p
   uint32_t lane_addr;  // (32 * quadrant) << 16
 };
 __device__ __forceinline__ EpiCtx epi_ctx(uint32_t tmem_base) {
@@ -303,31 +335,31 @@ __device__ __forceinline__ void epi_wait_d(const Smem& s, const EpiCtx& e) {
   mbar_wait(&s.c->d_full[e.step_ctr & 1u], (e.step_ctr >> 1) & 1u);
   tc_fence_after();
 }
-__device__ __forceinline__ void epi_load32(const EpiCtx& e, int col, float (&v)[32]) {
-  tmem_ld32(e.tmem_base + e.lane_addr + (e.step_ctr & 1u) * 256u + (uint32_t)col, v);
+__device__ __forceinline__ void epi_load16(const EpiCtx& e, int col, float (&v)[CW]) {
+  tmem_ld16(e.tmem_base + e.lane_addr + (e.step_ctr & 1u) * 256u + (uint32_t)col, v);
 }
 
-// Visit the 32-column chunks this thread owns in the current accumulator: f(chunk, col, v[32]); chunk = sub, sub + 4
-// (only chunks < n_chunks exist for narrow steps).  Not unrolled: the bodies are large and the kernels are I-cache bound
-// otherwise; latency is hidden by the other three epilogue warps of the scheduler.
+// Visit the 16-column chunks this thread owns in the current accumulator: f(pass, col, v[16]), col = 64*pass + 16*sub, for the
+// passes whose columns exist (col < n_cols).  One pass of the four subs covers exactly one 64-column K block of the next
+// layer's A operand, so the MMA warp can restart after a quarter of the epilogue (clock64 trace: it used to wait for half).
 template <class F>
-__device__ __forceinline__ void epi_for_chunks(const EpiCtx& e, int n_chunks, F&& f) {
+__device__ __forceinline__ void epi_for_chunks(const EpiCtx& e, int n_cols, F&& f) {
   const uint32_t base = e.tmem_base + e.lane_addr + (e.step_ctr & 1u) * 256u;
 #pragma unroll 1
-  for (int pass = 0; pass < 2; ++pass) {
-    const int chunk = e.sub + 4 * pass;
-    if (chunk < n_chunks) {
-      float v[32];
-      tmem_ld32(base + (uint32_t)(chunk * 32), v);
-      f(chunk, chunk * 32, v);
+  for (int pass = 0; pass < 4; ++pass) {
+    const int col = 64 * pass + CW * e.sub;
+    if (col < n_cols) {
+      float v[CW];
+      tmem_ld16(base + (uint32_t)col, v);
+      f(pass, col, v);
     }
   }
 }
 // v[i] += bias[col + i] with 128-bit loads
-__device__ __forceinline__ void add_bias32(float (&v)[32], const float* __restrict__ bias, int col) {
+__device__ __forceinline__ void add_bias16(float (&v)[CW], const float* __restrict__ bias, int col) {
   const float4* b4 = reinterpret_cast<const float4*>(bias + col);
 #pragma unroll
-  for (int t = 0; t < 8; ++t) {
+  for (int t = 0; t < 4; ++t) {
     const float4 b = __ldg(b4 + t);
     v[4 * t] += b.x; v[4 * t + 1] += b.y; v[4 * t + 2] += b.z; v[4 * t + 3] += b.w;
   }
@@ -336,14 +368,14 @@ __device__ __forceinline__ void add_bias32(float (&v)[32], const float* __restri
 __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
   return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
 }
-// Write 32 consecutive activation values (columns col..col+31 of this thread's row) as fp16 hi/lo into the A buffer.
-__device__ __forceinline__ void epi_store_a32(const Smem& s, int row, int col, const float (&v)[32]) {
+// Write 16 consecutive activation values (columns col..col+15 of this thread's row) as fp16 hi/lo into the A buffer.
+__device__ __forceinline__ void epi_store_a16(const Smem& s, int row, int col, const float (&v)[CW]) {
   const int kb = col >> 6;
   unsigned char* hi_row = s.a + kb * A_KB_BYTES + row * 128;
   unsigned char* lo_row = hi_row + A_PART_BYTES;
   const int c0 = (col & 63) >> 3;  // first 16-byte chunk
 #pragma unroll
-  for (int t = 0; t < 4; ++t) {
+  for (int t = 0; t < 2; ++t) {
     uint32_t h[4], l[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {  // packed cvt.rn.f16x2.f32 (F2FP, ALU pipe) - scalar F2F would queue on the XU pipe with the MUFUs
@@ -372,7 +404,7 @@ __device__ __forceinline__ void epi_store_a1(const Smem& s, int row, int col, fl
   *reinterpret_cast<__half*>(hi_row + phys) = h;
   *reinterpret_cast<__half*>(hi_row + A_PART_BYTES + phys) = __float2half_rn(x - __half2float(h));
 }
-// this thread's 32 columns of K-block kb are written: publish to the MMA warp (2 subs x 128 rows = 256 arrivals per block)
+// this thread's 16 columns of K-block kb are written: publish to the MMA warp (4 subs x 128 rows = 512 arrivals per block)
 __device__ __forceinline__ void epi_signal_a(const Smem& s, int kb) {
   tc_fence_before();
   fence_proxy_async_smem();

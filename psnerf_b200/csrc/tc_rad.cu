@@ -80,9 +80,9 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
       float p[3] = {0.f, 0.f, 0.f}, vd[3] = {0.f, 0.f, 1.f};
       if (idx < M) gen_point(gen, idx, p, vd);
       const float x[3] = {p[0] / g.rescale, p[1] / g.rescale, p[2] / g.rescale};
-      if (sub < 2) {
+      {
 #pragma unroll 1
-        for (int k = sub * 32; k < sub * 32 + 32; ++k) epi_store_a1(s, row, k, k < g.pe_dim ? pe_entry_r(x, k) : 0.f);
+        for (int k = sub * CW; k < sub * CW + CW; ++k) epi_store_a1(s, row, k, k < g.pe_dim ? pe_entry_r(x, k) : 0.f);
         epi_signal_a(s, 0);
       }
       // ---- s0..s7: geo forward --------------------------------------------------------------------------------------
@@ -94,10 +94,10 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
         const bool pre_skip = (l + 1 == g.skip);
         const int n_out = g.n_out[l];
         const float cc = pre_skip ? PSN_SOFTPLUS_C * PSN_INV_SQRT2 : PSN_SOFTPLUS_C;
-        epi_for_chunks(e, 8, [&](int chunk, int col, float (&v)[32]) {
-          add_bias32(v, bias, col);
+        epi_for_chunks(e, 256, [&](int pass, int col, float (&v)[CW]) {
+          add_bias16(v, bias, col);
 #pragma unroll
-          for (int t = 0; t < 8; ++t) {
+          for (int t = 0; t < 4; ++t) {
             float sg[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) v[4 * t + u] = softplus_scaled_d(v[4 * t + u], cc, &sg[u]);
@@ -110,19 +110,19 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
           if (l == 7 && g.with_app) {
             const float4* w4 = reinterpret_cast<const float4*>(g.w_row + col);
 #pragma unroll
-            for (int t = 0; t < 8; ++t) {
+            for (int t = 0; t < 4; ++t) {
               const float4 w = __ldg(w4 + t);
               part = fmaf(v[4 * t], w.x, part); part = fmaf(v[4 * t + 1], w.y, part);
               part = fmaf(v[4 * t + 2], w.z, part); part = fmaf(v[4 * t + 3], w.w, part);
             }
           }
-          epi_store_a32(s, row, col, v);
-          if (pre_skip && col + 32 > n_out) {
+          epi_store_a16(s, row, col, v);
+          if (pre_skip && col + CW > n_out) {
 #pragma unroll 1
-            for (int k = (n_out > col ? n_out : col); k < col + 32; ++k)
+            for (int k = (n_out > col ? n_out : col); k < col + CW; ++k)
               epi_store_a1(s, row, k, pe_entry_r(x, k - n_out) * PSN_INV_SQRT2);
           }
-          epi_signal_a(s, chunk >> 1);
+          epi_signal_a(s, pass);
         });
         e.step_ctr++;
       }
@@ -130,26 +130,26 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
       if (g.with_app) {
         // ---- s8: feature head -> A (no activation) ---------------------------------------------------------------------
         epi_wait_d(s, e);
-        epi_for_chunks(e, 8, [&](int chunk, int col, float (&v)[32]) {
-          add_bias32(v, g.bias_feat, col);
-          epi_store_a32(s, row, col, v);
-          epi_signal_a(s, chunk >> 1);
+        epi_for_chunks(e, 256, [&](int pass, int col, float (&v)[CW]) {
+          add_bias16(v, g.bias_feat, col);
+          epi_store_a16(s, row, col, v);
+          epi_signal_a(s, pass);
         });
         e.step_ctr++;
         // ---- s9: appearance layer 0, feature part -> parked; then the reverse seed dz_7 -> A -------------------------------
         epi_wait_d(s, e);
-        epi_for_chunks(e, 8, [&](int chunk, int col, float (&v)[32]) {
+        epi_for_chunks(e, 256, [&](int pass, int col, float (&v)[CW]) {
 #pragma unroll
-          for (int t = 0; t < 8; ++t)
+          for (int t = 0; t < 4; ++t)
             parked[(size_t)((col >> 2) + t) * TILE_M + row] = make_float4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
 #pragma unroll
-          for (int t = 0; t < 8; ++t) {
+          for (int t = 0; t < 4; ++t) {
             const float4 sg = stash[(size_t)(7 * 64 + (col >> 2) + t) * TILE_M + row];
             const float4 w = __ldg(reinterpret_cast<const float4*>(g.w_row + col) + t);
             v[4 * t] = w.x * sg.x; v[4 * t + 1] = w.y * sg.y; v[4 * t + 2] = w.z * sg.z; v[4 * t + 3] = w.w * sg.w;
           }
-          epi_store_a32(s, row, col, v);
-          epi_signal_a(s, chunk >> 1);
+          epi_store_a16(s, row, col, v);
+          epi_signal_a(s, pass);
         });
         e.step_ctr++;
       }
@@ -159,20 +159,20 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
         epi_wait_d(s, e);
         const bool is_skip = (l == g.skip);
         const int nprev = g.n_out[l - 1];
-        epi_for_chunks(e, 8, [&](int chunk, int col, float (&v)[32]) {
+        epi_for_chunks(e, 256, [&](int pass, int col, float (&v)[CW]) {
           if (is_skip) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] *= PSN_INV_SQRT2;
-            if (col + 32 > nprev) {  // encoding part of the skip input: contributes J_pe^T directly
+            for (int i = 0; i < CW; ++i) v[i] *= PSN_INV_SQRT2;
+            if (col + CW > nprev) {  // encoding part of the skip input: contributes J_pe^T directly
 #pragma unroll 1
-              for (int i = 0; i < 32; ++i) {
+              for (int i = 0; i < CW; ++i) {
                 const int k = col + i - nprev;
                 if (k >= 0 && k < g.pe_dim) {
                   int cc;
                   const float jv = pe_jac(x, k, &cc);
                   float vi = 0.f;
 #pragma unroll
-                  for (int u = 0; u < 32; ++u) vi = (u == i) ? v[u] : vi;
+                  for (int u = 0; u < CW; ++u) vi = (u == i) ? v[u] : vi;
                   const float t = jv * vi;
                   g_acc[0] += cc == 0 ? t : 0.f; g_acc[1] += cc == 1 ? t : 0.f; g_acc[2] += cc == 2 ? t : 0.f;
                 }
@@ -180,34 +180,34 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
             }
           }
 #pragma unroll
-          for (int t = 0; t < 8; ++t) {  // the L2 latency of the stash is covered by the other epilogue warps of the scheduler
+          for (int t = 0; t < 4; ++t) {  // the L2 latency of the stash is covered by the other epilogue warps of the scheduler
             const float4 q = stash[(size_t)((l - 1) * 64 + (col >> 2) + t) * TILE_M + row];
             v[4 * t] *= q.x; v[4 * t + 1] *= q.y; v[4 * t + 2] *= q.z; v[4 * t + 3] *= q.w;
           }
-          if (col + 32 > nprev) {
+          if (col + CW > nprev) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
+            for (int i = 0; i < CW; ++i)
               if (col + i >= nprev) v[i] = 0.f;
           }
-          epi_store_a32(s, row, col, v);
-          epi_signal_a(s, chunk >> 1);
+          epi_store_a16(s, row, col, v);
+          epi_signal_a(s, pass);
         });
         e.step_ctr++;
       }
       // ---- s17: reverse layer 0 -> gradient ------------------------------------------------------------------------------
       epi_wait_d(s, e);
-      if (sub < 2) {  // d logit / d pe: columns 0..pe_dim-1 of this step (sub 0: 0..31, sub 1: 32..63)
-        float v[32];
-        epi_load32(e, sub * 32, v);
+      if (sub * CW < g.pe_dim) {  // d logit / d pe: columns 0..pe_dim-1 of this step, 16 per sub
+        float v[CW];
+        epi_load16(e, sub * CW, v);
 #pragma unroll 1
-        for (int i = 0; i < 32; ++i) {
-          const int k = sub * 32 + i;
+        for (int i = 0; i < CW; ++i) {
+          const int k = sub * CW + i;
           if (k < g.pe_dim) {
             int cc;
             const float jv = pe_jac(x, k, &cc);
             float vi = 0.f;
 #pragma unroll
-            for (int u = 0; u < 32; ++u) vi = (u == i) ? v[u] : vi;
+            for (int u = 0; u < CW; ++u) vi = (u == i) ? v[u] : vi;
             const float t = jv * vi;
             g_acc[0] += cc == 0 ? t : 0.f; g_acc[1] += cc == 1 ? t : 0.f; g_acc[2] += cc == 2 ? t : 0.f;
           }
@@ -243,22 +243,22 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
             epi_store_a1(s, row, k, val);
           }
           epi_signal_a(s, 0);
-        } else if (sub == 1) {
-          epi_signal_a(s, 0);  // second of the two arrival groups of K block 0 (sub 0 wrote all 64 columns)
+        } else {
+          epi_signal_a(s, 0);  // the other three arrival groups of K block 0 (sub 0 wrote all 64 columns)
         }
         // ---- s18: appearance layer 0 (rest) + parked + bias, ReLU ------------------------------------------------------------
         epi_wait_d(s, e);
-        epi_for_chunks(e, 8, [&](int chunk, int col, float (&v)[32]) {
+        epi_for_chunks(e, 256, [&](int pass, int col, float (&v)[CW]) {
 #pragma unroll
-          for (int t = 0; t < 8; ++t) {
+          for (int t = 0; t < 4; ++t) {
             const float4 pk = parked[(size_t)((col >> 2) + t) * TILE_M + row];
             v[4 * t] += pk.x; v[4 * t + 1] += pk.y; v[4 * t + 2] += pk.z; v[4 * t + 3] += pk.w;
           }
-          add_bias32(v, g.abias[0], col);
+          add_bias16(v, g.abias[0], col);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-          epi_store_a32(s, row, col, v);
-          epi_signal_a(s, chunk >> 1);
+          for (int i = 0; i < CW; ++i) v[i] = fmaxf(v[i], 0.f);
+          epi_store_a16(s, row, col, v);
+          epi_signal_a(s, pass);
         });
         e.step_ctr++;
         // ---- s19..s21: appearance layers 1..3 -------------------------------------------------------------------------------
@@ -266,20 +266,20 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
         for (int l = 1; l <= 3; ++l) {
           epi_wait_d(s, e);
           const float* bias = g.abias[l];
-          epi_for_chunks(e, 8, [&](int chunk, int col, float (&v)[32]) {
-            add_bias32(v, bias, col);
+          epi_for_chunks(e, 256, [&](int pass, int col, float (&v)[CW]) {
+            add_bias16(v, bias, col);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-            epi_store_a32(s, row, col, v);
-            epi_signal_a(s, chunk >> 1);
+            for (int i = 0; i < CW; ++i) v[i] = fmaxf(v[i], 0.f);
+            epi_store_a16(s, row, col, v);
+            epi_signal_a(s, pass);
           });
           e.step_ctr++;
         }
         // ---- s22: appearance layer 4 -> rgb ------------------------------------------------------------------------------------
         epi_wait_d(s, e);
         if (sub == 0) {
-          float v[32];
-          epi_load32(e, 0, v);
+          float v[CW];
+          epi_load16(e, 0, v);
           if (idx < M) {
             rgb[idx * 3 + 0] = tanhf(v[0] + __ldg(g.abias[4] + 0)) * 0.5f + 0.5f;
             rgb[idx * 3 + 1] = tanhf(v[1] + __ldg(g.abias[4] + 1)) * 0.5f + 0.5f;
@@ -352,6 +352,10 @@ size_t tc_stash_bytes() {
 static int launch_tc_rad(const TcRadArgs& a, const PointGen& gen, long long M, const int* M_dev, float* rgb, float* alpha,
                          float* grad, cudaStream_t st) {
   PSN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_rad, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  {
+    const int rcr = check_launch_regs((const void*)k_tc_rad, "k_tc_rad");
+    if (rcr) return rcr;
+  }
   const long long tiles = M_dev ? (long long)num_ctas() : (M + TILE_M - 1) / TILE_M;
   const int grid = (int)(tiles < num_ctas() ? tiles : num_ctas());
   count_launch();

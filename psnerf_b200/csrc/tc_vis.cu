@@ -104,46 +104,46 @@ k_tc_vis(TcVisArgs g, float* __restrict__ vis) {
       const long long n = pb * TILE_M + row;
       const bool valid = n < g.Ns;
       const long long nn = valid ? n : g.Ns - 1;
-      // layer 0: relu(P0[n] + L0[l]) for this thread's two 32-column chunks
+      // layer 0: relu(P0[n] + L0[l]) for this thread's four 16-column chunks
 #pragma unroll 1
-      for (int pass = 0; pass < 2; ++pass) {
-        const int chunk = sub + 4 * pass, col = chunk * 32;
-        float v[32];
+      for (int pass = 0; pass < 4; ++pass) {
+        const int col = 64 * pass + CW * sub;
+        float v[CW];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 4; ++i) {
           const float4 a = __ldg(reinterpret_cast<const float4*>(g.P0 + nn * 256 + col) + i);
           const float4 b = __ldg(reinterpret_cast<const float4*>(g.L0 + (long long)l * 256 + col) + i);
           v[4 * i + 0] = fmaxf(a.x + b.x, 0.f); v[4 * i + 1] = fmaxf(a.y + b.y, 0.f);
           v[4 * i + 2] = fmaxf(a.z + b.z, 0.f); v[4 * i + 3] = fmaxf(a.w + b.w, 0.f);
         }
-        epi_store_a32(s, row, col, v);
-        epi_signal_a(s, chunk >> 1);
+        epi_store_a16(s, row, col, v);
+        epi_signal_a(s, pass);
       }
       float part = 0.f;
 #pragma unroll 1
       for (int st = 0; st < 7; ++st) {
         epi_wait_d(s, e);
         const float* bias = g.bias[st];
-        epi_for_chunks(e, 8, [&](int chunk, int col, float (&v)[32]) {
+        epi_for_chunks(e, 256, [&](int pass, int col, float (&v)[CW]) {
           if (st == 4) {  // skip layer: + P5[n] (bias folded) + L5[l]
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < 4; ++i) {
               const float4 a = __ldg(reinterpret_cast<const float4*>(g.P5 + nn * 256 + col) + i);
               const float4 b = __ldg(reinterpret_cast<const float4*>(g.L5 + (long long)l * 256 + col) + i);
               v[4 * i + 0] += a.x + b.x; v[4 * i + 1] += a.y + b.y; v[4 * i + 2] += a.z + b.z; v[4 * i + 3] += a.w + b.w;
             }
           } else {
-            add_bias32(v, bias, col);
+            add_bias16(v, bias, col);
           }
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+          for (int i = 0; i < CW; ++i) v[i] = fmaxf(v[i], 0.f);
           if (st < 6) {
-            epi_store_a32(s, row, col, v);
-            epi_signal_a(s, chunk >> 1);
+            epi_store_a16(s, row, col, v);
+            epi_signal_a(s, pass);
           } else {
             const float4* w4 = reinterpret_cast<const float4*>(g.w_last + col);
 #pragma unroll
-            for (int t = 0; t < 8; ++t) {
+            for (int t = 0; t < 4; ++t) {
               const float4 w = __ldg(w4 + t);
               part = fmaf(v[4 * t], w.x, part); part = fmaf(v[4 * t + 1], w.y, part);
               part = fmaf(v[4 * t + 2], w.z, part); part = fmaf(v[4 * t + 3], w.w, part);
@@ -209,6 +209,10 @@ int tc_s2_visibility(const psn_mlp* net, int nf, const float* pts, long long Ns,
   a.Ns = Ns;
   a.L = L;
   PSN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_vis, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  {
+    const int rcr = check_launch_regs((const void*)k_tc_vis, "k_tc_vis");
+    if (rcr) return rcr;
+  }
   const long long n_tiles = ((Ns + TILE_M - 1) / TILE_M) * L;
   const int grid = (int)(n_tiles < num_ctas() ? n_tiles : num_ctas());
   count_launch();

@@ -39,14 +39,16 @@ def test_every_geo_layer_matches_the_oracle(s1, variant):
     pc = pts.cuda().contiguous()
     lib = B.load()
     for l in range(8):
+        ncmp = 256
         act = torch.nn.functional.softplus(pre[l], beta=100)
-        if l == 3:
+        if l == 3:  # columns >= 217 of the skip layer's input are the encoding, written separately (not part of the dump)
             act = torch.cat([act, pe], -1) / (2 ** 0.5)
+            ncmp = 217
         dump = torch.full((M, 256), float("nan"), device="cuda")
         logits = torch.empty(M, device="cuda")
         B.check(lib.psn_tc_debug_layer(g.handle, C.c_void_p(pc.data_ptr()), M, l, C.c_void_p(dump.data_ptr()),
                                        C.c_void_p(logits.data_ptr()), engine._stream()), "psn_tc_debug_layer")
-        assert util.rel_l2(dump.cpu(), act) < 2e-5, "layer %d" % l
+        assert util.rel_l2(dump.cpu()[:, :ncmp], act[:, :ncmp]) < 2e-5, "layer %d" % l
         assert util.max_abs(logits.cpu(), out[:, 0]) < 1e-4
 
 
