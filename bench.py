@@ -312,8 +312,16 @@ def main():
         roof = None
         if rad:
             tf = rad["rows_per_launch"] * MFLOP_RAD * 1e6 / (rad["ms_per_launch"] * 1e-3) / 1e12
+            traffic = None  # dram read+write bytes per launch of this kernel on this workload, from the committed ncu capture
+            try:
+                with open(os.path.join(ROOT, "profiles", "r1_ncu_final.json")) as f:
+                    traffic = json.load(f)["radiance"]["metrics"]["dram_bytes_total"] if precision == "tc" else None
+            except Exception:
+                pass
             roof = {"bound": "tensor", "kernel": "radiance (geo fwd + analytic normal + app MLP), %s path" % precision,
-                    "achieved": tf, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": tf / peaks["tflops"], "traffic": None,
+                    "achieved": tf, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": tf / peaks["tflops"], "traffic": traffic,
+                    "traffic_note": "ncu --set full, profiles/r1_ncu_final.json: dominated by the fp32 sigma' stash of the analytic-normal "
+                                    "pass (8 KB/sample written + read; algorithmic I/O is 20 B/sample); DRAM is at 22 % of peak, not the limiter",
                     "peak_source": peaks["src"], "flops_per_row": MFLOP_RAD * 1e6,
                     "issued_frac": (3.0 * tf / peaks["tflops"]) if precision == "tc" else None}
             occ = kern.get("occ_march")
