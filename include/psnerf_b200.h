@@ -168,6 +168,41 @@ int psn_tc_debug_layer(const psn_mlp* geo, const float* pts, int64_t M, int laye
 /* Bring-up tool: clock64() timeline of one tile of the tensor-core occupancy kernel; trace is int64[256] on the device. */
 int psn_tc_debug_trace(const psn_mlp* geo, const float* pts, int64_t M, float* out, long long* trace, void* stream);
 
+/* ---- stage-2 train step (BASELINE config 5): PSNetwork.forward + backward, stage2/trainer.py:394-410 ------------------------
+ * Gradient-carrying parts (renderer.py:193-199,211-231,251-262 with light_vis_detach = vis_rgb_detach = True): the per-point nets
+ * through the SG shading of all L lights and their jittered re-evaluation, light directions / intensities, and visibility_net
+ * through the Lt vis-train lights.  Networks are given as views of the live torch parameters. */
+typedef struct {
+  int n_layers, skip, final_act;   /* as psn_mlp_desc for PSN_NET_S2 */
+  const int* in_dims;              /* host */
+  const int* out_dims;             /* host */
+  const float* const* W;           /* host array of device pointers: [out,in] row-major */
+  const float* const* b;
+  float* const* dW;                /* backward only: gradients are ACCUMULATED into these (caller zero-fills) */
+  float* const* db;
+} psn_train_net;
+
+int64_t psn_s2_train_tape_bytes(const psn_train_net* normal_net, const psn_train_net* albedo_net, const psn_train_net* rough_net,
+                                const psn_train_net* vis_net, int64_t Ns, int L, int Lt);
+/* Forward: image-shaped outputs exactly as psn_shade_stage2, plus per-surface-point albedo_j[Ns,3], weights_j[Ns,nbt]
+ * (networks re-evaluated at jitter_pts, nullable) and vis_train[Lt,Ns] (raw visibility_net outputs for lights_vt, nullable).
+ * vis_packed: the packed visibility net for the detached L-light pass.  tape keeps the activations for the backward call. */
+int psn_s2_train_forward(const psn_train_net* normal_net, const psn_train_net* albedo_net, const psn_train_net* rough_net,
+                         const psn_train_net* vis_net, const psn_mlp* vis_packed, const float* lobe, const psn_shade_params* prm,
+                         const float* pts, const float* view, const int32_t* pix, int64_t Ns, int64_t N, const float* lights, int L,
+                         const float* intensity, const float* jitter_pts, const float* lights_vt, int Lt, float* rgb, float* spec,
+                         float* vis, float* normal, float* albedo, float* sgw, float* albedo_j, float* weights_j, float* vis_train,
+                         void* tape, int64_t tape_bytes, void* ws, int64_t ws_bytes, int precision, void* stream);
+/* Backward: g_* are gradients w.r.t. the forward outputs (any may be NULL = zero): g_rgb/g_spec [L,N,3], g_normal [N,3],
+ * g_albedo [N,3], g_sgw [N,nbt], g_albedo_j [Ns,3], g_weights_j [Ns,nbt], g_vis_train [Lt,Ns].  Writes (accumulates) parameter
+ * gradients through the psn_train_net views, d_lights [L,3] and d_intensity (scalar / [L] / [L,3] per prm->intensity_kind). */
+int psn_s2_train_backward(const psn_train_net* normal_net, const psn_train_net* albedo_net, const psn_train_net* rough_net,
+                          const psn_train_net* vis_net, const float* lobe, const psn_shade_params* prm, const float* view,
+                          const int32_t* pix, int64_t Ns, int64_t N, const float* lights, int L, const float* intensity, int Lt,
+                          const float* g_rgb, const float* g_spec, const float* g_normal, const float* g_albedo, const float* g_sgw,
+                          const float* g_albedo_j, const float* g_weights_j, const float* g_vis_train, float* d_lights,
+                          float* d_intensity, void* tape, int64_t tape_bytes, void* ws, int64_t ws_bytes, void* stream);
+
 /* alpha compositing of per-sample (rgb, alpha): rendering.py:196-197,214-216. */
 int psn_composite(const float* rgb_s /*[N,S,3]*/, const float* alpha /*[N,S]*/, int64_t N, int S,
                   int white_background, float* rgb /*[N,3]*/, float* acc /*[N]*/, void* stream);

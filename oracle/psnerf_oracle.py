@@ -510,9 +510,11 @@ def psnetwork_forward(sd, conf, inp, noise=None):
         inten = inp.get("light_intensity", float(conf.get("brdf.light_intensity", 4.0)))
         if torch.is_tensor(inten) and inten.shape[0] > 1:
             inten = inten.repeat_interleave(Ns, dim=0)
-        vis = s2_mlp(sd, "visibility_net", torch.cat([pemb.tile(L, 1), embed(l, nf)], -1),
+        lv = l.detach() if conf.get("train.light_vis_detach", False) else l  # renderer.py:192-195
+        vis = s2_mlp(sd, "visibility_net", torch.cat([pemb.tile(L, 1), embed(lv, nf)], -1),
                      [int(conf["visibility.net.mlp_skip_at"])], None)
-        rgb = (brdf * inten * cos * vis.clamp(0, 1)).clamp(0, 1)
+        vr = vis.detach() if conf.get("train.vis_rgb_detach", False) else vis  # renderer.py:196-199
+        rgb = (brdf * inten * cos * vr.clamp(0, 1)).clamp(0, 1)
         vis_v[me] = vis.expand(rgb.shape)
         rgb_v[me] = rgb
         alb_v[smask] = albedo
@@ -528,6 +530,8 @@ def psnetwork_forward(sd, conf, inp, noise=None):
         if "light_vis_train" in inp:
             Lt = inp["light_vis_train"].shape[0]
             lt = inp["light_vis_train"][:, None].expand(-1, points.shape[1], -1)[smask.expand(Lt, -1)]
+            if conf.get("train.light_vis_detach", False):
+                lt = lt.detach()
             vt = torch.ones_like(points)
             if Lt > 1:
                 vt = vt.repeat(Lt, 1, 1)
@@ -540,6 +544,34 @@ def psnetwork_forward(sd, conf, inp, noise=None):
            "sg_specular_rgb_values": rough_v, "normal_pred": normal_pred, "visibility": vis_v, "sg_weight": w_v}
     out.update(out_extra)
     return out
+
+
+def main_loss(out, rgb_gt, inp, sg_rgb_weight=1.0, albedo_smooth_weight=0.05, rough_smooth_weight=0.01, vis_weight=1.0):
+    """MainLoss with loss_type L1 (stage2/model/loss.py:6-98), device agnostic."""
+    mask = out["network_object_mask"] & out["object_mask"]
+    if mask.sum() == 0:
+        return torch.zeros((), dtype=rgb_gt.dtype)
+    me = mask.expand(rgb_gt.shape[0], -1)
+    loss = sg_rgb_weight * F.l1_loss(out["sg_rgb_values"][me].reshape(-1, 3), rgb_gt[me].reshape(-1, 3))
+    if "albedo_jitter" in out and albedo_smooth_weight > 0:
+        m1 = mask.expand(out["albedo_values"].shape[0], -1)
+        loss = loss + albedo_smooth_weight * F.l1_loss(out["albedo_values"][m1], out["albedo_jitter"][m1])
+    if "rough_jitter" in out and rough_smooth_weight > 0:
+        m1 = mask.expand(out["rough_values"].shape[0], -1)
+        loss = loss + rough_smooth_weight * F.l1_loss(out["rough_values"][m1], out["rough_jitter"][m1])
+    if "vis_train" in out and "vis_train_gt" in inp:
+        mv = mask.expand(inp["vis_train_gt"].shape[0], -1)
+        loss = loss + vis_weight * F.l1_loss(out["vis_train"][..., 0][mv].reshape(-1), inp["vis_train_gt"][mv].reshape(-1))
+    return loss
+
+
+def normal_loss(out, normal_weight=1.0):
+    """NormalLoss without the (unused, jitter std 0) smoothness term (stage2/model/loss.py:102-141)."""
+    mask = (out["network_object_mask"] & out["object_mask"])
+    if mask.sum() == 0:
+        return torch.zeros((), dtype=out["normal_pred"].dtype)
+    gt = F.normalize(out["normal_values"], dim=-1)
+    return normal_weight * F.mse_loss(out["normal_pred"][mask].reshape(-1, 3), gt[mask].reshape(-1, 3))
 
 
 def split_input(model_input, total_pixels, n_pixels=1024):

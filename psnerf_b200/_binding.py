@@ -30,6 +30,12 @@ class UnisurfParams(C.Structure):
                 ("white_background", C.c_int)]
 
 
+class TrainNet(C.Structure):
+    _fields_ = [("n_layers", C.c_int), ("skip", C.c_int), ("final_act", C.c_int), ("in_dims", C.POINTER(C.c_int)),
+                ("out_dims", C.POINTER(C.c_int)), ("W", C.POINTER(C.c_void_p)), ("b", C.POINTER(C.c_void_p)),
+                ("dW", C.POINTER(C.c_void_p)), ("db", C.POINTER(C.c_void_p))]
+
+
 class ShadeParams(C.Structure):
     _fields_ = [("n_freqs_xyz", C.c_int), ("n_freqs_normal", C.c_int), ("nbasis", C.c_int), ("specular_rgb", C.c_int),
                 ("intensity_kind", C.c_int), ("intensity", C.c_float)]
@@ -82,6 +88,13 @@ def load():
     lib.psn_s2_visibility.argtypes = [vp, i32, vp, i64, vp, i32, vp, vp, i64, i32, vp]
     lib.psn_tc_debug_layer.argtypes = [vp, vp, i64, i32, vp, vp, vp]
     lib.psn_tc_debug_trace.argtypes = [vp, vp, i64, vp, vp, vp]
+    tn = C.POINTER(TrainNet)
+    lib.psn_s2_train_tape_bytes.argtypes = [tn, tn, tn, tn, i64, i32, i32]
+    lib.psn_s2_train_tape_bytes.restype = i64
+    lib.psn_s2_train_forward.argtypes = [tn, tn, tn, tn, vp, vp, C.POINTER(ShadeParams), vp, vp, vp, i64, i64, vp, i32, vp, vp, vp, i32,
+                                         vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, i64, i32, vp]
+    lib.psn_s2_train_backward.argtypes = [tn, tn, tn, tn, vp, C.POINTER(ShadeParams), vp, vp, i64, i64, vp, i32, vp, i32,
+                                          vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, i64, vp]
     lib.psn_composite.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp]
     _lib = lib
     return lib

@@ -58,6 +58,10 @@ extern "C" int64_t psn_workspace_bytes(const char* op, int64_t n_rays, int64_t n
     return (int64_t)(align256((size_t)chunk * S * 4) + 4096);
   }
   if (!strcmp(op, "shade") || !strcmp(op, "s2_vis")) return (int64_t)s2_workspace_bytes(N, n_lights);
+  if (!strcmp(op, "s2_train")) {  // n_rays = max(pixels, surface points), n_samples = vis-train lights, n_lights = L
+    const long long rows = N * (S > 1 ? S : 1);
+    return (int64_t)(s2_workspace_bytes(N, n_lights) + (size_t)rows * (2 * 512 + 32) * 4 + (size_t)N * 64 * 4 + 8192);
+  }
   psn::set_error("psn_workspace_bytes: unknown op '%s'", op);
   return -1;
 }

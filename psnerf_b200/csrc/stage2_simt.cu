@@ -335,6 +335,10 @@ int s2_visibility_simt(const psn_mlp* vis_net, int nf, const float* pts, long lo
 
 int tc_s2_visibility(const psn_mlp* vis_net, int nf, const float* pts, long long Ns, const float* lights, int L, float* vis,
                      void* ws, size_t ws_bytes, cudaStream_t st);  // tc path
+int s2_shade_images(const float* n_s, const float* a_s, const float* w_s, const float* view, const float* v_raw, const float* lights,
+                    const float* lobe, const float* intensity, const psn_shade_params* prm, const int32_t* pix, long long Ns, long long N,
+                    int L, float* rgb, float* spec, float* vis, float* normal, float* albedo, float* sgw, int write_normal, int* sop,
+                    cudaStream_t st);
 
 }  // namespace psn
 
@@ -398,20 +402,33 @@ extern "C" int psn_shade_stage2(const psn_mlp* normal_net, const psn_mlp* albedo
     }
     if (rc) return rc;
   }
+  return s2_shade_images(normal_net ? n_s : normal_in, a_s, w_s, view, v_s, lights, lobe, intensity, prm, pix, Ns, N, L, rgb, spec,
+                         vis_net ? vis : nullptr, normal, albedo, sgw, normal_net ? 1 : 0, sop, st);
+}
+
+namespace psn {
+// SG shading + image-shaped writes from per-surface-point quantities (shared by the inference and the train-step forward).
+int s2_shade_images(const float* n_s, const float* a_s, const float* w_s, const float* view, const float* v_raw, const float* lights,
+                    const float* lobe, const float* intensity, const psn_shade_params* prm, const int32_t* pix, long long Ns, long long N,
+                    int L, float* rgb, float* spec, float* vis, float* normal, float* albedo, float* sgw, int write_normal, int* sop,
+                    cudaStream_t st) {
+  const int nbt = prm->specular_rgb ? 3 * prm->nbasis : prm->nbasis;
   psn::count_launch();
   k_fill_int<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(sop, N, -1);
   if (Ns > 0) { psn::count_launch(); k_slot_of_pixel<<<(unsigned)((Ns + 255) / 256), 256, 0, st>>>(pix, Ns, sop); }
   ShadeArgs a;
   memset(&a, 0, sizeof(a));
-  a.normal = normal_net ? n_s : normal_in;
-  a.albedo = a_s; a.weights = w_s; a.view = view; a.vis = v_s; a.lights = lights; a.lobe = lobe; a.intensity = intensity;
+  a.normal = n_s;
+  a.albedo = a_s; a.weights = w_s; a.view = view; a.vis = v_raw; a.lights = lights; a.lobe = lobe; a.intensity = intensity;
   a.slot_of_pixel = sop;
-  a.rgb = rgb; a.spec = spec; a.vis_out = vis_net ? vis : nullptr; a.normal_out = normal; a.albedo_out = albedo; a.sgw_out = sgw;
+  a.rgb = rgb; a.spec = spec; a.vis_out = v_raw ? vis : nullptr; a.normal_out = normal; a.albedo_out = albedo; a.sgw_out = sgw;
   a.N = N; a.Ns = Ns; a.L = L; a.nbasis = prm->nbasis; a.specular_rgb = prm->specular_rgb; a.nbt = nbt;
-  a.intensity_kind = prm->intensity_kind; a.intensity_scalar = prm->intensity; a.write_normal = normal_net ? 1 : 0;
+  a.intensity_kind = prm->intensity_kind; a.intensity_scalar = prm->intensity; a.write_normal = write_normal;
   dim3 grid((unsigned)((N + 255) / 256), (unsigned)(L + 1));
   psn::count_launch();
   k_s2_shade<<<grid, 256, 0, st>>>(a);
   PSN_CUDA_CHECK(cudaGetLastError());
   return PSN_OK;
 }
+}  // namespace psn
+

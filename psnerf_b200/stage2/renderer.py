@@ -132,8 +132,68 @@ class PSNetwork(nn.Module):
     def _prec(self):
         return engine.default_precision() if self.precision is None else {"fp32": B.PREC_FP32, "tc": B.PREC_TC}[self.precision]
 
-    @torch.no_grad()
     def forward(self, input, albedo_new=None, basis_new=None, noise=None):
+        """Inference (no autograd graph) unless gradients are enabled and a parameter / the lights require them, in which case
+        the differentiable train-step path (psn_s2_train_forward / _backward, stage2/train.py) runs."""
+        if next(self.parameters()).device.type != "cuda":
+            raise RuntimeError("psnerf_b200: PSNetwork must live on a CUDA device (no CPU fallback)")
+        wants_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters()) or
+                                                  (torch.is_tensor(input.get("light_direction")) and input["light_direction"].requires_grad))
+        if wants_grad:
+            return self._forward_train(input, noise)
+        with torch.no_grad():
+            return self._forward_eval(input, albedo_new, basis_new, noise)
+
+    def _surface(self, input, dev):
+        """Camera rays + gather of the surface pixels (renderer.py:118-125,162)."""
+        uv, pose, K = input["uv"], input["pose"], input["intrinsics"]
+        assert uv.shape[0] == 1
+        Kc, Pc = K.detach().float().cpu(), pose.detach().float().cpu()
+        dirs = engine.rays_from_pixels(uv[0].to(dev), Pc[0, :3, :3].reshape(-1).tolist(), Pc[0, :3, 3].tolist(),
+                                       float(Kc[0, 0, 0]), float(Kc[0, 1, 1]), float(Kc[0, 0, 2]), float(Kc[0, 1, 2]), stage2=True)
+        smask = input["surface_mask"].to(dev)
+        pix = torch.nonzero(smask[0], as_tuple=False).squeeze(-1).to(torch.int32).contiguous()
+        pixl = pix.long()
+        surf = engine.f32c(input["points"].to(dev).float()[0][pixl])
+        view = engine.f32c(-dirs[pixl])
+        return surf, view, pix, pixl, uv.shape[1]
+
+    def _forward_train(self, input, noise=None):
+        from .train import S2TrainStep, flat_params
+        if not (self.shape_pregen and self.normal_mlp and self.visibility):
+            raise NotImplementedError("psnerf_b200 train step: needs shape_pregen, normal_mlp and visibility (all shipped confs)")
+        if not (self.light_vis_detach and self.conf.get_bool("train.vis_rgb_detach", default=False)):
+            raise NotImplementedError("psnerf_b200 train step: implemented for light_vis_detach = vis_rgb_detach = True (all shipped confs)")
+        dev = next(self.parameters()).device
+        with torch.no_grad():
+            surf, view, pix, pixl, N = self._surface(input, dev)
+        Ns = int(pix.shape[0])
+        lights = input["light_direction"].to(dev)
+        inten = input.get("light_intensity", None)
+        if torch.is_tensor(inten):
+            inten = inten.to(dev)
+        jp = None
+        if self.xyz_jitter_std > 0 and Ns > 0:
+            z = noise["xyz"].to(dev) if (noise is not None and "xyz" in noise) else torch.randn(Ns, 3, device=dev)
+            jp = surf + z * self.xyz_jitter_std
+        lvt = input["light_vis_train"].to(dev) if ("light_vis_train" in input and Ns > 0) else None
+        rgb, spec, vis, normal, albedo, sgw, aj, wj, vt = S2TrainStep.apply(self, (surf, view, pix, N), lights, inten, jp, lvt,
+                                                                            *flat_params(self))
+        out = {"points": input["points"], "object_mask": input["object_mask"], "network_object_mask": input["surface_mask"],
+               "sg_rgb_values": rgb, "normal_values": input["normal"], "sg_diffuse_albedo_values": albedo,
+               "sg_specular_rgb_values": spec, "normal_pred": normal, "visibility": vis, "sg_weight": sgw}
+        if jp is not None:
+            albedo_jitter = torch.ones(1, N, 3, device=dev).index_put((torch.zeros_like(pixl), pixl), aj)
+            rough_jitter = torch.ones(1, N, self.nbasis, device=dev).index_put((torch.zeros_like(pixl), pixl), wj)
+            out.update({"albedo_values": albedo, "albedo_jitter": albedo_jitter, "rough_values": sgw, "rough_jitter": rough_jitter})
+        if lvt is not None:
+            Lt = lvt.shape[0]
+            base = torch.ones(Lt, N, 3, device=dev)
+            idx_l = torch.arange(Lt, device=dev).unsqueeze(1).expand(Lt, Ns)
+            out["vis_train"] = base.index_put((idx_l, pixl.unsqueeze(0).expand(Lt, Ns)), vt.unsqueeze(-1).expand(Lt, Ns, 3))
+        return out
+
+    def _forward_eval(self, input, albedo_new=None, basis_new=None, noise=None):
         if not self.shape_pregen:
             raise NotImplementedError("psnerf_b200: train.shape_pregen=False is not a shipped configuration")
         if albedo_new is not None or basis_new is not None:

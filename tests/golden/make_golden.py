@@ -140,9 +140,58 @@ def make_stage2():
     np.savez_compressed(os.path.join(HERE, "stage2_shade.npz"), **out)
 
 
+def make_stage2_grads():
+    """Gradients of the REAL reference's PSNetwork (autograd) for a train-like step: trainable light directions and per-light
+    intensities, 2 vis-train lights, xyz jitter; scalar = sum of outputs against fixed cotangents (the reference's loss module
+    hard-codes .cuda(), stage2/model/loss.py:30,61, so it cannot run here)."""
+    m2 = ref_loader.load_stage2()
+    conf = synth.stage2_conf()
+    torch.manual_seed(0)
+    model = m2.PSNetwork(ref_loader.DictConf(conf))
+    sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+    sd1 = synth.perturb_state_dict(sd0, rel=0.5, seed=1)
+    model.load_state_dict(sd1)
+    model.train()
+    h, w, L = 12, 10, 5
+    inp = synth.stage2_input(h, w, L, all_surface=False, seed=21, mask_frac=0.6)
+    g = torch.Generator().manual_seed(77)
+    lraw = torch.randn(L, 3, generator=g)
+    lraw.requires_grad_(True)
+    inten = (1.0 + torch.rand(L, 1, generator=g)).requires_grad_(True)
+    inp["light_direction"] = torch.nn.functional.normalize(lraw, p=2, dim=-1)
+    inp["light_intensity"] = inten
+    inp["light_vis_train"] = synth.lights(2, seed=9)
+    ns = int(inp["surface_mask"].sum())
+    std = conf["brdf.net.xyz_jitter_std"]
+    torch.manual_seed(4242)
+    z = torch.normal(0, torch.ones(ns, 3) * std) / std        # what the reference will draw (renderer.py:212)
+    torch.manual_seed(4242)
+    out = model(inp)
+    keys = ["sg_rgb_values", "normal_pred", "albedo_values", "rough_values", "albedo_jitter", "rough_jitter", "vis_train"]
+    cot = {k: torch.randn(out[k].shape, generator=g) for k in keys}
+    scalar = sum((out[k] * cot[k]).sum() for k in keys)
+    params = dict(model.named_parameters())
+    names = [n for n, p_ in params.items() if p_.requires_grad]
+    grads = torch.autograd.grad(scalar, [params[n] for n in names] + [lraw, inten], allow_unused=True)
+    res = {"xyz_noise": np_(z), "light_raw": np_(lraw), "light_intensity": np_(inten), "scalar": np.array(float(scalar))}
+    for k in keys:
+        res["cot_" + k] = np_(cot[k])
+        res["out_" + k] = np_(out[k])
+    for n, gr in zip(names, grads[:-2]):
+        gr = torch.zeros_like(params[n]) if gr is None else gr
+        res["gsum_" + n] = np.array([float(gr.double().sum()), float(gr.double().abs().sum())])
+        if gr.numel() <= 256:
+            res["g_" + n] = np_(gr)
+    res["g_light_raw"] = np_(grads[-2])
+    res["g_light_intensity"] = np_(grads[-1])
+    np.savez_compressed(os.path.join(HERE, "stage2_grads.npz"), **res)
+    print("stage2_grads: scalar", float(scalar), "params", len(names), "surface", ns)
+
+
 if __name__ == "__main__":
     make_stage1_net()
     make_stage1_render()
     make_stage2()
-    for f in ("stage1_net", "stage1_render", "stage2_shade"):
+    make_stage2_grads()
+    for f in ("stage1_net", "stage1_render", "stage2_shade", "stage2_grads"):
         print(f, os.path.getsize(os.path.join(HERE, f + ".npz")) // 1024, "KB")

@@ -1,0 +1,133 @@
+"""Stage-2 train step (BASELINE config 5): forward values and every gradient against torch autograd through the CPU oracle
+(itself pinned to the real reference's autograd by tests/golden/stage2_grads.npz)."""
+import numpy as np
+import pytest
+import torch
+
+import psnerf_oracle as O
+import util
+from psnerf_b200 import synth
+
+pytestmark = pytest.mark.gpu
+KEYS = ["sg_rgb_values", "normal_pred", "albedo_values", "rough_values", "albedo_jitter", "rough_jitter", "vis_train"]
+
+
+def _model(conf, sd, prec):
+    from psnerf_b200.stage2 import PSNetwork
+    m = PSNetwork(conf)
+    m.load_state_dict(sd)
+    m = m.cuda().train()
+    m.precision = prec
+    return m
+
+
+def _case(h, w, L, Lt, seed, frac=0.6, per_light_rgb=False):
+    inp = synth.stage2_input(h, w, L, all_surface=False, seed=seed, mask_frac=frac)
+    g = torch.Generator().manual_seed(seed + 1)
+    lraw = torch.randn(L, 3, generator=g)
+    inten = 1.0 + torch.rand(L, 3 if per_light_rgb else 1, generator=g)
+    inp["light_vis_train"] = synth.lights(Lt, seed=seed + 2)
+    ns = int(inp["surface_mask"].sum())
+    z = torch.randn(ns, 3, generator=g)
+    cot = None
+    return inp, lraw, inten, z, g
+
+
+def _run_oracle(conf, sd, inp, lraw, inten, z, cot):
+    sdg = {k: v.clone().requires_grad_(v.dtype.is_floating_point and "lobe" not in k) for k, v in sd.items()}
+    lr = lraw.clone().requires_grad_(True)
+    it = inten.clone().requires_grad_(True)
+    i2 = dict(inp)
+    i2["light_direction"] = torch.nn.functional.normalize(lr, p=2, dim=-1)
+    i2["light_intensity"] = it
+    out = O.psnetwork_forward(sdg, conf, i2, noise={"xyz": z})
+    scalar = sum((out[k] * cot[k]).sum() for k in KEYS)
+    names = [k for k, v in sdg.items() if v.requires_grad]
+    grads = torch.autograd.grad(scalar, [sdg[k] for k in names] + [lr, it], allow_unused=True)
+    gd = {n: (torch.zeros_like(sdg[n]) if g is None else g) for n, g in zip(names, grads[:-2])}
+    return out, gd, grads[-2], grads[-1]
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tc"])
+@pytest.mark.parametrize("shape", [(12, 10, 5, 2, False), (32, 24, 9, 3, True)])
+def test_train_step_gradients_vs_oracle_autograd(shape, prec):
+    h, w, L, Lt, rgb_int = shape
+    conf, sds = util.stage2_state_dicts()
+    sd = sds["trained"]
+    inp, lraw, inten, z, g = _case(h, w, L, Lt, seed=21, per_light_rgb=rgb_int)
+    m = _model(conf, sd, prec)
+    lr = lraw.clone().cuda().requires_grad_(True)
+    it = inten.clone().cuda().requires_grad_(True)
+    ci = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in inp.items()}
+    ci["light_direction"] = torch.nn.functional.normalize(lr, p=2, dim=-1)
+    ci["light_intensity"] = it
+    out = m(ci, noise={"xyz": z})
+    cot = {k: torch.randn(out[k].shape, generator=g) for k in KEYS}
+    ref_out, ref_g, ref_gl, ref_gi = _run_oracle(conf, sd, inp, lraw, inten, z, cot)
+    tol = 2e-5 if prec == "fp32" else 2e-4
+    for k in KEYS:
+        assert tuple(out[k].shape) == tuple(ref_out[k].shape), k
+        assert util.max_abs(out[k].detach().cpu(), ref_out[k].detach()) < tol, k
+    scalar = sum((out[k] * cot[k].cuda()).sum() for k in KEYS)
+    scalar.backward()
+    params = dict(m.named_parameters())
+    for n, gr in ref_g.items():
+        got = params[n].grad
+        got = torch.zeros_like(params[n]) if got is None else got
+        scale = max(1.0, float(gr.abs().max()))
+        assert util.max_abs(got.cpu(), gr) < 3e-4 * scale, n
+        assert util.rel_l2(got.cpu(), gr) < 2e-3 or float(gr.abs().max()) < 1e-6, n
+    assert util.max_abs(lr.grad.cpu(), ref_gl) < 3e-4 * max(1.0, float(ref_gl.abs().max()))
+    assert util.max_abs(it.grad.cpu(), ref_gi) < 3e-4 * max(1.0, float(ref_gi.abs().max()))
+
+
+def test_train_step_matches_reference_fixture():
+    """Same case as tests/golden/stage2_grads.npz (gradients of the REAL reference)."""
+    g = util.golden("stage2_grads")
+    conf, sds = util.stage2_state_dicts()
+    m = _model(conf, sds["trained"], "fp32")
+    inp = synth.stage2_input(12, 10, 5, all_surface=False, seed=21, mask_frac=0.6)
+    lr = torch.from_numpy(g["light_raw"]).cuda().requires_grad_(True)
+    it = torch.from_numpy(g["light_intensity"]).cuda().requires_grad_(True)
+    ci = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in inp.items()}
+    ci["light_direction"] = torch.nn.functional.normalize(lr, p=2, dim=-1)
+    ci["light_intensity"] = it
+    ci["light_vis_train"] = synth.lights(2, seed=9).cuda()
+    out = m(ci, noise={"xyz": torch.from_numpy(g["xyz_noise"])})
+    scalar = sum((out[k] * torch.from_numpy(g["cot_" + k]).cuda()).sum() for k in KEYS)
+    assert abs(float(scalar) - float(g["scalar"])) < 2e-3
+    scalar.backward()
+    for n, p in m.named_parameters():
+        if "gsum_" + n not in g.files:
+            continue
+        gr = torch.zeros_like(p) if p.grad is None else p.grad
+        ref = g["gsum_" + n]
+        assert abs(float(gr.double().sum()) - ref[0]) <= 5e-4 * max(1.0, ref[1]), n
+        assert abs(float(gr.double().abs().sum()) - ref[1]) <= 5e-4 * max(1.0, ref[1]), n
+    assert util.max_abs(lr.grad.cpu(), g["g_light_raw"]) < 3e-4 * max(1.0, float(np.abs(g["g_light_raw"]).max()))
+    assert util.max_abs(it.grad.cpu(), g["g_light_intensity"]) < 3e-4 * max(1.0, float(np.abs(g["g_light_intensity"]).max()))
+
+
+def test_optimizer_step_reduces_loss():
+    """A few Adam steps on the restated MainLoss + NormalLoss decrease the loss (end-to-end train loop smoke)."""
+    from psnerf_b200.stage2.loss import MainLoss, NormalLoss
+    conf, sds = util.stage2_state_dicts()
+    m = _model(conf, sds["init"], "tc")
+    inp = synth.stage2_input(48, 48, 12, all_surface=False, seed=5, mask_frac=0.7)
+    ci = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in inp.items()}
+    ci["light_vis_train"] = synth.lights(4, seed=3).cuda()
+    gen = torch.Generator().manual_seed(0)
+    gt = {"rgb": torch.rand(12, 48 * 48, 3, generator=gen).cuda()}
+    ci["vis_train_gt"] = torch.rand(4, 48 * 48, generator=gen).cuda()
+    ci["visibility"] = torch.rand(12, 48 * 48, generator=gen).cuda()
+    lm, ln = MainLoss(1.0, "L1", 0.05, 0.01, 1.0), NormalLoss(1.0, 0.05)
+    opt = torch.optim.Adam(m.parameters(), lr=5e-4)
+    losses = []
+    for _ in range(6):
+        out = m(ci)
+        loss = lm(out, gt, ci)["loss"] + ln(out)["loss"]
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0]
