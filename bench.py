@@ -201,6 +201,35 @@ def extra_workloads(dev, precision, rend, view, peaks):
     tf2 = samples * MFLOP_OCC * 1e6 / (ms2 * 1e-3) / 1e12
     out["shadow_visibility_96L_x128"] = {"surface_points": int(surf.shape[0]), "ms": ms2, "Msamples_per_s": samples / ms2 / 1e3,
                                          "algorithmic_TFLOPs": tf2, "frac_of_peak": tf2 / peaks["tflops"]}
+    # BASELINE configs[4]: stage-2 train step, 4096 in-mask pixels x 96 lights (+ 8 vis-train lights, xyz jitter), fwd + bwd + Adam
+    from psnerf_b200.stage2.loss import MainLoss, NormalLoss
+    ps.train()
+    n_px = 4096
+    tin = synth.stage2_input(64, 64, 96, all_surface=True, seed=11)
+    tin = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in tin.items()}
+    gen = torch.Generator().manual_seed(1)
+    lraw = torch.nn.Parameter(synth.lights(96).to(dev) + 0.01)
+    linten = torch.nn.Parameter(torch.full((96, 1), 2.0, device=dev))
+    tin["light_vis_train"] = synth.lights(8, seed=5).to(dev)
+    tin["vis_train_gt"] = torch.rand(8, n_px, generator=gen).to(dev)
+    tin["visibility"] = torch.rand(96, n_px, generator=gen).to(dev)
+    gt = {"rgb": torch.rand(96, n_px, 3, generator=gen).to(dev)}
+    lm, ln = MainLoss(1.0, "L1", 0.05, 0.01, 1.0), NormalLoss(1.0, 0.05)
+    opt = torch.optim.Adam(list(ps.parameters()) + [lraw, linten], lr=5e-4)
+
+    def train_step():
+        tin["light_direction"] = torch.nn.functional.normalize(lraw, p=2, dim=-1)
+        tin["light_intensity"] = linten
+        o = ps(tin)
+        loss = lm(o, gt, tin)["loss"] + ln(o)["loss"]
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+    ms3 = _time_cuda(train_step, reps=5)
+    out["stage2_train_step_4096px_96L_8vis"] = {"ms_fwd_bwd_adam": ms3, "Mpairs_per_s": n_px * 96 / ms3 / 1e3,
+                                                "note": "PSNetwork.forward + MainLoss/NormalLoss + backward + Adam (stage2/trainer.py:394-410); "
+                                                        "96-light visibility pass detached (tensor-core inference kernel), fp32 GEMM backward"}
+    ps.eval()
     return out
 
 

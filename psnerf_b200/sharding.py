@@ -35,3 +35,27 @@ def gather_pixels(local, n_rays, rank, world, tile=128, group=None):
         idx = shard_indices(n_rays, r, world, tile).to(local.device)
         full[idx] = out[r * pad: r * pad + counts[r]]
     return full
+
+
+def allreduce_gradients(module, world, group=None, average=True):
+    """Data-parallel train step: ONE all_reduce of the flattened gradients per step
+    (668 K floats for the stage-2 networks; latency bound, NVLS on NVSwitch).  Parameters without a gradient contribute zeros
+    so that every rank reduces the same layout."""
+    if world == 1:
+        return
+    params = [p for p in module.parameters() if p.requires_grad]
+    if not params:
+        return
+    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).float() for p in params])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    if average:
+        flat /= world
+    off = 0
+    for p in params:
+        n = p.numel()
+        g = flat[off:off + n].view_as(p)
+        if p.grad is None:
+            p.grad = g.clone()
+        else:
+            p.grad.copy_(g)
+        off += n

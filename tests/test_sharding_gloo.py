@@ -56,3 +56,48 @@ def test_gather_pixels_world2_gloo():
     want = torch.stack([ids * 2.0, ids + 0.5, -ids], -1)
     for r in range(world):
         assert torch.equal(res[r], want)
+
+
+def _grad_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    m = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.ReLU(), torch.nn.Linear(7, 2))
+    x = torch.arange(20, dtype=torch.float32).reshape(4, 5) / 10 + rank      # each rank sees a different ray shard
+    m(x).sum().backward()
+    if rank == 1:
+        m[2].bias.grad = None                                                # a parameter that got no gradient on this rank
+    sharding.allreduce_gradients(m, world)
+    q.put((rank, [p.grad.clone() for p in m.parameters()]))
+    dist.destroy_process_group()
+
+
+def test_allreduce_gradients_world2_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # reference: average of the two ranks' gradients computed serially
+    torch.manual_seed(0)
+    m = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.ReLU(), torch.nn.Linear(7, 2))
+    acc = None
+    for rank in range(world):
+        m.zero_grad()
+        x = torch.arange(20, dtype=torch.float32).reshape(4, 5) / 10 + rank
+        m(x).sum().backward()
+        gs = [p.grad.clone() for p in m.parameters()]
+        if rank == 1:
+            gs[3] = torch.zeros_like(gs[3])
+        acc = gs if acc is None else [a + b for a, b in zip(acc, gs)]
+    want = [a / world for a in acc]
+    for r in range(world):
+        for got, w in zip(res[r], want):
+            assert torch.allclose(got, w, atol=1e-6)
