@@ -180,7 +180,7 @@ def extra_workloads(dev, precision, rend, view, peaks):
     out = {}
     conf = synth.stage2_conf()
     torch.manual_seed(0)
-    ps = PSNetwork(conf).to(dev)
+    ps = PSNetwork(conf).to(dev).eval()
     ps.precision = precision
     inp = synth.stage2_input(H, W, 96, all_surface=True)
     inp = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in inp.items()}

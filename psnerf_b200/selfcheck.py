@@ -42,7 +42,7 @@ def run_smoke(verbose=True):
     inp = synth.stage2_input(12, 12, 5, all_surface=False)
     with torch.no_grad():
         ref2 = O.psnetwork_forward(sd2, conf, inp)
-    ps = ps.to(dev)
+    ps = ps.to(dev).eval()
     for prec in precisions:
         ps.precision = prec
         out2 = ps({k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in inp.items()})

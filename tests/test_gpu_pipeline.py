@@ -20,7 +20,7 @@ def _models(prec="fp32"):
     r = Renderer(net, cfg, device=torch.device("cuda"))
     ps = PSNetwork(conf)
     ps.load_state_dict(s2["trained"])
-    ps = ps.cuda()
+    ps = ps.cuda().eval()
     ps.precision = prec
     return cfg, s1["init"], r, conf, s2["trained"], ps
 

@@ -26,7 +26,7 @@ def make_model(conf, sd, prec):
     from psnerf_b200.stage2 import PSNetwork
     m = PSNetwork(conf)
     m.load_state_dict(sd)
-    m = m.cuda()
+    m = m.cuda().eval()
     m.precision = prec
     return m
 

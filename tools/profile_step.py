@@ -35,7 +35,7 @@ if not a.stage2:
 else:
     conf = synth.stage2_conf()
     torch.manual_seed(0)
-    m = PSNetwork(conf).to(dev)
+    m = PSNetwork(conf).to(dev).eval()
     m.precision = a.precision
     inp = synth.stage2_input(H, W, 96, all_surface=True)
     inp = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in inp.items()}
