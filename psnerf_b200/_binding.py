@@ -9,7 +9,7 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libpsnerf_b200.so")
+LIB_PATH = os.environ.get("PSNERF_B200_LIB") or os.path.join(_HERE, "lib", "libpsnerf_b200.so")  # env override: bring-up builds
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "psnerf_b200.h")
 
 PREC_FP32, PREC_TC = 0, 1

@@ -22,14 +22,6 @@ struct TcGeoArgs {
   float rescale;
 };
 
-// entry idx of [p, sin(2^0 p), cos(2^0 p), ...] (network.py:141-150)
-__device__ __forceinline__ float pe_entry(const float x[3], int idx) {
-  if (idx < 3) return idx == 0 ? x[0] : (idx == 1 ? x[1] : x[2]);  // selects, not a dynamically indexed local array
-  const int j = idx - 3, oct = j / 6, r = j - 6 * oct, c = r % 3;
-  const float a = (float)(1 << oct) * (c == 0 ? x[0] : (c == 1 ? x[1] : x[2]));
-  return r < 3 ? sinf(a) : cosf(a);
-}
-
 constexpr int MODE_OUT = 0, MODE_SHADOW = 1, MODE_DEBUG = 2;  // MODE_DEBUG = MODE_OUT + layer dump / clock64 trace hooks
 
 template <int MODE>
@@ -47,7 +39,7 @@ k_tc_occ(TcGeoArgs g, PointGen gen, long long M_host, const int* M_dev, int out_
   if (warp < EPI_WARP0) {
     regs_shrink_control();
     if (warp == 0 && lane == 0) producer_loop(s, g.prog, iters);
-    if (warp == 1 && lane == 0) mma_loop(s, g.prog, iters, tmem_base, MODE == MODE_DEBUG ? trace : nullptr);
+    if (warp == 1) mma_loop(s, g.prog, iters, tmem_base, MODE == MODE_DEBUG ? trace : nullptr);
     __syncwarp();
   } else {
     regs_grow_epilogue();
@@ -58,23 +50,31 @@ k_tc_occ(TcGeoArgs g, PointGen gen, long long M_host, const int* M_dev, int out_
       const long long idx = tile * TILE_M + row;
       float p[3] = {0.f, 0.f, 0.f}, vdummy[3];
       if (idx < M) gen_point(gen, idx, p, vdummy);
-      const float x[3] = {p[0] / g.rescale, p[1] / g.rescale, p[2] / g.rescale};
+      {
+        const float x[3] = {p[0] / g.rescale, p[1] / g.rescale, p[2] / g.rescale};
+        epi_write_pe(s, row, sub, x, g.octaves);
+      }
+      named_bar_sync(1, EPI_THREADS);  // encoding table complete (also: every warp is done with the previous tile's staging area)
       {  // layer-0 operand: the point encoding, zero padded to one 64-wide K block (16 columns per sub)
-#pragma unroll 1
-        for (int k = sub * CW; k < sub * CW + CW; ++k) epi_store_a1(s, row, k, k < g.pe_dim ? pe_entry(x, k) : 0.f);
+        float v[CW];
+#pragma unroll
+        for (int i = 0; i < CW; ++i) {
+          const int k = sub * CW + i;
+          v[i] = k < g.pe_dim ? s.pe[k * TILE_M + row] : 0.f;
+        }
+        epi_store_a16(e, e.a_col0(), sub * CW, v);
         epi_signal_a(s, 0);
       }
       float part = 0.f;  // partial logit over this thread's 64 columns
 #pragma unroll 1
       for (int l = 0; l < 8; ++l) {
-        epi_wait_d(s, e);
         const bool tr = (MODE == MODE_DEBUG) && trace && it == TRACE_ITER && blockIdx.x == 0 && row == 0;
-        if (tr) trace[64 + sub * 40 + l * 5] = clock64();
         const float* bias = g.bias[l];
         const bool pre_skip = (l + 1 == g.skip);
         const int n_out = g.n_out[l];
         const float cc = pre_skip ? PSN_SOFTPLUS_C * 0.70710678118654752440f : PSN_SOFTPLUS_C;
-        epi_for_chunks(e, 256, [&](int pass, int col, float (&v)[CW]) {
+        epi_for_chunks(s, e, [&](int pass, int col, float (&v)[CW]) {
+          if (tr && pass == 0) trace[64 + sub * 40 + l * 5] = clock64();
           add_bias16(v, bias, col);
 #pragma unroll
           for (int i = 0; i < CW; ++i) v[i] = softplus_scaled(v[i], cc);
@@ -85,12 +85,14 @@ k_tc_occ(TcGeoArgs g, PointGen gen, long long M_host, const int* M_dev, int out_
             }
           }
           if (l < 7) {
-            epi_store_a16(s, row, col, v);
             if (pre_skip && col + CW > n_out) {  // columns n_out.. of the skip layer's input are pe/sqrt2 (network.py:90-91)
-#pragma unroll 1
-              for (int k = (n_out > col ? n_out : col); k < col + CW; ++k)
-                epi_store_a1(s, row, k, pe_entry(x, k - n_out) * 0.70710678118654752440f);
+#pragma unroll
+              for (int i = 0; i < CW; ++i) {
+                const int k = col + i - n_out;
+                if (k >= 0) v[i] = (k < g.pe_dim ? s.pe[k * TILE_M + row] : 0.f) * 0.70710678118654752440f;
+              }
             }
+            epi_store_a16(e, e.d_col0(), col, v);
             epi_signal_a(s, pass);
             if (tr) trace[64 + sub * 40 + l * 5 + 1 + pass] = clock64();
           } else {
@@ -105,12 +107,12 @@ k_tc_occ(TcGeoArgs g, PointGen gen, long long M_host, const int* M_dev, int out_
         });
         e.step_ctr++;
       }
-      tc_fence_before();  // order this tile's last TMEM reads before the next tile's MMAs (via a_ready)
-      float* stage = epi_stage(s);  // [4 subs][128 rows]
-      stage[sub * TILE_M + row] = part;
+      tc_fence_before();  // order this tile's last TMEM reads before the next tile's operand stores / MMAs
+      s.stage[sub * TILE_M + row].x = part;
       named_bar_sync(1, EPI_THREADS);
       if (sub == 0) {
-        const float z = ((stage[row] + stage[TILE_M + row]) + (stage[2 * TILE_M + row] + stage[3 * TILE_M + row])) + __ldg(g.b_logit);
+        const float z = ((s.stage[row].x + s.stage[TILE_M + row].x) + (s.stage[2 * TILE_M + row].x + s.stage[3 * TILE_M + row].x)) +
+                        __ldg(g.b_logit);
         if (MODE != MODE_SHADOW) {
           if (idx < M) {
             float o = z;
@@ -145,7 +147,8 @@ k_tc_occ(TcGeoArgs g, PointGen gen, long long M_host, const int* M_dev, int out_
           if (row == 0) out[tile] = 1.f - (s.c->g3[8] + s.c->g3[9] + s.c->g3[10] + s.c->g3[11]);
         }
       }
-      named_bar_sync(1, EPI_THREADS);  // the staging area (A buffer) and g3 are reused by the next tile
+      // no trailing barrier: the staging area, the encoding table and g3 are next written after the next tile's encoding
+      // barrier / a later sub-0 barrier, which every reader of this tile has to reach first
     }
   }
   teardown(tmem_base);

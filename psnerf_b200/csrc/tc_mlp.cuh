@@ -1,24 +1,29 @@
 // tcgen05 / TMEM / mbarrier / bulk-copy primitives and the layer-pipelined fused-MLP machinery (sm_100a).
 //
 // One CTA (one per SM, persistent) owns a 128-row tile.  Per "step" (one Linear layer)
-//     D[128 x N] (fp32, TMEM)  =  A[128 x K] (fp16 hi+lo, shared)  x  W[N x K]^T (fp16 hi+lo, shared ring)
+//     D[128 x N] (fp32, TMEM)  =  A[128 x K] (fp16 hi+lo, TMEM)  x  W[N x K]^T (fp16 hi+lo, shared ring)
 // is evaluated as three UMMA passes  A_hi W_hi + A_lo W_hi + A_hi W_lo  (error-compensated split operands:
 // the dropped A_lo W_lo term is 2^-22 relative, fp32 accumulate) so the result tracks an fp32 GEMM.
 //
-// Shared memory: A = 4 K-blocks x (hi 16 KB + lo 16 KB), K-major, 128-byte swizzle (the canonical UMMA layout
-// Swizzle<3,4,3>: 16-byte chunk c of row r lives at chunk c ^ (r & 7)); weight ring = 3 stages x 32 KB, each one
-// pre-swizzled [N rows][64 K] tile streamed from L2 with cp.async.bulk (UBLKCP) + mbarrier complete_tx.
-// TMEM: two 256-column fp32 accumulators (all 512 columns).
+// TMEM (all 512 columns) = two 256-column regions R0 / R1.  Step sc accumulates D into R[sc & 1]; the epilogue converts that
+// accumulator IN PLACE into the next step's A operand: the 16 fp32 columns [16c, 16c+16) of a row become 8 columns of packed
+// fp16 hi (K elements 16c..16c+15, two per 32-bit column, even k in the low half) followed by 8 columns of packed fp16 lo, so
+// K-step c of step sc+1 reads its A operand straight from TMEM (tcgen05.mma with A in TMEM) at R[sc & 1] + 16c (hi) and
+// + 16c + 8 (lo) while it accumulates into the other region.  Activations therefore never touch shared memory: the MMA reads
+// only the weight operand from smem (8 KB per instruction instead of 12 KB) and the epilogue's stores go to TMEM
+// (tcgen05.st), which is what lifts the shared-memory bandwidth ceiling the first version of these kernels ran into
+// (ncu: tensor pipe 54 % active with the smem tensor-read path already at 40 %).
+// Shared memory: weight ring = 6 stages x 32 KB, each one pre-swizzled [N rows][64 K] K-major SWIZZLE_128B tile streamed
+// from L2 with cp.async.bulk (UBLKCP) + mbarrier complete_tx; a [40][128] fp32 point-encoding table; an 8 KB staging area.
 //
 // Warp roles: warp 0 = TMEM allocator + weight producer (one lane), warp 1 = MMA issuer (one lane), warps 2-3 idle (the
 // control warpgroup releases registers with setmaxnreg.dec);
 // warps 4..19 = epilogue: warp w reads TMEM lanes 32*(w%4).. and is "sub" s = (w-4)/4 of its lane quadrant; in pass p sub s
-// owns columns [64p + 16s, +16), so every pass completes one K block of the next layer and the MMA warp restarts early.  Four epilogue warps per scheduler hide the MUFU / TMEM / L2 latencies that two could not
-// (ncu: issue slots 34 % busy, tensor pipe waiting); registers are rebalanced with setmaxnreg (control 32, epilogue 112).
-// Layer pipelining: the epilogue of step L rewrites the A buffer in place (every MMA of step L has retired when
-// d_full fires) K-block by K-block and signals a_ready[kb]; the MMA warp starts step L+1's K-block kb as soon as
-// that block is ready, accumulating into the OTHER TMEM buffer - so tensor work of step L+1 overlaps the
-// activation math of step L and the tensor pipe only idles for the first 64-column chunk of each layer.
+// owns columns [64p + 16s, +16), so every pass completes one 64-wide K block of the next layer.
+// Layer pipelining: the epilogue of step L signals a_ready[kb] after each pass and the MMA warp starts step L+1's K block kb at
+// once.  The LAST K block of every step is issued as columns [0, 64) (twelve N = 64 MMAs, committed to d_q[buf][0]) followed by
+// the remaining columns (d_q[buf][1]): epilogue pass 0 needs only the first part, so it starts a quarter of a K block after the
+// last a_ready instead of a whole one and the tensor pipe works on the other columns underneath pass 0.
 #pragma once
 #include "common.cuh"
 
@@ -27,30 +32,30 @@ namespace tc {
 
 constexpr int TILE_M = 128;
 constexpr int KBLK = 64;                      // K elements per block (128 bytes of fp16)
-constexpr int A_PART_BYTES = TILE_M * 128;    // one K-block of one part (hi or lo): 16 KB
-constexpr int A_KB_BYTES = 2 * A_PART_BYTES;  // hi + lo
-constexpr int A_MAX_KB = 4;
-constexpr int A_BYTES = A_MAX_KB * A_KB_BYTES;  // 128 KB
-constexpr int W_STAGE_BYTES = 256 * 128;        // 32 KB: [256 N rows][64 K] fp16
-constexpr int W_STAGES = 3;
+constexpr int A_MAX_KB = 4;                   // K <= 256
+constexpr int W_STAGE_BYTES = 256 * 128;      // 32 KB: [256 N rows][64 K] fp16
+constexpr int W_STAGES = 6;
+constexpr int PE_K = 40;                      // rows of the fp32 point-encoding table (39 used at 6 octaves)
+constexpr int PE_BYTES = PE_K * TILE_M * 4;   // pe[k][row]
+constexpr int STAGE_BYTES = 4 * TILE_M * 16;  // cross-sub reduction staging: float4 [4 subs][128 rows]
 constexpr int NUM_THREADS = 640;  // warpgroup 0 = control (setmaxnreg 32), warpgroups 1-4 = epilogue (setmaxnreg 112)
 constexpr int EPI_WARP0 = 4;
 constexpr int EPI_THREADS = 512;
 constexpr int EPI_SUBS = 4;       // epilogue warps per TMEM lane quadrant
 constexpr int CW = 16;            // columns per epilogue chunk: in pass p sub s owns columns [64 p + 16 s, +16)
-constexpr int A_READY_ARRIVALS = 512;  // a K block (64 columns) is written by 4 subs x 128 rows in ONE pass
+constexpr int A_READY_ARRIVALS = 16;   // a K block (64 columns) is written by the 16 epilogue warps in ONE pass; lane 0 of each arrives
 
 // ---- shared-memory control block (after the 1024-aligned A and W regions) ---------------------------------
 struct Ctrl {
   unsigned long long w_full[W_STAGES];
   unsigned long long w_empty[W_STAGES];
   unsigned long long a_ready[A_MAX_KB];
-  unsigned long long d_full[2];
+  unsigned long long d_q[2][2];   // accumulator buffer x {columns [0, 64), columns [64, N)}
   unsigned int tmem_base;
   unsigned int pad;
   float g3[64];            // scratch of the shadow-ray transmittance scan
 };
-constexpr int SMEM_BYTES = A_BYTES + W_STAGES * W_STAGE_BYTES + (int)sizeof(Ctrl);  // dynamic smem is declared __align__(1024)
+constexpr int SMEM_BYTES = W_STAGES * W_STAGE_BYTES + PE_BYTES + STAGE_BYTES + (int)sizeof(Ctrl);  // dynamic smem is declared __align__(1024)
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory of sm_100");
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------------
@@ -112,12 +117,13 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
 // kind::f16, A = B = fp16 (format 0), D = fp32, both K-major, M = 128
 __device__ __forceinline__ uint32_t umma_idesc(uint32_t n) { return (1u << 4) | ((n >> 3) << 17) | (8u << 24); }
 
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] * B[smem]^T : A operand = 8 TMEM columns (16 packed fp16 of K per row) at tmem_a
+__device__ __forceinline__ void umma_ts_f16(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed
@@ -174,6 +180,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 32 lanes x 16 consecutive 32-bit columns: thread (lane i) writes row (lane_base + i), columns col..col+15
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // register re-allocation between warpgroups (all 4 warps of a warpgroup must execute it)
 // The CTA's register pool is what it was launched with (ptxas: 96 regs x 640 threads); setmaxnreg.inc BLOCKS until the pool
 // has room, so the budget must close exactly: 4 control warps x 32 + 16 epilogue warps x 112 = 96 x 20 warps.
@@ -208,16 +225,18 @@ struct Program {
 
 // ---- shared-memory carve-up ---------------------------------------------------------------------------------------
 struct Smem {
-  unsigned char* a;   // A buffer, 1024-aligned
   unsigned char* w;   // weight ring, 1024-aligned
+  float* pe;          // [PE_K][TILE_M] point encoding of the current tile (written by the epilogue warps)
+  float4* stage;      // [4 subs][TILE_M] cross-sub reduction staging
   Ctrl* c;
 };
 __device__ __forceinline__ Smem carve(unsigned char* raw) {
   Smem s;
   if (smem_u32(raw) & 1023u) __trap();  // SWIZZLE_128B operands need 1024-byte alignment
-  s.a = raw;
-  s.w = s.a + A_BYTES;
-  s.c = reinterpret_cast<Ctrl*>(s.w + W_STAGES * W_STAGE_BYTES);
+  s.w = raw;
+  s.pe = reinterpret_cast<float*>(s.w + W_STAGES * W_STAGE_BYTES);
+  s.stage = reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(s.pe) + PE_BYTES);
+  s.c = reinterpret_cast<Ctrl*>(reinterpret_cast<unsigned char*>(s.stage) + STAGE_BYTES);
   return s;
 }
 
@@ -227,7 +246,8 @@ __device__ __forceinline__ uint32_t setup(const Smem& s) {
   if (threadIdx.x == 0) {
     for (int i = 0; i < W_STAGES; ++i) { mbar_init(&s.c->w_full[i], 1); mbar_init(&s.c->w_empty[i], 1); }
     for (int i = 0; i < A_MAX_KB; ++i) mbar_init(&s.c->a_ready[i], A_READY_ARRIVALS);
-    for (int i = 0; i < 2; ++i) mbar_init(&s.c->d_full[i], 1);
+    for (int i = 0; i < 2; ++i)
+      for (int q = 0; q < 2; ++q) mbar_init(&s.c->d_q[i][q], 1);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc_512(&s.c->tmem_base);
@@ -260,53 +280,93 @@ __device__ __forceinline__ void producer_loop(const Smem& s, const Program& prog
   }
 }
 
-// ---- MMA issuer (warp 1, lane 0) -------------------------------------------------------------------------------------
-// trace (optional, bring-up tool): for CTA 0, tile iteration TRACE_ITER the MMA lane stores clock64() after every a_ready wait
-// (slot st*8 + kb) and after the step's last commit (slot st*8 + 7).
+// ---- MMA issuer (warp 1, all lanes converged; one elected lane issues) -----------------------------------------------
+// The whole warp runs the loop and waits on the barriers; tcgen05.mma / tcgen05.commit sit under an elect.sync predicate.
+// ptxas then emits straight-line UTCHMMA sequences.  (Issuing from an `if (lane == 0)` branch instead wraps EVERY UTCHMMA
+// in an ELECT / BRA.U.ANY retry loop plus per-instruction descriptor arithmetic: the clock64 timeline showed ~86 cycles per
+// issue, which made the N = 64 MMAs of the split tail issue-bound.)
+// trace (optional, bring-up tool): for CTA 0, tile iteration TRACE_ITER the elected lane stores clock64() after every a_ready
+// wait (slot st*8 + kb) and after the step's last commit has been issued (slot st*8 + 7).
 constexpr int TRACE_ITER = 3;
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// descriptor of a K-major SWIZZLE_128B operand = constant high word | (address >> 4) in the low word: advancing the start
+// address by `bytes` (a multiple of 16 that does not leave the 256 KB window) is an add on the low word
+constexpr uint64_t UMMA_DESC_HI = ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint64_t umma_desc_at(uint32_t lo, uint32_t bytes) { return UMMA_DESC_HI | (uint64_t)(lo + (bytes >> 4)); }
+
 __device__ __forceinline__ void mma_loop(const Smem& s, const Program& prog, long long iters, uint32_t tmem_base,
                                          long long* trace = nullptr) {
   uint32_t stage = 0, phase = 0;   // weight ring
   uint32_t a_phase = 0;            // bit kb = parity to wait for on a_ready[kb]
-  uint32_t step_ctr = 0;           // selects the TMEM accumulator
-  const uint32_t a_base = smem_u32(s.a), w_base = smem_u32(s.w);
+  uint32_t step_ctr = 0;           // selects the TMEM regions
+  const uint32_t w_base = smem_u32(s.w);
   for (long long it = 0; it < iters; ++it) {
     for (int st = 0; st < prog.n_steps; ++st, ++step_ctr) {
       const Step sp = prog.step[st];
+      const uint32_t buf = step_ctr & 1u;
+      const uint32_t d_addr = tmem_base + buf * 256u;           // accumulator of this step
+      const uint32_t a_addr = tmem_base + (buf ^ 1u) * 256u;    // its A operand = the previous step's accumulator, converted in place
       const uint32_t idesc = umma_idesc(sp.n_pad);
-      const uint32_t d_addr = tmem_base + (step_ctr & 1u) * 256u;
       for (int kb = 0; kb < sp.nkb; ++kb) {
         mbar_wait(&s.c->a_ready[kb], (a_phase >> kb) & 1u);
         a_phase ^= (1u << kb);
-        tc_fence_after();
-        if (trace && it == TRACE_ITER && blockIdx.x == 0) trace[st * 8 + kb] = clock64();
-        const uint32_t a_hi = a_base + kb * A_KB_BYTES, a_lo = a_hi + A_PART_BYTES;
-        // W_hi tile: A_hi W_hi + A_lo W_hi
-        mbar_wait(&s.c->w_full[stage], phase);
-        tc_fence_after();
-        {
-          const uint32_t wb = w_base + stage * W_STAGE_BYTES;
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            umma_f16(d_addr, umma_desc(a_hi + ks * 32), umma_desc(wb + ks * 32), idesc, (kb | ks) ? 1u : 0u);
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) umma_f16(d_addr, umma_desc(a_lo + ks * 32), umma_desc(wb + ks * 32), idesc, 1u);
-        }
-        umma_commit(&s.c->w_empty[stage]);
+        const uint32_t a_kb = a_addr + (uint32_t)kb * 64u;
+        // this K block's two weight stages (hi tile, lo tile)
+        const uint32_t st_hi = stage, ph_hi = phase;
         if (++stage == W_STAGES) { stage = 0; phase ^= 1u; }
-        // W_lo tile: A_hi W_lo
-        mbar_wait(&s.c->w_full[stage], phase);
-        tc_fence_after();
-        {
-          const uint32_t wb = w_base + stage * W_STAGE_BYTES;
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) umma_f16(d_addr, umma_desc(a_hi + ks * 32), umma_desc(wb + ks * 32), idesc, 1u);
-        }
-        umma_commit(&s.c->w_empty[stage]);
+        const uint32_t st_lo = stage, ph_lo = phase;
         if (++stage == W_STAGES) { stage = 0; phase ^= 1u; }
+        mbar_wait(&s.c->w_full[st_hi], ph_hi);
+        mbar_wait(&s.c->w_full[st_lo], ph_lo);
+        tc_fence_after();
+        const uint32_t lo_hi = umma_desc_lo(w_base + st_hi * W_STAGE_BYTES), lo_lo = umma_desc_lo(w_base + st_lo * W_STAGE_BYTES);
+        if (elect_one()) {
+          if (trace && it == TRACE_ITER && blockIdx.x == 0) trace[st * 8 + kb] = clock64();
+          if (kb + 1 < sp.nkb) {
+            // A_hi W_hi + A_lo W_hi + A_hi W_lo over the four K-steps of the block, all N columns
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t bh = umma_desc_at(lo_hi, ks * 32), bl = umma_desc_at(lo_lo, ks * 32);
+              umma_ts_f16(d_addr, a_kb + ks * 16, bh, idesc, (kb | ks) ? 1u : 0u);
+              umma_ts_f16(d_addr, a_kb + ks * 16 + 8, bh, idesc, 1u);
+              umma_ts_f16(d_addr, a_kb + ks * 16, bl, idesc, 1u);
+            }
+          } else {
+            // last K block of the step: columns [0, 64) first, committed on their own (d_q[buf][0]) so that epilogue pass 0
+            // starts a quarter of a K block after the last a_ready; the remaining columns follow underneath that pass
+            const uint32_t n0 = sp.n_pad < 64 ? (uint32_t)sp.n_pad : 64u;
+            const uint32_t id0 = umma_idesc(n0);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t bh = umma_desc_at(lo_hi, ks * 32), bl = umma_desc_at(lo_lo, ks * 32);
+              umma_ts_f16(d_addr, a_kb + ks * 16, bh, id0, (kb | ks) ? 1u : 0u);
+              umma_ts_f16(d_addr, a_kb + ks * 16 + 8, bh, id0, 1u);
+              umma_ts_f16(d_addr, a_kb + ks * 16, bl, id0, 1u);
+            }
+            umma_commit(&s.c->d_q[buf][0]);
+            if (sp.n_pad > 64) {
+              const uint32_t id1 = umma_idesc((uint32_t)sp.n_pad - 64u);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {  // weight rows 64.. start 64 * 128 bytes into the tile
+                const uint64_t bh = umma_desc_at(lo_hi, 8192 + ks * 32), bl = umma_desc_at(lo_lo, 8192 + ks * 32);
+                umma_ts_f16(d_addr + 64u, a_kb + ks * 16, bh, id1, (kb | ks) ? 1u : 0u);
+                umma_ts_f16(d_addr + 64u, a_kb + ks * 16 + 8, bh, id1, 1u);
+                umma_ts_f16(d_addr + 64u, a_kb + ks * 16, bl, id1, 1u);
+              }
+            }
+            umma_commit(&s.c->d_q[buf][1]);
+          }
+          umma_commit(&s.c->w_empty[st_hi]);
+          umma_commit(&s.c->w_empty[st_lo]);
+          if (trace && it == TRACE_ITER && blockIdx.x == 0 && kb + 1 == sp.nkb) trace[st * 8 + 7] = clock64();
+        }
+        __syncwarp();
       }
-      umma_commit(&s.c->d_full[step_ctr & 1u]);
-      if (trace && it == TRACE_ITER && blockIdx.x == 0) trace[st * 8 + 7] = clock64();
     }
   }
 }
@@ -318,6 +378,9 @@ struct EpiCtx {
   int row;             // tile row owned by this thread (TMEM lane)
   int sub;             // 0..3: owns columns [64 p + 16 sub, +16) in pass p
   uint32_t lane_addr;  // (32 * quadrant) << 16
+  // first TMEM column of the current step's accumulator / of the region the current step's A operand lives in
+  __device__ __forceinline__ uint32_t d_col0() const { return (step_ctr & 1u) * 256u; }
+  __device__ __forceinline__ uint32_t a_col0() const { return ((step_ctr & 1u) ^ 1u) * 256u; }
 };
 __device__ __forceinline__ EpiCtx epi_ctx(uint32_t tmem_base) {
   EpiCtx e;
@@ -330,29 +393,33 @@ __device__ __forceinline__ EpiCtx epi_ctx(uint32_t tmem_base) {
   e.lane_addr = (uint32_t)(q * 32) << 16;
   return e;
 }
-// wait for the accumulator of the current step
+// wait for part q of the current step's accumulator: 0 = columns [0, 64), 1 = the rest
+__device__ __forceinline__ void epi_wait_q(const Smem& s, const EpiCtx& e, int q) {
+  mbar_wait(&s.c->d_q[e.step_ctr & 1u][q], (e.step_ctr >> 1) & 1u);
+  tc_fence_after();
+}
+// wait for the whole accumulator of the current step
 __device__ __forceinline__ void epi_wait_d(const Smem& s, const EpiCtx& e) {
-  mbar_wait(&s.c->d_full[e.step_ctr & 1u], (e.step_ctr >> 1) & 1u);
+  mbar_wait(&s.c->d_q[e.step_ctr & 1u][0], (e.step_ctr >> 1) & 1u);
+  mbar_wait(&s.c->d_q[e.step_ctr & 1u][1], (e.step_ctr >> 1) & 1u);
   tc_fence_after();
 }
 __device__ __forceinline__ void epi_load16(const EpiCtx& e, int col, float (&v)[CW]) {
-  tmem_ld16(e.tmem_base + e.lane_addr + (e.step_ctr & 1u) * 256u + (uint32_t)col, v);
+  tmem_ld16(e.tmem_base + e.lane_addr + e.d_col0() + (uint32_t)col, v);
 }
 
-// Visit the 16-column chunks this thread owns in the current accumulator: f(pass, col, v[16]), col = 64*pass + 16*sub, for the
-// passes whose columns exist (col < n_cols).  One pass of the four subs covers exactly one 64-column K block of the next
-// layer's A operand, so the MMA warp can restart after a quarter of the epilogue (clock64 trace: it used to wait for half).
+// Visit the 16-column chunks this thread owns in the current accumulator: f(pass, col, v[16]), col = 64*pass + 16*sub.  Pass 0
+// waits for columns [0, 64) only; one pass of the four subs covers exactly one 64-column K block of the next step's A operand.
 template <class F>
-__device__ __forceinline__ void epi_for_chunks(const EpiCtx& e, int n_cols, F&& f) {
-  const uint32_t base = e.tmem_base + e.lane_addr + (e.step_ctr & 1u) * 256u;
+__device__ __forceinline__ void epi_for_chunks(const Smem& s, const EpiCtx& e, F&& f) {
+  const uint32_t base = e.tmem_base + e.lane_addr + e.d_col0();
 #pragma unroll 1
   for (int pass = 0; pass < 4; ++pass) {
+    if (pass < 2) epi_wait_q(s, e, pass);
     const int col = 64 * pass + CW * e.sub;
-    if (col < n_cols) {
-      float v[CW];
-      tmem_ld16(base + (uint32_t)col, v);
-      f(pass, col, v);
-    }
+    float v[CW];
+    tmem_ld16(base + (uint32_t)col, v);
+    f(pass, col, v);
   }
 }
 // v[i] += bias[col + i] with 128-bit loads
@@ -365,50 +432,56 @@ __device__ __forceinline__ void add_bias16(float (&v)[CW], const float* __restri
   }
 }
 
-__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
-  return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+// Write 16 consecutive activation values (K elements col..col+15 of this thread's row) as the A operand of K-step col/16 of the
+// region starting at TMEM column col0: 8 columns of packed fp16 hi, then 8 columns of packed fp16 lo (see the file header).
+// Packed cvt.rn.f16x2.f32 (F2FP, ALU pipe) - scalar F2F would queue on the XU pipe with the MUFUs.
+__device__ __forceinline__ void epi_store_a16(const EpiCtx& e, uint32_t col0, int col, const float (&v)[CW]) {
+  uint32_t r[16];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+#ifdef PSN_TC_SWAP_HALVES  // bring-up only: the other packing order of the two K elements of a column
+    const float x0 = v[2 * u + 1], x1 = v[2 * u];
+#else
+    const float x0 = v[2 * u], x1 = v[2 * u + 1];
+#endif
+    const __half2 hh = __floats2half2_rn(x0, x1);  // .x (low half) = x0 = the even K element
+    const float2 hf = __half22float2(hh);
+    const __half2 ll = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+    r[u] = *reinterpret_cast<const uint32_t*>(&hh);
+    r[8 + u] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+  tmem_st16(e.tmem_base + e.lane_addr + col0 + (uint32_t)col, r);
 }
-// Write 16 consecutive activation values (columns col..col+15 of this thread's row) as fp16 hi/lo into the A buffer.
-__device__ __forceinline__ void epi_store_a16(const Smem& s, int row, int col, const float (&v)[CW]) {
-  const int kb = col >> 6;
-  unsigned char* hi_row = s.a + kb * A_KB_BYTES + row * 128;
-  unsigned char* lo_row = hi_row + A_PART_BYTES;
-  const int c0 = (col & 63) >> 3;  // first 16-byte chunk
-#pragma unroll
-  for (int t = 0; t < 2; ++t) {
-    uint32_t h[4], l[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {  // packed cvt.rn.f16x2.f32 (F2FP, ALU pipe) - scalar F2F would queue on the XU pipe with the MUFUs
-      const float x0 = v[t * 8 + 2 * u], x1 = v[t * 8 + 2 * u + 1];
-      const __half2 hh = __floats2half2_rn(x0, x1);
-      const float2 hf = __half22float2(hh);
-      const __half2 ll = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
-      h[u] = *reinterpret_cast<const uint32_t*>(&hh);
-      l[u] = *reinterpret_cast<const uint32_t*>(&ll);
-    }
-    const int phys = ((c0 + t) ^ (row & 7)) * 16;
-    *reinterpret_cast<uint4*>(hi_row + phys) = make_uint4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<uint4*>(lo_row + phys) = make_uint4(l[0], l[1], l[2], l[3]);
+// this warp's 16 columns of K-block kb are written: publish to the MMA warp (one arrival per epilogue warp, 16 per block)
+__device__ __forceinline__ void epi_signal_a(const Smem& s, int kb) {
+  tmem_st_wait();
+  tc_fence_before();
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(&s.c->a_ready[kb]);
+}
+
+// Point encoding [x, sin(2^0 x), cos(2^0 x), ...] (network.py:141-150) of this thread's row into the smem table pe[k][row]:
+// sub s evaluates the sincos pairs m = s, s+4, ... (m = 3*octave + coordinate).  Callers follow with a barrier over the
+// epilogue threads; the table then serves the layer-0 operand, the skip-layer concat and the encoding Jacobian.
+__device__ __forceinline__ void epi_write_pe(const Smem& s, int row, int sub, const float (&x)[3], int octaves) {
+  if (sub == 0) { s.pe[row] = x[0]; s.pe[TILE_M + row] = x[1]; s.pe[2 * TILE_M + row] = x[2]; }
+#pragma unroll 1
+  for (int m = sub; m < 3 * octaves; m += EPI_SUBS) {
+    const int oct = m / 3, c = m - 3 * oct;
+    float sn, cs;
+    sincosf((float)(1 << oct) * (c == 0 ? x[0] : (c == 1 ? x[1] : x[2])), &sn, &cs);
+    s.pe[(3 + 6 * oct + c) * TILE_M + row] = sn;
+    s.pe[(6 + 6 * oct + c) * TILE_M + row] = cs;
   }
 }
-// Cross-sub reductions (fixed order => bit-reproducible): every sub parks its per-row partials in the LAST K block of the A
-// buffer, which is dead whenever this is used (after the accumulator wait of a step whose epilogue does not rewrite it).
-__device__ __forceinline__ float* epi_stage(const Smem& s) { return reinterpret_cast<float*>(s.a + 3 * A_KB_BYTES); }
-
-// single element (column col of this thread's row): used for the few encoding columns that are not MMA outputs
-__device__ __forceinline__ void epi_store_a1(const Smem& s, int row, int col, float x) {
-  const int kb = col >> 6, kk = col & 63;
-  unsigned char* hi_row = s.a + kb * A_KB_BYTES + row * 128;
-  const int phys = (((kk >> 3) ^ (row & 7)) << 4) + (kk & 7) * 2;
-  const __half h = __float2half_rn(x);
-  *reinterpret_cast<__half*>(hi_row + phys) = h;
-  *reinterpret_cast<__half*>(hi_row + A_PART_BYTES + phys) = __float2half_rn(x - __half2float(h));
-}
-// this thread's 16 columns of K-block kb are written: publish to the MMA warp (4 subs x 128 rows = 512 arrivals per block)
-__device__ __forceinline__ void epi_signal_a(const Smem& s, int kb) {
-  tc_fence_before();
-  fence_proxy_async_smem();
-  mbar_arrive(&s.c->a_ready[kb]);
+// d pe[k] / d x[coord] from the table: 1 for k < 3; f cos(f x) = f * pe[k+3] for a sin entry; -f sin(f x) = -f * pe[k-3] for a cos entry
+__device__ __forceinline__ float pe_jac_tab(const Smem& s, int row, int k, int* coord) {
+  if (k < 3) { *coord = k; return 1.f; }
+  const int j = k - 3, oct = j / 6, r = j - 6 * oct;
+  const float f = (float)(1 << oct);
+  if (r < 3) { *coord = r; return f * s.pe[(k + 3) * TILE_M + row]; }
+  *coord = r - 3;
+  return -f * s.pe[(k - 3) * TILE_M + row];
 }
 
 // softplus(beta=100) on pre-scaled accumulators: zs = 100*log2(e)*z  ->  softplus(z) = c * max(zs, lg2(1 + 2^min(zs,40))),

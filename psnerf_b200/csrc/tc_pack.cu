@@ -33,7 +33,7 @@ static int tc_plan(const psn_mlp* net, TcPlanItem* items) {
   int n = 0;
   const int nl = net->n_layers;
   if (net->kind == PSN_NET_GEO) {
-    if (nl != 9 || net->in_dims[0] > 64) return 0;
+    if (nl != 9 || net->in_dims[0] > tc::PE_K) return 0;  // the kernels keep the point encoding in a [PE_K][128] smem table
     for (int l = 0; l < nl; ++l) {
       if (l > 0 && net->in_dims[l] != 256) return 0;
       if (l < nl - 1 && (net->out_dims[l] > 256 || net->out_dims[l] <= 128)) return 0;

@@ -16,9 +16,25 @@
 namespace psn {
 using namespace tc;
 
-constexpr int SCR_STASH_F4 = 8 * 64 * TILE_M;        // float4 elements: [layer][col/4][row]
-constexpr int SCR_PART_F4 = 64 * TILE_M;             // [col/4][row]
-constexpr int SCR_F4_PER_CTA = SCR_STASH_F4 + SCR_PART_F4;
+// Per-CTA scratch (global, sized to stay L2-resident: 148 x 640 KB = 92.5 MB of the 126 MB L2):
+//   stash  : sigma'(z) of the 8 x 256 hidden units of the tile's rows as unorm16, uint4 [layer][col/8][row]   (512 KB)
+//   parked : fp32 partial pre-activation of appearance layer 0, float4 [col/4][row]                          (128 KB)
+// unorm16 keeps the analytic normal within 4e-6 rel-L2 / 2.5e-5 per-row of the fp32-stash result (fp16 would cost 8e-5 /
+// 6e-4); the first version stashed fp32 (166 MB over all CTAs) and ncu showed every byte of it going to DRAM and back.
+constexpr int SCR_STASH_U4 = 8 * 32 * TILE_M;
+constexpr int SCR_PART_F4 = 64 * TILE_M;
+constexpr int SCR_U4_PER_CTA = SCR_STASH_U4 + SCR_PART_F4;
+
+// sigma' in [0, 1] -> unorm16 via the 2^23 magic-number add (FFMA + PRMT: no F2I / I2F on the XU pipe next to the MUFUs)
+__device__ __forceinline__ uint32_t q16_pair(float a, float b) {
+  const uint32_t ua = __float_as_uint(fmaf(a, 65535.f, 8388608.f)), ub = __float_as_uint(fmaf(b, 65535.f, 8388608.f));
+  return __byte_perm(ua, ub, 0x5410);
+}
+__device__ __forceinline__ void dq16_pair(uint32_t w, float& a, float& b) {  // exact integers 0..65535 as floats
+  a = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)) - 8388608.f;
+  b = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)) - 8388608.f;
+}
+#define PSN_INV_U16 1.52590218966964e-05f  /* 1 / 65535 */
 
 struct TcRadArgs {
   Program prog;
@@ -31,23 +47,16 @@ struct TcRadArgs {
   float rescale;
   const float* abias[5];
   int octaves_view, pe_view_dim;
-  float4* scratch;
+  uint4* scratch;
   int with_app;  // 1: radiance (23 steps), 0: gradient only (16 steps)
 };
 
+// entry idx of [v, sin(2^0 v), cos(2^0 v), ...] (network.py:141-150), used for the per-tile view-direction encoding
 __device__ __forceinline__ float pe_entry_r(const float x[3], int idx) {
   if (idx < 3) return idx == 0 ? x[0] : (idx == 1 ? x[1] : x[2]);  // selects, not a dynamically indexed local array
   const int j = idx - 3, oct = j / 6, r = j - 6 * oct, c = r % 3;
   const float a = (float)(1 << oct) * (c == 0 ? x[0] : (c == 1 ? x[1] : x[2]));
   return r < 3 ? sinf(a) : cosf(a);
-}
-// d pe[idx] / d x[c]  (0 unless idx belongs to coordinate c)
-__device__ __forceinline__ float pe_jac(const float x[3], int idx, int* coord) {
-  if (idx < 3) { *coord = idx; return 1.f; }
-  const int j = idx - 3, oct = j / 6, r = j - 6 * oct, c = r % 3;
-  const float f = (float)(1 << oct), a = f * (c == 0 ? x[0] : (c == 1 ? x[1] : x[2]));
-  *coord = c;
-  return r < 3 ? f * cosf(a) : -f * sinf(a);
 }
 
 #define PSN_INV_SQRT2 0.70710678118654752440f
@@ -66,45 +75,58 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
   if (warp < EPI_WARP0) {
     regs_shrink_control();
     if (warp == 0 && lane == 0) producer_loop(s, g.prog, iters);
-    if (warp == 1 && lane == 0) mma_loop(s, g.prog, iters, tmem_base);
+    if (warp == 1) mma_loop(s, g.prog, iters, tmem_base);
     __syncwarp();
   } else {
     regs_grow_epilogue();
     EpiCtx e = epi_ctx(tmem_base);
     const int row = e.row, sub = e.sub;
-    float4* stash = g.scratch + (size_t)blockIdx.x * SCR_F4_PER_CTA;
-    float4* parked = stash + SCR_STASH_F4;
+    uint4* stash = g.scratch + (size_t)blockIdx.x * SCR_U4_PER_CTA;
+    float4* parked = reinterpret_cast<float4*>(stash + SCR_STASH_U4);
     for (long long it = 0; it < iters; ++it) {
       const long long tile = blockIdx.x + it * gridDim.x;
       const long long idx = tile * TILE_M + row;
       float p[3] = {0.f, 0.f, 0.f}, vd[3] = {0.f, 0.f, 1.f};
       if (idx < M) gen_point(gen, idx, p, vd);
-      const float x[3] = {p[0] / g.rescale, p[1] / g.rescale, p[2] / g.rescale};
       {
-#pragma unroll 1
-        for (int k = sub * CW; k < sub * CW + CW; ++k) epi_store_a1(s, row, k, k < g.pe_dim ? pe_entry_r(x, k) : 0.f);
+        const float x[3] = {p[0] / g.rescale, p[1] / g.rescale, p[2] / g.rescale};
+        epi_write_pe(s, row, sub, x, g.octaves);
+      }
+      named_bar_sync(1, EPI_THREADS);  // encoding table complete
+      {
+        float v[CW];
+#pragma unroll
+        for (int i = 0; i < CW; ++i) {
+          const int k = sub * CW + i;
+          v[i] = k < g.pe_dim ? s.pe[k * TILE_M + row] : 0.f;
+        }
+        epi_store_a16(e, e.a_col0(), sub * CW, v);
         epi_signal_a(s, 0);
       }
       // ---- s0..s7: geo forward --------------------------------------------------------------------------------------
       float part = 0.f;
 #pragma unroll 1
       for (int l = 0; l < 8; ++l) {
-        epi_wait_d(s, e);
         const float* bias = g.gbias[l];
         const bool pre_skip = (l + 1 == g.skip);
         const int n_out = g.n_out[l];
         const float cc = pre_skip ? PSN_SOFTPLUS_C * PSN_INV_SQRT2 : PSN_SOFTPLUS_C;
-        epi_for_chunks(e, 256, [&](int pass, int col, float (&v)[CW]) {
+        epi_for_chunks(s, e, [&](int pass, int col, float (&v)[CW]) {
           add_bias16(v, bias, col);
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            float sg[4];
+          for (int t = 0; t < 2; ++t) {
+            float sg[8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) v[4 * t + u] = softplus_scaled_d(v[4 * t + u], cc, &sg[u]);
-            stash[(size_t)(l * 64 + (col >> 2) + t) * TILE_M + row] = make_float4(sg[0], sg[1], sg[2], sg[3]);
+            for (int u = 0; u < 8; ++u) v[8 * t + u] = softplus_scaled_d(v[8 * t + u], cc, &sg[u]);
+            stash[(size_t)(l * 32 + (col >> 3) + t) * TILE_M + row] =
+                make_uint4(q16_pair(sg[0], sg[1]), q16_pair(sg[2], sg[3]), q16_pair(sg[4], sg[5]), q16_pair(sg[6], sg[7]));
             if (l == 7 && !g.with_app) {  // gradient only: seed dz_7 = W_last[0,:] * sigma'(z_7) directly
-              const float4 w = __ldg(reinterpret_cast<const float4*>(g.w_row + col) + t);
-              v[4 * t] = w.x * sg[0]; v[4 * t + 1] = w.y * sg[1]; v[4 * t + 2] = w.z * sg[2]; v[4 * t + 3] = w.w * sg[3];
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const float4 w = __ldg(reinterpret_cast<const float4*>(g.w_row + col) + 2 * t + h);
+                v[8 * t + 4 * h] = w.x * sg[4 * h]; v[8 * t + 4 * h + 1] = w.y * sg[4 * h + 1];
+                v[8 * t + 4 * h + 2] = w.z * sg[4 * h + 2]; v[8 * t + 4 * h + 3] = w.w * sg[4 * h + 3];
+              }
             }
           }
           if (l == 7 && g.with_app) {
@@ -116,12 +138,14 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
               part = fmaf(v[4 * t + 2], w.z, part); part = fmaf(v[4 * t + 3], w.w, part);
             }
           }
-          epi_store_a16(s, row, col, v);
-          if (pre_skip && col + CW > n_out) {
-#pragma unroll 1
-            for (int k = (n_out > col ? n_out : col); k < col + CW; ++k)
-              epi_store_a1(s, row, k, pe_entry_r(x, k - n_out) * PSN_INV_SQRT2);
+          if (pre_skip && col + CW > n_out) {  // columns n_out.. of the skip layer's input are pe/sqrt2 (network.py:90-91)
+#pragma unroll
+            for (int i = 0; i < CW; ++i) {
+              const int k = col + i - n_out;
+              if (k >= 0) v[i] = (k < g.pe_dim ? s.pe[k * TILE_M + row] : 0.f) * PSN_INV_SQRT2;
+            }
           }
+          epi_store_a16(e, e.d_col0(), col, v);
           epi_signal_a(s, pass);
         });
         e.step_ctr++;
@@ -129,26 +153,30 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
       float g_acc[3] = {0.f, 0.f, 0.f};  // this thread's share of J_pe^T (d logit / d pe)
       if (g.with_app) {
         // ---- s8: feature head -> A (no activation) ---------------------------------------------------------------------
-        epi_wait_d(s, e);
-        epi_for_chunks(e, 256, [&](int pass, int col, float (&v)[CW]) {
+        epi_for_chunks(s, e, [&](int pass, int col, float (&v)[CW]) {
           add_bias16(v, g.bias_feat, col);
-          epi_store_a16(s, row, col, v);
+          epi_store_a16(e, e.d_col0(), col, v);
           epi_signal_a(s, pass);
         });
         e.step_ctr++;
         // ---- s9: appearance layer 0, feature part -> parked; then the reverse seed dz_7 -> A -------------------------------
-        epi_wait_d(s, e);
-        epi_for_chunks(e, 256, [&](int pass, int col, float (&v)[CW]) {
+        epi_for_chunks(s, e, [&](int pass, int col, float (&v)[CW]) {
 #pragma unroll
           for (int t = 0; t < 4; ++t)
             parked[(size_t)((col >> 2) + t) * TILE_M + row] = make_float4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const float4 sg = stash[(size_t)(7 * 64 + (col >> 2) + t) * TILE_M + row];
-            const float4 w = __ldg(reinterpret_cast<const float4*>(g.w_row + col) + t);
-            v[4 * t] = w.x * sg.x; v[4 * t + 1] = w.y * sg.y; v[4 * t + 2] = w.z * sg.z; v[4 * t + 3] = w.w * sg.w;
+          for (int t = 0; t < 2; ++t) {
+            const uint4 q = __ldcg(&stash[(size_t)(7 * 32 + (col >> 3) + t) * TILE_M + row]);
+            float sg[8];
+            dq16_pair(q.x, sg[0], sg[1]); dq16_pair(q.y, sg[2], sg[3]); dq16_pair(q.z, sg[4], sg[5]); dq16_pair(q.w, sg[6], sg[7]);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const float4 w = __ldg(reinterpret_cast<const float4*>(g.w_row + col) + 2 * t + h);
+              v[8 * t + 4 * h] = (w.x * PSN_INV_U16) * sg[4 * h]; v[8 * t + 4 * h + 1] = (w.y * PSN_INV_U16) * sg[4 * h + 1];
+              v[8 * t + 4 * h + 2] = (w.z * PSN_INV_U16) * sg[4 * h + 2]; v[8 * t + 4 * h + 3] = (w.w * PSN_INV_U16) * sg[4 * h + 3];
+            }
           }
-          epi_store_a16(s, row, col, v);
+          epi_store_a16(e, e.d_col0(), col, v);
           epi_signal_a(s, pass);
         });
         e.step_ctr++;
@@ -156,40 +184,35 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
       // ---- s10..s16: reverse through layers 7..1 -----------------------------------------------------------------------------
 #pragma unroll 1
       for (int l = 7; l >= 1; --l) {
-        epi_wait_d(s, e);
         const bool is_skip = (l == g.skip);
         const int nprev = g.n_out[l - 1];
-        epi_for_chunks(e, 256, [&](int pass, int col, float (&v)[CW]) {
-          if (is_skip) {
+        const float scale = is_skip ? PSN_INV_SQRT2 * PSN_INV_U16 : PSN_INV_U16;
+        epi_for_chunks(s, e, [&](int pass, int col, float (&v)[CW]) {
+          if (is_skip && col + CW > nprev) {  // encoding part of the skip input: contributes J_pe^T directly
 #pragma unroll
-            for (int i = 0; i < CW; ++i) v[i] *= PSN_INV_SQRT2;
-            if (col + CW > nprev) {  // encoding part of the skip input: contributes J_pe^T directly
-#pragma unroll 1
-              for (int i = 0; i < CW; ++i) {
-                const int k = col + i - nprev;
-                if (k >= 0 && k < g.pe_dim) {
-                  int cc;
-                  const float jv = pe_jac(x, k, &cc);
-                  float vi = 0.f;
-#pragma unroll
-                  for (int u = 0; u < CW; ++u) vi = (u == i) ? v[u] : vi;
-                  const float t = jv * vi;
-                  g_acc[0] += cc == 0 ? t : 0.f; g_acc[1] += cc == 1 ? t : 0.f; g_acc[2] += cc == 2 ? t : 0.f;
-                }
+            for (int i = 0; i < CW; ++i) {
+              const int k = col + i - nprev;
+              if (k >= 0 && k < g.pe_dim) {
+                int cc;
+                const float t = pe_jac_tab(s, row, k, &cc) * (v[i] * PSN_INV_SQRT2);
+                g_acc[0] += cc == 0 ? t : 0.f; g_acc[1] += cc == 1 ? t : 0.f; g_acc[2] += cc == 2 ? t : 0.f;
               }
             }
           }
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {  // the L2 latency of the stash is covered by the other epilogue warps of the scheduler
-            const float4 q = stash[(size_t)((l - 1) * 64 + (col >> 2) + t) * TILE_M + row];
-            v[4 * t] *= q.x; v[4 * t + 1] *= q.y; v[4 * t + 2] *= q.z; v[4 * t + 3] *= q.w;
+          for (int t = 0; t < 2; ++t) {  // the L2 latency of the stash is covered by the other epilogue warps of the scheduler
+            const uint4 q = __ldcg(&stash[(size_t)((l - 1) * 32 + (col >> 3) + t) * TILE_M + row]);
+            float sg[8];
+            dq16_pair(q.x, sg[0], sg[1]); dq16_pair(q.y, sg[2], sg[3]); dq16_pair(q.z, sg[4], sg[5]); dq16_pair(q.w, sg[6], sg[7]);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[8 * t + u] = (v[8 * t + u] * scale) * sg[u];
           }
           if (col + CW > nprev) {
 #pragma unroll
             for (int i = 0; i < CW; ++i)
               if (col + i >= nprev) v[i] = 0.f;
           }
-          epi_store_a16(s, row, col, v);
+          epi_store_a16(e, e.d_col0(), col, v);
           epi_signal_a(s, pass);
         });
         e.step_ctr++;
@@ -199,78 +222,70 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
       if (sub * CW < g.pe_dim) {  // d logit / d pe: columns 0..pe_dim-1 of this step, 16 per sub
         float v[CW];
         epi_load16(e, sub * CW, v);
-#pragma unroll 1
+#pragma unroll
         for (int i = 0; i < CW; ++i) {
           const int k = sub * CW + i;
           if (k < g.pe_dim) {
             int cc;
-            const float jv = pe_jac(x, k, &cc);
-            float vi = 0.f;
-#pragma unroll
-            for (int u = 0; u < CW; ++u) vi = (u == i) ? v[u] : vi;
-            const float t = jv * vi;
+            const float t = pe_jac_tab(s, row, k, &cc) * v[i];
             g_acc[0] += cc == 0 ? t : 0.f; g_acc[1] += cc == 1 ? t : 0.f; g_acc[2] += cc == 2 ? t : 0.f;
           }
         }
       }
       e.step_ctr++;
       tc_fence_before();
-      float4* stage = reinterpret_cast<float4*>(epi_stage(s));  // [4 subs][128 rows] (g_acc.xyz, logit partial)
-      stage[sub * TILE_M + row] = make_float4(g_acc[0], g_acc[1], g_acc[2], part);
+      s.stage[sub * TILE_M + row] = make_float4(g_acc[0], g_acc[1], g_acc[2], part);
       named_bar_sync(1, EPI_THREADS);
-      float gr[3] = {0.f, 0.f, 0.f};
-      float logit = 0.f;
-      if (sub == 0) {
-        const float4 a0 = stage[row], a1 = stage[TILE_M + row], a2 = stage[2 * TILE_M + row], a3 = stage[3 * TILE_M + row];
+      float gr[3], logit;
+      {  // fixed summation order => bit-reproducible; every sub needs the gradient for its share of the next operand
+        const float4 a0 = s.stage[row], a1 = s.stage[TILE_M + row], a2 = s.stage[2 * TILE_M + row], a3 = s.stage[3 * TILE_M + row];
         gr[0] = ((a0.x + a1.x) + (a2.x + a3.x)) / g.rescale;
         gr[1] = ((a0.y + a1.y) + (a2.y + a3.y)) / g.rescale;
         gr[2] = ((a0.z + a1.z) + (a2.z + a3.z)) / g.rescale;
         logit = ((a0.w + a1.w) + (a2.w + a3.w)) + __ldg(g.b_logit);
-        if (grad_out && idx < M) { grad_out[idx * 3] = gr[0]; grad_out[idx * 3 + 1] = gr[1]; grad_out[idx * 3 + 2] = gr[2]; }
       }
-      named_bar_sync(1, EPI_THREADS);  // staging area read before anybody rewrites the A buffer
+      if (sub == 0 && grad_out && idx < M) { grad_out[idx * 3] = gr[0]; grad_out[idx * 3 + 1] = gr[1]; grad_out[idx * 3 + 2] = gr[2]; }
       if (g.with_app) {
-        if (sub == 0) {  // [p, PE(view/|view|), gradient] -> K block 0 (network.py:98,127-132)
+        {  // [p, PE(view/|view|), gradient, 0...] -> K block 0, 16 columns per sub (network.py:98,127-132)
           const float nv = sqrtf(vd[0] * vd[0] + vd[1] * vd[1] + vd[2] * vd[2]);
           const float vn[3] = {vd[0] / nv, vd[1] / nv, vd[2] / nv};
           const int o_g = 3 + g.pe_view_dim;
-#pragma unroll 1
-          for (int k = 0; k < KBLK; ++k) {
+          float v[CW];
+#pragma unroll
+          for (int i = 0; i < CW; ++i) {
+            const int k = sub * CW + i;
             float val = 0.f;
             if (k < 3) val = (k == 0 ? p[0] : (k == 1 ? p[1] : p[2]));
             else if (k < o_g) val = pe_entry_r(vn, k - 3);
             else if (k < o_g + 3) val = (k == o_g ? gr[0] : (k == o_g + 1 ? gr[1] : gr[2]));
-            epi_store_a1(s, row, k, val);
+            v[i] = val;
           }
+          epi_store_a16(e, e.a_col0(), sub * CW, v);
           epi_signal_a(s, 0);
-        } else {
-          epi_signal_a(s, 0);  // the other three arrival groups of K block 0 (sub 0 wrote all 64 columns)
         }
         // ---- s18: appearance layer 0 (rest) + parked + bias, ReLU ------------------------------------------------------------
-        epi_wait_d(s, e);
-        epi_for_chunks(e, 256, [&](int pass, int col, float (&v)[CW]) {
+        epi_for_chunks(s, e, [&](int pass, int col, float (&v)[CW]) {
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
-            const float4 pk = parked[(size_t)((col >> 2) + t) * TILE_M + row];
+            const float4 pk = __ldcg(&parked[(size_t)((col >> 2) + t) * TILE_M + row]);
             v[4 * t] += pk.x; v[4 * t + 1] += pk.y; v[4 * t + 2] += pk.z; v[4 * t + 3] += pk.w;
           }
           add_bias16(v, g.abias[0], col);
 #pragma unroll
           for (int i = 0; i < CW; ++i) v[i] = fmaxf(v[i], 0.f);
-          epi_store_a16(s, row, col, v);
+          epi_store_a16(e, e.d_col0(), col, v);
           epi_signal_a(s, pass);
         });
         e.step_ctr++;
         // ---- s19..s21: appearance layers 1..3 -------------------------------------------------------------------------------
 #pragma unroll 1
         for (int l = 1; l <= 3; ++l) {
-          epi_wait_d(s, e);
           const float* bias = g.abias[l];
-          epi_for_chunks(e, 256, [&](int pass, int col, float (&v)[CW]) {
+          epi_for_chunks(s, e, [&](int pass, int col, float (&v)[CW]) {
             add_bias16(v, bias, col);
 #pragma unroll
             for (int i = 0; i < CW; ++i) v[i] = fmaxf(v[i], 0.f);
-            epi_store_a16(s, row, col, v);
+            epi_store_a16(e, e.d_col0(), col, v);
             epi_signal_a(s, pass);
           });
           e.step_ctr++;
@@ -337,14 +352,14 @@ static int make_tc_rad(const psn_mlp* geo, const psn_mlp* app, void* scratch, Tc
   a->octaves = geo->desc.octaves;
   a->pe_dim = 3 + 6 * geo->desc.octaves;
   a->rescale = geo->desc.rescale;
-  a->scratch = (float4*)scratch;
+  a->scratch = (uint4*)scratch;
   PSN_REQUIRE(a->skip >= 2 && a->skip <= 7 && geo->fwd[a->skip - 1].N + a->pe_dim == 256, PSN_ERR_SHAPE,
               "tensor path: the skip layer input must be exactly 256 wide");
   return PSN_OK;
 }
 
 size_t tc_stash_bytes() {
-  const size_t tc = (size_t)num_ctas() * SCR_F4_PER_CTA * sizeof(float4);
+  const size_t tc = (size_t)num_ctas() * SCR_U4_PER_CTA * sizeof(uint4);
   const size_t si = simt_stash_bytes();
   return tc > si ? tc : si;
 }

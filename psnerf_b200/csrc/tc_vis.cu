@@ -92,7 +92,7 @@ k_tc_vis(TcVisArgs g, float* __restrict__ vis) {
   if (warp < EPI_WARP0) {
     regs_shrink_control();
     if (warp == 0 && lane == 0) producer_loop(s, g.prog, iters);
-    if (warp == 1 && lane == 0) mma_loop(s, g.prog, iters, tmem_base);
+    if (warp == 1) mma_loop(s, g.prog, iters, tmem_base);
     __syncwarp();
   } else {
     regs_grow_epilogue();
@@ -104,7 +104,7 @@ k_tc_vis(TcVisArgs g, float* __restrict__ vis) {
       const long long n = pb * TILE_M + row;
       const bool valid = n < g.Ns;
       const long long nn = valid ? n : g.Ns - 1;
-      // layer 0: relu(P0[n] + L0[l]) for this thread's four 16-column chunks
+      // layer 0: relu(P0[n] + L0[l]) for this thread's four 16-column chunks -> A operand of the first tensor step
 #pragma unroll 1
       for (int pass = 0; pass < 4; ++pass) {
         const int col = 64 * pass + CW * sub;
@@ -116,15 +116,14 @@ k_tc_vis(TcVisArgs g, float* __restrict__ vis) {
           v[4 * i + 0] = fmaxf(a.x + b.x, 0.f); v[4 * i + 1] = fmaxf(a.y + b.y, 0.f);
           v[4 * i + 2] = fmaxf(a.z + b.z, 0.f); v[4 * i + 3] = fmaxf(a.w + b.w, 0.f);
         }
-        epi_store_a16(s, row, col, v);
+        epi_store_a16(e, e.a_col0(), col, v);
         epi_signal_a(s, pass);
       }
       float part = 0.f;
 #pragma unroll 1
       for (int st = 0; st < 7; ++st) {
-        epi_wait_d(s, e);
         const float* bias = g.bias[st];
-        epi_for_chunks(e, 256, [&](int pass, int col, float (&v)[CW]) {
+        epi_for_chunks(s, e, [&](int pass, int col, float (&v)[CW]) {
           if (st == 4) {  // skip layer: + P5[n] (bias folded) + L5[l]
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -138,7 +137,7 @@ k_tc_vis(TcVisArgs g, float* __restrict__ vis) {
 #pragma unroll
           for (int i = 0; i < CW; ++i) v[i] = fmaxf(v[i], 0.f);
           if (st < 6) {
-            epi_store_a16(s, row, col, v);
+            epi_store_a16(e, e.d_col0(), col, v);
             epi_signal_a(s, pass);
           } else {
             const float4* w4 = reinterpret_cast<const float4*>(g.w_last + col);
@@ -153,12 +152,12 @@ k_tc_vis(TcVisArgs g, float* __restrict__ vis) {
         e.step_ctr++;
       }
       tc_fence_before();
-      float* stage = epi_stage(s);  // [4 subs][128 rows]
-      stage[sub * TILE_M + row] = part;
+      named_bar_sync(1, EPI_THREADS);  // every sub-0 warp has read the previous tile's staging area
+      s.stage[sub * TILE_M + row].x = part;
       named_bar_sync(1, EPI_THREADS);
       if (sub == 0 && valid)
-        vis[(long long)l * g.Ns + n] = ((stage[row] + stage[TILE_M + row]) + (stage[2 * TILE_M + row] + stage[3 * TILE_M + row])) + __ldg(g.b_last);
-      named_bar_sync(1, EPI_THREADS);
+        vis[(long long)l * g.Ns + n] = ((s.stage[row].x + s.stage[TILE_M + row].x) + (s.stage[2 * TILE_M + row].x + s.stage[3 * TILE_M + row].x)) +
+                                       __ldg(g.b_last);
     }
   }
   teardown(tmem_base);

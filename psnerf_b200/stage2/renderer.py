@@ -133,11 +133,12 @@ class PSNetwork(nn.Module):
         return engine.default_precision() if self.precision is None else {"fp32": B.PREC_FP32, "tc": B.PREC_TC}[self.precision]
 
     def forward(self, input, albedo_new=None, basis_new=None, noise=None):
-        """Inference (no autograd graph) unless gradients are enabled and a parameter / the lights require them, in which case
-        the differentiable train-step path (psn_s2_train_forward / _backward, stage2/train.py) runs."""
+        """Inference (no autograd graph) unless the module is in train() mode, gradients are enabled and a parameter / the
+        lights require them, in which case the differentiable train-step path (psn_s2_train_forward / _backward,
+        stage2/train.py) runs.  eval() always takes the inference kernels (stage2/eval.py calls model.eval())."""
         if next(self.parameters()).device.type != "cuda":
             raise RuntimeError("psnerf_b200: PSNetwork must live on a CUDA device (no CPU fallback)")
-        wants_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters()) or
+        wants_grad = self.training and torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters()) or
                                                   (torch.is_tensor(input.get("light_direction")) and input["light_direction"].requires_grad))
         if wants_grad:
             return self._forward_train(input, noise)
