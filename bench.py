@@ -341,16 +341,20 @@ def main():
         roof = None
         if rad:
             tf = rad["rows_per_launch"] * MFLOP_RAD * 1e6 / (rad["ms_per_launch"] * 1e-3) / 1e12
-            traffic = None  # dram read+write bytes per launch of this kernel on this workload, from the committed ncu capture
+            traffic, traffic_src = None, None  # dram read+write bytes per launch of this kernel on this workload (committed ncu capture)
             try:
-                with open(os.path.join(ROOT, "profiles", "r1_ncu_final.json")) as f:
-                    traffic = json.load(f)["radiance"]["metrics"]["dram_bytes_total"] if precision == "tc" else None
+                cands = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.startswith("r1_ncu_v") and f.endswith(".json"))
+                with open(os.path.join(ROOT, "profiles", cands[-1])) as f:
+                    caps = [c for c in json.load(f) if "k_tc_rad" in c["kernel"]]
+                big = max(caps, key=lambda c: c["metrics"]["gpu__time_duration.sum"]["value"])
+                traffic, traffic_src = (big["dram_bytes_total"], cands[-1]) if precision == "tc" else (None, None)
             except Exception:
                 pass
             roof = {"bound": "tensor", "kernel": "radiance (geo fwd + analytic normal + app MLP), %s path" % precision,
                     "achieved": tf, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": tf / peaks["tflops"], "traffic": traffic,
-                    "traffic_note": "ncu --set full, profiles/r1_ncu_final.json: dominated by the fp32 sigma' stash of the analytic-normal "
-                                    "pass (8 KB/sample written + read; algorithmic I/O is 20 B/sample); DRAM is at 22 % of peak, not the limiter",
+                    "traffic_note": "ncu --set full, profiles/%s: the unorm16 sigma' stash + fp32 parked partial of the analytic-normal pass "
+                                    "(5 KB/sample written, re-read from L2; algorithmic I/O is 20 B/sample); DRAM stays below 15 %% of peak"
+                                    % traffic_src,
                     "peak_source": peaks["src"], "flops_per_row": MFLOP_RAD * 1e6,
                     "issued_frac": (3.0 * tf / peaks["tflops"]) if precision == "tc" else None}
             occ = kern.get("occ_march")

@@ -285,8 +285,9 @@ __device__ __forceinline__ void producer_loop(const Smem& s, const Program& prog
 // ptxas then emits straight-line UTCHMMA sequences.  (Issuing from an `if (lane == 0)` branch instead wraps EVERY UTCHMMA
 // in an ELECT / BRA.U.ANY retry loop plus per-instruction descriptor arithmetic: the clock64 timeline showed ~86 cycles per
 // issue, which made the N = 64 MMAs of the split tail issue-bound.)
-// trace (optional, bring-up tool): for CTA 0, tile iteration TRACE_ITER the elected lane stores clock64() after every a_ready
-// wait (slot st*8 + kb) and after the step's last commit has been issued (slot st*8 + 7).
+// trace (optional, bring-up tool): for CTA 0, tile iteration TRACE_ITER the elected lane stores clock64() of every passed
+// a_ready wait (slot st*8 + kb), the cycles the step spent waiting for activations / weight stages (slots +4 / +5) and the
+// time the step's last commit was issued (slot st*8 + 7).
 constexpr int TRACE_ITER = 3;
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -312,9 +313,12 @@ __device__ __forceinline__ void mma_loop(const Smem& s, const Program& prog, lon
       const uint32_t d_addr = tmem_base + buf * 256u;           // accumulator of this step
       const uint32_t a_addr = tmem_base + (buf ^ 1u) * 256u;    // its A operand = the previous step's accumulator, converted in place
       const uint32_t idesc = umma_idesc(sp.n_pad);
+      long long t_wait_a = 0, t_wait_w = 0;  // bring-up trace only (dead code otherwise)
       for (int kb = 0; kb < sp.nkb; ++kb) {
+        const long long tw0 = trace ? clock64() : 0;
         mbar_wait(&s.c->a_ready[kb], (a_phase >> kb) & 1u);
         a_phase ^= (1u << kb);
+        const long long tw1 = trace ? clock64() : 0;
         const uint32_t a_kb = a_addr + (uint32_t)kb * 64u;
         // this K block's two weight stages (hi tile, lo tile)
         const uint32_t st_hi = stage, ph_hi = phase;
@@ -324,9 +328,14 @@ __device__ __forceinline__ void mma_loop(const Smem& s, const Program& prog, lon
         mbar_wait(&s.c->w_full[st_hi], ph_hi);
         mbar_wait(&s.c->w_full[st_lo], ph_lo);
         tc_fence_after();
+        if (trace) { t_wait_a += tw1 - tw0; t_wait_w += clock64() - tw1; }
         const uint32_t lo_hi = umma_desc_lo(w_base + st_hi * W_STAGE_BYTES), lo_lo = umma_desc_lo(w_base + st_lo * W_STAGE_BYTES);
         if (elect_one()) {
-          if (trace && it == TRACE_ITER && blockIdx.x == 0) trace[st * 8 + kb] = clock64();
+          if (trace && it == TRACE_ITER && blockIdx.x == 0) {
+            trace[st * 8 + kb] = tw1;
+            trace[st * 8 + 4] = t_wait_a;  // cycles this step spent waiting for activations ...
+            trace[st * 8 + 5] = t_wait_w;  // ... and for weight stages
+          }
           if (kb + 1 < sp.nkb) {
             // A_hi W_hi + A_lo W_hi + A_hi W_lo over the four K-steps of the block, all N columns
 #pragma unroll
@@ -487,6 +496,9 @@ __device__ __forceinline__ float pe_jac_tab(const Smem& s, int row, int k, int* 
 // softplus(beta=100) on pre-scaled accumulators: zs = 100*log2(e)*z  ->  softplus(z) = c * max(zs, lg2(1 + 2^min(zs,40))),
 // c = ln2/100 (times any layer constant).  2 MUFU + 4 ALU ops; for zs > ~25 the lg2 term equals zs in fp32, so the max
 // reproduces PyTorch's linear branch (threshold 20) to <1e-9 without a compare/select.
+// (Measured alternative, profiles/README.md: one MUFU + a degree-6 FMA-pipe polynomial for lg2(1 + u) halves the XU load but
+// costs five more issue slots per activation; with the epilogue warps sharing schedulers with the MMA / producer warps the
+// march kernel got 6 % slower, so the two-MUFU form stays.)
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }

@@ -27,10 +27,11 @@ torch.cuda.synchronize()
 t = trace.cpu().tolist()
 t0 = min(x for x in t if x > 0)
 rel = lambda x: (x - t0) if x > 0 else -1
-print("layer | MMA: a_ready kb0 kb1 kb2 kb3 | commit || epilogue sub0: wake p0 p1 p2 p3 | sub3: wake p0 p1 p2 p3")
+print("layer | MMA: a_ready kb0 kb1 kb2 kb3 | commit | wait_a wait_w || epilogue sub0: wake p0 p1 p2 p3 | sub3: wake p0 p1 p2 p3")
 for l in range(8):
     mm = [rel(t[l * 8 + k]) for k in range(4)]
     cm = rel(t[l * 8 + 7])
     e0 = [rel(t[64 + 0 * 40 + l * 5 + k]) for k in range(5)]
     e3 = [rel(t[64 + 3 * 40 + l * 5 + k]) for k in range(5)]
-    print("%5d | %6d %6d %6d %6d | %6d || %6d %6d %6d %6d %6d | %6d %6d %6d %6d %6d" % (l, *mm, cm, *e0, *e3))
+    print("%5d | %6d %6d %6d %6d | %6d | %6d %6d || %6d %6d %6d %6d %6d | %6d %6d %6d %6d %6d" %
+          (l, *mm, cm, t[l * 8 + 4], t[l * 8 + 5], *e0, *e3))
