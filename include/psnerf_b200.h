@@ -153,6 +153,16 @@ int psn_shade_stage2(const psn_mlp* normal_net, const psn_mlp* albedo_net, const
                      float* rgb, float* spec, float* vis, float* normal, float* albedo, float* sgw,
                      void* ws, int64_t ws_bytes, int precision, void* stream);
 
+/* Material editing (stage2/eval.py:116-132, renderer.py:167-168,175-181): psn_shade_stage2 with the albedo of every surface
+ * point replaced by albedo_new[3] and / or its SG weights by weights_new[nbt] (device pointers, either may be NULL). */
+int psn_shade_stage2_edit(const psn_mlp* normal_net, const psn_mlp* albedo_net, const psn_mlp* rough_net,
+                          const psn_mlp* vis_net, const float* lobe, const psn_shade_params* prm,
+                          const float* pts, const float* view, const float* normal_in, const int32_t* pix,
+                          int64_t Ns, int64_t N, const float* lights /*[L,3]*/, int L, const float* intensity,
+                          const float* albedo_new, const float* weights_new,
+                          float* rgb, float* spec, float* vis, float* normal, float* albedo, float* sgw,
+                          void* ws, int64_t ws_bytes, int precision, void* stream);
+
 /* Per-point stage-2 nets only (albedo / rough evaluated at jittered points, renderer.py:211-231): outputs are
  * per surface point: albedo[Ns,3] (sigmoid), weights[Ns,nbt] (relu). */
 int psn_s2_point_nets(const psn_mlp* albedo_net, const psn_mlp* rough_net, int n_freqs, const float* pts,

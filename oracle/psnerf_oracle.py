@@ -458,11 +458,12 @@ def camera_params(uv, pose, intrinsics):
     return F.normalize(dirs, dim=2), cam_loc
 
 
-def psnetwork_forward(sd, conf, inp, noise=None):
+def psnetwork_forward(sd, conf, inp, noise=None, albedo_new=None, basis_new=None):
     """PSNetwork.forward for the shipped configuration family (renderer.py:110-266):
     render_model=sgbasis, shape_pregen, normal_mlp, visibility.  ``conf`` is a flat dict
     (see psnerf_b200.synth.stage2_conf).  ``noise`` optionally supplies 'xyz' [Ns,3] N(0,1) samples
-    (scaled by xyz_jitter_std) in place of torch.normal (renderer.py:212).
+    (scaled by xyz_jitter_std) in place of torch.normal (renderer.py:212).  ``albedo_new`` ([3]) / ``basis_new`` (lobe index)
+    are the material-editing overrides of stage2/eval.py:116-132 (renderer.py:167-168,175-181).
     """
     nb = int(conf.get("train.nbasis", 9))
     spec_rgb = bool(conf.get("train.specular_rgb", False))
@@ -499,7 +500,13 @@ def psnetwork_forward(sd, conf, inp, noise=None):
         pemb = embed(surf, nf)
         albedo = s2_mlp(sd, "albedo_net", pemb, [int(conf["brdf.net.mlp_skip_at"])], "sigmoid")
         rough = s2_mlp(sd, "rough_net", pemb, [int(conf.get("brdf.sgnet.mlp_skip_at", 2))], None)
+        if albedo_new is not None:  # renderer.py:167-168
+            albedo = torch.as_tensor(albedo_new, dtype=dt)[None].expand_as(albedo)
         weights = torch.relu(rough)
+        if basis_new is not None:  # renderer.py:175-181: a single lobe with weight 2^k/100 in every colour channel
+            wn = torch.zeros_like(weights)
+            wn.view(-1, 3 if spec_rgb else 1, nb)[:, :, basis_new] = 2 ** basis_new / 100
+            weights = wn.reshape(-1, nbt)
         if L > 1:
             brdf, spec = sg_basis(sd["sgbasis.lobe"], v.tile(L, 1), normal.tile(L, 1), l, albedo.tile(L, 1),
                                   weights.tile(L, 1), spec_rgb, nb)
@@ -572,6 +579,35 @@ def normal_loss(out, normal_weight=1.0):
         return torch.zeros((), dtype=out["normal_pred"].dtype)
     gt = F.normalize(out["normal_values"], dim=-1)
     return normal_weight * F.mse_loss(out["normal_pred"][mask].reshape(-1, 3), gt[mask].reshape(-1, 3))
+
+
+def latlong_light_grid(envmap_h, envmap_w, envmap_radius=1.0):
+    """gen_light_xyz + sph2cart (stage2/utils/eval_utils.py:64-99,255-296): lat-long texel centres, poles excluded."""
+    lat_step = np.pi / (envmap_h + 2)
+    lng_step = 2 * np.pi / (envmap_w + 2)
+    lats = np.linspace(np.pi / 2 - lat_step, -np.pi / 2 + lat_step, envmap_h)
+    lngs = np.linspace(np.pi - lng_step, -np.pi + lng_step, envmap_w)
+    lngs, lats = np.meshgrid(lngs, lats)
+    z = envmap_radius * np.sin(lats)
+    x = envmap_radius * np.cos(lats) * np.cos(lngs)
+    y = envmap_radius * np.cos(lats) * np.sin(lngs)
+    sin_colat = np.sin(np.pi / 2 - lats)
+    return np.stack((x, y, z), -1).reshape(-1, 3), (4 * np.pi * sin_colat / np.sum(sin_colat)).reshape(-1)
+
+
+def envmap_relight(sd, conf, inp, env_light, light_xyz, light_batch=64):
+    """Envmap relighting loop of stage2/eval.py:196-219: per-light renders summed and clipped, visibility averaged."""
+    rgbs, viss = [], []
+    env_light = torch.as_tensor(env_light).float().reshape(-1, 3)
+    xyz = torch.as_tensor(light_xyz).float().reshape(-1, 3)
+    for s in range(0, xyz.shape[0], light_batch):
+        i2 = dict(inp)
+        i2["light_direction"] = F.normalize(xyz[s:s + light_batch], p=2, dim=-1)
+        i2["light_intensity"] = env_light[s:s + light_batch]
+        out = psnetwork_forward(sd, conf, i2)
+        rgbs.append(out["sg_rgb_values"].numpy())
+        viss.append(out["visibility"].numpy())
+    return {"rgb": torch.from_numpy(np.concatenate(rgbs, 0).sum(0).clip(0, 1)), "visibility": torch.from_numpy(np.concatenate(viss, 0).mean(0))}
 
 
 def split_input(model_input, total_pixels, n_pixels=1024):

@@ -84,6 +84,8 @@ def load():
     lib.psn_shadow_visibility.argtypes = [vp, vp, vp, i64, i32, f32, f32, i32, f32, vp, vp, i64, i32, vp]
     lib.psn_shade_stage2.argtypes = [vp, vp, vp, vp, vp, C.POINTER(ShadeParams), vp, vp, vp, vp, i64, i64, vp, i32,
                                      vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, vp]
+    lib.psn_shade_stage2_edit.argtypes = [vp, vp, vp, vp, vp, C.POINTER(ShadeParams), vp, vp, vp, vp, i64, i64, vp, i32,
+                                          vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, vp]
     lib.psn_s2_point_nets.argtypes = [vp, vp, i32, vp, i64, vp, vp, i32, i32, vp]
     lib.psn_s2_visibility.argtypes = [vp, i32, vp, i64, vp, i32, vp, vp, i64, i32, vp]
     lib.psn_tc_debug_layer.argtypes = [vp, vp, i64, i32, vp, vp, vp]

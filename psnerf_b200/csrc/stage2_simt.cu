@@ -360,11 +360,44 @@ extern "C" int psn_s2_visibility(const psn_mlp* vis_net, int n_freqs, const floa
   return s2_visibility_simt(vis_net, n_freqs, pts, Ns, lights, L, vis, (cudaStream_t)stream);
 }
 
+// dst[i, :] = src[:] for i < rows (material editing: one albedo / one SG weight vector for every surface point)
+__global__ void k_broadcast_row(const float* __restrict__ src, int width, long long rows, float* __restrict__ dst) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < rows * width) dst[i] = src[i % width];
+}
+
+static int shade_stage2_impl(const psn_mlp* normal_net, const psn_mlp* albedo_net, const psn_mlp* rough_net,
+                             const psn_mlp* vis_net, const float* lobe, const psn_shade_params* prm, const float* pts,
+                             const float* view, const float* normal_in, const int32_t* pix, int64_t Ns, int64_t N,
+                             const float* lights, int L, const float* intensity, const float* albedo_new, const float* weights_new,
+                             float* rgb, float* spec, float* vis, float* normal, float* albedo, float* sgw, void* ws, int64_t ws_bytes,
+                             int precision, void* stream);
+
 extern "C" int psn_shade_stage2(const psn_mlp* normal_net, const psn_mlp* albedo_net, const psn_mlp* rough_net,
                                 const psn_mlp* vis_net, const float* lobe, const psn_shade_params* prm, const float* pts,
                                 const float* view, const float* normal_in, const int32_t* pix, int64_t Ns, int64_t N,
                                 const float* lights, int L, const float* intensity, float* rgb, float* spec, float* vis,
                                 float* normal, float* albedo, float* sgw, void* ws, int64_t ws_bytes, int precision, void* stream) {
+  return shade_stage2_impl(normal_net, albedo_net, rough_net, vis_net, lobe, prm, pts, view, normal_in, pix, Ns, N, lights, L, intensity,
+                           nullptr, nullptr, rgb, spec, vis, normal, albedo, sgw, ws, ws_bytes, precision, stream);
+}
+
+extern "C" int psn_shade_stage2_edit(const psn_mlp* normal_net, const psn_mlp* albedo_net, const psn_mlp* rough_net,
+                                     const psn_mlp* vis_net, const float* lobe, const psn_shade_params* prm, const float* pts,
+                                     const float* view, const float* normal_in, const int32_t* pix, int64_t Ns, int64_t N,
+                                     const float* lights, int L, const float* intensity, const float* albedo_new,
+                                     const float* weights_new, float* rgb, float* spec, float* vis, float* normal, float* albedo,
+                                     float* sgw, void* ws, int64_t ws_bytes, int precision, void* stream) {
+  return shade_stage2_impl(normal_net, albedo_net, rough_net, vis_net, lobe, prm, pts, view, normal_in, pix, Ns, N, lights, L, intensity,
+                           albedo_new, weights_new, rgb, spec, vis, normal, albedo, sgw, ws, ws_bytes, precision, stream);
+}
+
+static int shade_stage2_impl(const psn_mlp* normal_net, const psn_mlp* albedo_net, const psn_mlp* rough_net,
+                             const psn_mlp* vis_net, const float* lobe, const psn_shade_params* prm, const float* pts,
+                             const float* view, const float* normal_in, const int32_t* pix, int64_t Ns, int64_t N,
+                             const float* lights, int L, const float* intensity, const float* albedo_new, const float* weights_new,
+                             float* rgb, float* spec, float* vis, float* normal, float* albedo, float* sgw, void* ws, int64_t ws_bytes,
+                             int precision, void* stream) {
   PSN_REQUIRE(albedo_net && rough_net && lobe && prm && lights && rgb && spec && albedo && sgw, PSN_ERR_ARG,
               "psn_shade_stage2: null argument");
   PSN_REQUIRE(Ns == 0 || (pts && view && pix), PSN_ERR_ARG, "psn_shade_stage2: null surface inputs");
@@ -390,6 +423,14 @@ extern "C" int psn_shade_stage2(const psn_mlp* normal_net, const psn_mlp* albedo
     if ((rc = s2_point_nets(normal_net, prm->n_freqs_normal, albedo_net, rough_net, prm->n_freqs_xyz, pts, Ns, n_s, a_s, w_s,
                             nbt, st)))
       return rc;
+  }
+  if (Ns > 0 && albedo_new) {  // renderer.py:167-168: every surface point gets the edited albedo
+    psn::count_launch();
+    k_broadcast_row<<<(unsigned)((Ns * 3 + 255) / 256), 256, 0, st>>>(albedo_new, 3, Ns, a_s);
+  }
+  if (Ns > 0 && weights_new) {  // renderer.py:175-181: ... and the edited SG weights
+    psn::count_launch();
+    k_broadcast_row<<<(unsigned)((Ns * nbt + 255) / 256), 256, 0, st>>>(weights_new, nbt, Ns, w_s);
   }
   if (vis_net) {
     ProfScope prof(PSN_PROF_S2_VIS, (long long)Ns * L, st);

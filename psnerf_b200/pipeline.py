@@ -3,6 +3,7 @@
   render_stage1_view   <- stage1/eval.py:82-119          (one library call per view instead of 256 x 1024-ray chunks)
   extract_shape        <- stage1/shape_extract.py:103-165 (points / normals / mask / per-light visibility of a view)
   render_stage2_view   <- stage2/eval.py:314-417          (all light batches of a view)
+  render_envmap_view   <- stage2/eval.py:173-231          (envmap relighting: RGB-intensity light grid, sum over lights)
   extract_and_shade    <- SURVEY.md §8f-1: stage-1 surface extraction feeding stage-2 shading directly, no .npy hand-off
   *_sharded            <- SURVEY.md §8e: rays of a view dealt over the ranks, one all_gather of pixels at the end
 
@@ -49,6 +50,34 @@ def render_stage2_view(model, model_input, light_dirs, light_batch=96, light_int
     for k in ("sg_rgb_values", "sg_specular_rgb_values", "visibility"):
         if k in res:
             res[k] = torch.cat([o[k] for o in outs], 0)
+    return res
+
+
+@torch.no_grad()
+def render_envmap_view(model, model_input, env_light, light_xyz, light_batch=64):
+    """Environment-map relighting of one view (stage2/eval.py:173-231): every texel of the (down-sampled) lat-long map is one
+    directional light with an RGB intensity; batches of `light_batch` lights go through PSNetwork.forward and the per-light
+    images are summed and clipped to [0, 1]; visibility is averaged over the lights.  env_light [Ld,3], light_xyz [Ld,3]
+    (synth.latlong_light_grid).  The sums are accumulated on the device in float64 (the reference concatenates every batch on
+    the host and sums there), so no [Ld, N, 3] stack ever exists."""
+    dev = next(model.parameters()).device
+    env_light = torch.as_tensor(env_light).float().reshape(-1, 3).to(dev)
+    dirs = torch.nn.functional.normalize(torch.as_tensor(light_xyz).float().reshape(-1, 3).to(dev), p=2, dim=-1)
+    Ld = dirs.shape[0]
+    rgb_sum = vis_sum = None
+    for s in range(0, Ld, light_batch):
+        inp = dict(model_input)
+        inp["light_direction"] = dirs[s:s + light_batch]
+        inp["light_intensity"] = env_light[s:s + light_batch]
+        out = model(inp)
+        r = out["sg_rgb_values"].double().sum(0)
+        rgb_sum = r if rgb_sum is None else rgb_sum + r
+        if "visibility" in out:
+            v = out["visibility"].double().sum(0)
+            vis_sum = v if vis_sum is None else vis_sum + v
+    res = {"rgb": rgb_sum.clamp(0, 1).float()}
+    if vis_sum is not None:
+        res["visibility"] = (vis_sum / Ld).float()
     return res
 
 

@@ -197,8 +197,6 @@ class PSNetwork(nn.Module):
     def _forward_eval(self, input, albedo_new=None, basis_new=None, noise=None):
         if not self.shape_pregen:
             raise NotImplementedError("psnerf_b200: train.shape_pregen=False is not a shipped configuration")
-        if albedo_new is not None or basis_new is not None:
-            raise NotImplementedError("material editing (albedo_new / basis_new) is a 'next' row (SURVEY.md §8f-4)")
         dev = next(self.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("psnerf_b200: PSNetwork must live on a CUDA device (no CPU fallback)")
@@ -244,14 +242,23 @@ class PSNetwork(nn.Module):
         sgw = torch.empty(1, N, self.nbasis, device=dev)
         ws = engine.workspace(dev, "shade", max(N, Ns), 1, L)
         P = engine._ptr
+        # material editing (stage2/eval.py:116-132 -> renderer.py:167-168,175-181): one albedo / one SG weight vector for all points
+        a_new = w_new = None
+        if albedo_new is not None:
+            a_new = engine.f32c(torch.as_tensor(albedo_new).to(dev).reshape(3))
+        if basis_new is not None:
+            nb = self.nbasis_lobes
+            wn = torch.zeros(3 if self.specular_rgb else 1, nb)
+            wn[:, basis_new] = torch.as_tensor(2.0 ** torch.as_tensor(basis_new, dtype=torch.float64) / 100).float()
+            w_new = engine.f32c(wn.reshape(-1).to(dev))
         with torch.cuda.device(dev):
-            B.check(lib.psn_shade_stage2(
+            B.check(lib.psn_shade_stage2_edit(
                 P(self.normal_net.packed().handle) if self.normal_mlp else C.c_void_p(0),
                 P(self.albedo_net.packed().handle), P(self.rough_net.packed().handle),
                 P(self.visibility_net.packed().handle) if self.visibility else C.c_void_p(0),
                 P(engine.f32c(self.sgbasis.lobe.detach())), C.byref(prm), P(surf), P(view), P(nin), P(pix), Ns, N,
-                P(lights), L, P(iptr), P(rgb), P(spec), P(vis), P(normal), P(albedo), P(sgw), P(ws), ws.numel(),
-                self._prec(), engine._stream()), "psn_shade_stage2")
+                P(lights), L, P(iptr), P(a_new), P(w_new), P(rgb), P(spec), P(vis), P(normal), P(albedo), P(sgw), P(ws),
+                ws.numel(), self._prec(), engine._stream()), "psn_shade_stage2_edit")
         out = {"points": input["points"], "object_mask": input["object_mask"], "network_object_mask": input["surface_mask"],
                "sg_rgb_values": rgb, "normal_values": input["normal"], "sg_diffuse_albedo_values": albedo,
                "sg_specular_rgb_values": spec}

@@ -135,3 +135,20 @@ def stage2_input(h, w, n_lights, pose=None, all_surface=True, seed=3, mask_frac=
         "object_mask": smask.clone(), "surface_mask": smask, "points": pts, "normal": nrm,
         "light_direction": lights(n_lights),
     }
+
+
+def latlong_light_grid(envmap_h, envmap_w=None, radius=1.0):
+    """Directions (and solid-angle weights) of the centres of an envmap_h x envmap_w latitude-longitude environment map, poles
+    excluded - the light set of the envmap relighting mode (stage2/utils/eval_utils.py:64-99 via stage2/eval.py:109-111,
+    light_h = 16 -> 512 lights).  Returns float64 numpy-free torch tensors xyz [h*w, 3], areas [h*w]."""
+    envmap_w = 2 * envmap_h if envmap_w is None else envmap_w
+    lat_step = math.pi / (envmap_h + 2)
+    lng_step = 2 * math.pi / (envmap_w + 2)
+    lats = torch.linspace(math.pi / 2 - lat_step, -math.pi / 2 + lat_step, envmap_h, dtype=torch.float64)
+    lngs = torch.linspace(math.pi - lng_step, -math.pi + lng_step, envmap_w, dtype=torch.float64)
+    lat = lats[:, None].expand(envmap_h, envmap_w)
+    lng = lngs[None, :].expand(envmap_h, envmap_w)
+    xyz = torch.stack([radius * torch.cos(lat) * torch.cos(lng), radius * torch.cos(lat) * torch.sin(lng), radius * torch.sin(lat)], -1)
+    sin_colat = torch.sin(math.pi / 2 - lat)
+    areas = 4 * math.pi * sin_colat / sin_colat.sum()
+    return xyz.reshape(-1, 3), areas.reshape(-1)

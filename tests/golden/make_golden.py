@@ -140,6 +140,51 @@ def make_stage2():
     np.savez_compressed(os.path.join(HERE, "stage2_shade.npz"), **out)
 
 
+def make_stage2_edit():
+    """Material editing (albedo_new / basis_new, stage2/eval.py:116-132) and an envmap-style batch of RGB intensities
+    (stage2/eval.py:199-203) through the REAL reference PSNetwork."""
+    m2 = ref_loader.load_stage2()
+    conf = synth.stage2_conf()
+    torch.manual_seed(0)
+    model = m2.PSNetwork(ref_loader.DictConf(conf))
+    sd1 = synth.perturb_state_dict({k: v.clone() for k, v in model.state_dict().items()}, rel=0.5, seed=1)
+    model.load_state_dict(sd1)
+    out = {}
+    for cname, (albedo_new, basis_new) in EDIT_CASES.items():
+        inp = edit_case_input()
+        torch.manual_seed(123)
+        with torch.no_grad():
+            res = model(inp, albedo_new=None if albedo_new is None else np.asarray(albedo_new, np.float32), basis_new=basis_new)
+        for k in ("sg_rgb_values", "sg_specular_rgb_values", "visibility", "sg_diffuse_albedo_values", "sg_weight"):
+            out["%s_%s" % (cname, k)] = np_(res[k])
+    out["checksum"] = checksum(sd1)
+    # light grid of the envmap mode: gen_light_xyz / sph2cart taken from the reference file by name (the module itself imports
+    # cv2 / imageio, absent here), light_h = 16 as in stage2/eval.py:100
+    import ast
+    src = open("/root/reference/stage2/utils/eval_utils.py").read()
+    tree = ast.parse(src)
+    want = {"gen_light_xyz", "sph2cart", "_warn_degree", "_convert_sph_conventions"}
+    code = "\n\n".join(ast.get_source_segment(src, n) for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in want)
+    ns = {"np": np}
+    exec(code, ns)
+    xyz, areas = ns["gen_light_xyz"](16, 32, envmap_radius=1)
+    out["envgrid_xyz"] = xyz.reshape(-1, 3)
+    out["envgrid_areas"] = areas.reshape(-1)
+    np.savez_compressed(os.path.join(HERE, "stage2_edit.npz"), **out)
+
+
+# name: (albedo_new, basis_new); shared with tests/util.py
+EDIT_CASES = {"albedo": ([0.2, 0.55, 0.31], None), "basis": (None, 4), "both": ([0.05, 0.1, 0.4], 7)}
+
+
+def edit_case_input():
+    h, w, L = 12, 14, 5
+    inp = synth.stage2_input(h, w, L, all_surface=False, seed=33, mask_frac=0.5)
+    g = torch.Generator().manual_seed(8)
+    inp["light_intensity"] = torch.rand(L, 3, generator=g) * 2.0  # env_light[lstart:lend] is [L,3]
+    return inp
+
+
 def make_stage2_grads():
     """Gradients of the REAL reference's PSNetwork (autograd) for a train-like step: trainable light directions and per-light
     intensities, 2 vis-train lights, xyz jitter; scalar = sum of outputs against fixed cotangents (the reference's loss module
@@ -193,5 +238,6 @@ if __name__ == "__main__":
     make_stage1_render()
     make_stage2()
     make_stage2_grads()
-    for f in ("stage1_net", "stage1_render", "stage2_shade", "stage2_grads"):
+    make_stage2_edit()
+    for f in ("stage1_net", "stage1_render", "stage2_shade", "stage2_grads", "stage2_edit"):
         print(f, os.path.getsize(os.path.join(HERE, f + ".npz")) // 1024, "KB")

@@ -52,6 +52,21 @@ def test_shading_vs_golden(variant, case, prec):
 
 
 @pytest.mark.parametrize("prec", PRECISIONS)
+@pytest.mark.parametrize("case", list(util.EDIT_CASES))
+def test_material_editing_vs_golden(case, prec):
+    """albedo_new / basis_new (psn_shade_stage2_edit) with [L,3] intensities vs the real reference's outputs."""
+    conf, sds = util.stage2_state_dicts()
+    m = make_model(conf, sds["trained"], prec)
+    g = util.golden("stage2_edit")
+    albedo_new, basis_new = util.EDIT_CASES[case]
+    out = m(to_cuda(util.edit_case_input()), albedo_new=None if albedo_new is None else np.asarray(albedo_new, np.float32),
+            basis_new=basis_new)
+    for k in util.EDIT_KEYS:
+        assert tuple(out[k].shape) == g["%s_%s" % (case, k)].shape, k
+        assert util.max_abs(out[k].cpu(), g["%s_%s" % (case, k)]) < TOL[prec] * (5 if k == "visibility" else 1), k
+
+
+@pytest.mark.parametrize("prec", PRECISIONS)
 @pytest.mark.parametrize("hw,L,frac", [((40, 50), 7, 0.3), ((33, 31), 96, 0.9), ((10, 10), 2, 0.0)])
 def test_shading_vs_oracle(hw, L, frac, prec):
     conf, sds = util.stage2_state_dicts()

@@ -64,3 +64,16 @@ def stage2_case_input(cname):
     if cname == "full":
         inp["light_intensity"] = torch.tensor([[1.0, 2.0, 0.5], [3.0, 1.0, 1.0], [0.3, 0.6, 2.0]])
     return inp
+
+
+# material-editing cases of tests/golden/make_golden.py:make_stage2_edit -- name: (albedo_new, basis_new)
+EDIT_CASES = {"albedo": ([0.2, 0.55, 0.31], None), "basis": (None, 4), "both": ([0.05, 0.1, 0.4], 7)}
+EDIT_KEYS = ("sg_rgb_values", "sg_specular_rgb_values", "visibility", "sg_diffuse_albedo_values", "sg_weight")
+
+
+def edit_case_input():
+    h, w, L = 12, 14, 5
+    inp = synth.stage2_input(h, w, L, all_surface=False, seed=33, mask_frac=0.5)
+    g = torch.Generator().manual_seed(8)
+    inp["light_intensity"] = torch.rand(L, 3, generator=g) * 2.0
+    return inp
