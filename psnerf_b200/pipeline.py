@@ -3,6 +3,7 @@
   render_stage1_view   <- stage1/eval.py:82-119          (one library call per view instead of 256 x 1024-ray chunks)
   extract_shape        <- stage1/shape_extract.py:103-165 (points / normals / mask / per-light visibility of a view)
   render_stage2_view   <- stage2/eval.py:314-417          (all light batches of a view)
+  occupancy_grid_logits<- stage1/model/extracting.py:84-96,137-155 (dense -logit grid for mesh export)
   render_envmap_view   <- stage2/eval.py:173-231          (envmap relighting: RGB-intensity light grid, sum over lights)
   extract_and_shade    <- SURVEY.md §8f-1: stage-1 surface extraction feeding stage-2 shading directly, no .npy hand-off
   *_sharded            <- SURVEY.md §8e: rays of a view dealt over the ranks, one all_gather of pixels at the end
@@ -51,6 +52,24 @@ def render_stage2_view(model, model_input, light_dirs, light_batch=96, light_int
         if k in res:
             res[k] = torch.cat([o[k] for o in outs], 0)
     return res
+
+
+@torch.no_grad()
+def occupancy_grid_logits(model, nx, padding=0.0, points=None):
+    """Dense-grid query of the occupancy field for mesh export (stage1/model/extracting.py:84-96,137-155 with
+    common.py:253-272): value_grid[nx,nx,nx] = model(p, return_logits=True) = -logit on the box_size * [-0.5, 0.5]^3 lattice,
+    box_size = 2 + padding; `points` ([M,3], e.g. the MISE query points already mapped into the box) replaces the lattice.
+    One library call on the device - the 100 000-point host round trips of Extractor3D.eval_points are gone; MISE / marching
+    cubes stay CPU code outside this package (SURVEY.md §2 #17-19)."""
+    dev = next(model.parameters()).device
+    if points is None:
+        box = 2.0 + padding
+        ax = torch.linspace(-0.5, 0.5, nx)  # float32 on the host exactly as make_3d_grid, then scaled
+        p = torch.stack([ax.view(-1, 1, 1).expand(nx, nx, nx), ax.view(1, -1, 1).expand(nx, nx, nx),
+                         ax.view(1, 1, -1).expand(nx, nx, nx)], -1).reshape(-1, 3)
+        vals = model((box * p).to(dev), None, return_logits=True).squeeze(-1)
+        return vals.reshape(nx, nx, nx)
+    return model(torch.as_tensor(points).float().to(dev), None, return_logits=True).squeeze(-1)
 
 
 @torch.no_grad()

@@ -84,3 +84,19 @@ def test_envmap_relighting_matches_oracle_loop(prec):
     tol = 2e-5 if prec == "fp32" else 2e-4
     assert util.max_abs(got["rgb"].cpu(), ref["rgb"]) < tol
     assert util.max_abs(got["visibility"].cpu(), ref["visibility"]) < 5 * tol
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tc"])
+def test_occupancy_grid_logits_vs_oracle(prec):
+    """Dense -logit lattice of the mesh-export path (extracting.py:84-96): 20^3 points (not a multiple of the 128-row tile)."""
+    cfg, sd, r, *_ = _models(prec)
+    nx, pad = 20, 0.1
+    grid = pipeline.occupancy_grid_logits(r.model, nx, padding=pad)
+    ax = torch.linspace(-0.5, 0.5, nx)
+    p = (2.0 + pad) * torch.stack(torch.meshgrid(ax, ax, ax, indexing="ij"), -1).reshape(-1, 3)
+    with torch.no_grad():
+        ref = O.network_forward(sd, cfg["model"], p, return_logits=True).reshape(nx, nx, nx)
+    assert grid.shape == (nx, nx, nx)
+    assert util.max_abs(grid.cpu(), ref) < (2e-5 if prec == "fp32" else 1e-4)
+    # the level set the mesh extractor thresholds (occupancy 0.5 <=> logit 0) has the same sign pattern
+    assert ((grid.cpu() > 0) == (ref > 0)).float().mean() > 0.999
