@@ -25,7 +25,7 @@ struct TcGeoArgs {
 constexpr int MODE_OUT = 0, MODE_SHADOW = 1, MODE_DEBUG = 2;  // MODE_DEBUG = MODE_OUT + layer dump / clock64 trace hooks
 
 template <int MODE>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 k_tc_occ(TcGeoArgs g, PointGen gen, long long M_host, const int* M_dev, int out_kind, float* out, float box, int dump_layer,
          float* dump, long long* trace) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -34,7 +34,7 @@ k_tc_occ(TcGeoArgs g, PointGen gen, long long M_host, const int* M_dev, int out_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long M = M_dev ? (long long)*M_dev : M_host;
   const long long n_tiles = (M + TILE_M - 1) / TILE_M;
-  const long long iters = (n_tiles > (long long)blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const long long iters = pair_iters(n_tiles);  // equal for both CTAs of the pair; surplus tiles are fully masked (idx >= M)
 
   if (warp < EPI_WARP0) {
     regs_shrink_control();
@@ -73,9 +73,10 @@ k_tc_occ(TcGeoArgs g, PointGen gen, long long M_host, const int* M_dev, int out_
         const bool pre_skip = (l + 1 == g.skip);
         const int n_out = g.n_out[l];
         const float cc = pre_skip ? PSN_SOFTPLUS_C * 0.70710678118654752440f : PSN_SOFTPLUS_C;
-        epi_for_chunks(s, e, [&](int pass, int col, float (&v)[CW]) {
+        epi_for_chunks_pf<Bias16>(s, e, [&](int col, Bias16& b) { load_bias16(bias, col, b); },
+                                  [&](int pass, int col, float (&v)[CW], const Bias16& b) {
           if (tr && pass == 0) trace[64 + sub * 40 + l * 5] = clock64();
-          add_bias16(v, bias, col);
+          add16(v, b.b);
 #pragma unroll
           for (int i = 0; i < CW; ++i) v[i] = softplus_scaled(v[i], cc);
           if (MODE == MODE_DEBUG) {
@@ -144,7 +145,7 @@ k_tc_occ(TcGeoArgs g, PointGen gen, long long M_host, const int* M_dev, int out_
           for (int off = 16; off > 0; off >>= 1) w += __shfl_xor_sync(0xffffffffu, w, off);
           if (lane == 0) s.c->g3[8 + q] = w;
           named_bar_sync(2, 128);
-          if (row == 0) out[tile] = 1.f - (s.c->g3[8] + s.c->g3[9] + s.c->g3[10] + s.c->g3[11]);
+          if (row == 0 && tile < n_tiles) out[tile] = 1.f - (s.c->g3[8] + s.c->g3[9] + s.c->g3[10] + s.c->g3[11]);
         }
       }
       // no trailing barrier: the staging area, the encoding table and g3 are next written after the next tile's encoding
@@ -155,6 +156,35 @@ k_tc_occ(TcGeoArgs g, PointGen gen, long long M_host, const int* M_dev, int out_
 }
 
 // ---- host -------------------------------------------------------------------------------------------------------------
+namespace tc {
+int tc_grid(const void* kernel, long long tiles) {
+  static int max_ctas = 0;  // one device per process
+  if (!max_ctas) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(num_ctas() & ~1));
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cudaLaunchAttribute at;
+    memset(&at, 0, sizeof(at));
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = CLUSTER; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+    cfg.attrs = &at;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) == cudaSuccess && n > 0) {
+      max_ctas = CLUSTER * n < (num_ctas() & ~1) ? CLUSTER * n : (num_ctas() & ~1);
+    } else {
+      (void)cudaGetLastError();
+      max_ctas = num_ctas() & ~1;
+    }
+  }
+  long long g = tiles < max_ctas ? tiles : max_ctas;
+  g = (g + 1) & ~1LL;
+  return (int)(g < CLUSTER ? CLUSTER : g);
+}
+}  // namespace tc
+
 static int make_tc_geo(const psn_mlp* geo, TcGeoArgs* a) {
   PSN_REQUIRE(geo && geo->kind == PSN_NET_GEO, PSN_ERR_ARG, "expected a PSN_NET_GEO handle");
   PSN_REQUIRE(geo->tc_ok, PSN_ERR_SHAPE,
@@ -190,7 +220,7 @@ static int launch_tc_occ(const TcGeoArgs& a, const PointGen& gen, long long M, c
     if (rcr) return rcr;
   }
   const long long tiles = M_dev ? (long long)num_ctas() : (M + TILE_M - 1) / TILE_M;
-  const int grid = (int)(tiles < num_ctas() ? tiles : num_ctas());
+  const int grid = tc_grid((const void*)k_tc_occ<MODE>, tiles);
   count_launch();
   k_tc_occ<MODE><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(a, gen, M, M_dev, out_kind, out, box, dump_layer, dump, trace);
   PSN_CUDA_CHECK(cudaGetLastError());

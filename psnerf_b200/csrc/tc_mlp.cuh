@@ -16,6 +16,12 @@
 // Shared memory: weight ring = 6 stages x 32 KB, each one pre-swizzled [N rows][64 K] K-major SWIZZLE_128B tile streamed
 // from L2 with cp.async.bulk (UBLKCP) + mbarrier complete_tx; a [40][128] fp32 point-encoding table; an 8 KB staging area.
 //
+// CTA pairs: the kernels launch as clusters of two CTAs (one TPC).  Both CTAs walk the same step program on different tiles, so
+// every weight tile is fetched from L2 ONCE per pair: CTA r issues the tiles with (tile index & 1) == r as a multicast bulk
+// copy that lands in both CTAs' rings and completes both CTAs' w_full barriers; a stage is refilled when BOTH MMA warps have
+// released it (tcgen05.commit multicast onto the w_empty barriers of the pair, 2 arrivals).  This halves the L2 -> SM weight
+// stream, which had become the limiter (clock64: ~1500 cycles / layer waiting for weight stages at 4 KB/clk chip-wide).
+//
 // Warp roles: warp 0 = TMEM allocator + weight producer (one lane), warp 1 = MMA issuer (one lane), warps 2-3 idle (the
 // control warpgroup releases registers with setmaxnreg.dec);
 // warps 4..19 = epilogue: warp w reads TMEM lanes 32*(w%4).. and is "sub" s = (w-4)/4 of its lane quadrant; in pass p sub s
@@ -43,6 +49,7 @@ constexpr int EPI_WARP0 = 4;
 constexpr int EPI_THREADS = 512;
 constexpr int EPI_SUBS = 4;       // epilogue warps per TMEM lane quadrant
 constexpr int CW = 16;            // columns per epilogue chunk: in pass p sub s owns columns [64 p + 16 s, +16)
+constexpr int CLUSTER = 2;             // CTAs per cluster sharing one weight stream (multicast)
 constexpr int A_READY_ARRIVALS = 16;   // a K block (64 columns) is written by the 16 epilogue warps in ONE pass; lane 0 of each arrives
 
 // ---- shared-memory control block (after the 1024-aligned A and W regions) ---------------------------------
@@ -94,6 +101,33 @@ __device__ __forceinline__ void mbar_wait_relaxed(void* bar, uint32_t parity) {
 // generic-proxy smem writes -> visible to the async proxy (UMMA operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+// all threads of both CTAs (also a CTA-wide barrier)
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// waits whose arrivals come from the other CTA of the pair (multicast tcgen05.commit)
+__device__ __forceinline__ bool mbar_try_wait_cluster(void* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(2000u)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster_relaxed(void* bar, uint32_t parity) {
+  while (!mbar_try_wait_cluster(bar, parity)) __nanosleep(32);
+}
+// bulk copy delivered to the same smem offset (and the same mbarrier offset) of every CTA in cta_mask
+__device__ __forceinline__ void bulk_g2s_multicast(void* smem_dst, const void* gmem_src, uint32_t bytes, void* bar, uint16_t cta_mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, void* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
                "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
@@ -127,6 +161,12 @@ __device__ __forceinline__ void umma_ts_f16(uint32_t tmem_d, uint32_t tmem_a, ui
       : "memory");
 }
 // arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed
+// same, arriving on the barrier at this offset in every CTA of cta_mask
+__device__ __forceinline__ void umma_commit_multicast(void* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
 __device__ __forceinline__ void umma_commit(void* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -152,6 +192,23 @@ __device__ __forceinline__ void tmem_ld32_wait(uint32_t (&r)[32]) {
                  "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
                  "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
                  "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+// issue / wait halves of the 16-column load: global loads placed between them overlap the TMEM read
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_wait(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
                :
                : "memory");
 }
@@ -210,6 +267,15 @@ inline int check_launch_regs(const void* kernel, const char* name) {
   return PSN_OK;
 }
 
+// Both CTAs of a pair must run the same number of tile iterations (they share every weight stage): the pair uses the count of
+// its even CTA, the odd one may get one masked dummy tile.  Round-robin tile assignment: tile = blockIdx.x + it * gridDim.x.
+__device__ __forceinline__ long long pair_iters(long long n_tiles) {
+  const long long b0 = (long long)(blockIdx.x & ~1u);
+  return n_tiles > b0 ? (n_tiles - b0 + gridDim.x - 1) / gridDim.x : 0;
+}
+// persistent grid: an even number of CTAs, at most 2 x the clusters the device can hold at once
+int tc_grid(const void* kernel, long long tiles);
+
 // ---- step table -------------------------------------------------------------------------------------------------
 struct Step {
   uint32_t w_off;  // byte offset (from the net's tile blob) of tile (kb=0, hi); tiles follow as [kb][hi, lo]
@@ -244,7 +310,7 @@ __device__ __forceinline__ Smem carve(unsigned char* raw) {
 __device__ __forceinline__ uint32_t setup(const Smem& s) {
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < W_STAGES; ++i) { mbar_init(&s.c->w_full[i], 1); mbar_init(&s.c->w_empty[i], 1); }
+    for (int i = 0; i < W_STAGES; ++i) { mbar_init(&s.c->w_full[i], 1); mbar_init(&s.c->w_empty[i], CLUSTER); }
     for (int i = 0; i < A_MAX_KB; ++i) mbar_init(&s.c->a_ready[i], A_READY_ARRIVALS);
     for (int i = 0; i < 2; ++i)
       for (int q = 0; q < 2; ++q) mbar_init(&s.c->d_q[i][q], 1);
@@ -252,28 +318,33 @@ __device__ __forceinline__ uint32_t setup(const Smem& s) {
   }
   if (warp == 0) tmem_alloc_512(&s.c->tmem_base);
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();  // barriers of BOTH CTAs are initialised before any multicast copy / commit can reach them
   tc_fence_after();
   return *reinterpret_cast<volatile uint32_t*>(&s.c->tmem_base);
 }
 __device__ __forceinline__ void teardown(uint32_t tmem_base) {
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();  // the peer's last multicast commits have landed on this CTA's barriers before its smem goes away
   if ((threadIdx.x >> 5) == 0) tmem_dealloc_512(tmem_base);
 }
 
 // ---- producer: stream every weight tile of `iters` tile-iterations through the ring (warp 0, lane 0) ------------------
+// Both CTAs of the pair run this loop over the same tile sequence; tile t is fetched (multicast) by CTA (t & 1).
 __device__ __forceinline__ void producer_loop(const Smem& s, const Program& prog, long long iters) {
   uint32_t stage = 0, phase = 0;
+  const uint32_t rank = cluster_ctarank();
+  uint32_t t_parity = 0;
   for (long long it = 0; it < iters; ++it) {
     for (int st = 0; st < prog.n_steps; ++st) {
       const Step sp = prog.step[st];
       const uint32_t tile_bytes = (uint32_t)sp.n_pad * 128u;
       const unsigned char* src = prog.blob[st] + sp.w_off;
-      for (int t = 0; t < 2 * sp.nkb; ++t) {
-        mbar_wait_relaxed(&s.c->w_empty[stage], phase ^ 1u);
-        mbar_arrive_expect_tx(&s.c->w_full[stage], tile_bytes);
-        bulk_g2s(s.w + stage * W_STAGE_BYTES, src + (size_t)t * tile_bytes, tile_bytes, &s.c->w_full[stage]);
+      for (int t = 0; t < 2 * sp.nkb; ++t, t_parity ^= 1u) {
+        mbar_wait_cluster_relaxed(&s.c->w_empty[stage], phase ^ 1u);     // released by the MMA warps of both CTAs
+        mbar_arrive_expect_tx(&s.c->w_full[stage], tile_bytes);          // this CTA's copy of the tile
+        if (t_parity == rank)
+          bulk_g2s_multicast(s.w + stage * W_STAGE_BYTES, src + (size_t)(t ^ 1) * tile_bytes, tile_bytes, &s.c->w_full[stage],
+                             (uint16_t)((1u << CLUSTER) - 1u));  // ring order per K block: lo tile, then hi tile (blob: hi, lo)
         if (++stage == W_STAGES) { stage = 0; phase ^= 1u; }
       }
     }
@@ -320,13 +391,13 @@ __device__ __forceinline__ void mma_loop(const Smem& s, const Program& prog, lon
         a_phase ^= (1u << kb);
         const long long tw1 = trace ? clock64() : 0;
         const uint32_t a_kb = a_addr + (uint32_t)kb * 64u;
-        // this K block's two weight stages (hi tile, lo tile)
-        const uint32_t st_hi = stage, ph_hi = phase;
-        if (++stage == W_STAGES) { stage = 0; phase ^= 1u; }
+        // this K block's two weight stages (lo tile first: it is consumed - and released - first)
         const uint32_t st_lo = stage, ph_lo = phase;
         if (++stage == W_STAGES) { stage = 0; phase ^= 1u; }
-        mbar_wait(&s.c->w_full[st_hi], ph_hi);
+        const uint32_t st_hi = stage, ph_hi = phase;
+        if (++stage == W_STAGES) { stage = 0; phase ^= 1u; }
         mbar_wait(&s.c->w_full[st_lo], ph_lo);
+        mbar_wait(&s.c->w_full[st_hi], ph_hi);
         tc_fence_after();
         if (trace) { t_wait_a += tw1 - tw0; t_wait_w += clock64() - tw1; }
         const uint32_t lo_hi = umma_desc_lo(w_base + st_hi * W_STAGE_BYTES), lo_lo = umma_desc_lo(w_base + st_lo * W_STAGE_BYTES);
@@ -337,14 +408,18 @@ __device__ __forceinline__ void mma_loop(const Smem& s, const Program& prog, lon
             trace[st * 8 + 5] = t_wait_w;  // ... and for weight stages
           }
           if (kb + 1 < sp.nkb) {
-            // A_hi W_hi + A_lo W_hi + A_hi W_lo over the four K-steps of the block, all N columns
+            // A_hi W_lo over the four K-steps (all N columns), release the lo stage, then A_hi W_hi + A_lo W_hi: the lo stage is
+            // back with the producer two thirds of a K block earlier
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) umma_ts_f16(d_addr, a_kb + ks * 16, umma_desc_at(lo_lo, ks * 32), idesc, (kb | ks) ? 1u : 0u);
+            umma_commit_multicast(&s.c->w_empty[st_lo], (uint16_t)((1u << CLUSTER) - 1u));
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
-              const uint64_t bh = umma_desc_at(lo_hi, ks * 32), bl = umma_desc_at(lo_lo, ks * 32);
-              umma_ts_f16(d_addr, a_kb + ks * 16, bh, idesc, (kb | ks) ? 1u : 0u);
+              const uint64_t bh = umma_desc_at(lo_hi, ks * 32);
+              umma_ts_f16(d_addr, a_kb + ks * 16, bh, idesc, 1u);
               umma_ts_f16(d_addr, a_kb + ks * 16 + 8, bh, idesc, 1u);
-              umma_ts_f16(d_addr, a_kb + ks * 16, bl, idesc, 1u);
             }
+            umma_commit_multicast(&s.c->w_empty[st_hi], (uint16_t)((1u << CLUSTER) - 1u));
           } else {
             // last K block of the step: columns [0, 64) first, committed on their own (d_q[buf][0]) so that epilogue pass 0
             // starts a quarter of a K block after the last a_ready; the remaining columns follow underneath that pass
@@ -369,9 +444,9 @@ __device__ __forceinline__ void mma_loop(const Smem& s, const Program& prog, lon
               }
             }
             umma_commit(&s.c->d_q[buf][1]);
+            umma_commit_multicast(&s.c->w_empty[st_lo], (uint16_t)((1u << CLUSTER) - 1u));
+            umma_commit_multicast(&s.c->w_empty[st_hi], (uint16_t)((1u << CLUSTER) - 1u));
           }
-          umma_commit(&s.c->w_empty[st_hi]);
-          umma_commit(&s.c->w_empty[st_lo]);
           if (trace && it == TRACE_ITER && blockIdx.x == 0 && kb + 1 == sp.nkb) trace[st * 8 + 7] = clock64();
         }
         __syncwarp();
@@ -430,6 +505,40 @@ __device__ __forceinline__ void epi_for_chunks(const Smem& s, const EpiCtx& e, F
     tmem_ld16(base + (uint32_t)col, v);
     f(pass, col, v);
   }
+}
+// Same walk with a software-pipelined side load: pre(col, buf) issues the global / L2 loads a chunk needs (bias, stashed
+// sigma', parked partials, per-point tables) into a register struct; it runs for pass 0 BEFORE the accumulator wait and for pass
+// p+1 between the issue and the wait of pass p's TMEM load, so the ~700-cycle L2 latency of those loads is off the critical
+// path of every pass (with four epilogue warps per scheduler it used to be exposed four times per layer).
+template <class Buf, class Pre, class F>
+__device__ __forceinline__ void epi_for_chunks_pf(const Smem& s, const EpiCtx& e, Pre&& pre, F&& f) {
+  const uint32_t base = e.tmem_base + e.lane_addr + e.d_col0();
+  Buf nxt;
+  pre(CW * e.sub, nxt);
+#pragma unroll 1
+  for (int pass = 0; pass < 4; ++pass) {
+    const Buf cur = nxt;
+    if (pass < 2) epi_wait_q(s, e, pass);
+    const int col = 64 * pass + CW * e.sub;
+    uint32_t r[CW];
+    tmem_ld16_issue(base + (uint32_t)col, r);
+    if (pass < 3) pre(col + 64, nxt);
+    tmem_ld16_wait(r);
+    float v[CW];
+#pragma unroll
+    for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(r[i]);
+    f(pass, col, v, cur);
+  }
+}
+struct Bias16 { float4 b[4]; };
+__device__ __forceinline__ void load_bias16(const float* __restrict__ bias, int col, Bias16& o) {
+  const float4* b4 = reinterpret_cast<const float4*>(bias + col);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) o.b[t] = __ldg(b4 + t);
+}
+__device__ __forceinline__ void add16(float (&v)[CW], const float4 (&b)[4]) {
+#pragma unroll
+  for (int t = 0; t < 4; ++t) { v[4 * t] += b[t].x; v[4 * t + 1] += b[t].y; v[4 * t + 2] += b[t].z; v[4 * t + 3] += b[t].w; }
 }
 // v[i] += bias[col + i] with 128-bit loads
 __device__ __forceinline__ void add_bias16(float (&v)[CW], const float* __restrict__ bias, int col) {

@@ -61,7 +61,7 @@ __device__ __forceinline__ float pe_entry_r(const float x[3], int idx) {
 
 #define PSN_INV_SQRT2 0.70710678118654752440f
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* __restrict__ rgb, float* __restrict__ alpha,
          float* __restrict__ grad_out) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -70,7 +70,7 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long M = M_dev ? (long long)*M_dev : M_host;
   const long long n_tiles = (M + TILE_M - 1) / TILE_M;
-  const long long iters = (n_tiles > (long long)blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const long long iters = pair_iters(n_tiles);  // equal for both CTAs of the pair; surplus tiles are fully masked (idx >= M)
 
   if (warp < EPI_WARP0) {
     regs_shrink_control();
@@ -111,8 +111,9 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
         const bool pre_skip = (l + 1 == g.skip);
         const int n_out = g.n_out[l];
         const float cc = pre_skip ? PSN_SOFTPLUS_C * PSN_INV_SQRT2 : PSN_SOFTPLUS_C;
-        epi_for_chunks(s, e, [&](int pass, int col, float (&v)[CW]) {
-          add_bias16(v, bias, col);
+        epi_for_chunks_pf<Bias16>(s, e, [&](int col, Bias16& b) { load_bias16(bias, col, b); },
+                                  [&](int pass, int col, float (&v)[CW], const Bias16& b) {
+          add16(v, b.b);
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
             float sg[8];
@@ -153,25 +154,32 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
       float g_acc[3] = {0.f, 0.f, 0.f};  // this thread's share of J_pe^T (d logit / d pe)
       if (g.with_app) {
         // ---- s8: feature head -> A (no activation) ---------------------------------------------------------------------
-        epi_for_chunks(s, e, [&](int pass, int col, float (&v)[CW]) {
-          add_bias16(v, g.bias_feat, col);
+        epi_for_chunks_pf<Bias16>(s, e, [&](int col, Bias16& b) { load_bias16(g.bias_feat, col, b); },
+                                  [&](int pass, int col, float (&v)[CW], const Bias16& b) {
+          add16(v, b.b);
           epi_store_a16(e, e.d_col0(), col, v);
           epi_signal_a(s, pass);
         });
         e.step_ctr++;
         // ---- s9: appearance layer 0, feature part -> parked; then the reverse seed dz_7 -> A -------------------------------
-        epi_for_chunks(s, e, [&](int pass, int col, float (&v)[CW]) {
+        struct Seed { uint4 q[2]; float4 w[4]; };
+        epi_for_chunks_pf<Seed>(s, e, [&](int col, Seed& o) {
+#pragma unroll
+          for (int t = 0; t < 2; ++t) o.q[t] = __ldcg(&stash[(size_t)(7 * 32 + (col >> 3) + t) * TILE_M + row]);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) o.w[t] = __ldg(reinterpret_cast<const float4*>(g.w_row + col) + t);
+        }, [&](int pass, int col, float (&v)[CW], const Seed& o) {
 #pragma unroll
           for (int t = 0; t < 4; ++t)
             parked[(size_t)((col >> 2) + t) * TILE_M + row] = make_float4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
-            const uint4 q = __ldcg(&stash[(size_t)(7 * 32 + (col >> 3) + t) * TILE_M + row]);
+            const uint4 q = o.q[t];
             float sg[8];
             dq16_pair(q.x, sg[0], sg[1]); dq16_pair(q.y, sg[2], sg[3]); dq16_pair(q.z, sg[4], sg[5]); dq16_pair(q.w, sg[6], sg[7]);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              const float4 w = __ldg(reinterpret_cast<const float4*>(g.w_row + col) + 2 * t + h);
+              const float4 w = o.w[2 * t + h];
               v[8 * t + 4 * h] = (w.x * PSN_INV_U16) * sg[4 * h]; v[8 * t + 4 * h + 1] = (w.y * PSN_INV_U16) * sg[4 * h + 1];
               v[8 * t + 4 * h + 2] = (w.z * PSN_INV_U16) * sg[4 * h + 2]; v[8 * t + 4 * h + 3] = (w.w * PSN_INV_U16) * sg[4 * h + 3];
             }
@@ -187,7 +195,11 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
         const bool is_skip = (l == g.skip);
         const int nprev = g.n_out[l - 1];
         const float scale = is_skip ? PSN_INV_SQRT2 * PSN_INV_U16 : PSN_INV_U16;
-        epi_for_chunks(s, e, [&](int pass, int col, float (&v)[CW]) {
+        struct Sig { uint4 q[2]; };
+        epi_for_chunks_pf<Sig>(s, e, [&](int col, Sig& o) {
+#pragma unroll
+          for (int t = 0; t < 2; ++t) o.q[t] = __ldcg(&stash[(size_t)((l - 1) * 32 + (col >> 3) + t) * TILE_M + row]);
+        }, [&](int pass, int col, float (&v)[CW], const Sig& o) {
           if (is_skip && col + CW > nprev) {  // encoding part of the skip input: contributes J_pe^T directly
 #pragma unroll
             for (int i = 0; i < CW; ++i) {
@@ -200,8 +212,8 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
             }
           }
 #pragma unroll
-          for (int t = 0; t < 2; ++t) {  // the L2 latency of the stash is covered by the other epilogue warps of the scheduler
-            const uint4 q = __ldcg(&stash[(size_t)((l - 1) * 32 + (col >> 3) + t) * TILE_M + row]);
+          for (int t = 0; t < 2; ++t) {
+            const uint4 q = o.q[t];
             float sg[8];
             dq16_pair(q.x, sg[0], sg[1]); dq16_pair(q.y, sg[2], sg[3]); dq16_pair(q.z, sg[4], sg[5]); dq16_pair(q.w, sg[6], sg[7]);
 #pragma unroll
@@ -264,13 +276,16 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
           epi_signal_a(s, 0);
         }
         // ---- s18: appearance layer 0 (rest) + parked + bias, ReLU ------------------------------------------------------------
-        epi_for_chunks(s, e, [&](int pass, int col, float (&v)[CW]) {
+        struct Park { float4 pk[4], b[4]; };
+        epi_for_chunks_pf<Park>(s, e, [&](int col, Park& o) {
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
-            const float4 pk = __ldcg(&parked[(size_t)((col >> 2) + t) * TILE_M + row]);
-            v[4 * t] += pk.x; v[4 * t + 1] += pk.y; v[4 * t + 2] += pk.z; v[4 * t + 3] += pk.w;
+            o.pk[t] = __ldcg(&parked[(size_t)((col >> 2) + t) * TILE_M + row]);
+            o.b[t] = __ldg(reinterpret_cast<const float4*>(g.abias[0] + col) + t);
           }
-          add_bias16(v, g.abias[0], col);
+        }, [&](int pass, int col, float (&v)[CW], const Park& o) {
+          add16(v, o.pk);
+          add16(v, o.b);
 #pragma unroll
           for (int i = 0; i < CW; ++i) v[i] = fmaxf(v[i], 0.f);
           epi_store_a16(e, e.d_col0(), col, v);
@@ -281,8 +296,9 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
 #pragma unroll 1
         for (int l = 1; l <= 3; ++l) {
           const float* bias = g.abias[l];
-          epi_for_chunks(s, e, [&](int pass, int col, float (&v)[CW]) {
-            add_bias16(v, bias, col);
+          epi_for_chunks_pf<Bias16>(s, e, [&](int col, Bias16& b) { load_bias16(bias, col, b); },
+                                    [&](int pass, int col, float (&v)[CW], const Bias16& b) {
+            add16(v, b.b);
 #pragma unroll
             for (int i = 0; i < CW; ++i) v[i] = fmaxf(v[i], 0.f);
             epi_store_a16(e, e.d_col0(), col, v);
@@ -372,7 +388,7 @@ static int launch_tc_rad(const TcRadArgs& a, const PointGen& gen, long long M, c
     if (rcr) return rcr;
   }
   const long long tiles = M_dev ? (long long)num_ctas() : (M + TILE_M - 1) / TILE_M;
-  const int grid = (int)(tiles < num_ctas() ? tiles : num_ctas());
+  const int grid = tc_grid((const void*)k_tc_rad, tiles);
   count_launch();
   k_tc_rad<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(a, gen, M, M_dev, rgb, alpha, grad);
   PSN_CUDA_CHECK(cudaGetLastError());

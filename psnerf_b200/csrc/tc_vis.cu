@@ -77,7 +77,7 @@ struct TcVisArgs {
   int L;
 };
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 k_tc_vis(TcVisArgs g, float* __restrict__ vis) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const Smem s = carve(smem_raw);
@@ -87,8 +87,8 @@ k_tc_vis(TcVisArgs g, float* __restrict__ vis) {
   const long long n_tiles = pblocks * g.L;
   const long long chunk = (n_tiles + gridDim.x - 1) / gridDim.x;
   const long long t0 = chunk * blockIdx.x;
-  const long long t1 = (t0 + chunk < n_tiles) ? t0 + chunk : n_tiles;
-  const long long iters = t1 > t0 ? t1 - t0 : 0;
+  const long long t1 = t0 + chunk;   // every CTA runs `chunk` iterations (the pair shares each weight stage); tiles >= n_tiles are masked
+  const long long iters = chunk;
   if (warp < EPI_WARP0) {
     regs_shrink_control();
     if (warp == 0 && lane == 0) producer_loop(s, g.prog, iters);
@@ -99,10 +99,11 @@ k_tc_vis(TcVisArgs g, float* __restrict__ vis) {
     EpiCtx e = epi_ctx(tmem_base);
     const int row = e.row, sub = e.sub;
     for (long long t = t0; t < t1; ++t) {
-      const long long pb = t / g.L;
-      const int l = (int)(t - pb * g.L);
+      const long long tt = t < n_tiles ? t : n_tiles - 1;  // dummy tiles recompute the last one and write nothing
+      const long long pb = tt / g.L;
+      const int l = (int)(tt - pb * g.L);
       const long long n = pb * TILE_M + row;
-      const bool valid = n < g.Ns;
+      const bool valid = n < g.Ns && t < n_tiles;
       const long long nn = valid ? n : g.Ns - 1;
       // layer 0: relu(P0[n] + L0[l]) for this thread's four 16-column chunks -> A operand of the first tensor step
 #pragma unroll 1
@@ -123,16 +124,26 @@ k_tc_vis(TcVisArgs g, float* __restrict__ vis) {
 #pragma unroll 1
       for (int st = 0; st < 7; ++st) {
         const float* bias = g.bias[st];
-        epi_for_chunks(s, e, [&](int pass, int col, float (&v)[CW]) {
+        struct Add2 { float4 a[4], b[4]; };
+        epi_for_chunks_pf<Add2>(s, e, [&](int col, Add2& o) {
           if (st == 4) {  // skip layer: + P5[n] (bias folded) + L5[l]
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float4 a = __ldg(reinterpret_cast<const float4*>(g.P5 + nn * 256 + col) + i);
-              const float4 b = __ldg(reinterpret_cast<const float4*>(g.L5 + (long long)l * 256 + col) + i);
-              v[4 * i + 0] += a.x + b.x; v[4 * i + 1] += a.y + b.y; v[4 * i + 2] += a.z + b.z; v[4 * i + 3] += a.w + b.w;
+              o.a[i] = __ldg(reinterpret_cast<const float4*>(g.P5 + nn * 256 + col) + i);
+              o.b[i] = __ldg(reinterpret_cast<const float4*>(g.L5 + (long long)l * 256 + col) + i);
             }
           } else {
-            add_bias16(v, bias, col);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              o.a[i] = __ldg(reinterpret_cast<const float4*>(bias + col) + i);
+              o.b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+        }, [&](int pass, int col, float (&v)[CW], const Add2& o) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            v[4 * i + 0] += o.a[i].x + o.b[i].x; v[4 * i + 1] += o.a[i].y + o.b[i].y;
+            v[4 * i + 2] += o.a[i].z + o.b[i].z; v[4 * i + 3] += o.a[i].w + o.b[i].w;
           }
 #pragma unroll
           for (int i = 0; i < CW; ++i) v[i] = fmaxf(v[i], 0.f);
@@ -213,7 +224,7 @@ int tc_s2_visibility(const psn_mlp* net, int nf, const float* pts, long long Ns,
     if (rcr) return rcr;
   }
   const long long n_tiles = ((Ns + TILE_M - 1) / TILE_M) * L;
-  const int grid = (int)(n_tiles < num_ctas() ? n_tiles : num_ctas());
+  const int grid = tc_grid((const void*)k_tc_vis, n_tiles);
   count_launch();
   k_tc_vis<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(a, vis);
   PSN_CUDA_CHECK(cudaGetLastError());

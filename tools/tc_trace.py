@@ -25,7 +25,7 @@ for _ in range(2):
                                    C.c_void_p(trace.data_ptr()), engine._stream()), "trace")
 torch.cuda.synchronize()
 t = trace.cpu().tolist()
-t0 = min(x for x in t if x > 0)
+t0 = min(t[l * 8] for l in range(8) if t[l * 8] > 0)  # time stamps only (slots +4 / +5 hold cycle counts)
 rel = lambda x: (x - t0) if x > 0 else -1
 print("layer | MMA: a_ready kb0 kb1 kb2 kb3 | commit | wait_a wait_w || epilogue sub0: wake p0 p1 p2 p3 | sub3: wake p0 p1 p2 p3")
 for l in range(8):
