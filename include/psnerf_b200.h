@@ -138,6 +138,10 @@ typedef struct {
   int specular_rgb;   /* train.specular_rgb: weights are [3, nbasis] */
   int intensity_kind; /* 0 scalar, 1 per-light [L,1], 2 per-light rgb [L,3] (renderer.py:188-190) */
   float intensity;    /* scalar intensity when intensity_kind == 0 */
+  int render_model;   /* train.render_model: 0 = sgbasis (sgbasis.py), 1 = microfacet (GGX, stage2/model/microfacet.py:35-114):
+                         rough_net then has ONE sigmoid output (the roughness), sgw is not written and spec is the per-PIXEL
+                         roughness image [N,3] (renderer.py:140-141,204-207) instead of [L,N,3] */
+  float fresnel_f0;   /* brdf.fresnel_f0 (Schlick), microfacet only */
 } psn_shade_params;
 
 /* PSNetwork.forward, eval path: stage2/model/renderer.py:110-266 with sgbasis.py:16-32, embedder.py:36.

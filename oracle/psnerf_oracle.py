@@ -445,6 +445,33 @@ def sg_basis(lobe, v, n, l, albedo, weights, specular_rgb, nbasis):
     return albedo + spec.expand_as(albedo), spec
 
 
+def _div_no_nan(x, y):
+    a = x / (y + 1e-6)  # microfacet.py:20-24
+    return torch.where(torch.isinf(a) | torch.isnan(a), torch.zeros_like(a), a)
+
+
+def microfacet_brdf(l, v, n, albedo, rough, f0=0.05):
+    """GGX microfacet BRDF (stage2/model/microfacet.py:35-114).  l [Np,L,3], v/n [Np,3], albedo [Np,3], rough [Np,1] -> [Np,L,3]."""
+    l = F.normalize(l, dim=2, eps=1e-6)
+    v = F.normalize(v, dim=1, eps=1e-6)
+    n = F.normalize(n, dim=1, eps=1e-6)
+    h = F.normalize(l + v[:, None, :], dim=2, eps=1e-6)
+    f = f0 + (1 - f0) * (1 - torch.einsum("ijk,ijk->ij", l, h)) ** 5          # Schlick (:108-113)
+    alpha = rough ** 2
+    cm = torch.einsum("ijk,ik->ij", h, n)                                      # GGX distribution (:94-106)
+    cm2 = cm ** 2
+    tm2 = _div_no_nan(1 - cm2, cm2)
+    d = _div_no_nan(alpha ** 2 * (cm > 0).to(l.dtype), np.pi * cm2 ** 2 * (alpha ** 2 + tm2) ** 2)
+    cv = torch.einsum("ij,ij->i", n, v)                                        # GGX geometry term (:76-92)
+    chi = (_div_no_nan(torch.einsum("ijk,ik->ij", h, v), cv[:, None]) > 0).to(l.dtype)
+    cv2 = torch.clamp(cv ** 2, 0.0, 1.0)
+    tv2 = torch.clamp(_div_no_nan(1 - cv2, cv2), 0.0, float("inf"))
+    g = _div_no_nan(chi * 2, 1 + torch.sqrt(1 + alpha ** 2 * tv2[:, None]))
+    ldn = torch.einsum("ijk,ik->ij", l, n)
+    micro = _div_no_nan(f * g * d, 4 * ldn.abs() * cv.abs()[:, None])
+    return micro[:, :, None].repeat(1, 1, 3) + (albedo / np.pi)[:, None, :]
+
+
 def camera_params(uv, pose, intrinsics):
     """Unit ray dirs + camera centre, pose-matrix branch (stage2/utils/rend_util.py:90-147)."""
     cam_loc = pose[:, :3, 3]
@@ -465,8 +492,9 @@ def psnetwork_forward(sd, conf, inp, noise=None, albedo_new=None, basis_new=None
     (scaled by xyz_jitter_std) in place of torch.normal (renderer.py:212).  ``albedo_new`` ([3]) / ``basis_new`` (lobe index)
     are the material-editing overrides of stage2/eval.py:116-132 (renderer.py:167-168,175-181).
     """
+    micro = conf.get("train.render_model", "sgbasis") == "microfacet"
     nb = int(conf.get("train.nbasis", 9))
-    spec_rgb = bool(conf.get("train.specular_rgb", False))
+    spec_rgb = bool(conf.get("train.specular_rgb", False)) and not micro
     nf = int(conf["brdf.net.n_freqs_xyz"])
     nfn = int(conf["normal.net.n_freqs_xyz"])
     uv, pose, K = inp["uv"], inp["pose"], inp["intrinsics"]
@@ -478,7 +506,7 @@ def psnetwork_forward(sd, conf, inp, noise=None, albedo_new=None, basis_new=None
     dt = points.dtype
     normal_pred = torch.ones_like(points)
     L = inp["light_direction"].shape[0]
-    nbt = nb * 3 if spec_rgb else nb
+    nbt = 1 if micro else (nb * 3 if spec_rgb else nb)
     rgb_v = torch.ones_like(points)
     alb_v = torch.ones_like(points)
     rough_v = torch.ones_like(points)
@@ -486,7 +514,8 @@ def psnetwork_forward(sd, conf, inp, noise=None, albedo_new=None, basis_new=None
     vis_v = torch.ones_like(points)
     if L > 1:
         rgb_v = rgb_v.repeat(L, 1, 1)
-        rough_v = rough_v.repeat(L, 1, 1)
+        if not micro:  # renderer.py:156-157
+            rough_v = rough_v.repeat(L, 1, 1)
         vis_v = vis_v.repeat(L, 1, 1)
     out_extra = {}
     Ns = surf.shape[0]
@@ -499,19 +528,27 @@ def psnetwork_forward(sd, conf, inp, noise=None, albedo_new=None, basis_new=None
         l = inp["light_direction"][:, None].expand(rgb_v.shape)[me]
         pemb = embed(surf, nf)
         albedo = s2_mlp(sd, "albedo_net", pemb, [int(conf["brdf.net.mlp_skip_at"])], "sigmoid")
-        rough = s2_mlp(sd, "rough_net", pemb, [int(conf.get("brdf.sgnet.mlp_skip_at", 2))], None)
+        if micro:  # renderer.py:73-74: Network(dim_emb, 1, W, depth) with the albedo net's trunk shape, sigmoid output
+            rough = s2_mlp(sd, "rough_net", pemb, [int(conf["brdf.net.mlp_skip_at"])], "sigmoid")
+        else:
+            rough = s2_mlp(sd, "rough_net", pemb, [int(conf.get("brdf.sgnet.mlp_skip_at", 2))], None)
         if albedo_new is not None:  # renderer.py:167-168
             albedo = torch.as_tensor(albedo_new, dtype=dt)[None].expand_as(albedo)
-        weights = torch.relu(rough)
-        if basis_new is not None:  # renderer.py:175-181: a single lobe with weight 2^k/100 in every colour channel
-            wn = torch.zeros_like(weights)
-            wn.view(-1, 3 if spec_rgb else 1, nb)[:, :, basis_new] = 2 ** basis_new / 100
-            weights = wn.reshape(-1, nbt)
-        if L > 1:
-            brdf, spec = sg_basis(sd["sgbasis.lobe"], v.tile(L, 1), normal.tile(L, 1), l, albedo.tile(L, 1),
-                                  weights.tile(L, 1), spec_rgb, nb)
+        if micro:  # renderer.py:171-172
+            brdf = microfacet_brdf(l.view(L, -1, 3).permute(1, 0, 2), v, normal, albedo, rough,
+                                   float(conf.get("brdf.fresnel_f0", 0.05))).permute(1, 0, 2).reshape(-1, 3)
+            weights = rough
         else:
-            brdf, spec = sg_basis(sd["sgbasis.lobe"], v, normal, l, albedo, weights, spec_rgb, nb)
+            weights = torch.relu(rough)
+            if basis_new is not None:  # renderer.py:175-181: a single lobe with weight 2^k/100 in every colour channel
+                wn = torch.zeros_like(weights)
+                wn.view(-1, 3 if spec_rgb else 1, nb)[:, :, basis_new] = 2 ** basis_new / 100
+                weights = wn.reshape(-1, nbt)
+            if L > 1:
+                brdf, spec = sg_basis(sd["sgbasis.lobe"], v.tile(L, 1), normal.tile(L, 1), l, albedo.tile(L, 1),
+                                      weights.tile(L, 1), spec_rgb, nb)
+            else:
+                brdf, spec = sg_basis(sd["sgbasis.lobe"], v, normal, l, albedo, weights, spec_rgb, nb)
         w_v[smask] = weights
         cos = torch.einsum("lni,ni->ln", l.view(L, -1, 3), normal).reshape(-1, 1)
         inten = inp.get("light_intensity", float(conf.get("brdf.light_intensity", 4.0)))
@@ -525,15 +562,23 @@ def psnetwork_forward(sd, conf, inp, noise=None, albedo_new=None, basis_new=None
         vis_v[me] = vis.expand(rgb.shape)
         rgb_v[me] = rgb
         alb_v[smask] = albedo
-        rough_v[me] = spec.expand(-1, 3)
+        if micro:
+            rough_v[smask] = rough.expand(-1, 3)  # renderer.py:206-207
+        else:
+            rough_v[me] = spec.expand(-1, 3)
         jstd = float(conf.get("brdf.net.xyz_jitter_std", 0))
         if jstd > 0 and noise is not None:
             pj = embed(surf + noise["xyz"] * jstd, nf)
             aj = torch.ones_like(points)
             aj[smask] = s2_mlp(sd, "albedo_net", pj, [int(conf["brdf.net.mlp_skip_at"])], "sigmoid")
-            rj = torch.ones_like(w_v)
-            rj[smask] = torch.relu(s2_mlp(sd, "rough_net", pj, [int(conf.get("brdf.sgnet.mlp_skip_at", 2))], None))
-            out_extra.update({"albedo_values": alb_v, "albedo_jitter": aj, "rough_values": w_v, "rough_jitter": rj})
+            if micro:  # renderer.py:224-226
+                rj = torch.ones_like(points)
+                rj[smask] = s2_mlp(sd, "rough_net", pj, [int(conf["brdf.net.mlp_skip_at"])], "sigmoid").expand(-1, 3)
+                out_extra.update({"albedo_values": alb_v, "albedo_jitter": aj, "rough_values": rough_v, "rough_jitter": rj})
+            else:
+                rj = torch.ones_like(w_v)
+                rj[smask] = torch.relu(s2_mlp(sd, "rough_net", pj, [int(conf.get("brdf.sgnet.mlp_skip_at", 2))], None))
+                out_extra.update({"albedo_values": alb_v, "albedo_jitter": aj, "rough_values": w_v, "rough_jitter": rj})
         if "light_vis_train" in inp:
             Lt = inp["light_vis_train"].shape[0]
             lt = inp["light_vis_train"][:, None].expand(-1, points.shape[1], -1)[smask.expand(Lt, -1)]
@@ -549,6 +594,8 @@ def psnetwork_forward(sd, conf, inp, noise=None, albedo_new=None, basis_new=None
     out = {"points": points, "object_mask": inp["object_mask"], "network_object_mask": smask,
            "sg_rgb_values": rgb_v, "normal_values": normals_in, "sg_diffuse_albedo_values": alb_v,
            "sg_specular_rgb_values": rough_v, "normal_pred": normal_pred, "visibility": vis_v, "sg_weight": w_v}
+    if micro:
+        del out["sg_weight"]  # renderer.py:263-264
     out.update(out_extra)
     return out
 

@@ -38,7 +38,7 @@ class TrainNet(C.Structure):
 
 class ShadeParams(C.Structure):
     _fields_ = [("n_freqs_xyz", C.c_int), ("n_freqs_normal", C.c_int), ("nbasis", C.c_int), ("specular_rgb", C.c_int),
-                ("intensity_kind", C.c_int), ("intensity", C.c_float)]
+                ("intensity_kind", C.c_int), ("intensity", C.c_float), ("render_model", C.c_int), ("fresnel_f0", C.c_float)]
 
 
 def declared_symbols():

@@ -171,9 +171,47 @@ struct ShadeArgs {
   const int* slot_of_pixel;
   float *rgb, *spec, *vis_out, *normal_out, *albedo_out, *sgw_out;
   long long N, Ns;
-  int L, nbasis, specular_rgb, nbt, intensity_kind, write_normal;
-  float intensity_scalar;
+  int L, nbasis, specular_rgb, nbt, intensity_kind, write_normal, microfacet;
+  float intensity_scalar, f0;
 };
+
+// x / (y + 1e-6) with inf / nan -> 0 (microfacet.py:20-24)
+__device__ __forceinline__ float div_no_nan(float x, float y) {
+  const float a = __fdiv_rn(x, __fadd_rn(y, 1e-6f));
+  return (isinf(a) || isnan(a)) ? 0.f : a;
+}
+__device__ __forceinline__ void normalize_eps(const float* v, float eps, float* o) {  // F.normalize(v, eps=eps)
+  const float n = fmaxf(sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]), eps);
+  o[0] = v[0] / n; o[1] = v[1] / n; o[2] = v[2] / n;
+}
+// GGX microfacet BRDF without the Lambert term (stage2/model/microfacet.py:35-114): Schlick Fresnel, GGX distribution and
+// Smith-GGX geometry term with the reference's clamps / divide_no_nan conventions; alpha = rough^2.
+__device__ __forceinline__ float microfacet_glossy(const float* l_in, const float* v_in, const float* n_in, float rough, float f0) {
+  const float kPi = 3.14159265358979323846f;
+  float l[3], v[3], n[3], h[3];
+  normalize_eps(l_in, 1e-6f, l); normalize_eps(v_in, 1e-6f, v); normalize_eps(n_in, 1e-6f, n);
+  const float hs[3] = {l[0] + v[0], l[1] + v[1], l[2] + v[2]};
+  normalize_eps(hs, 1e-6f, h);
+  const float ldh = l[0] * h[0] + l[1] * h[1] + l[2] * h[2];
+  const float om = 1.f - ldh;
+  const float f = f0 + (1.f - f0) * (om * om * om * om * om);
+  const float alpha = rough * rough, a2 = alpha * alpha;
+  // D
+  const float cm = h[0] * n[0] + h[1] * n[1] + h[2] * n[2];
+  const float cm2 = cm * cm;
+  const float tm2 = div_no_nan(1.f - cm2, cm2);
+  const float dd = kPi * (cm2 * cm2) * ((a2 + tm2) * (a2 + tm2));
+  const float d = div_no_nan(a2 * (cm > 0.f ? 1.f : 0.f), dd);
+  // G
+  const float cv = n[0] * v[0] + n[1] * v[1] + n[2] * v[2];
+  const float ct = h[0] * v[0] + h[1] * v[1] + h[2] * v[2];
+  const float chi = div_no_nan(ct, cv) > 0.f ? 1.f : 0.f;
+  const float cv2 = fminf(fmaxf(cv * cv, 0.f), 1.f);
+  const float tv2 = fmaxf(div_no_nan(1.f - cv2, cv2), 0.f);
+  const float g = div_no_nan(chi * 2.f, 1.f + sqrtf(1.f + a2 * tv2));
+  const float ldn = l[0] * n[0] + l[1] * n[1] + l[2] * n[2];
+  return div_no_nan(f * g * d, 4.f * fabsf(ldn) * fabsf(cv));
+}
 
 __global__ void k_fill_int(int* p, long long n, int v) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -201,7 +239,12 @@ __global__ void k_s2_shade(ShadeArgs a) {
       if (a.write_normal) a.normal_out[px * 3 + c] = n[c];
       a.albedo_out[px * 3 + c] = al[c];
     }
-    for (int k = 0; k < a.nbt; ++k) a.sgw_out[px * a.nbt + k] = (slot >= 0) ? a.weights[(long long)slot * a.nbt + k] : 0.f;
+    if (a.microfacet) {  // roughness image, pre-filled with 1 (renderer.py:140-141,204-207)
+      const float r = (slot >= 0) ? a.weights[slot] : 1.f;
+      a.spec[px * 3] = r; a.spec[px * 3 + 1] = r; a.spec[px * 3 + 2] = r;
+    } else {
+      for (int k = 0; k < a.nbt; ++k) a.sgw_out[px * a.nbt + k] = (slot >= 0) ? a.weights[(long long)slot * a.nbt + k] : 0.f;
+    }
     return;
   }
   const long long o = ((long long)l * a.N + px) * 3;
@@ -209,7 +252,7 @@ __global__ void k_s2_shade(ShadeArgs a) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       a.rgb[o + c] = 1.f;
-      a.spec[o + c] = 1.f;
+      if (!a.microfacet) a.spec[o + c] = 1.f;
       if (a.vis_out) a.vis_out[o + c] = 1.f;
     }
     return;
@@ -217,6 +260,27 @@ __global__ void k_s2_shade(ShadeArgs a) {
   const float* nn = a.normal + (long long)slot * 3;
   const float* vv = a.view + (long long)slot * 3;
   const float* ll = a.lights + (long long)l * 3;
+  if (a.microfacet) {  // brdf = glossy + albedo / pi (microfacet.py:62-72), then the common shading line renderer.py:187-199
+    const float gl = microfacet_glossy(ll, vv, nn, a.weights[slot], a.f0);
+    const float cosv = ll[0] * nn[0] + ll[1] * nn[1] + ll[2] * nn[2];
+    float visr = 1.f, visc = 1.f;
+    if (a.vis) {
+      visr = a.vis[(long long)l * a.Ns + slot];
+      visc = fminf(fmaxf(visr, 0.f), 1.f);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float brdf = gl + a.albedo[(long long)slot * 3 + c] / 3.14159265358979323846f;
+      float I = a.intensity_scalar;
+      if (a.intensity_kind == 1) I = a.intensity[l];
+      else if (a.intensity_kind == 2) I = a.intensity[l * 3 + c];
+      float r = brdf * I * cosv;
+      if (a.vis) r = r * visc;
+      a.rgb[o + c] = fminf(fmaxf(r, 0.f), 1.f);
+      if (a.vis_out) a.vis_out[o + c] = visr;
+    }
+    return;
+  }
   // h = F.normalize(l + v); (h*n).sum(-1) - 1 with torch's separate roundings (sgbasis.py:24-25): the lobe sharpness
   // lambda <= e^10 amplifies every ulp of this dot product 2e4 times, so no FMA contraction here.
   const float hx = __fadd_rn(ll[0], vv[0]), hy = __fadd_rn(ll[1], vv[1]), hz = __fadd_rn(ll[2], vv[2]);
@@ -398,15 +462,16 @@ static int shade_stage2_impl(const psn_mlp* normal_net, const psn_mlp* albedo_ne
                              const float* lights, int L, const float* intensity, const float* albedo_new, const float* weights_new,
                              float* rgb, float* spec, float* vis, float* normal, float* albedo, float* sgw, void* ws, int64_t ws_bytes,
                              int precision, void* stream) {
-  PSN_REQUIRE(albedo_net && rough_net && lobe && prm && lights && rgb && spec && albedo && sgw, PSN_ERR_ARG,
-              "psn_shade_stage2: null argument");
+  PSN_REQUIRE(albedo_net && rough_net && prm && lights && rgb && spec && albedo, PSN_ERR_ARG, "psn_shade_stage2: null argument");
+  PSN_REQUIRE(prm->render_model == 1 || (lobe && sgw), PSN_ERR_ARG, "psn_shade_stage2: sgbasis needs lobe and sgw");
+  PSN_REQUIRE(prm->render_model == 0 || prm->render_model == 1, PSN_ERR_ARG, "psn_shade_stage2: render_model %d", prm->render_model);
   PSN_REQUIRE(Ns == 0 || (pts && view && pix), PSN_ERR_ARG, "psn_shade_stage2: null surface inputs");
   PSN_REQUIRE(normal_net || normal_in || Ns == 0, PSN_ERR_ARG, "psn_shade_stage2: need normal_net or normal_in");
   PSN_REQUIRE(!normal_net || normal, PSN_ERR_ARG, "psn_shade_stage2: normal output required with normal_net");
   PSN_REQUIRE(!vis_net || vis, PSN_ERR_ARG, "psn_shade_stage2: vis output required with visibility_net");
   PSN_REQUIRE(L >= 1 && N >= Ns, PSN_ERR_ARG, "psn_shade_stage2: L=%d N=%lld Ns=%lld", L, (long long)N, (long long)Ns);
   PSN_REQUIRE(prm->intensity_kind == 0 || intensity, PSN_ERR_ARG, "psn_shade_stage2: per-light intensity pointer is null");
-  const int nbt = prm->specular_rgb ? 3 * prm->nbasis : prm->nbasis;
+  const int nbt = prm->render_model == 1 ? 1 : (prm->specular_rgb ? 3 * prm->nbasis : prm->nbasis);
   PSN_REQUIRE(nbt <= 32, PSN_ERR_SHAPE, "psn_shade_stage2: %d SG weights > 32", nbt);
   cudaStream_t st = (cudaStream_t)stream;
   Workspace w(ws, ws_bytes);
@@ -453,7 +518,7 @@ int s2_shade_images(const float* n_s, const float* a_s, const float* w_s, const 
                     const float* lobe, const float* intensity, const psn_shade_params* prm, const int32_t* pix, long long Ns, long long N,
                     int L, float* rgb, float* spec, float* vis, float* normal, float* albedo, float* sgw, int write_normal, int* sop,
                     cudaStream_t st) {
-  const int nbt = prm->specular_rgb ? 3 * prm->nbasis : prm->nbasis;
+  const int nbt = prm->render_model == 1 ? 1 : (prm->specular_rgb ? 3 * prm->nbasis : prm->nbasis);
   psn::count_launch();
   k_fill_int<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(sop, N, -1);
   if (Ns > 0) { psn::count_launch(); k_slot_of_pixel<<<(unsigned)((Ns + 255) / 256), 256, 0, st>>>(pix, Ns, sop); }
@@ -465,6 +530,8 @@ int s2_shade_images(const float* n_s, const float* a_s, const float* w_s, const 
   a.rgb = rgb; a.spec = spec; a.vis_out = v_raw ? vis : nullptr; a.normal_out = normal; a.albedo_out = albedo; a.sgw_out = sgw;
   a.N = N; a.Ns = Ns; a.L = L; a.nbasis = prm->nbasis; a.specular_rgb = prm->specular_rgb; a.nbt = nbt;
   a.intensity_kind = prm->intensity_kind; a.intensity_scalar = prm->intensity; a.write_normal = write_normal;
+  a.microfacet = prm->render_model == 1 ? 1 : 0;
+  a.f0 = prm->fresnel_f0;
   dim3 grid((unsigned)((N + 255) / 256), (unsigned)(L + 1));
   psn::count_launch();
   k_s2_shade<<<grid, 256, 0, st>>>(a);

@@ -457,6 +457,7 @@ extern "C" int psn_s2_train_forward(const psn_train_net* nn, const psn_train_net
   PSN_REQUIRE(!vn || (vis_packed && vis), PSN_ERR_ARG, "psn_s2_train_forward: visibility needs the packed net and the vis output");
   PSN_REQUIRE(!lights_vt || (vn && vis_train && Lt > 0), PSN_ERR_ARG, "psn_s2_train_forward: vis-train lights need visibility_net");
   cudaStream_t st = (cudaStream_t)stream;
+  PSN_REQUIRE(prm->render_model == 0, PSN_ERR_SHAPE, "stage-2 train step: only render_model = sgbasis is implemented");
   const int nbt = prm->specular_rgb ? 3 * prm->nbasis : prm->nbasis;
   PSN_REQUIRE(rn->out_dims[rn->n_layers - 1] == nbt && nbt <= 27, PSN_ERR_SHAPE, "rough_net output %d != %d", rn->out_dims[rn->n_layers - 1], nbt);
   S2Tape t;
@@ -531,6 +532,7 @@ extern "C" int psn_s2_train_backward(const psn_train_net* nn, const psn_train_ne
   if (vn && (rc = check_net(vn, "visibility_net", g_vis_train != nullptr))) return rc;
   if (Ns == 0) return PSN_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  PSN_REQUIRE(prm->render_model == 0, PSN_ERR_SHAPE, "stage-2 train step: only render_model = sgbasis is implemented");
   const int nbt = prm->specular_rgb ? 3 * prm->nbasis : prm->nbasis;
   S2Tape t;
   carve_tape((float*)tape, nn, an, rn, vn, Ns, L, g_vis_train ? Lt : (Lt > 0 ? Lt : 0), nbt, &t);

@@ -90,21 +90,28 @@ class PSNetwork(nn.Module):
             conf = _DictConf(conf)
         self.conf = conf
         self.render_model = conf.get_string("train.render_model", default="sgbasis")
-        if self.render_model != "sgbasis":
-            raise NotImplementedError("psnerf_b200: only render_model=sgbasis (all shipped confs) is implemented")
+        if self.render_model not in ("sgbasis", "microfacet"):
+            raise NotImplementedError("psnerf_b200: render_model must be sgbasis or microfacet (renderer.py:62-67)")
+        self.microfacet = self.render_model == "microfacet"
+        self.fresnel_f0 = conf.get_float("brdf.fresnel_f0", default=0.05)
         nbasis = conf.get_int("train.nbasis", default=9)
-        self.specular_rgb = conf.get_bool("train.specular_rgb", default=False)
-        self.sgbasis = SGBasis(nbasis=nbasis, specular_rgb=self.specular_rgb)
+        self.specular_rgb = conf.get_bool("train.specular_rgb", default=False) and not self.microfacet
+        if not self.microfacet:
+            self.sgbasis = SGBasis(nbasis=nbasis, specular_rgb=self.specular_rgb)
         self.n_freqs = conf.get_int("brdf.net.n_freqs_xyz")
         dim_emb = 3 + 6 * self.n_freqs if self.n_freqs > 0 else 3
         W, depth = conf.get_int("brdf.net.mlp_width"), conf.get_int("brdf.net.mlp_depth")
         self.albedo_net = Network(dim_emb, 3, W, depth, skip_at=[conf.get_int("brdf.net.mlp_skip_at")])
         self.nbasis_lobes = nbasis
-        if self.specular_rgb:
-            nbasis *= 3
-        self.rough_net = Normal_Network(dim_emb, nbasis, conf.get_int("brdf.sgnet.mlp_width", 128),
-                                        conf.get_int("brdf.sgnet.mlp_depth", 4),
-                                        skip_at=[conf.get_int("brdf.sgnet.mlp_skip_at", 2)])
+        if self.microfacet:  # renderer.py:73-74: one sigmoid roughness per point, same trunk shape as the albedo net
+            self.rough_net = Network(dim_emb, 1, W, depth, skip_at=[conf.get_int("brdf.net.mlp_skip_at")])
+            nbasis = 1
+        else:
+            if self.specular_rgb:
+                nbasis *= 3
+            self.rough_net = Normal_Network(dim_emb, nbasis, conf.get_int("brdf.sgnet.mlp_width", 128),
+                                            conf.get_int("brdf.sgnet.mlp_depth", 4),
+                                            skip_at=[conf.get_int("brdf.sgnet.mlp_skip_at", 2)])
         self.nbasis = nbasis
         self.light_int = conf.get_float("brdf.light_intensity", default=4.0)
         self.shape_pregen = conf.get_bool("train.shape_pregen", default=False)
@@ -161,6 +168,8 @@ class PSNetwork(nn.Module):
 
     def _forward_train(self, input, noise=None):
         from .train import S2TrainStep, flat_params
+        if self.microfacet:
+            raise NotImplementedError("psnerf_b200 train step: render_model=microfacet is inference-only (no shipped conf trains it)")
         if not (self.shape_pregen and self.normal_mlp and self.visibility):
             raise NotImplementedError("psnerf_b200 train step: needs shape_pregen, normal_mlp and visibility (all shipped confs)")
         if not (self.light_vis_detach and self.conf.get_bool("train.vis_rgb_detach", default=False)):
@@ -233,9 +242,10 @@ class PSNetwork(nn.Module):
                 ikind, iptr = 2, t.reshape(1, 3).expand(L, 3).contiguous()
         else:
             iscalar = float(inten)
-        prm = B.ShadeParams(self.n_freqs, self.n_freqs_n, self.nbasis_lobes, 1 if self.specular_rgb else 0, ikind, iscalar)
+        prm = B.ShadeParams(self.n_freqs, self.n_freqs_n, self.nbasis_lobes, 1 if self.specular_rgb else 0, ikind, iscalar,
+                            1 if self.microfacet else 0, self.fresnel_f0)
         rgb = torch.empty(L, N, 3, device=dev)
-        spec = torch.empty(L, N, 3, device=dev)
+        spec = torch.empty(1 if self.microfacet else L, N, 3, device=dev)  # microfacet: the per-pixel roughness image
         vis = torch.empty(L, N, 3, device=dev) if self.visibility else None
         normal = torch.empty(1, N, 3, device=dev) if self.normal_mlp else None
         albedo = torch.empty(1, N, 3, device=dev)
@@ -246,7 +256,7 @@ class PSNetwork(nn.Module):
         a_new = w_new = None
         if albedo_new is not None:
             a_new = engine.f32c(torch.as_tensor(albedo_new).to(dev).reshape(3))
-        if basis_new is not None:
+        if basis_new is not None and not self.microfacet:  # renderer.py:175 sits in the sgbasis branch
             nb = self.nbasis_lobes
             wn = torch.zeros(3 if self.specular_rgb else 1, nb)
             wn[:, basis_new] = torch.as_tensor(2.0 ** torch.as_tensor(basis_new, dtype=torch.float64) / 100).float()
@@ -256,8 +266,9 @@ class PSNetwork(nn.Module):
                 P(self.normal_net.packed().handle) if self.normal_mlp else C.c_void_p(0),
                 P(self.albedo_net.packed().handle), P(self.rough_net.packed().handle),
                 P(self.visibility_net.packed().handle) if self.visibility else C.c_void_p(0),
-                P(engine.f32c(self.sgbasis.lobe.detach())), C.byref(prm), P(surf), P(view), P(nin), P(pix), Ns, N,
-                P(lights), L, P(iptr), P(a_new), P(w_new), P(rgb), P(spec), P(vis), P(normal), P(albedo), P(sgw), P(ws),
+                P(None if self.microfacet else engine.f32c(self.sgbasis.lobe.detach())), C.byref(prm), P(surf), P(view), P(nin),
+                P(pix), Ns, N, P(lights), L, P(iptr), P(a_new), P(w_new), P(rgb), P(spec), P(vis), P(normal), P(albedo),
+                P(None if self.microfacet else sgw), P(ws),
                 ws.numel(), self._prec(), engine._stream()), "psn_shade_stage2_edit")
         out = {"points": input["points"], "object_mask": input["object_mask"], "network_object_mask": input["surface_mask"],
                "sg_rgb_values": rgb, "normal_values": input["normal"], "sg_diffuse_albedo_values": albedo,
@@ -273,9 +284,15 @@ class PSNetwork(nn.Module):
                                               engine._stream()), "psn_s2_point_nets")
             albedo_jitter = torch.ones(1, N, 3, device=dev)
             albedo_jitter[0, pixl] = aj
-            rough_jitter = torch.ones(1, N, self.nbasis, device=dev)
-            rough_jitter[0, pixl] = wj
-            out.update({"albedo_values": albedo, "albedo_jitter": albedo_jitter, "rough_values": sgw,
+            if self.microfacet:  # renderer.py:224-226: [1,N,3] roughness images
+                rough_jitter = torch.ones(1, N, 3, device=dev)
+                rough_jitter[0, pixl] = wj.expand(-1, 3)
+                rough_ori = spec
+            else:
+                rough_jitter = torch.ones(1, N, self.nbasis, device=dev)
+                rough_jitter[0, pixl] = wj
+                rough_ori = sgw
+            out.update({"albedo_values": albedo, "albedo_jitter": albedo_jitter, "rough_values": rough_ori,
                         "rough_jitter": rough_jitter})
         if self.normal_mlp:
             out["normal_pred"] = normal
@@ -294,5 +311,6 @@ class PSNetwork(nn.Module):
                                 "psn_s2_visibility")
                     vt[:, pixl, :] = raw.unsqueeze(-1).expand(-1, -1, 3)
                 out["vis_train"] = vt
-        out["sg_weight"] = sgw
+        if not self.microfacet:
+            out["sg_weight"] = sgw
         return out

@@ -158,6 +158,21 @@ def make_stage2_edit():
         for k in ("sg_rgb_values", "sg_specular_rgb_values", "visibility", "sg_diffuse_albedo_values", "sg_weight"):
             out["%s_%s" % (cname, k)] = np_(res[k])
     out["checksum"] = checksum(sd1)
+    # render_model = microfacet (GGX; no shipped conf uses it): REAL reference PSNetwork under the same seed protocol
+    confm = synth.stage2_conf(**{"train.render_model": "microfacet"})
+    torch.manual_seed(0)
+    mm = m2.PSNetwork(ref_loader.DictConf(confm))
+    sdm = synth.perturb_state_dict({k: v.clone() for k, v in mm.state_dict().items()}, rel=0.5, seed=1)
+    mm.load_state_dict(sdm)
+    for cname in ("multi", "single"):
+        inp = micro_case_input(cname)
+        torch.manual_seed(123)
+        with torch.no_grad():
+            res = mm(inp)
+        for k in ("sg_rgb_values", "sg_specular_rgb_values", "visibility", "sg_diffuse_albedo_values", "normal_pred"):
+            out["micro_%s_%s" % (cname, k)] = np_(res[k])
+        assert "sg_weight" not in res
+    out["micro_checksum"] = checksum(sdm)
     # light grid of the envmap mode: gen_light_xyz / sph2cart taken from the reference file by name (the module itself imports
     # cv2 / imageio, absent here), light_h = 16 as in stage2/eval.py:100
     import ast
@@ -182,6 +197,15 @@ def edit_case_input():
     inp = synth.stage2_input(h, w, L, all_surface=False, seed=33, mask_frac=0.5)
     g = torch.Generator().manual_seed(8)
     inp["light_intensity"] = torch.rand(L, 3, generator=g) * 2.0  # env_light[lstart:lend] is [L,3]
+    return inp
+
+
+def micro_case_input(cname):
+    if cname == "multi":
+        inp = synth.stage2_input(12, 14, 5, all_surface=False, seed=33, mask_frac=0.5)
+        inp["light_intensity"] = torch.rand(5, 3, generator=torch.Generator().manual_seed(8)) * 2.0
+    else:
+        inp = synth.stage2_input(9, 11, 1, all_surface=True, seed=34)
     return inp
 
 

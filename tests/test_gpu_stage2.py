@@ -52,6 +52,21 @@ def test_shading_vs_golden(variant, case, prec):
 
 
 @pytest.mark.parametrize("prec", PRECISIONS)
+@pytest.mark.parametrize("case", ["multi", "single"])
+def test_microfacet_vs_golden(case, prec):
+    """render_model = microfacet (psn_shade_params.render_model = 1) vs the real reference's outputs."""
+    conf, sd = util.stage2_micro_state_dict()
+    m = make_model(conf, sd, prec)
+    g = util.golden("stage2_edit")
+    out = m(to_cuda(util.micro_case_input(case)))
+    assert "sg_weight" not in out
+    for k in util.MICRO_KEYS:
+        assert tuple(out[k].shape) == g["micro_%s_%s" % (case, k)].shape, k
+        # the GGX lobe divides by cos^2 terms: a few 1e-5 of headroom over the SG path on the rgb image
+        assert util.max_abs(out[k].cpu(), g["micro_%s_%s" % (case, k)]) < TOL[prec] * (5 if k in ("visibility", "sg_rgb_values") else 1), k
+
+
+@pytest.mark.parametrize("prec", PRECISIONS)
 @pytest.mark.parametrize("case", list(util.EDIT_CASES))
 def test_material_editing_vs_golden(case, prec):
     """albedo_new / basis_new (psn_shade_stage2_edit) with [L,3] intensities vs the real reference's outputs."""

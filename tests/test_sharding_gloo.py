@@ -25,7 +25,7 @@ def _worker(rank, world, port, n_rays, q):
     # a fake "render": pixel value = f(ray id); every rank must end up with the identical full image
     local = torch.stack([idx.float() * 2.0, idx.float() + 0.5, -idx.float()], -1)
     full = sharding.gather_pixels(local, n_rays, rank, world)
-    q.put((rank, full))
+    q.put((rank, full.numpy()))  # plain ndarray: a torch tensor travels as a shared-memory handle that dies with this process
     dist.destroy_process_group()
 
 
@@ -55,7 +55,7 @@ def test_gather_pixels_world2_gloo():
     ids = torch.arange(n_rays).float()
     want = torch.stack([ids * 2.0, ids + 0.5, -ids], -1)
     for r in range(world):
-        assert torch.equal(res[r], want)
+        assert torch.equal(torch.from_numpy(res[r]), want)
 
 
 def _grad_worker(rank, world, port, q):
@@ -69,7 +69,7 @@ def _grad_worker(rank, world, port, q):
     if rank == 1:
         m[2].bias.grad = None                                                # a parameter that got no gradient on this rank
     sharding.allreduce_gradients(m, world)
-    q.put((rank, [p.grad.clone() for p in m.parameters()]))
+    q.put((rank, [p.grad.clone().numpy() for p in m.parameters()]))
     dist.destroy_process_group()
 
 
@@ -100,4 +100,4 @@ def test_allreduce_gradients_world2_gloo():
     want = [a / world for a in acc]
     for r in range(world):
         for got, w in zip(res[r], want):
-            assert torch.allclose(got, w, atol=1e-6)
+            assert torch.allclose(torch.from_numpy(got), w, atol=1e-6)

@@ -77,3 +77,24 @@ def edit_case_input():
     g = torch.Generator().manual_seed(8)
     inp["light_intensity"] = torch.rand(L, 3, generator=g) * 2.0
     return inp
+
+
+MICRO_KEYS = ("sg_rgb_values", "sg_specular_rgb_values", "visibility", "sg_diffuse_albedo_values", "normal_pred")
+
+
+def micro_case_input(cname):
+    """render_model = microfacet cases of make_golden.py:make_stage2_edit."""
+    if cname == "multi":
+        inp = synth.stage2_input(12, 14, 5, all_surface=False, seed=33, mask_frac=0.5)
+        inp["light_intensity"] = torch.rand(5, 3, generator=torch.Generator().manual_seed(8)) * 2.0
+    else:
+        inp = synth.stage2_input(9, 11, 1, all_surface=True, seed=34)
+    return inp
+
+
+def stage2_micro_state_dict():
+    from psnerf_b200.stage2 import PSNetwork
+    conf = synth.stage2_conf(**{"train.render_model": "microfacet"})
+    torch.manual_seed(0)
+    sd0 = {k: v.detach().clone() for k, v in PSNetwork(conf).state_dict().items()}
+    return conf, synth.perturb_state_dict(sd0, rel=0.5, seed=1)
