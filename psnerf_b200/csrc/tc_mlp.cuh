@@ -605,9 +605,9 @@ __device__ __forceinline__ float pe_jac_tab(const Smem& s, int row, int k, int* 
 // softplus(beta=100) on pre-scaled accumulators: zs = 100*log2(e)*z  ->  softplus(z) = c * max(zs, lg2(1 + 2^min(zs,40))),
 // c = ln2/100 (times any layer constant).  2 MUFU + 4 ALU ops; for zs > ~25 the lg2 term equals zs in fp32, so the max
 // reproduces PyTorch's linear branch (threshold 20) to <1e-9 without a compare/select.
-// (Measured alternative, profiles/README.md: one MUFU + a degree-6 FMA-pipe polynomial for lg2(1 + u) halves the XU load but
-// costs five more issue slots per activation; with the epilogue warps sharing schedulers with the MMA / producer warps the
-// march kernel got 6 % slower, so the two-MUFU form stays.)
+// (Measured alternatives, profiles/README.md: one MUFU + a degree-6 FMA-pipe polynomial for lg2(1 + u) halves the XU load but
+// costs five more issue slots per activation - the march kernel got 8 % slower; applying it to every 2nd / 4th element was
+// within run-to-run noise of this form, so the two-MUFU form stays.)
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
