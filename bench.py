@@ -343,11 +343,14 @@ def main():
             tf = rad["rows_per_launch"] * MFLOP_RAD * 1e6 / (rad["ms_per_launch"] * 1e-3) / 1e12
             traffic, traffic_src = None, None  # dram read+write bytes per launch of this kernel on this workload (committed ncu capture)
             try:
-                cands = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.startswith("r1_ncu_v") and f.endswith(".json"))
-                with open(os.path.join(ROOT, "profiles", cands[-1])) as f:
-                    caps = [c for c in json.load(f) if "k_tc_rad" in c["kernel"]]
-                big = max(caps, key=lambda c: c["metrics"]["gpu__time_duration.sum"]["value"])
-                traffic, traffic_src = (big["dram_bytes_total"], cands[-1]) if precision == "tc" else (None, None)
+                cands = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if "_ncu_v" in f and f.endswith(".json"))
+                for name in reversed(cands):  # newest summary that holds a capture of the radiance kernel
+                    with open(os.path.join(ROOT, "profiles", name)) as f:
+                        caps = [c for c in json.load(f) if "k_tc_rad" in c["kernel"]]
+                    if caps and precision == "tc":
+                        big = max(caps, key=lambda c: c["metrics"]["gpu__time_duration.sum"]["value"])
+                        traffic, traffic_src = big["dram_bytes_total"], name
+                        break
             except Exception:
                 pass
             roof = {"bound": "tensor", "kernel": "radiance (geo fwd + analytic normal + app MLP), %s path" % precision,
