@@ -182,6 +182,12 @@ int psn_tc_debug_layer(const psn_mlp* geo, const float* pts, int64_t M, int laye
 /* Bring-up tool: clock64() timeline of one tile of the tensor-core occupancy kernel; trace is int64[256] on the device. */
 int psn_tc_debug_trace(const psn_mlp* geo, const float* pts, int64_t M, float* out, long long* trace, void* stream);
 
+/* Same for the radiance kernel (23 steps per tile): MMA-lane slots step*8 + {0..3 a_ready, 4 wait-activations, 5 wait-weights,
+ * 7 last commit}; trace[192 + step] = epilogue of the step finished (row 0).  stash: psn_workspace-style scratch of at least
+ * 148 * 640 KB. */
+int psn_tc_debug_trace_rad(const psn_mlp* geo, const psn_mlp* app, const float* pts, const float* views, int64_t M,
+                           float* rgb, float* alpha, void* stash, long long* trace, void* stream);
+
 /* ---- stage-2 train step (BASELINE config 5): PSNetwork.forward + backward, stage2/trainer.py:394-410 ------------------------
  * Gradient-carrying parts (renderer.py:193-199,211-231,251-262 with light_vis_detach = vis_rgb_detach = True): the per-point nets
  * through the SG shading of all L lights and their jittered re-evaluation, light directions / intensities, and visibility_net

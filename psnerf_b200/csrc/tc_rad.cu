@@ -51,19 +51,14 @@ struct TcRadArgs {
   int with_app;  // 1: radiance (23 steps), 0: gradient only (16 steps)
 };
 
-// entry idx of [v, sin(2^0 v), cos(2^0 v), ...] (network.py:141-150), used for the per-tile view-direction encoding
-__device__ __forceinline__ float pe_entry_r(const float x[3], int idx) {
-  if (idx < 3) return idx == 0 ? x[0] : (idx == 1 ? x[1] : x[2]);  // selects, not a dynamically indexed local array
-  const int j = idx - 3, oct = j / 6, r = j - 6 * oct, c = r % 3;
-  const float a = (float)(1 << oct) * (c == 0 ? x[0] : (c == 1 ? x[1] : x[2]));
-  return r < 3 ? sinf(a) : cosf(a);
-}
-
 #define PSN_INV_SQRT2 0.70710678118654752440f
 
+// TRACE (bring-up tool only): clock64 timeline of tile iteration TRACE_ITER of CTA 0 - MMA-lane slots as in mma_loop, plus
+// trace[192 + step] / trace[224 + step] = time at which row 0 / sub 0 finished / started the epilogue of that step.
+template <bool TRACE>
 __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* __restrict__ rgb, float* __restrict__ alpha,
-         float* __restrict__ grad_out) {
+         float* __restrict__ grad_out, long long* trace) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const Smem s = carve(smem_raw);
   const uint32_t tmem_base = setup(s);
@@ -75,12 +70,17 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
   if (warp < EPI_WARP0) {
     regs_shrink_control();
     if (warp == 0 && lane == 0) producer_loop(s, g.prog, iters);
-    if (warp == 1) mma_loop(s, g.prog, iters, tmem_base);
+    if (warp == 1) mma_loop(s, g.prog, iters, tmem_base, TRACE ? trace : nullptr);
     __syncwarp();
   } else {
     regs_grow_epilogue();
     EpiCtx e = epi_ctx(tmem_base);
     const int row = e.row, sub = e.sub;
+    int tstep = 0;  // trace only
+#define PSN_RAD_MARK(slot)                                                                                        \
+  do {                                                                                                              \
+    if (TRACE && trace && it == TRACE_ITER && blockIdx.x == 0 && row == 0 && sub == 0) trace[(slot) + tstep] = clock64(); \
+  } while (0)
     uint4* stash = g.scratch + (size_t)blockIdx.x * SCR_U4_PER_CTA;
     float4* parked = reinterpret_cast<float4*>(stash + SCR_STASH_U4);
     for (long long it = 0; it < iters; ++it) {
@@ -105,6 +105,7 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
       }
       // ---- s0..s7: geo forward --------------------------------------------------------------------------------------
       float part = 0.f;
+      tstep = 0;
 #pragma unroll 1
       for (int l = 0; l < 8; ++l) {
         const float* bias = g.gbias[l];
@@ -149,6 +150,8 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
           epi_store_a16(e, e.d_col0(), col, v);
           epi_signal_a(s, pass);
         });
+        PSN_RAD_MARK(192);
+        ++tstep;
         e.step_ctr++;
       }
       float g_acc[3] = {0.f, 0.f, 0.f};  // this thread's share of J_pe^T (d logit / d pe)
@@ -160,6 +163,8 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
           epi_store_a16(e, e.d_col0(), col, v);
           epi_signal_a(s, pass);
         });
+        PSN_RAD_MARK(192);
+        ++tstep;
         e.step_ctr++;
         // ---- s9: appearance layer 0, feature part -> parked; then the reverse seed dz_7 -> A -------------------------------
         struct Seed { uint4 q[2]; float4 w[4]; };
@@ -187,6 +192,8 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
           epi_store_a16(e, e.d_col0(), col, v);
           epi_signal_a(s, pass);
         });
+        PSN_RAD_MARK(192);
+        ++tstep;
         e.step_ctr++;
       }
       // ---- s10..s16: reverse through layers 7..1 -----------------------------------------------------------------------------
@@ -227,6 +234,8 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
           epi_store_a16(e, e.d_col0(), col, v);
           epi_signal_a(s, pass);
         });
+        PSN_RAD_MARK(192);
+        ++tstep;
         e.step_ctr++;
       }
       // ---- s17: reverse layer 0 -> gradient ------------------------------------------------------------------------------
@@ -244,6 +253,8 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
           }
         }
       }
+      PSN_RAD_MARK(192);
+      ++tstep;
       e.step_ctr++;
       tc_fence_before();
       s.stage[sub * TILE_M + row] = make_float4(g_acc[0], g_acc[1], g_acc[2], part);
@@ -259,8 +270,13 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
       if (sub == 0 && grad_out && idx < M) { grad_out[idx * 3] = gr[0]; grad_out[idx * 3 + 1] = gr[1]; grad_out[idx * 3 + 2] = gr[2]; }
       if (g.with_app) {
         {  // [p, PE(view/|view|), gradient, 0...] -> K block 0, 16 columns per sub (network.py:98,127-132)
+          // The view encoding goes through the smem table (the point encoding in it is dead after the Jacobian reads above, which
+          // every warp finished before the staging barrier): three sincosf per thread instead of sixteen sinf / cosf selections -
+          // the clock64 timeline showed 16 000 idle MMA cycles per tile at this hand-over.
           const float nv = sqrtf(vd[0] * vd[0] + vd[1] * vd[1] + vd[2] * vd[2]);
           const float vn[3] = {vd[0] / nv, vd[1] / nv, vd[2] / nv};
+          epi_write_pe(s, row, sub, vn, g.octaves_view);
+          named_bar_sync(1, EPI_THREADS);
           const int o_g = 3 + g.pe_view_dim;
           float v[CW];
 #pragma unroll
@@ -268,7 +284,7 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
             const int k = sub * CW + i;
             float val = 0.f;
             if (k < 3) val = (k == 0 ? p[0] : (k == 1 ? p[1] : p[2]));
-            else if (k < o_g) val = pe_entry_r(vn, k - 3);
+            else if (k < o_g) val = s.pe[(k - 3) * TILE_M + row];
             else if (k < o_g + 3) val = (k == o_g ? gr[0] : (k == o_g + 1 ? gr[1] : gr[2]));
             v[i] = val;
           }
@@ -291,6 +307,8 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
           epi_store_a16(e, e.d_col0(), col, v);
           epi_signal_a(s, pass);
         });
+        PSN_RAD_MARK(192);
+        ++tstep;
         e.step_ctr++;
         // ---- s19..s21: appearance layers 1..3 -------------------------------------------------------------------------------
 #pragma unroll 1
@@ -304,7 +322,9 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
             epi_store_a16(e, e.d_col0(), col, v);
             epi_signal_a(s, pass);
           });
-          e.step_ctr++;
+          PSN_RAD_MARK(192);
+        ++tstep;
+        e.step_ctr++;
         }
         // ---- s22: appearance layer 4 -> rgb ------------------------------------------------------------------------------------
         epi_wait_d(s, e);
@@ -318,6 +338,8 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
             alpha[idx] = 1.f / (1.f + __expf(10.f * logit));
           }
         }
+        PSN_RAD_MARK(192);
+        ++tstep;
         e.step_ctr++;
         tc_fence_before();
       }
@@ -359,6 +381,7 @@ static int make_tc_rad(const psn_mlp* geo, const psn_mlp* app, void* scratch, Tc
     a->octaves_view = app->desc.octaves;
     a->pe_view_dim = 3 + 6 * app->desc.octaves;
     PSN_REQUIRE(3 + a->pe_view_dim + 3 + 256 == app->in_dims[0], PSN_ERR_SHAPE, "app net input layout mismatch");
+    PSN_REQUIRE(a->pe_view_dim <= PE_K, PSN_ERR_SHAPE, "tensor path: view encoding wider than %d", PE_K);
   }
   a->prog.n_steps = n;
   a->bias_feat = geo->fwd[8].bias;
@@ -381,16 +404,18 @@ size_t tc_stash_bytes() {
 }
 
 static int launch_tc_rad(const TcRadArgs& a, const PointGen& gen, long long M, const int* M_dev, float* rgb, float* alpha,
-                         float* grad, cudaStream_t st) {
-  PSN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_rad, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+                         float* grad, cudaStream_t st, long long* trace = nullptr) {
+  const void* kfn = trace ? (const void*)k_tc_rad<true> : (const void*)k_tc_rad<false>;
+  PSN_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   {
-    const int rcr = check_launch_regs((const void*)k_tc_rad, "k_tc_rad");
+    const int rcr = check_launch_regs(kfn, "k_tc_rad");
     if (rcr) return rcr;
   }
   const long long tiles = M_dev ? (long long)num_ctas() : (M + TILE_M - 1) / TILE_M;
-  const int grid = tc_grid((const void*)k_tc_rad, tiles);
+  const int grid = tc_grid(kfn, tiles);
   count_launch();
-  k_tc_rad<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(a, gen, M, M_dev, rgb, alpha, grad);
+  if (trace) k_tc_rad<true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(a, gen, M, M_dev, rgb, alpha, grad, trace);
+  else k_tc_rad<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(a, gen, M, M_dev, rgb, alpha, grad, nullptr);
   PSN_CUDA_CHECK(cudaGetLastError());
   return PSN_OK;
 }
@@ -414,3 +439,20 @@ int tc_gradient(const psn_mlp* geo, const PointGen& gen, long long M, const int*
 }
 
 }  // namespace psn
+
+using namespace psn;
+
+// Bring-up tool: clock64() timeline of one tile of the radiance kernel (explicit points / view directions): trace is int64[256].
+extern "C" int psn_tc_debug_trace_rad(const psn_mlp* geo, const psn_mlp* app, const float* pts, const float* views, int64_t M,
+                                      float* rgb, float* alpha, void* stash, long long* trace, void* stream) {
+  PSN_REQUIRE(geo && app && pts && views && rgb && alpha && stash && trace, PSN_ERR_ARG, "psn_tc_debug_trace_rad: bad argument");
+  TcRadArgs a;
+  int rc = make_tc_rad(geo, app, stash, &a);
+  if (rc) return rc;
+  PointGen gen;
+  memset(&gen, 0, sizeof(gen));
+  gen.kind = GEN_EXPLICIT;
+  gen.pts = pts;
+  gen.views = views;
+  return launch_tc_rad(a, gen, M, nullptr, rgb, alpha, nullptr, (cudaStream_t)stream, trace);
+}
