@@ -223,6 +223,25 @@ int psn_s2_train_backward(const psn_train_net* normal_net, const psn_train_net* 
                           const float* g_albedo_j, const float* g_weights_j, const float* g_vis_train, float* d_lights,
                           float* d_intensity, void* tape, int64_t tape_bytes, void* ws, int64_t ws_bytes, void* stream);
 
+/* ---- stage-1 train step: the differentiable field (stage1/model/network.py:85-136 under autograd, create_graph normals) ----------
+ * psn_train_net views carry the EFFECTIVE weights (weight norm folded: W = g v / |v|, network.py:64,77) of the geo net
+ * (n_layers = 9, skip = index of the layer whose input is cat[x, pe]/sqrt2) and of the appearance net (nullable: gradient-only
+ * evaluation, e.g. the surface normals of rendering.py:203-211).  Forward outputs per sample: rgb [M,3] (app only), logit [M]
+ * (nullable), grad [M,3] = d logit / d p.  The backward takes the cotangents of those three (any may be NULL) and ACCUMULATES
+ * the weight / bias gradients, including the double-backward route through grad.  tape: psn_s1_train_tape_bytes, written by
+ * the forward, consumed (and clobbered) by ONE backward; ws: psn_s1_train_ws_bytes. */
+int64_t psn_s1_train_tape_bytes(const psn_train_net* geo, const psn_train_net* app, int octaves, int octaves_view, int64_t M);
+int64_t psn_s1_train_ws_bytes(const psn_train_net* geo, const psn_train_net* app, int octaves, int octaves_view, int64_t M);
+int psn_s1_train_forward(const psn_train_net* geo, const psn_train_net* app, int octaves, int octaves_view, float rescale,
+                         const float* pts, const float* views, int64_t M, float* rgb, float* logit, float* grad,
+                         void* tape, int64_t tape_bytes, void* ws, int64_t ws_bytes, void* stream);
+int psn_s1_train_backward(const psn_train_net* geo, const psn_train_net* app, int octaves, int octaves_view, float rescale,
+                          int64_t M, const float* g_rgb, const float* g_logit, const float* g_grad,
+                          void* tape, int64_t tape_bytes, void* ws, int64_t ws_bytes, void* stream);
+/* Backward of psn_composite: d_rgb_s [N,S,3], d_alpha [N,S] from g_rgb [N,3] / g_acc [N] (either may be NULL), S <= 256. */
+int psn_composite_bwd(const float* rgb_s, const float* alpha, int64_t N, int S, int white_background,
+                      const float* g_rgb, const float* g_acc, float* d_rgb_s, float* d_alpha, void* stream);
+
 /* alpha compositing of per-sample (rgb, alpha): rendering.py:196-197,214-216. */
 int psn_composite(const float* rgb_s /*[N,S,3]*/, const float* alpha /*[N,S]*/, int64_t N, int S,
                   int white_background, float* rgb /*[N,3]*/, float* acc /*[N]*/, void* stream);

@@ -349,6 +349,45 @@ def unisurf_render(sd, cfg_all, pixels, camera_mat, world_mat, it=100000, noise=
     return out
 
 
+def unisurf_train(sd, cfg_all, pixels, camera_mat, world_mat, it=100000, neigh_u=None, noise=None):
+    """Renderer.unisurf with eval_=False (the training forward, rendering.py:50-226), differentiable w.r.t. the tensors of
+    ``sd``: radiance samples with create_graph normals (network.py:117,130-132), compositing, surface normals and the
+    normal-consistency term diff_norm (rendering.py:199-212).  The surface search and the sample depths carry no gradient
+    (rendering.py:79-87 runs under no_grad).  ``neigh_u`` [Ns,3] replaces torch.rand_like (rendering.py:204)."""
+    mcfg, rcfg = cfg_all["model"], cfg_all["rendering"]
+    with torch.no_grad():
+        sd0 = {k: v.detach() for k, v in sd.items()}
+        base = unisurf_render(sd0, cfg_all, pixels, camera_mat, world_mat, it=it, noise=noise, return_aux=True)
+        depth, pts, obj = base["aux"]["depth"], base["aux"]["points"], base["mask_pred"]
+        ray0, rayd = pixels_to_rays(pixels, camera_mat, world_mat)
+    o, d = ray0.reshape(-1, 3), rayd.reshape(-1, 3)
+    N, S = depth.shape
+    p_fg = (o.unsqueeze(1) + d.unsqueeze(1) * depth.unsqueeze(-1)).reshape(-1, 3)
+    v_fg = (-1 * d.unsqueeze(1).repeat(1, S, 1)).reshape(-1, 3)
+    x = geo_forward(sd, p_fg, mcfg)
+    v = positional_encoding(v_fg / torch.norm(v_fg, dim=-1, keepdim=True), mcfg["octaves_pe_views"])
+    n = geo_gradient_analytic(sd, p_fg, mcfg)  # differentiable restatement of gradient(p, create_graph=True)
+    rgb_s = app_forward(sd, p_fg, n, v, x[..., 1:]).reshape(N, S, 3)
+    alpha = torch.sigmoid(x[..., :1] * -10.0).view(N, S)
+    w = composite(alpha)
+    rgb = torch.sum(w.unsqueeze(-1) * rgb_s, dim=-2)
+    sp = pts[obj]
+    Ns = sp.shape[0]
+    if neigh_u is None:
+        neigh_u = torch.rand_like(sp)
+    pp = torch.cat([sp, sp + (neigh_u - 0.5) * 0.01], 0)
+    g = geo_gradient_analytic(sd, pp, mcfg)[:, 0, :]
+    nrm = g / (g.norm(2, dim=1).unsqueeze(-1) + 10 ** (-5))
+    normal = torch.zeros_like(rgb)
+    normal[obj] = nrm[:Ns]
+    diff_norm = torch.norm(nrm[:Ns] - nrm[Ns:], dim=-1)
+    acc = torch.sum(w, -1)
+    if rcfg["white_background"]:
+        rgb = rgb + (1.0 - acc.unsqueeze(-1))
+    return {"rgb": rgb.reshape(1, -1, 3), "mask_pred": obj, "diff_norm": diff_norm, "normal_pred": normal.reshape(1, -1, 3),
+            "acc_map": acc.reshape(1, -1)}
+
+
 def light_visibility(sd, mcfg, surf, light_dir, lnear=0.1, lfar=3.5, n_steps=128, box=1.1):
     """Shadow-ray transmittance per (light, surface point), light-major [L*Ns] (rendering.py:378-408)."""
     dt = surf.dtype

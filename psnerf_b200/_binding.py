@@ -92,6 +92,13 @@ def load():
     lib.psn_tc_debug_trace.argtypes = [vp, vp, i64, vp, vp, vp]
     lib.psn_tc_debug_trace_rad.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp, vp, vp]
     tn = C.POINTER(TrainNet)
+    lib.psn_s1_train_tape_bytes.argtypes = [tn, tn, i32, i32, i64]
+    lib.psn_s1_train_tape_bytes.restype = i64
+    lib.psn_s1_train_ws_bytes.argtypes = [tn, tn, i32, i32, i64]
+    lib.psn_s1_train_ws_bytes.restype = i64
+    lib.psn_s1_train_forward.argtypes = [tn, tn, i32, i32, f32, vp, vp, i64, vp, vp, vp, vp, i64, vp, i64, vp]
+    lib.psn_s1_train_backward.argtypes = [tn, tn, i32, i32, f32, i64, vp, vp, vp, vp, i64, vp, i64, vp]
+    lib.psn_composite_bwd.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp, vp, vp]
     lib.psn_s2_train_tape_bytes.argtypes = [tn, tn, tn, tn, i64, i32, i32]
     lib.psn_s2_train_tape_bytes.restype = i64
     lib.psn_s2_train_forward.argtypes = [tn, tn, tn, tn, vp, vp, C.POINTER(ShadeParams), vp, vp, vp, i64, i64, vp, i32, vp, vp, vp, i32,

@@ -1,0 +1,122 @@
+// fp32 GEMM + element-wise pieces shared by the train-step translation units (stage2_train.cu, stage1_train.cu).
+#pragma once
+#include "common.cuh"
+
+namespace psn {
+
+// ---------------------------------------------------------------------------------------------------------------------
+// fp32 GEMM, 64x64x16 tiles, 256 threads, 4x4 per thread.
+//   FORM 0 (NT): C[m,n] = sum_k A[m,k] B[n,k]      forward Linear        (A = X [M,K], B = W [N,K])
+//   FORM 1 (NN): C[m,n] = sum_k A[m,k] B[k,n]      input gradient        (A = dZ [M,K], B = W [K,N])
+//   FORM 2 (TN): C[m,n] += sum_k A[k,m] B[k,n]     weight gradient       (A = dZ [K,M], B = X [K,N]); split over k, atomicAdd
+// EPI: 0 none, 1 +bias, 2 +bias relu, 3 +bias sigmoid
+// ---------------------------------------------------------------------------------------------------------------------
+template <int FORM>
+__global__ void __launch_bounds__(256)
+k_gemm(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc,
+       const float* __restrict__ bias, int M, int N, int K, int epi, int k_per_split) {
+  __shared__ __align__(16) float As[16][68];
+  __shared__ __align__(16) float Bs[16][68];
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int kbeg = (FORM == 2) ? blockIdx.z * k_per_split : 0;
+  const int kend = (FORM == 2) ? min(K, kbeg + k_per_split) : K;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = kbeg; k0 < kend; k0 += 16) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int idx = threadIdx.x + 256 * j;
+      if (FORM == 2) {
+        const int m = idx & 63, k = idx >> 6;
+        As[k][m] = (k0 + k < kend && m0 + m < M) ? A[(size_t)(k0 + k) * lda + m0 + m] : 0.f;
+      } else {
+        const int k = idx & 15, m = idx >> 4;
+        As[k][m] = (k0 + k < kend && m0 + m < M) ? A[(size_t)(m0 + m) * lda + k0 + k] : 0.f;
+      }
+      if (FORM == 0) {
+        const int k = idx & 15, n = idx >> 4;
+        Bs[k][n] = (k0 + k < kend && n0 + n < N) ? B[(size_t)(n0 + n) * ldb + k0 + k] : 0.f;
+      } else {
+        const int n = idx & 63, k = idx >> 6;
+        Bs[k][n] = (k0 + k < kend && n0 + n < N) ? B[(size_t)(k0 + k) * ldb + n0 + n] : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j];
+      if (FORM == 2) {
+        atomicAdd(&C[(size_t)m * ldc + n], v);
+      } else {
+        if (epi >= 1) v += bias[n];
+        if (epi == 2) v = fmaxf(v, 0.f);
+        if (epi == 3) v = 1.f / (1.f + expf(-v));
+        C[(size_t)m * ldc + n] = v;
+      }
+    }
+  }
+}
+
+// dZ[r, c] = dY[r, c] * act'(Y[r, c]);  kind 0: identity, 2: relu (Y > 0), 3: sigmoid (Y (1 - Y))
+static __global__ void k_act_bwd(const float* __restrict__ dY, int lddy, const float* __restrict__ Y, int ldy, float* __restrict__ dZ, int lddz,
+                          long long rows, int ncols, int kind) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * ncols) return;
+  const long long r = i / ncols;
+  const int c = (int)(i - r * ncols);
+  const float g = dY[r * lddy + c], y = Y[r * ldy + c];
+  dZ[r * lddz + c] = kind == 2 ? (y > 0.f ? g : 0.f) : kind == 3 ? g * y * (1.f - y) : g;
+}
+static __global__ void k_colsum(const float* __restrict__ dZ, int ld, long long rows, int ncols, float* __restrict__ db) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncols) return;
+  const long long r0 = (long long)blockIdx.y * 1024, r1 = min(rows, r0 + 1024);
+  float s = 0.f;
+  for (long long r = r0; r < r1; ++r) s += dZ[r * ld + c];
+  atomicAdd(&db[c], s);
+}
+static inline unsigned nblk(long long n, int t = 256) { return (unsigned)((n + t - 1) / t); }
+
+static int gemm(int form, const float* A, int lda, const float* B, int ldb, float* C, int ldc, const float* bias, long long M, int N,
+                long long K, int epi, cudaStream_t st) {
+  if (M == 0 || N == 0 || K == 0) return PSN_OK;
+  count_launch();
+  if (form == 0) {
+    dim3 g((N + 63) / 64, (unsigned)((M + 63) / 64));
+    k_gemm<0><<<g, 256, 0, st>>>(A, lda, B, ldb, C, ldc, bias, (int)M, N, (int)K, epi, 0);
+  } else if (form == 1) {
+    dim3 g((N + 63) / 64, (unsigned)((M + 63) / 64));
+    k_gemm<1><<<g, 256, 0, st>>>(A, lda, B, ldb, C, ldc, bias, (int)M, N, (int)K, epi, 0);
+  } else {
+    const int kps = 512;
+    dim3 g((N + 63) / 64, (unsigned)((M + 63) / 64), (unsigned)((K + kps - 1) / kps));
+    k_gemm<2><<<g, 256, 0, st>>>(A, lda, B, ldb, C, ldc, bias, (int)M, N, (int)K, 0, kps);
+  }
+  PSN_CUDA_CHECK(cudaGetLastError());
+  return PSN_OK;
+}
+
+
+}  // namespace psn

@@ -4,7 +4,9 @@ Same constructor argument (cfg_all['model']), same parameter names (lin{l}.weigh
 lina{l}.*: reference checkpoints load unchanged), same initialisation draws under a given torch seed, same
 forward / gradient / infer_occ / infer_app signatures.  The arithmetic runs in the CUDA library
 (psn_occupancy, psn_infer_occ, psn_gradient, psn_radiance); there is no CPU implementation.
-Inference only: outputs carry no autograd graph.
+In eval() mode (or under no_grad) the outputs carry no autograd graph (tensor-core or fp32 inference kernels); in train()
+mode with gradients enabled forward(p, ray_d) and gradient(p) run the differentiable fp32 path of stage1/train.py
+(psn_s1_train_forward / _backward), including the create_graph normals the appearance MLP consumes.
 """
 import math
 
@@ -104,7 +106,13 @@ class NeuralNetwork(nn.Module):
         out = engine.infer_occ(g, p.reshape(-1, 3), self.feat_size + 1, self._prec())
         return out.reshape(*shp, self.feat_size + 1)
 
+    def _differentiable(self):
+        return self.training and torch.is_grad_enabled() and any(q.requires_grad for q in self.parameters())
+
     def gradient(self, p, tflag=True):
+        if tflag and self._differentiable():  # network.py:108-120 with create_graph=True
+            from . import train as T
+            return T.field(self, p.detach().reshape(-1, 3), None)[2].unsqueeze(1)
         g, _ = self._packed()
         return engine.gradient(g, p.detach().reshape(-1, 3), self._prec()).unsqueeze(1)
 
@@ -117,6 +125,11 @@ class NeuralNetwork(nn.Module):
         flat = p.detach().reshape(-1, 3)
         if only_occupancy:
             return engine.occupancy(g, flat, B.OUT_ALPHA, self._prec()).reshape(*shp, 1)
+        if ray_d is not None and self._differentiable():
+            from . import train as T
+            rgb, logit, _ = T.field(self, flat, ray_d.detach().reshape(-1, 3))
+            rgb = rgb.reshape(*shp, 3)
+            return (rgb, torch.sigmoid(-10.0 * logit).reshape(*shp, 1)) if return_addocc else rgb
         if ray_d is not None:
             rgb, alpha = engine.radiance(g, a, flat, ray_d.detach().reshape(-1, 3), self._prec())
             rgb = rgb.reshape(*shp, 3)

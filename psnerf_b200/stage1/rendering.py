@@ -63,6 +63,8 @@ class Renderer(nn.Module):
     def forward(self, pixels, camera_mat, world_mat, scale_mat, rendering_technique, add_noise=True, eval_=False, it=0,
                 visibility=False, light_dir=None):
         if rendering_technique == "unisurf":
+            if self.model.training and torch.is_grad_enabled() and not eval_ and any(p.requires_grad for p in self.model.parameters()):
+                return self.unisurf_train(pixels, camera_mat, world_mat, it=it, add_noise=add_noise)
             return self.unisurf(pixels, camera_mat, world_mat, scale_mat, it=it, add_noise=add_noise, eval_=eval_)
         if rendering_technique == "phong_renderer":
             return self.phong_renderer(pixels, camera_mat, world_mat, scale_mat)
@@ -82,6 +84,64 @@ class Renderer(nn.Module):
         d = engine.raymarch(g, origin, ray_direction[0], depth_range[0], rad, int(n_steps[0]), n_secant_steps, 0.5,
                             self.model._prec())
         return d.unsqueeze(0)
+
+    def _unisurf_plan(self, g, origin, dirs, it):
+        """UnisurfParams of a call: interval half-width delta(it) and the full_steps switch (rendering.py:116-127)."""
+        cfg = self.cfg
+        near = float(cfg["near"])
+        steps, steps_out = int(cfg["num_points_in"]), int(cfg["num_points_out"])
+        delta = float(torch.max(cfg["interval_start"] * torch.exp(-1 * cfg["interval_decay"] * it * torch.ones(1)),
+                                cfg["interval_end"] * torch.ones(1)))
+        full_ok = it > 5000
+        if full_ok and not near > 0:
+            d0 = engine.raymarch(g, origin, dirs, near, cfg["radius"], int(cfg["ray_marching_steps"]), 8, 0.5, self.model._prec())
+            hit = (d0.abs() != np.inf) & (d0 != 0)
+            dnp = torch.clamp(d0[hit] - delta, min=near)
+            full_ok = bool((dnp != 0.0).all())
+        return B.UnisurfParams(near, float(cfg["radius"]), delta, 0.5, int(cfg["ray_marching_steps"]), 8, steps,
+                               steps_out if full_ok else 0, 1 if self.white_background else 0)
+
+    def unisurf_train(self, pixels, camera_mat, world_mat, it=100000, add_noise=True, noise=None):
+        """Training forward of Renderer.unisurf (rendering.py:50-226 with eval_=False, called from training.py:180): the outputs
+        carry an autograd graph to every parameter of the field.  The surface search and the sample depths are computed by the
+        inference kernels without gradient (rendering.py:79-87 is under no_grad in the reference too); the radiance samples with
+        their create_graph normals, the compositing and the surface normals run through the differentiable CUDA path
+        (stage1/train.py: psn_s1_train_forward / _backward, psn_composite / _bwd).  ``noise`` optionally supplies the random
+        draws: 'depth' [N,S] uniform samples (rendering.py:139,163) and 'neigh' [Ns,3] (rendering.py:204)."""
+        from . import train as T
+        noise = noise or {}
+        with torch.no_grad():
+            g, a = self._geo_app()
+            origin, dirs = self._rays(pixels, camera_mat, world_mat)
+            N = dirs.shape[0]
+            prm = self._unisurf_plan(g, origin, dirs, it)
+            S = prm.steps_in + prm.steps_out
+            u = None
+            if add_noise:
+                u = noise["depth"].to(dirs.device) if "depth" in noise else torch.rand(N, S, device=dirs.device)
+            info = engine.render_unisurf(g, a, origin, dirs, prm, noise=u, want_sample_depth=True, precision=self.model._prec())
+            obj, pts = self._surface(info["depth"], origin, dirs)
+            o = torch.tensor(origin, dtype=torch.float32, device=dirs.device)
+            p_fg = (o[None, None, :] + dirs[:, None, :] * info["sample_depth"][:, :, None]).reshape(-1, 3)
+            v_fg = (-dirs)[:, None, :].expand(N, S, 3).reshape(-1, 3)
+            sp = pts[obj]
+            Ns = sp.shape[0]
+            nu = noise["neigh"].to(dirs.device) if "neigh" in noise else torch.rand_like(sp)
+            pp = torch.cat([sp, sp + (nu - 0.5) * 0.01], 0)
+        params = T.effective_params(self.model)
+        rgb_s, logit, _ = T.field(self.model, p_fg, v_fg, params)
+        alpha = torch.sigmoid(-10.0 * logit).view(N, S)  # network.py:134
+        rgb, acc = T.composite(rgb_s.view(N, S, 3), alpha, bool(self.white_background))
+        norm_pred = torch.zeros(N, 3, device=dirs.device)
+        if Ns > 0:
+            _, _, gg = T.field(self.model, pp, None, params)
+            normals_ = gg / (gg.norm(2, dim=1).unsqueeze(-1) + 10 ** (-5))
+            norm_pred = norm_pred.index_put((torch.nonzero(obj).squeeze(-1),), normals_[:Ns])
+            diff_norm = torch.norm(normals_[:Ns] - normals_[Ns:], dim=-1)
+        else:
+            diff_norm = torch.zeros(0, device=dirs.device)
+        return {"rgb": rgb.reshape(1, -1, 3), "mask_pred": obj, "diff_norm": diff_norm,
+                "normal_pred": norm_pred.reshape(1, -1, 3), "acc_map": acc.reshape(1, -1)}
 
     @torch.no_grad()
     def unisurf(self, pixels, camera_mat, world_mat, scale_mat, add_noise=False, it=100000, eval_=False):

@@ -209,6 +209,58 @@ def micro_case_input(cname):
     return inp
 
 
+S1_TRAIN_CASE = dict(h=12, w=10, s_in=12, s_out=6, msteps=64, it=100000, pose=(25.0, 15.0))
+S1_TRAIN_KEYS = ["rgb", "normal_pred", "acc_map", "diff_norm"]
+
+
+def make_stage1_grads():
+    """Gradients of the REAL reference's stage-1 training forward (Renderer.unisurf, eval_=False, add_noise=False) w.r.t. every
+    parameter of the field: scalar = sum of the differentiable outputs against fixed cotangents.  torch.rand_like (neighbour
+    points of the normal-consistency term, rendering.py:204) is recorded through a wrapper so that the restatement can be fed
+    the same draw."""
+    net_mod, rend_mod, common = ref_loader.load_stage1()
+    _, model, variants = stage1_variants(net_mod)
+    c = S1_TRAIN_CASE
+    cfg = synth.stage1_cfg(num_points_in=c["s_in"], num_points_out=c["s_out"], ray_marching_steps=c["msteps"])
+    model.load_state_dict(variants["trained"])
+    model.train()
+    rend = rend_mod.Renderer(model, cfg, device=torch.device("cpu"))
+    pix = synth.pixel_grid_xmajor(c["h"], c["w"])
+    K, pose = synth.intrinsics(c["h"], c["w"]), synth.look_at_pose(*c["pose"])
+    drawn = []
+    orig = torch.rand_like
+
+    def recording(t, *a, **k):
+        r = orig(t, *a, **k)
+        drawn.append(r.clone())
+        return r
+    torch.manual_seed(99)
+    torch.rand_like = recording
+    try:
+        out = rend(pix, K, pose, torch.eye(4)[None], "unisurf", add_noise=False, eval_=False, it=c["it"])
+    finally:
+        torch.rand_like = orig
+    assert len(drawn) == 1
+    g = torch.Generator().manual_seed(5)
+    cot = {k: torch.randn(out[k].shape, generator=g) for k in S1_TRAIN_KEYS}
+    scalar = sum((out[k] * cot[k]).sum() for k in S1_TRAIN_KEYS)
+    params = dict(model.named_parameters())
+    names = sorted(params)
+    grads = torch.autograd.grad(scalar, [params[n] for n in names], allow_unused=True)
+    res = {"neigh_u": np_(drawn[0]), "scalar": np.array(float(scalar)), "mask": np_(out["mask_pred"])}
+    for k in S1_TRAIN_KEYS:
+        res["cot_" + k] = np_(cot[k])
+        res["out_" + k] = np_(out[k])
+    for n, gr in zip(names, grads):
+        gr = torch.zeros_like(params[n]) if gr is None else gr
+        res["gsum_" + n] = np.array([float(gr.double().sum()), float(gr.double().abs().sum())])
+        if gr.numel() <= 300:
+            res["g_" + n] = np_(gr)
+    res["checksum"] = checksum(variants["trained"])
+    np.savez_compressed(os.path.join(HERE, "stage1_grads.npz"), **res)
+    print("stage1_grads: scalar", float(scalar), "params", len(names), "surface", int(out["mask_pred"].sum()))
+
+
 def make_stage2_grads():
     """Gradients of the REAL reference's PSNetwork (autograd) for a train-like step: trainable light directions and per-light
     intensities, 2 vis-train lights, xyz jitter; scalar = sum of outputs against fixed cotangents (the reference's loss module
@@ -263,5 +315,6 @@ if __name__ == "__main__":
     make_stage2()
     make_stage2_grads()
     make_stage2_edit()
-    for f in ("stage1_net", "stage1_render", "stage2_shade", "stage2_grads", "stage2_edit"):
+    make_stage1_grads()
+    for f in ("stage1_net", "stage1_render", "stage2_shade", "stage2_grads", "stage2_edit", "stage1_grads"):
         print(f, os.path.getsize(os.path.join(HERE, f + ".npz")) // 1024, "KB")

@@ -98,3 +98,14 @@ def stage2_micro_state_dict():
     torch.manual_seed(0)
     sd0 = {k: v.detach().clone() for k, v in PSNetwork(conf).state_dict().items()}
     return conf, synth.perturb_state_dict(sd0, rel=0.5, seed=1)
+
+
+# stage-1 training case of make_golden.py:make_stage1_grads
+S1_TRAIN_CASE = dict(h=12, w=10, s_in=12, s_out=6, msteps=64, it=100000, pose=(25.0, 15.0))
+S1_TRAIN_KEYS = ["rgb", "normal_pred", "acc_map", "diff_norm"]
+
+
+def s1_train_inputs():
+    c = S1_TRAIN_CASE
+    cfg = synth.stage1_cfg(num_points_in=c["s_in"], num_points_out=c["s_out"], ray_marching_steps=c["msteps"])
+    return cfg, synth.pixel_grid_xmajor(c["h"], c["w"]), synth.intrinsics(c["h"], c["w"]), synth.look_at_pose(*c["pose"])
