@@ -230,6 +230,42 @@ def extra_workloads(dev, precision, rend, view, peaks):
                                                 "note": "PSNetwork.forward + MainLoss/NormalLoss + backward + Adam (stage2/trainer.py:394-410); "
                                                         "96-light visibility pass detached (tensor-core inference kernel), fp32 GEMM backward"}
     ps.eval()
+    # Stage-1 analogue of configs[4]: 4096 random rays x 128 samples of the bench view, training forward
+    # (inference-kernel surface search + differentiable fp32 field incl. the double-backward normals) + Loss + backward + Adam
+    try:
+        from psnerf_b200.stage1 import Loss
+        net = rend.model
+        net.train()
+        gen = torch.Generator().manual_seed(2)
+        n_rays = 4096
+        pix_all = synth.pixel_grid_xmajor(H, W)
+        sel = torch.randperm(H * W, generator=gen)[:n_rays]
+        pix_t = pix_all[:, sel].to(dev)
+        rgb_gt = torch.rand(1, n_rays, 3, generator=gen).to(dev)
+        n_gt = torch.nn.functional.normalize(torch.randn(1, n_rays, 3, generator=gen), dim=-1).to(dev)
+        n_mask = torch.rand(1, n_rays, generator=gen).to(dev) > 0.5
+        m_gt = (torch.rand(1, n_rays, generator=gen) > 0.5).float().to(dev)
+        m_valid = torch.ones(1, n_rays, dtype=torch.bool, device=dev)
+        crit = Loss(1.0, 0.01, 0.05, 0.1, device=dev)
+        opt1 = torch.optim.Adam(net.parameters(), lr=1e-6)  # tiny rate: the timing loop must not walk the field away
+
+        def s1_step():
+            o = rend(pix_t, K, pose, None, "unisurf", add_noise=True, eval_=False, it=100000)
+            loss = crit(o, rgb_gt, n_gt, n_mask, o["acc_map"], m_gt, m_valid)["loss"]
+            opt1.zero_grad(set_to_none=True)
+            loss.backward()
+            opt1.step()
+        ms4 = _time_cuda(s1_step, reps=3)
+        samples = n_rays * (S_IN + S_OUT)
+        out["stage1_train_step_4096rays_x128"] = {
+            "ms_fwd_bwd_adam": ms4, "Msamples_per_s": samples / ms4 / 1e3,
+            "note": "Renderer.forward('unisurf', eval_=False) + Loss + backward + Adam (stage1/model/training.py:46-60,141-198): fp32 GEMM "
+                    "forward/backward with saved activations, create_graph normals by a hand-derived second-order pass"}
+        net.eval()
+        del opt1
+        torch.cuda.empty_cache()
+    except Exception as e:  # an extra: never let it take the headline line down
+        out["stage1_train_step_4096rays_x128"] = {"error": repr(e)[:300]}
     return out
 
 

@@ -213,6 +213,13 @@ S1_TRAIN_CASE = dict(h=12, w=10, s_in=12, s_out=6, msteps=64, it=100000, pose=(2
 S1_TRAIN_KEYS = ["rgb", "normal_pred", "acc_map", "diff_norm"]
 
 
+def s1_loss_ground_truth(n):
+    g = torch.Generator().manual_seed(6)
+    return {"rgb": torch.rand(1, n, 3, generator=g), "normal": torch.nn.functional.normalize(torch.randn(1, n, 3, generator=g), dim=-1),
+            "norm_mask": torch.rand(1, n, generator=g) > 0.4, "mask": (torch.rand(1, n, generator=g) > 0.5).float(),
+            "mask_valid": torch.rand(1, n, generator=g) > 0.1}
+
+
 def make_stage1_grads():
     """Gradients of the REAL reference's stage-1 training forward (Renderer.unisurf, eval_=False, add_noise=False) w.r.t. every
     parameter of the field: scalar = sum of the differentiable outputs against fixed cotangents.  torch.rand_like (neighbour
@@ -257,6 +264,15 @@ def make_stage1_grads():
         if gr.numel() <= 300:
             res["g_" + n] = np_(gr)
     res["checksum"] = checksum(variants["trained"])
+    # loss terms of the REAL reference Loss (stage1/model/losses.py) on these outputs with seeded ground truth
+    losses = ref_loader._load("psnerf_ref_stage1.losses", os.path.join(ref_loader.REF, "stage1/model/losses.py"), "psnerf_ref_stage1")
+    gt = s1_loss_ground_truth(out["rgb"].shape[1])
+    crit = losses.Loss(1.0, 0.01, 0.05, 0.1, device=torch.device("cpu"))
+    with torch.no_grad():
+        terms = crit({k: out[k].detach() for k in out if torch.is_tensor(out[k])}, gt["rgb"], gt["normal"], gt["norm_mask"],
+                     out["acc_map"].detach(), gt["mask"], gt["mask_valid"])
+    for k, v in terms.items():
+        res["loss_" + k] = np.array(float(v))
     np.savez_compressed(os.path.join(HERE, "stage1_grads.npz"), **res)
     print("stage1_grads: scalar", float(scalar), "params", len(names), "surface", int(out["mask_pred"].sum()))
 

@@ -44,6 +44,17 @@ def test_constructor_weights_equal_reference():
     np.testing.assert_array_equal(util.checksum(s2["init"]), g2["init_checksum"])
 
 
+def test_stage1_loss_equals_reference_loss():
+    """psnerf_b200.stage1.Loss on the reference's own training outputs vs the loss terms the REAL reference Loss produced."""
+    from psnerf_b200.stage1 import Loss
+    g = util.golden("stage1_grads")
+    out = {k: torch.from_numpy(g["out_" + k]) for k in util.S1_TRAIN_KEYS}
+    gt = util.s1_loss_ground_truth(out["rgb"].shape[1])
+    terms = Loss(1.0, 0.01, 0.05, 0.1)(out, gt["rgb"], gt["normal"], gt["norm_mask"], out["acc_map"], gt["mask"], gt["mask_valid"])
+    for k in ("fullrgb_loss", "grad_loss", "normal_loss", "mask_loss", "loss"):
+        assert abs(float(terms[k]) - float(g["loss_" + k])) < 1e-5 * max(1.0, abs(float(g["loss_" + k]))), k
+
+
 def test_abi_exports_every_declared_symbol(lib_built):
     from psnerf_b200 import _binding
     names = _binding.declared_symbols()

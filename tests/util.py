@@ -109,3 +109,10 @@ def s1_train_inputs():
     c = S1_TRAIN_CASE
     cfg = synth.stage1_cfg(num_points_in=c["s_in"], num_points_out=c["s_out"], ray_marching_steps=c["msteps"])
     return cfg, synth.pixel_grid_xmajor(c["h"], c["w"]), synth.intrinsics(c["h"], c["w"]), synth.look_at_pose(*c["pose"])
+
+
+def s1_loss_ground_truth(n):
+    g = torch.Generator().manual_seed(6)
+    return {"rgb": torch.rand(1, n, 3, generator=g), "normal": torch.nn.functional.normalize(torch.randn(1, n, 3, generator=g), dim=-1),
+            "norm_mask": torch.rand(1, n, generator=g) > 0.4, "mask": (torch.rand(1, n, generator=g) > 0.5).float(),
+            "mask_valid": torch.rand(1, n, generator=g) > 0.1}
