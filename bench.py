@@ -91,7 +91,7 @@ def build_model(device, precision):
     from psnerf_b200.stage1 import NeuralNetwork, Renderer
     cfg = synth.stage1_cfg(num_points_in=S_IN, num_points_out=S_OUT, ray_marching_steps=MARCH)
     torch.manual_seed(0)
-    net = NeuralNetwork(cfg)  # geometric init: sphere-like occupancy, ~17 % of the rays hit the surface
+    net = NeuralNetwork(cfg).eval()  # geometric init: sphere-like occupancy, ~17 % of the rays hit the surface
     net.precision = precision
     return cfg, net, Renderer(net, cfg, device=device)
 

@@ -21,7 +21,7 @@ def run_smoke(verbose=True):
     # ---- stage 1: 16x16 view, 64 march steps, 12+4 samples per ray
     cfg = synth.stage1_cfg(num_points_in=12, num_points_out=4, ray_marching_steps=64)
     torch.manual_seed(0)
-    net = NeuralNetwork(cfg)
+    net = NeuralNetwork(cfg).eval()
     sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
     h = w = 16
     pix, K, pose = synth.pixel_grid_xmajor(h, w), synth.intrinsics(h, w), synth.look_at_pose(15.0, 10.0)

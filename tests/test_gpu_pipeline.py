@@ -16,6 +16,7 @@ def _models(prec="fp32"):
     conf, s2 = util.stage2_state_dicts()
     net = NeuralNetwork(cfg)
     net.load_state_dict(s1["init"])
+    net.eval()
     net.precision = prec
     r = Renderer(net, cfg, device=torch.device("cuda"))
     ps = PSNetwork(conf)

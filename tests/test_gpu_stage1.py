@@ -34,7 +34,7 @@ def make_model(cfg, sd, prec):
     from psnerf_b200.stage1 import NeuralNetwork
     m = NeuralNetwork(cfg)
     m.load_state_dict(sd)
-    m = m.cuda()
+    m = m.cuda().eval()  # inference tests: train() mode with gradients enabled selects the differentiable path
     m.precision = prec
     return m
 

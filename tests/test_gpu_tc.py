@@ -20,7 +20,7 @@ def _model(cfg, sd):
     from psnerf_b200.stage1 import NeuralNetwork
     m = NeuralNetwork(cfg)
     m.load_state_dict(sd)
-    m = m.cuda()
+    m = m.cuda().eval()
     m.precision = "tc"
     return m
 

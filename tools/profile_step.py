@@ -23,7 +23,7 @@ H = W = a.res
 if not a.stage2:
     cfg = synth.stage1_cfg(num_points_in=96, num_points_out=32, ray_marching_steps=256)
     torch.manual_seed(0)
-    net = NeuralNetwork(cfg)
+    net = NeuralNetwork(cfg).eval()
     net.precision = a.precision
     r = Renderer(net, cfg, device=dev)
     pix = synth.pixel_grid_xmajor(H, W).to(dev)

@@ -18,7 +18,7 @@ dist.init_process_group("nccl", device_id=dev)
 h = w = 96
 cfg = synth.stage1_cfg(num_points_in=24, num_points_out=8, ray_marching_steps=128)
 torch.manual_seed(0)
-net = NeuralNetwork(cfg)
+net = NeuralNetwork(cfg).eval()
 net.precision = os.environ.get("PSN_PRECISION", "tc")
 r = Renderer(net, cfg, device=dev)
 K, pose = synth.intrinsics(h, w), synth.look_at_pose(20.0, 10.0)

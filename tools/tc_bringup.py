@@ -21,7 +21,7 @@ def main():
     lib = B.load()
     for variant in ("init", "trained"):
         sd = sds[variant]
-        m = NeuralNetwork(cfg)
+        m = NeuralNetwork(cfg).eval()
         m.load_state_dict(sd)
         m = m.cuda()
         g, _ = m._packed()

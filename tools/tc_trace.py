@@ -13,7 +13,7 @@ from psnerf_b200.stage1 import NeuralNetwork  # noqa: E402
 
 cfg = synth.stage1_cfg()
 torch.manual_seed(0)
-m = NeuralNetwork(cfg).cuda()
+m = NeuralNetwork(cfg).cuda().eval()
 g, _ = m._packed()
 M = 148 * 128 * 8
 pts = (torch.rand(M, 3, device="cuda") * 2.4 - 1.2).contiguous()

@@ -15,7 +15,7 @@ NAMES = (["geo fwd %d" % l for l in range(8)] + ["feature head", "app L0 feat (p
          ["reverse L0 -> grad", "app L0 rest", "app L1", "app L2", "app L3", "app L4 -> rgb"])
 cfg = synth.stage1_cfg()
 torch.manual_seed(0)
-m = NeuralNetwork(cfg).cuda()
+m = NeuralNetwork(cfg).cuda().eval()
 g, a = m._packed()
 M = 148 * 128 * 8
 pts = (torch.rand(M, 3, device="cuda") * 2.4 - 1.2).contiguous()
