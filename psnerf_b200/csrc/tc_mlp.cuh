@@ -399,7 +399,15 @@ __device__ __forceinline__ void mma_loop(const Smem& s, const Program& prog, lon
         mbar_wait(&s.c->w_full[st_lo], ph_lo);
         mbar_wait(&s.c->w_full[st_hi], ph_hi);
         tc_fence_after();
-        if (trace) { t_wait_a += tw1 - tw0; t_wait_w += clock64() - tw1; }
+        if (trace) {
+          const long long tw2 = clock64();
+          t_wait_a += tw1 - tw0;
+          t_wait_w += tw2 - tw1;
+          if (it == TRACE_ITER && blockIdx.x == 0 && st >= 1 && st <= 4 && (threadIdx.x & 31) == 0) {
+            trace[224 + (st - 1) * 8 + kb] = tw1 - tw0;      // per K block: wait for activations ...
+            trace[224 + (st - 1) * 8 + 4 + kb] = tw2 - tw1;  // ... and for its two weight stages (layers 1..4)
+          }
+        }
         const uint32_t lo_hi = umma_desc_lo(w_base + st_hi * W_STAGE_BYTES), lo_lo = umma_desc_lo(w_base + st_lo * W_STAGE_BYTES);
         if (elect_one()) {
           if (trace && it == TRACE_ITER && blockIdx.x == 0) {

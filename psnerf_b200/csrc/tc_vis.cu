@@ -98,28 +98,43 @@ k_tc_vis(TcVisArgs g, float* __restrict__ vis) {
     regs_grow_epilogue();
     EpiCtx e = epi_ctx(tmem_base);
     const int row = e.row, sub = e.sub;
-    for (long long t = t0; t < t1; ++t) {
-      const long long tt = t < n_tiles ? t : n_tiles - 1;  // dummy tiles recompute the last one and write nothing
+    // tile -> (point row, light, validity); dummy tiles (t >= n_tiles) recompute the last real one and write nothing
+    auto locate = [&](long long t_, long long& nn_, int& l_, long long& n_, bool& valid_) {
+      const long long tt = t_ < n_tiles ? t_ : n_tiles - 1;
       const long long pb = tt / g.L;
-      const int l = (int)(tt - pb * g.L);
-      const long long n = pb * TILE_M + row;
-      const bool valid = n < g.Ns && t < n_tiles;
-      const long long nn = valid ? n : g.Ns - 1;
-      // layer 0: relu(P0[n] + L0[l]) for this thread's four 16-column chunks -> A operand of the first tensor step
-#pragma unroll 1
-      for (int pass = 0; pass < 4; ++pass) {
-        const int col = 64 * pass + CW * sub;
-        float v[CW];
+      l_ = (int)(tt - pb * g.L);
+      n_ = pb * TILE_M + row;
+      valid_ = n_ < g.Ns && t_ < n_tiles;
+      nn_ = valid_ ? n_ : g.Ns - 1;
+    };
+    // layer 0 of a tile: relu(P0[n] + L0[l]) for the 16 columns [col, col+16) -> A operand of the first tensor step
+    auto layer0_chunk = [&](long long nn_, int l_, uint32_t col0, int pass, int col) {
+      float v[CW];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 a = __ldg(reinterpret_cast<const float4*>(g.P0 + nn * 256 + col) + i);
-          const float4 b = __ldg(reinterpret_cast<const float4*>(g.L0 + (long long)l * 256 + col) + i);
-          v[4 * i + 0] = fmaxf(a.x + b.x, 0.f); v[4 * i + 1] = fmaxf(a.y + b.y, 0.f);
-          v[4 * i + 2] = fmaxf(a.z + b.z, 0.f); v[4 * i + 3] = fmaxf(a.w + b.w, 0.f);
-        }
-        epi_store_a16(e, e.a_col0(), col, v);
-        epi_signal_a(s, pass);
+      for (int i = 0; i < 4; ++i) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(g.P0 + nn_ * 256 + col) + i);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(g.L0 + (long long)l_ * 256 + col) + i);
+        v[4 * i + 0] = fmaxf(a.x + b.x, 0.f); v[4 * i + 1] = fmaxf(a.y + b.y, 0.f);
+        v[4 * i + 2] = fmaxf(a.z + b.z, 0.f); v[4 * i + 3] = fmaxf(a.w + b.w, 0.f);
       }
+      epi_store_a16(e, col0, col, v);
+      epi_signal_a(s, pass);
+    };
+    long long nn, n, nn2 = 0, n2 = 0;
+    int l, l2 = 0;
+    bool valid, valid2 = false;
+    if (iters > 0) {
+      locate(t0, nn, l, n, valid);
+#pragma unroll 1
+      for (int pass = 0; pass < 4; ++pass) layer0_chunk(nn, l, e.a_col0(), pass, 64 * pass + CW * sub);
+    }
+    for (long long t = t0; t < t1; ++t) {
+      // The next tile's layer 0 is produced INSIDE the last epilogue of this one: pass p of the last step frees accumulator columns
+      // [64p, 64p+64) and the next tile's K block p goes straight into them, so the MMA warp starts the next tile while this one is
+      // still being reduced (the epilogue of this kernel is cheap - ReLU - and the hand-over used to leave the tensor pipe idle for
+      // four exposed table loads plus a layer-time per tile).
+      const bool has_next = t + 1 < t1;
+      if (has_next) locate(t + 1, nn2, l2, n2, valid2);
       float part = 0.f;
 #pragma unroll 1
       for (int st = 0; st < 7; ++st) {
@@ -158,6 +173,7 @@ k_tc_vis(TcVisArgs g, float* __restrict__ vis) {
               part = fmaf(v[4 * t], w.x, part); part = fmaf(v[4 * t + 1], w.y, part);
               part = fmaf(v[4 * t + 2], w.z, part); part = fmaf(v[4 * t + 3], w.w, part);
             }
+            if (has_next) layer0_chunk(nn2, l2, e.d_col0(), pass, col);
           }
         });
         e.step_ctr++;
@@ -169,6 +185,7 @@ k_tc_vis(TcVisArgs g, float* __restrict__ vis) {
       if (sub == 0 && valid)
         vis[(long long)l * g.Ns + n] = ((s.stage[row].x + s.stage[TILE_M + row].x) + (s.stage[2 * TILE_M + row].x + s.stage[3 * TILE_M + row].x)) +
                                        __ldg(g.b_last);
+      nn = nn2; l = l2; n = n2; valid = valid2;
     }
   }
   teardown(tmem_base);

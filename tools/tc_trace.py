@@ -35,3 +35,7 @@ for l in range(8):
     e3 = [rel(t[64 + 3 * 40 + l * 5 + k]) for k in range(5)]
     print("%5d | %6d %6d %6d %6d | %6d | %6d %6d || %6d %6d %6d %6d %6d | %6d %6d %6d %6d %6d" %
           (l, *mm, cm, t[l * 8 + 4], t[l * 8 + 5], *e0, *e3))
+print("per K block (layers 1..4): wait for activations kb0..3 | wait for weight stages kb0..3")
+for l in range(1, 5):
+    print("%5d | %s | %s" % (l, " ".join("%6d" % t[224 + (l - 1) * 8 + k] for k in range(4)),
+                           " ".join("%6d" % t[224 + (l - 1) * 8 + 4 + k] for k in range(4))))
