@@ -386,32 +386,34 @@ __device__ __forceinline__ void mma_loop(const Smem& s, const Program& prog, lon
       const uint32_t idesc = umma_idesc(sp.n_pad);
       long long t_wait_a = 0, t_wait_w = 0;  // bring-up trace only (dead code otherwise)
       for (int kb = 0; kb < sp.nkb; ++kb) {
+        // this K block's two weight stages (lo tile first: it is consumed - and released - first).  They are checked BEFORE the
+        // activations: the weights are normally long there (the checks cost ~100 cycles of barrier round trip each), whereas the
+        // a_ready -> first MMA latency sits on the critical epilogue -> MMA -> epilogue chain of every layer.
         const long long tw0 = trace ? clock64() : 0;
-        mbar_wait(&s.c->a_ready[kb], (a_phase >> kb) & 1u);
-        a_phase ^= (1u << kb);
-        const long long tw1 = trace ? clock64() : 0;
-        const uint32_t a_kb = a_addr + (uint32_t)kb * 64u;
-        // this K block's two weight stages (lo tile first: it is consumed - and released - first)
         const uint32_t st_lo = stage, ph_lo = phase;
         if (++stage == W_STAGES) { stage = 0; phase ^= 1u; }
         const uint32_t st_hi = stage, ph_hi = phase;
         if (++stage == W_STAGES) { stage = 0; phase ^= 1u; }
         mbar_wait(&s.c->w_full[st_lo], ph_lo);
         mbar_wait(&s.c->w_full[st_hi], ph_hi);
+        const long long tw1 = trace ? clock64() : 0;
+        mbar_wait(&s.c->a_ready[kb], (a_phase >> kb) & 1u);
+        a_phase ^= (1u << kb);
         tc_fence_after();
+        const uint32_t a_kb = a_addr + (uint32_t)kb * 64u;
         if (trace) {
           const long long tw2 = clock64();
-          t_wait_a += tw1 - tw0;
-          t_wait_w += tw2 - tw1;
+          t_wait_w += tw1 - tw0;
+          t_wait_a += tw2 - tw1;
           if (it == TRACE_ITER && blockIdx.x == 0 && st >= 1 && st <= 4 && (threadIdx.x & 31) == 0) {
-            trace[224 + (st - 1) * 8 + kb] = tw1 - tw0;      // per K block: wait for activations ...
-            trace[224 + (st - 1) * 8 + 4 + kb] = tw2 - tw1;  // ... and for its two weight stages (layers 1..4)
+            trace[224 + (st - 1) * 8 + kb] = tw2 - tw1;      // per K block: wait for activations ...
+            trace[224 + (st - 1) * 8 + 4 + kb] = tw1 - tw0;  // ... and for its two weight stages (layers 1..4)
           }
         }
         const uint32_t lo_hi = umma_desc_lo(w_base + st_hi * W_STAGE_BYTES), lo_lo = umma_desc_lo(w_base + st_lo * W_STAGE_BYTES);
         if (elect_one()) {
           if (trace && it == TRACE_ITER && blockIdx.x == 0) {
-            trace[st * 8 + kb] = tw1;
+            trace[st * 8 + kb] = clock64();
             trace[st * 8 + 4] = t_wait_a;  // cycles this step spent waiting for activations ...
             trace[st * 8 + 5] = t_wait_w;  // ... and for weight stages
           }
