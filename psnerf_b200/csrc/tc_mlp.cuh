@@ -94,13 +94,6 @@ __device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
-// for waits that are not on the critical path (weight producer): sleep between polls instead of burning issue slots
-__device__ __forceinline__ void mbar_wait_relaxed(void* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) __nanosleep(64);
-}
-// generic-proxy smem writes -> visible to the async proxy (UMMA operand reads)
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 // all threads of both CTAs (also a CTA-wide barrier)
 __device__ __forceinline__ void cluster_sync_all() {
@@ -128,12 +121,6 @@ __device__ __forceinline__ void bulk_g2s_multicast(void* smem_dst, const void* g
                "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
                : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, void* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
-               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
 __device__ __forceinline__ void tmem_alloc_512(uint32_t* smem_dst) {  // whole warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(smem_dst)) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -144,10 +131,6 @@ __device__ __forceinline__ void tmem_dealloc_512(uint32_t taddr) {  // whole war
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// K-major, 128-byte-swizzled operand descriptor: start>>4 | LBO(16 B, ignored)<<16 | SBO(1024 B)<<32 | version 1 | SW128
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
 // kind::f16, A = B = fp16 (format 0), D = fp32, both K-major, M = 128
 __device__ __forceinline__ uint32_t umma_idesc(uint32_t n) { return (1u << 4) | ((n >> 3) << 17) | (8u << 24); }
 
@@ -171,30 +154,6 @@ __device__ __forceinline__ void umma_commit(void* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// 32 lanes x 32 consecutive fp32 columns: thread (lane i) receives row (lane_base + i), columns col..col+31.
-// Issue and wait are separate so that the next chunk's load overlaps the current chunk's math; the wait names every
-// destination register as read-write so the compiler cannot consume (or move) them before the load has landed.
-__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld32_wait(uint32_t (&r)[32]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
-                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
-                 "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
-                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
-               :
-               : "memory");
-}
 // issue / wait halves of the 16-column load: global loads placed between them overlap the TMEM read
 __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
@@ -229,14 +188,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  tmem_ld32_issue(taddr, r);
-  tmem_ld32_wait(r);
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
 // 32 lanes x 16 consecutive 32-bit columns: thread (lane i) writes row (lane_base + i), columns col..col+15
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(
@@ -365,8 +316,10 @@ __device__ __forceinline__ bool elect_one() {
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
   return pred != 0;
 }
-// descriptor of a K-major SWIZZLE_128B operand = constant high word | (address >> 4) in the low word: advancing the start
-// address by `bytes` (a multiple of 16 that does not leave the 256 KB window) is an add on the low word
+// Shared-memory descriptor of a K-major SWIZZLE_128B operand: start address >> 4 in bits 0-13, leading-dimension byte offset
+// (ignored for swizzled K-major layouts; 1) in bits 16-29, stride between 8-row swizzle atoms 1024 B >> 4 in bits 32-45, descriptor
+// version 1 at bit 46, layout type SWIZZLE_128B (2) in bits 61-63.  Only the low word depends on the address, so advancing the
+// start by `bytes` (a multiple of 16 that stays inside the 256 KB window) is an add on the low word.
 constexpr uint64_t UMMA_DESC_HI = ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 __device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
 __device__ __forceinline__ uint64_t umma_desc_at(uint32_t lo, uint32_t bytes) { return UMMA_DESC_HI | (uint64_t)(lo + (bytes >> 4)); }
@@ -502,21 +455,9 @@ __device__ __forceinline__ void epi_load16(const EpiCtx& e, int col, float (&v)[
   tmem_ld16(e.tmem_base + e.lane_addr + e.d_col0() + (uint32_t)col, v);
 }
 
-// Visit the 16-column chunks this thread owns in the current accumulator: f(pass, col, v[16]), col = 64*pass + 16*sub.  Pass 0
+// Visit the 16-column chunks this thread owns in the current accumulator: f(pass, col, v[16], buf), col = 64*pass + 16*sub.  Pass 0
 // waits for columns [0, 64) only; one pass of the four subs covers exactly one 64-column K block of the next step's A operand.
-template <class F>
-__device__ __forceinline__ void epi_for_chunks(const Smem& s, const EpiCtx& e, F&& f) {
-  const uint32_t base = e.tmem_base + e.lane_addr + e.d_col0();
-#pragma unroll 1
-  for (int pass = 0; pass < 4; ++pass) {
-    if (pass < 2) epi_wait_q(s, e, pass);
-    const int col = 64 * pass + CW * e.sub;
-    float v[CW];
-    tmem_ld16(base + (uint32_t)col, v);
-    f(pass, col, v);
-  }
-}
-// Same walk with a software-pipelined side load: pre(col, buf) issues the global / L2 loads a chunk needs (bias, stashed
+// The walk carries a software-pipelined side load: pre(col, buf) issues the global / L2 loads a chunk needs (bias, stashed
 // sigma', parked partials, per-point tables) into a register struct; it runs for pass 0 BEFORE the accumulator wait and for pass
 // p+1 between the issue and the wait of pass p's TMEM load, so the ~700-cycle L2 latency of those loads is off the critical
 // path of every pass (with four epilogue warps per scheduler it used to be exposed four times per layer).
@@ -550,16 +491,6 @@ __device__ __forceinline__ void add16(float (&v)[CW], const float4 (&b)[4]) {
 #pragma unroll
   for (int t = 0; t < 4; ++t) { v[4 * t] += b[t].x; v[4 * t + 1] += b[t].y; v[4 * t + 2] += b[t].z; v[4 * t + 3] += b[t].w; }
 }
-// v[i] += bias[col + i] with 128-bit loads
-__device__ __forceinline__ void add_bias16(float (&v)[CW], const float* __restrict__ bias, int col) {
-  const float4* b4 = reinterpret_cast<const float4*>(bias + col);
-#pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    const float4 b = __ldg(b4 + t);
-    v[4 * t] += b.x; v[4 * t + 1] += b.y; v[4 * t + 2] += b.z; v[4 * t + 3] += b.w;
-  }
-}
-
 // Write 16 consecutive activation values (K elements col..col+15 of this thread's row) as the A operand of K-step col/16 of the
 // region starting at TMEM column col0: 8 columns of packed fp16 hi, then 8 columns of packed fp16 lo (see the file header).
 // Packed cvt.rn.f16x2.f32 (F2FP, ALU pipe) - scalar F2F would queue on the XU pipe with the MUFUs.
