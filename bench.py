@@ -132,7 +132,7 @@ def run_reference(args):
                        "sample": sample},
             "cpu_baseline": {"value": val, "unit": "Msamples/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def cpu_baseline_quick():
@@ -269,7 +269,31 @@ def extra_workloads(dev, precision, rend, view, peaks):
     return out
 
 
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to stdout when
+    NCCL_DEBUG=VERSION is set, as it is on the GPU boxes), so file descriptor 1 is pointed at stderr for the whole run and the
+    JSON line goes to a private duplicate of the original stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -416,7 +440,7 @@ def main():
             line["other_workloads"] = extra_workloads(dev, precision, rend, views[0], peaks)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_quick()
-        print(json.dumps(line))
+        emit(line)
     if dist:
         td.destroy_process_group()
 
