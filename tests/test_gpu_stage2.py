@@ -138,3 +138,23 @@ def test_properties_at_baseline_light_count():
     un = (rb < 1) & (rb > 0)
     assert float((rb[un] - 2 * ra[un]).abs().max()) < 1e-5
     assert torch.equal(a["visibility"], b["visibility"])
+
+
+@pytest.mark.parametrize("prec", PRECISIONS)
+def test_editing_and_microfacet_edge_cases(prec):
+    """Material editing with an empty surface mask (every output keeps its pre-fill) and the microfacet jitter branch."""
+    conf, sds = util.stage2_state_dicts()
+    m = make_model(conf, sds["trained"], prec)
+    inp = synth.stage2_input(9, 7, 3, all_surface=False, seed=2, mask_frac=0.0)
+    out = m(to_cuda(inp), albedo_new=np.asarray([0.1, 0.2, 0.3], np.float32), basis_new=2)
+    assert float((out["sg_rgb_values"] - 1).abs().max()) == 0.0 and float(out["sg_weight"].abs().max()) == 0.0
+    confm, sdm = util.stage2_micro_state_dict()
+    mm = make_model(confm, sdm, prec)
+    inp = synth.stage2_input(8, 8, 2, all_surface=False, seed=3, mask_frac=0.5)
+    ns = int(inp["surface_mask"].sum())
+    z = torch.randn(ns, 3, generator=torch.Generator().manual_seed(1))
+    out = mm(to_cuda(inp), noise={"xyz": z})
+    ref = O.psnetwork_forward(sdm, confm, inp, noise={"xyz": z})
+    for k in ("albedo_jitter", "rough_jitter", "rough_values", "sg_rgb_values"):
+        assert tuple(out[k].shape) == tuple(ref[k].shape), k
+        assert util.max_abs(out[k].cpu(), ref[k]) < TOL[prec] * 5, k

@@ -122,3 +122,20 @@ def test_unisurf_train_step_matches_reference_fixture():
     out3 = rend(pix.cuda(), K, pose, None, "unisurf", add_noise=False, eval_=True, it=util.S1_TRAIN_CASE["it"])
     assert not out3["rgb"].requires_grad
     assert util.max_abs(out3["rgb"].cpu(), g["out_rgb"]) < 5e-5
+
+
+def test_unisurf_train_step_without_surface_hits():
+    """A camera that looks away from the object: no surface point, empty diff_norm, zero normals - forward and backward still run."""
+    from psnerf_b200.stage1 import Renderer
+    cfg0, sds = util.stage1_state_dicts()
+    cfg = synth.stage1_cfg(num_points_in=8, num_points_out=4, ray_marching_steps=32)
+    model = _model(sds["init"], cfg)
+    rend = Renderer(model, cfg, device=torch.device("cuda"))
+    pose = synth.look_at_pose(10.0, 5.0).clone()
+    pose[0, :3, :3] = -pose[0, :3, :3]  # flip the viewing direction: every ray leaves the scene
+    pix = synth.pixel_grid_xmajor(6, 5).cuda()
+    out = rend(pix, synth.intrinsics(6, 5), pose, None, "unisurf", add_noise=True, eval_=False, it=100000)
+    assert int(out["mask_pred"].sum()) == 0 and out["diff_norm"].numel() == 0
+    assert float(out["normal_pred"].abs().max()) == 0.0
+    (out["rgb"].sum() + out["acc_map"].sum()).backward()
+    assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
