@@ -181,6 +181,8 @@ int psn_tc_debug_layer(const psn_mlp* geo, const float* pts, int64_t M, int laye
 
 /* Bring-up tool: clock64() timeline of one tile of the tensor-core occupancy kernel; trace is int64[256] on the device. */
 int psn_tc_debug_trace(const psn_mlp* geo, const float* pts, int64_t M, float* out, long long* trace, void* stream);
+/* same, epilogue time stamps taken by the warps of TMEM lane quadrant `quadrant` (0..3; each quadrant lives on its own scheduler) */
+int psn_tc_debug_trace_q(const psn_mlp* geo, const float* pts, int64_t M, float* out, long long* trace, int quadrant, void* stream);
 
 /* Same for the radiance kernel (23 steps per tile): MMA-lane slots step*8 + {0..3 a_ready, 4 wait-activations, 5 wait-weights,
  * 7 last commit}; trace[192 + step] = epilogue of the step finished (row 0).  stash: psn_workspace-style scratch of at least

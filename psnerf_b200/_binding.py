@@ -90,6 +90,7 @@ def load():
     lib.psn_s2_visibility.argtypes = [vp, i32, vp, i64, vp, i32, vp, vp, i64, i32, vp]
     lib.psn_tc_debug_layer.argtypes = [vp, vp, i64, i32, vp, vp, vp]
     lib.psn_tc_debug_trace.argtypes = [vp, vp, i64, vp, vp, vp]
+    lib.psn_tc_debug_trace_q.argtypes = [vp, vp, i64, vp, vp, i32, vp]
     lib.psn_tc_debug_trace_rad.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp, vp, vp]
     tn = C.POINTER(TrainNet)
     lib.psn_s1_train_tape_bytes.argtypes = [tn, tn, i32, i32, i64]

@@ -68,7 +68,8 @@ k_tc_occ(TcGeoArgs g, PointGen gen, long long M_host, const int* M_dev, int out_
       float part = 0.f;  // partial logit over this thread's 64 columns
 #pragma unroll 1
       for (int l = 0; l < 8; ++l) {
-        const bool tr = (MODE == MODE_DEBUG) && trace && it == TRACE_ITER && blockIdx.x == 0 && row == 0;
+        // timeline hook: lane 0 of the epilogue warps of ONE TMEM lane quadrant (dump_layer doubles as the quadrant selector there)
+        const bool tr = (MODE == MODE_DEBUG) && trace && it == TRACE_ITER && blockIdx.x == 0 && row == 32 * (dump_layer < 0 ? 0 : dump_layer & 3);
         const float* bias = g.bias[l];
         const bool pre_skip = (l + 1 == g.skip);
         const int n_out = g.n_out[l];
@@ -266,7 +267,11 @@ extern "C" int psn_tc_debug_layer(const psn_mlp* geo, const float* pts, int64_t 
 
 // Bring-up tool: clock64() timeline of one tile of the occupancy kernel (see TRACE_ITER in tc_mlp.cuh): trace[256] int64 device.
 extern "C" int psn_tc_debug_trace(const psn_mlp* geo, const float* pts, int64_t M, float* out, long long* trace, void* stream) {
-  PSN_REQUIRE(geo && pts && out && trace, PSN_ERR_ARG, "psn_tc_debug_trace: bad argument");
+  return psn_tc_debug_trace_q(geo, pts, M, out, trace, 0, stream);
+}
+extern "C" int psn_tc_debug_trace_q(const psn_mlp* geo, const float* pts, int64_t M, float* out, long long* trace, int quadrant,
+                                    void* stream) {
+  PSN_REQUIRE(geo && pts && out && trace && quadrant >= 0 && quadrant < 4, PSN_ERR_ARG, "psn_tc_debug_trace: bad argument");
   TcGeoArgs a;
   int rc = make_tc_geo(geo, &a);
   if (rc) return rc;
@@ -274,5 +279,5 @@ extern "C" int psn_tc_debug_trace(const psn_mlp* geo, const float* pts, int64_t 
   memset(&gen, 0, sizeof(gen));
   gen.kind = GEN_EXPLICIT;
   gen.pts = pts;
-  return launch_tc_occ<MODE_DEBUG>(a, gen, M, nullptr, PSN_OUT_ALPHA, out, 0.f, -1, nullptr, (cudaStream_t)stream, trace);
+  return launch_tc_occ<MODE_DEBUG>(a, gen, M, nullptr, PSN_OUT_ALPHA, out, 0.f, quadrant, nullptr, (cudaStream_t)stream, trace);
 }

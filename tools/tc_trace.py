@@ -39,3 +39,16 @@ print("per K block (layers 1..4): wait for activations kb0..3 | wait for weight 
 for l in range(1, 5):
     print("%5d | %s | %s" % (l, " ".join("%6d" % t[224 + (l - 1) * 8 + k] for k in range(4)),
                            " ".join("%6d" % t[224 + (l - 1) * 8 + 4 + k] for k in range(4))))
+# pass end times of layers 1..3 for the four TMEM lane quadrants (one scheduler each; quadrant 1 shares its scheduler with the MMA warp)
+for q in range(4):
+    trace.zero_()
+    for _ in range(2):
+        B.check(lib.psn_tc_debug_trace_q(g.handle, C.c_void_p(pts.data_ptr()), M, C.c_void_p(out.data_ptr()),
+                                         C.c_void_p(trace.data_ptr()), q, engine._stream()), "trace")
+    torch.cuda.synchronize()
+    tq = trace.cpu().tolist()
+    t0q = min(tq[l * 8] for l in range(8) if tq[l * 8] > 0)
+    rows = []
+    for l in range(1, 4):
+        rows.append(" ".join("%6d" % (tq[64 + s_ * 40 + l * 5 + 4] - t0q) for s_ in range(4)))
+    print("quadrant %d: end of pass 3 of layers 1..3 for subs 0..3 | %s" % (q, " | ".join(rows)))
