@@ -1,5 +1,6 @@
 #!/bin/bash
-# One gpurun call: tensor-path bring-up report (both packing-order builds), then the GPU tests, a tile timeline and the bench.
+# One gpurun call: tensor-path bring-up report (per-layer error vs the CPU oracle), the GPU tests, a tile timeline and the bench;
+# PSN_NCU=1 adds the `ncu --set full` capture of the stage-1 tensor kernels.
 mkdir -p gpurun_out
 echo "== bringup std" > gpurun_out/bringup.log
 timeout 240 python tools/tc_bringup.py >> gpurun_out/bringup.log 2>&1; echo "rc=$?" >> gpurun_out/bringup.log
