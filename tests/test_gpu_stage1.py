@@ -239,3 +239,35 @@ def test_phong_renderer_runs(s1):
     same = (out["rgb"].cpu() == 1).all(-1) == (ref["rgb"] == 1).all(-1)
     assert same.float().mean() > 0.98
     assert util.max_abs(out["rgb"].cpu()[same], ref["rgb"][same]) < 1e-3
+
+
+@pytest.mark.parametrize("prec", PRECISIONS)
+def test_full_size_render_properties(s1, prec):
+    """BASELINE configs[1] at full size (512 x 512 rays, 128 samples, 256 march steps): properties that need no CPU reference.
+    Rays are independent, so a render of a ray subset must reproduce the full render at those rays bit for bit (different tile
+    composition, different CTA pairing), two renders of the same view are identical (fixed-order reductions), the opacity is a
+    convex weight sum, hit rays carry unit normals and missed rays none."""
+    from psnerf_b200.stage1 import Renderer
+    _, sds = s1
+    cfg = synth.stage1_cfg(num_points_in=96, num_points_out=32, ray_marching_steps=256)
+    r = Renderer(make_model(cfg, sds["init"], prec), cfg, device=torch.device("cuda"))
+    H = W = 512
+    pix = synth.pixel_grid_xmajor(H, W).cuda()
+    K, pose = synth.intrinsics(H, W), synth.look_at_pose(20.0, 10.0)
+    full = r(pix, K, pose, None, "unisurf", add_noise=False, eval_=True, it=100000)
+    again = r(pix, K, pose, None, "unisurf", add_noise=False, eval_=True, it=100000)
+    for k in ("rgb", "normal_pred", "acc_map"):
+        assert torch.equal(full[k], again[k]), k
+    idx = torch.arange(37, H * W, 61, device="cuda")[:4099]  # ragged count, strided over the image
+    part = r(pix[:, idx], K, pose, None, "unisurf", add_noise=False, eval_=True, it=100000)
+    assert torch.equal(part["mask_pred"], full["mask_pred"][idx])
+    for k in ("rgb", "normal_pred", "acc_map"):
+        assert torch.equal(part[k][0], full[k][0][idx]), k
+    acc, rgb, nrm, mask = full["acc_map"][0], full["rgb"][0], full["normal_pred"][0], full["mask_pred"]
+    assert torch.isfinite(rgb).all() and float(acc.min()) >= 0 and float(acc.max()) <= 1 + 1e-3
+    assert float(rgb.min()) >= -1e-5 and float(rgb.max()) <= 1 + 1e-3
+    n_hit = int(mask.sum())
+    assert 0.05 * H * W < n_hit < 0.5 * H * W            # the sphere-like init field covers part of the view
+    ln = nrm.norm(dim=-1)
+    assert float((ln[mask] - 1).abs().max()) < 1e-3 and float(ln[~mask].max()) == 0.0
+    assert float(acc[mask].mean()) > 0.9  # hit rays are opaque (missed rays of the soft init field still gather some opacity)
