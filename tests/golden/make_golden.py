@@ -213,6 +213,23 @@ S1_TRAIN_CASE = dict(h=12, w=10, s_in=12, s_out=6, msteps=64, it=100000, pose=(2
 S1_TRAIN_KEYS = ["rgb", "normal_pred", "acc_map", "diff_norm"]
 
 
+def make_stage1_phong():
+    """Renderer.phong_renderer (rendering.py:228-293; 512 march steps, headlight Phong shading) of the REAL reference."""
+    net_mod, rend_mod, common = ref_loader.load_stage1()
+    _, model, variants = stage1_variants(net_mod)
+    cfg = synth.stage1_cfg()
+    out = {}
+    for vname, sd in variants.items():
+        model.load_state_dict(sd)
+        rend = rend_mod.Renderer(model, cfg, device=torch.device("cpu"))
+        with torch.no_grad():
+            res = rend(synth.pixel_grid_xmajor(12, 12), synth.intrinsics(12, 12), synth.look_at_pose(10.0, 5.0), torch.eye(4)[None],
+                       "phong_renderer")
+        out[vname + "_rgb"] = np_(res["rgb"])
+        print("phong", vname, "shaded pixels", int((res["rgb"] != 1).any(-1).sum()))
+    np.savez_compressed(os.path.join(HERE, "stage1_phong.npz"), **out)
+
+
 def s1_loss_ground_truth(n):
     g = torch.Generator().manual_seed(6)
     return {"rgb": torch.rand(1, n, 3, generator=g), "normal": torch.nn.functional.normalize(torch.randn(1, n, 3, generator=g), dim=-1),
@@ -332,5 +349,6 @@ if __name__ == "__main__":
     make_stage2_grads()
     make_stage2_edit()
     make_stage1_grads()
-    for f in ("stage1_net", "stage1_render", "stage2_shade", "stage2_grads", "stage2_edit", "stage1_grads"):
+    make_stage1_phong()
+    for f in ("stage1_net", "stage1_render", "stage2_shade", "stage2_grads", "stage2_edit", "stage1_grads", "stage1_phong"):
         print(f, os.path.getsize(os.path.join(HERE, f + ".npz")) // 1024, "KB")
