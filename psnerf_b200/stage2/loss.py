@@ -37,7 +37,7 @@ class MainLoss(nn.Module):
             rough_loss = self._masked(self.smooth_loss, model_outputs["rough_values"], model_outputs["rough_jitter"], mask)
             loss = loss + self.rough_smooth_weight * rough_loss
         lterm = {"sg_rgb_loss": sg_rgb_loss, "albedo_smooth_loss": albedo_loss, "rough_smooth_loss": rough_loss}
-        if model_input is not None and "visibility" in model_outputs and ("visibility" in model_input or "vis_train_gt" in model_input):
+        if model_input is not None and "visibility" in model_input and "visibility" in model_outputs:  # loss.py:81
             if "vis_train_gt" in model_input and "vis_train" in model_outputs:
                 vis_loss = self._masked(self.img_loss, model_outputs["vis_train"][..., 0], model_input["vis_train_gt"].to(dev), mask, (-1,))
             elif "light_vis_train" in model_input and "vis_train" in model_outputs:

@@ -213,6 +213,53 @@ S1_TRAIN_CASE = dict(h=12, w=10, s_in=12, s_out=6, msteps=64, it=100000, pose=(2
 S1_TRAIN_KEYS = ["rgb", "normal_pred", "acc_map", "diff_norm"]
 
 
+def s2_loss_ground_truth(L, n, Lt):
+    g = torch.Generator().manual_seed(12)
+    return {"rgb": torch.rand(L, n, 3, generator=g), "visibility": torch.rand(L, n, generator=g), "vis_train_gt": torch.rand(Lt, n, generator=g)}
+
+
+def make_stage2_losses():
+    """MainLoss / NormalLoss of the REAL reference (stage2/model/loss.py) on the outputs of the real PSNetwork for the train-like
+    case of make_stage2_grads.  The reference hard-codes .cuda() (loss.py:30,61): torch.Tensor.cuda is replaced by the identity for
+    the duration of the call (no source edit)."""
+    m2 = ref_loader.load_stage2()
+    lossmod = ref_loader._load("model.loss", os.path.join(ref_loader.REF, "stage2/model/loss.py"), "model")
+    conf = synth.stage2_conf()
+    torch.manual_seed(0)
+    model = m2.PSNetwork(ref_loader.DictConf(conf))
+    sd1 = synth.perturb_state_dict({k: v.clone() for k, v in model.state_dict().items()}, rel=0.5, seed=1)
+    model.load_state_dict(sd1)
+    h, w, L, Lt = 12, 10, 5, 2
+    inp = synth.stage2_input(h, w, L, all_surface=False, seed=21, mask_frac=0.6)
+    inp["light_vis_train"] = synth.lights(Lt, seed=9)
+    gt = s2_loss_ground_truth(L, h * w, Lt)
+    inp["visibility"], inp["vis_train_gt"] = gt["visibility"], gt["vis_train_gt"]
+    ns = int(inp["surface_mask"].sum())
+    std = conf["brdf.net.xyz_jitter_std"]
+    torch.manual_seed(4242)
+    z = torch.normal(0, torch.ones(ns, 3) * std) / std
+    torch.manual_seed(4242)
+    with torch.no_grad():
+        out = model(inp)
+    orig = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        with torch.no_grad():
+            lm = lossmod.MainLoss(1.0, "L1", 0.05, 0.01, 1.0)(out, {"rgb": gt["rgb"]}, inp)
+            ln = lossmod.NormalLoss(1.0, 0.05)(out)
+    finally:
+        torch.Tensor.cuda = orig
+    res = {"xyz_noise": np_(z)}
+    for k, v in lm.items():
+        if v is not None:
+            res["main_" + k] = np.array(float(v))
+    for k, v in ln.items():
+        if v is not None:
+            res["normal_" + k] = np.array(float(v))
+    np.savez_compressed(os.path.join(HERE, "stage2_loss.npz"), **res)
+    print("stage2_loss", {k: float(v) for k, v in res.items() if k != "xyz_noise"})
+
+
 def make_stage1_phong():
     """Renderer.phong_renderer (rendering.py:228-293; 512 march steps, headlight Phong shading) of the REAL reference."""
     net_mod, rend_mod, common = ref_loader.load_stage1()
@@ -350,5 +397,6 @@ if __name__ == "__main__":
     make_stage2_edit()
     make_stage1_grads()
     make_stage1_phong()
-    for f in ("stage1_net", "stage1_render", "stage2_shade", "stage2_grads", "stage2_edit", "stage1_grads", "stage1_phong"):
+    make_stage2_losses()
+    for f in ("stage1_net", "stage1_render", "stage2_shade", "stage2_grads", "stage2_edit", "stage1_grads", "stage1_phong", "stage2_loss"):
         print(f, os.path.getsize(os.path.join(HERE, f + ".npz")) // 1024, "KB")

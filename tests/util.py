@@ -116,3 +116,8 @@ def s1_loss_ground_truth(n):
     return {"rgb": torch.rand(1, n, 3, generator=g), "normal": torch.nn.functional.normalize(torch.randn(1, n, 3, generator=g), dim=-1),
             "norm_mask": torch.rand(1, n, generator=g) > 0.4, "mask": (torch.rand(1, n, generator=g) > 0.5).float(),
             "mask_valid": torch.rand(1, n, generator=g) > 0.1}
+
+
+def s2_loss_ground_truth(L, n, Lt):
+    g = torch.Generator().manual_seed(12)
+    return {"rgb": torch.rand(L, n, 3, generator=g), "visibility": torch.rand(L, n, generator=g), "vis_train_gt": torch.rand(Lt, n, generator=g)}
