@@ -389,6 +389,49 @@ def make_stage2_grads():
     print("stage2_grads: scalar", float(scalar), "params", len(names), "surface", ns)
 
 
+def general_case():
+    """Inputs of the split/merge fixture: a 2500-pixel model_input (3 chunks at the reference's 1024) and per-chunk outputs
+    of rank 1, 2, 3 and 4 (the ranks PSNetwork.forward returns: [N] masks, [1,N] flags, [1,N,3] colours, [L,1,N,3] per-light)."""
+    g = torch.Generator().manual_seed(41)
+    n = 2500
+    inp = {"uv": torch.rand(1, n, 2, generator=g), "object_mask": torch.rand(1, n, generator=g) > 0.3,
+           "points": torch.randn(1, n, 3, generator=g), "normal": torch.randn(1, n, 3, generator=g),
+           "visibility": torch.rand(1, n, 2, generator=g), "intrinsics": torch.eye(4)[None], "pose": torch.eye(4)[None],
+           "light_direction": torch.randn(2, 3, generator=g)}
+    return inp, n
+
+
+def general_chunk_outputs(chunk):
+    m = chunk["uv"].shape[1]
+    return {"mask": chunk["object_mask"].reshape(-1), "flag": chunk["object_mask"].float(), "rgb": chunk["points"] * 2,
+            "per_light": chunk["visibility"].permute(2, 0, 1)[..., None].expand(2, 1, m, 3).contiguous(), "none": None}
+
+
+def make_stage2_general():
+    """split_input / merge_output of the REAL stage2/utils/general.py:23-53 on CPU (its .cuda() on the index is made a no-op)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("psnerf_ref_general", os.path.join(ref_loader.REF, "stage2/utils/general.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    inp, n = general_case()
+    saved = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        chunks = gen.split_input(inp, n)
+    finally:
+        torch.Tensor.cuda = saved
+    out = {"n_chunks": np.array(len(chunks)), "chunk_sizes": np.array([c["uv"].shape[1] for c in chunks]),
+           "keys": np.array(sorted(chunks[0].keys()))}
+    for i, c in enumerate(chunks):
+        for k in ("uv", "object_mask", "points", "normal", "visibility"):
+            out["c%d_%s" % (i, k)] = np.array([float(c[k].double().sum()), float(c[k][0, 0].double().sum()), float(c[k][0, -1].double().sum())])
+    merged = gen.merge_output([general_chunk_outputs(c) for c in chunks], n, 1)
+    out["merged_keys"] = np.array(sorted(merged.keys()))
+    for k, v in merged.items():
+        out["m_" + k] = np_(v)
+    np.savez_compressed(os.path.join(HERE, "stage2_general.npz"), **out)
+
+
 if __name__ == "__main__":
     make_stage1_net()
     make_stage1_render()
@@ -398,5 +441,6 @@ if __name__ == "__main__":
     make_stage1_grads()
     make_stage1_phong()
     make_stage2_losses()
-    for f in ("stage1_net", "stage1_render", "stage2_shade", "stage2_grads", "stage2_edit", "stage1_grads", "stage1_phong", "stage2_loss"):
+    make_stage2_general()
+    for f in ("stage1_net", "stage1_render", "stage2_shade", "stage2_grads", "stage2_edit", "stage1_grads", "stage1_phong", "stage2_loss", "stage2_general"):
         print(f, os.path.getsize(os.path.join(HERE, f + ".npz")) // 1024, "KB")

@@ -121,3 +121,20 @@ def s1_loss_ground_truth(n):
 def s2_loss_ground_truth(L, n, Lt):
     g = torch.Generator().manual_seed(12)
     return {"rgb": torch.rand(L, n, 3, generator=g), "visibility": torch.rand(L, n, generator=g), "vis_train_gt": torch.rand(Lt, n, generator=g)}
+
+
+def general_case():
+    """Same inputs as tests/golden/make_golden.py:general_case (the split/merge fixture)."""
+    g = torch.Generator().manual_seed(41)
+    n = 2500
+    inp = {"uv": torch.rand(1, n, 2, generator=g), "object_mask": torch.rand(1, n, generator=g) > 0.3,
+           "points": torch.randn(1, n, 3, generator=g), "normal": torch.randn(1, n, 3, generator=g),
+           "visibility": torch.rand(1, n, 2, generator=g), "intrinsics": torch.eye(4)[None], "pose": torch.eye(4)[None],
+           "light_direction": torch.randn(2, 3, generator=g)}
+    return inp, n
+
+
+def general_chunk_outputs(chunk):
+    m = chunk["uv"].shape[1]
+    return {"mask": chunk["object_mask"].reshape(-1), "flag": chunk["object_mask"].float(), "rgb": chunk["points"] * 2,
+            "per_light": chunk["visibility"].permute(2, 0, 1)[..., None].expand(2, 1, m, 3).contiguous(), "none": None}
