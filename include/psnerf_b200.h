@@ -244,6 +244,29 @@ int psn_s1_train_backward(const psn_train_net* geo, const psn_train_net* app, in
 int psn_composite_bwd(const float* rgb_s, const float* alpha, int64_t N, int S, int white_background,
                       const float* g_rgb, const float* g_acc, float* d_rgb_s, float* d_alpha, void* stream);
 
+/* ---- fused optimizer steps of the train loops ---------------------------------------------------------------
+ * psn_adam_step replaces torch.optim.Adam.step() (stage1/train.py:62, stage2/trainer.py:116; amsgrad = False): ONE launch
+ * updates every listed tensor in place (param, exp_avg, exp_avg_sq; grad is read).  `step` is the 1-based update count AFTER this
+ * call's increment (torch's state['step']); tensors whose counts differ need separate calls.  weight_decay is torch's L2 term
+ * (grad + weight_decay * param).  All pointers are contiguous fp32 device memory; the tensor list itself is HOST memory.
+ * psn_sparse_adam_step replaces torch.optim.SparseAdam.step() for one [R, D] embedding (stage2/trainer.py:165: the per-light
+ * direction [llen,3] and intensity [llen,1] tables): only the rows named in `rows` [K] (int64, device; duplicates are summed
+ * in entry order like coalesce(), rows outside [0, R) are ignored) move, by grad_values [K, D].  K <= 65536. */
+typedef struct psn_adam_tensor {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  int64_t numel;
+} psn_adam_tensor;
+typedef struct psn_adam_hyper {
+  float lr, beta1, beta2, eps, weight_decay;
+  int64_t step;
+} psn_adam_hyper;
+int psn_adam_step(const psn_adam_tensor* tensors, int n_tensors, const psn_adam_hyper* hyper, void* stream);
+int psn_sparse_adam_step(float* param, float* exp_avg, float* exp_avg_sq, int64_t R, int D, const int64_t* rows,
+                         const float* grad_values, int64_t K, const psn_adam_hyper* hyper, void* stream);
+
 /* alpha compositing of per-sample (rgb, alpha): rendering.py:196-197,214-216. */
 int psn_composite(const float* rgb_s /*[N,S,3]*/, const float* alpha /*[N,S]*/, int64_t N, int S,
                   int white_background, float* rgb /*[N,3]*/, float* acc /*[N]*/, void* stream);

@@ -726,3 +726,45 @@ def psnr(a, b):
     """10 log10(1/mse), 100 dB when identical (stage2/utils/metrics.py:38-51)."""
     mse = float(torch.mean((a.double() - b.double()) ** 2))
     return 100.0 if mse == 0 else 10.0 * math.log10(1.0 / mse)
+
+
+# ----------------------------------------------------------------------------------------------
+# Optimizer steps of the train loops (the arithmetic lives in torch.optim, pinned pytorch=1.8.0:
+# torch/optim/_functional.py adam() / sparse_adam(); call sites stage1/train.py:62,
+# stage2/trainer.py:116,165).  Pinned against torch.optim.Adam / SparseAdam of this container
+# in tests/test_oracle_golden.py.
+# ----------------------------------------------------------------------------------------------
+def adam_step(p, g, m, v, step, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+    """One torch.optim.Adam update (amsgrad=False) of numpy fp32 arrays; step = count after the increment.  Returns (p, m, v)."""
+    f = np.float32
+    b1, b2 = betas
+    g = g.astype(f)
+    if weight_decay != 0:
+        g = g + f(weight_decay) * p
+    m = m * f(b1) + g * f(1 - b1)
+    v = v * f(b2) + g * g * f(1 - b2)
+    bc1 = 1 - b1 ** step
+    bc2 = 1 - b2 ** step
+    denom = np.sqrt(v) / f(math.sqrt(bc2)) + f(eps)
+    p = p - f(lr / bc1) * (m / denom)
+    return p.astype(f), m.astype(f), v.astype(f)
+
+
+def sparse_adam_step(p, rows, gv, m, v, step, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+    """One torch.optim.SparseAdam update of the [R,D] table p for the sparse gradient (rows [K], gv [K,D]); duplicate rows are
+    summed first (coalesce), untouched rows keep p, m and v.  Returns (p, m, v)."""
+    f = np.float32
+    b1, b2 = betas
+    p, m, v = p.copy(), m.copy(), v.copy()
+    uniq = sorted(set(int(r) for r in rows))
+    g = np.zeros((len(uniq), p.shape[1]), f)
+    for k, r in enumerate(rows):
+        g[uniq.index(int(r))] += gv[k]
+    bc1 = 1 - b1 ** step
+    bc2 = 1 - b2 ** step
+    step_size = f(lr * math.sqrt(bc2) / bc1)
+    for i, r in enumerate(uniq):
+        m[r] = m[r] + (g[i] - m[r]) * f(1 - b1)
+        v[r] = v[r] + (g[i] * g[i] - v[r]) * f(1 - b2)
+        p[r] = p[r] - step_size * (m[r] / (np.sqrt(v[r]) + f(eps)))
+    return p, m, v

@@ -36,6 +36,16 @@ class TrainNet(C.Structure):
                 ("dW", C.POINTER(C.c_void_p)), ("db", C.POINTER(C.c_void_p))]
 
 
+class AdamTensor(C.Structure):
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("numel", C.c_int64)]
+
+
+class AdamHyper(C.Structure):
+    _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float),
+                ("step", C.c_int64)]
+
+
 class ShadeParams(C.Structure):
     _fields_ = [("n_freqs_xyz", C.c_int), ("n_freqs_normal", C.c_int), ("nbasis", C.c_int), ("specular_rgb", C.c_int),
                 ("intensity_kind", C.c_int), ("intensity", C.c_float), ("render_model", C.c_int), ("fresnel_f0", C.c_float)]
@@ -107,6 +117,8 @@ def load():
     lib.psn_s2_train_backward.argtypes = [tn, tn, tn, tn, vp, C.POINTER(ShadeParams), vp, vp, i64, i64, vp, i32, vp, i32,
                                           vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, i64, vp]
     lib.psn_composite.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp]
+    lib.psn_adam_step.argtypes = [C.POINTER(AdamTensor), i32, C.POINTER(AdamHyper), vp]
+    lib.psn_sparse_adam_step.argtypes = [vp, vp, vp, i64, i32, vp, vp, i64, C.POINTER(AdamHyper), vp]
     _lib = lib
     return lib
 

@@ -84,6 +84,57 @@ def test_no_cpu_fallback():
         p(synth.stage2_input(4, 4, 2))
 
 
+def test_fused_optimizers_host_contract(lib_built):
+    """psnerf_b200.optim.{Adam,SparseAdam} without a GPU: argument validation of the C entry points, torch-compatible state_dict
+    layout (a torch.optim.Adam checkpoint resumes and the state goes back), MultiStepLR drives param_groups, and no CPU fallback."""
+    import ctypes as C
+    from psnerf_b200 import _binding as B
+    from psnerf_b200 import optim
+    h = B.AdamHyper(1e-3, 0.9, 0.999, 1e-8, 0.0, 0)
+    assert lib_built.psn_adam_step(None, 0, C.byref(h), None) < 0 and b"step" in lib_built.psn_last_error()
+    h.step = 1
+    assert lib_built.psn_adam_step(None, 0, C.byref(h), None) == 0  # empty list: nothing to launch
+    assert lib_built.psn_adam_step(None, 2, C.byref(h), None) < 0
+    h.beta1 = 1.0
+    assert lib_built.psn_sparse_adam_step(None, None, None, 4, 3, None, None, 2, C.byref(h), None) < 0
+    h.beta1, h.weight_decay = 0.9, 0.1
+    assert lib_built.psn_sparse_adam_step(None, None, None, 4, 3, None, None, 2, C.byref(h), None) < 0
+    assert b"weight decay" in lib_built.psn_last_error()
+    h.weight_decay = 0.0
+    assert lib_built.psn_sparse_adam_step(None, None, None, 4, 3, None, None, 0, C.byref(h), None) == 0  # K = 0
+    assert lib_built.psn_sparse_adam_step(None, None, None, 4, 3, None, None, 2, C.byref(h), None) < 0  # null pointers
+
+    p = torch.nn.Parameter(torch.ones(4, 3))
+    ot = torch.optim.Adam([p], lr=1e-2)
+    p.grad = torch.ones(4, 3)
+    ot.step()
+    ot.step()
+    om = optim.Adam([p], lr=1e-2)
+    om.load_state_dict(ot.state_dict())
+    assert optim._step_int(om.state[p]["step"]) == 2 and set(om.state[p]) == {"step", "exp_avg", "exp_avg_sq"}
+    back = torch.optim.Adam([p], lr=1e-2)
+    back.load_state_dict(om.state_dict())
+    assert torch.equal(back.state[p]["exp_avg"], ot.state[p]["exp_avg"])
+    sched = torch.optim.lr_scheduler.MultiStepLR(om, [1], gamma=0.5)
+    om.param_groups[0]["params"][0].grad = None
+    om.step()  # nothing has a gradient: a no-op even without a GPU
+    sched.step()
+    assert om.param_groups[0]["lr"] == pytest.approx(5e-3)
+    p.grad = torch.ones(4, 3)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        om.step()
+    with pytest.raises(RuntimeError, match="amsgrad"):
+        optim.Adam([p], amsgrad=True)
+    with pytest.raises(RuntimeError, match="dense"):
+        optim.SparseAdam([p]).step()
+    e = torch.nn.Embedding(5, 3, sparse=True)
+    e(torch.tensor([1, 1, 3])).sum().backward()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        optim.SparseAdam(list(e.parameters())).step()
+    with pytest.raises(RuntimeError, match="sparse"):
+        optim.Adam(list(e.parameters())).step()
+
+
 def test_arange_pixels_is_xmajor():
     from psnerf_b200.stage1 import arange_pixels
     import psnerf_oracle as O
