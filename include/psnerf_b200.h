@@ -10,7 +10,11 @@
  *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, no implicit sync.
  *  - Return 0 on success, <0 on error (PSN_ERR_*); psn_last_error() gives the message (thread local).
  *  - `precision`: PSN_PREC_FP32 = fp32 FFMA kernels; PSN_PREC_TC = tcgen05 tensor-core kernels with
- *    error-compensated fp16 split operands (hi+lo, 3 MMAs per product), fp32 accumulate in TMEM.
+ *    error-compensated fp16 split operands (hi+lo, 3 MMAs per product), fp32 accumulate in TMEM;
+ *    PSN_PREC_TC_MIXED = the same kernels, except that the radiance program (psn_radiance, psn_render_unisurf) keeps the split
+ *    product only for the eight softplus layers that decide alpha and runs the feature head, the reverse sweep that feeds the
+ *    appearance MLP and the appearance MLP itself as single fp16 passes (rgb within 1e-5 rel-L2 of PSN_PREC_TC; alpha, depth,
+ *    masks and the surface-normal output are bit-identical to PSN_PREC_TC).  EXPERIMENTAL: opt-in, not the default.
  *  - No CPU fallback exists: every entry point fails with PSN_ERR_CUDA without a sm_100 device.
  */
 #ifndef PSNERF_B200_H
@@ -30,6 +34,7 @@ extern "C" {
 
 #define PSN_PREC_FP32 0
 #define PSN_PREC_TC 1
+#define PSN_PREC_TC_MIXED 2
 
 #define PSN_NET_GEO 0 /* stage1/model/network.py:37-66 lin0..lin8 (softplus beta=100, skip concat /sqrt2) */
 #define PSN_NET_APP 1 /* stage1/model/network.py:71-79 lina0..lina4 (ReLU, tanh*0.5+0.5)               */
@@ -188,7 +193,7 @@ int psn_tc_debug_trace_q(const psn_mlp* geo, const float* pts, int64_t M, float*
  * 7 last commit}; trace[192 + step] = epilogue of the step finished (row 0).  stash: psn_workspace-style scratch of at least
  * 148 * 640 KB. */
 int psn_tc_debug_trace_rad(const psn_mlp* geo, const psn_mlp* app, const float* pts, const float* views, int64_t M,
-                           float* rgb, float* alpha, void* stash, long long* trace, void* stream);
+                           float* rgb, float* alpha, void* stash, long long* trace, int mixed, void* stream);
 
 /* ---- stage-2 train step (BASELINE config 5): PSNetwork.forward + backward, stage2/trainer.py:394-410 ------------------------
  * Gradient-carrying parts (renderer.py:193-199,211-231,251-262 with light_vis_detach = vis_rgb_detach = True): the per-point nets

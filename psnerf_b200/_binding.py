@@ -12,7 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PSNERF_B200_LIB") or os.path.join(_HERE, "lib", "libpsnerf_b200.so")  # env override: bring-up builds
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "psnerf_b200.h")
 
-PREC_FP32, PREC_TC = 0, 1
+PREC_FP32, PREC_TC, PREC_TC_MIXED = 0, 1, 2
+PRECISIONS = {"fp32": PREC_FP32, "tc": PREC_TC, "tc_mixed": PREC_TC_MIXED}
 NET_GEO, NET_APP, NET_S2 = 0, 1, 2
 OUT_ALPHA, OUT_NEG_LOGIT, OUT_LOGIT = 0, 1, 2
 
@@ -101,7 +102,7 @@ def load():
     lib.psn_tc_debug_layer.argtypes = [vp, vp, i64, i32, vp, vp, vp]
     lib.psn_tc_debug_trace.argtypes = [vp, vp, i64, vp, vp, vp]
     lib.psn_tc_debug_trace_q.argtypes = [vp, vp, i64, vp, vp, i32, vp]
-    lib.psn_tc_debug_trace_rad.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp, vp, vp]
+    lib.psn_tc_debug_trace_rad.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp, vp, i32, vp]
     tn = C.POINTER(TrainNet)
     lib.psn_s1_train_tape_bytes.argtypes = [tn, tn, i32, i32, i64]
     lib.psn_s1_train_tape_bytes.restype = i64

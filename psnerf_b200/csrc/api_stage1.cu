@@ -14,23 +14,23 @@ static int occupancy_any(const psn_mlp* geo, const PointGen& gen, long long M, c
   const int tag = gen.kind == GEN_MARCH ? PSN_PROF_OCC_MARCH : gen.kind == GEN_INDEXED_DEPTH ? PSN_PROF_OCC_SECANT
                 : gen.kind == GEN_SHADOW ? PSN_PROF_SHADOW : PSN_PROF_OCC_OTHER;
   ProfScope prof(tag, M, st);
-  if (precision == PSN_PREC_TC) return tc_occupancy(geo, gen, M, M_dev, out_kind, out, st);
+  if (prec_is_tc(precision)) return tc_occupancy(geo, gen, M, M_dev, out_kind, out, st);
   return simt_occupancy(geo, gen, M, M_dev, out_kind, out, 0, st);
 }
 static int gradient_any(const psn_mlp* geo, const PointGen& gen, long long M, const int* M_dev, float* grad, void* stash,
                         int precision, cudaStream_t st) {
   ProfScope prof(PSN_PROF_GRADIENT, M, st);
-  if (precision == PSN_PREC_TC) return tc_gradient(geo, gen, M, M_dev, grad, stash, st);
+  if (prec_is_tc(precision)) return tc_gradient(geo, gen, M, M_dev, grad, stash, st);
   return simt_gradient(geo, gen, M, M_dev, grad, stash, st);
 }
 static int radiance_any(const psn_mlp* geo, const psn_mlp* app, const PointGen& gen, long long M, float* rgb, float* alpha,
                         void* stash, int precision, cudaStream_t st) {
   ProfScope prof(PSN_PROF_RADIANCE, M, st);
-  if (precision == PSN_PREC_TC) return tc_radiance(geo, app, gen, M, rgb, alpha, stash, st);
+  if (prec_is_tc(precision)) return tc_radiance(geo, app, gen, M, rgb, alpha, stash, precision == PSN_PREC_TC_MIXED, st);
   return simt_radiance(geo, app, gen, M, rgb, alpha, stash, st);
 }
 
-static size_t stash_bytes(int precision) { return precision == PSN_PREC_TC ? tc_stash_bytes() : simt_stash_bytes(); }
+static size_t stash_bytes(int precision) { return prec_is_tc(precision) ? tc_stash_bytes() : simt_stash_bytes(); }
 
 static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
@@ -83,7 +83,7 @@ extern "C" int psn_infer_occ(const psn_mlp* geo, const float* pts, int64_t M, fl
   memset(&gen, 0, sizeof(gen));
   gen.kind = GEN_EXPLICIT;
   gen.pts = pts;
-  if (precision == PSN_PREC_TC) return tc_infer_occ(geo, gen, M, out, (cudaStream_t)stream);
+  if (prec_is_tc(precision)) return tc_infer_occ(geo, gen, M, out, (cudaStream_t)stream);
   return simt_occupancy(geo, gen, M, nullptr, PSN_OUT_LOGIT, out, 1, (cudaStream_t)stream);
 }
 
@@ -253,7 +253,7 @@ extern "C" int psn_shadow_visibility(const psn_mlp* geo, const float* surf, cons
     gen.lnear = lnear;
     gen.lfar = lfar;
     int rc;
-    if (precision == PSN_PREC_TC && n_steps == 128) {
+    if (prec_is_tc(precision) && n_steps == 128) {
       ProfScope prof(PSN_PROF_SHADOW, nl * Ns * n_steps, st);
       rc = tc_shadow(geo, gen, nl * Ns, box, vis + l0 * Ns, st);  // fused march + transmittance, no HBM round trip
       if (rc) return rc;

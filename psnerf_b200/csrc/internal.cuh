@@ -28,7 +28,9 @@ int tc_infer_occ(const psn_mlp* geo, const PointGen& gen, long long M, float* ou
 int tc_gradient(const psn_mlp* geo, const PointGen& gen, long long M, const int* M_dev, float* grad, void* stash,
                 cudaStream_t st);
 int tc_radiance(const psn_mlp* geo, const psn_mlp* app, const PointGen& gen, long long M, float* rgb, float* alpha,
-                void* stash, cudaStream_t st);
+                void* stash, int mixed, cudaStream_t st);
+// PSN_PREC_TC and PSN_PREC_TC_MIXED both select the tcgen05 kernels; they differ only in the radiance program (tc_rad.cu)
+inline bool prec_is_tc(int precision) { return precision == PSN_PREC_TC || precision == PSN_PREC_TC_MIXED; }
 int tc_shadow(const psn_mlp* geo, const PointGen& gen, long long pairs, float box, float* vis, cudaStream_t st);
 size_t tc_stash_bytes();
 

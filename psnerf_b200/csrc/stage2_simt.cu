@@ -419,7 +419,7 @@ extern "C" int psn_s2_point_nets(const psn_mlp* albedo_net, const psn_mlp* rough
 extern "C" int psn_s2_visibility(const psn_mlp* vis_net, int n_freqs, const float* pts, int64_t Ns, const float* lights, int L,
                                  float* vis, void* ws, int64_t ws_bytes, int precision, void* stream) {
   PSN_REQUIRE(vis_net && (Ns == 0 || L == 0 || (pts && lights && vis)), PSN_ERR_ARG, "psn_s2_visibility: null argument");
-  if (precision == PSN_PREC_TC) return tc_s2_visibility(vis_net, n_freqs, pts, Ns, lights, L, vis, ws, (size_t)ws_bytes,
+  if (prec_is_tc(precision)) return tc_s2_visibility(vis_net, n_freqs, pts, Ns, lights, L, vis, ws, (size_t)ws_bytes,
                                                         (cudaStream_t)stream);
   return s2_visibility_simt(vis_net, n_freqs, pts, Ns, lights, L, vis, (cudaStream_t)stream);
 }
@@ -499,7 +499,7 @@ static int shade_stage2_impl(const psn_mlp* normal_net, const psn_mlp* albedo_ne
   }
   if (vis_net) {
     ProfScope prof(PSN_PROF_S2_VIS, (long long)Ns * L, st);
-    if (precision == PSN_PREC_TC) {
+    if (prec_is_tc(precision)) {
       const size_t off = (w.used + 255) / 256 * 256;
       rc = tc_s2_visibility(vis_net, prm->n_freqs_xyz, pts, Ns, lights, L, v_s, (char*)ws + off,
                             (size_t)ws_bytes > off ? (size_t)ws_bytes - off : 0, st);

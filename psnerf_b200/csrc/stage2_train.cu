@@ -383,7 +383,7 @@ extern "C" int psn_s2_train_forward(const psn_train_net* nn, const psn_train_net
     }
     if (vn) {  // detached L-light pass on the inference kernels
       ProfScope prof(PSN_PROF_S2_VIS, (long long)Ns * L, st);
-      if (precision == PSN_PREC_TC) {
+      if (prec_is_tc(precision)) {
         const size_t off = (w.used + 255) / 256 * 256;
         rc = tc_s2_visibility(vis_packed, nf, pts, Ns, lights, L, t.v_raw, (char*)ws + off, (size_t)ws_bytes > off ? (size_t)ws_bytes - off : 0, st);
       } else {

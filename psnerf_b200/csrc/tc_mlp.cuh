@@ -197,6 +197,11 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // register re-allocation between warpgroups (all 4 warps of a warpgroup must execute it)
@@ -230,7 +235,9 @@ int tc_grid(const void* kernel, long long tiles);
 // ---- step table -------------------------------------------------------------------------------------------------
 struct Step {
   uint32_t w_off;  // byte offset (from the net's tile blob) of tile (kb=0, hi); tiles follow as [kb][hi, lo]
-  uint16_t nkb;    // K blocks of 64
+  uint8_t nkb;     // K blocks of 64
+  uint8_t single;  // 1: ONE pass A_hi W_hi (plain fp16 operands) - only the hi tiles are streamed and the producing epilogue
+                   // writes only the hi half of the A operand (epi_store_a16 hi_only); 0: the three-pass split product
   uint16_t n_pad;  // N (multiple of 16, <= 256); a tile is n_pad x 128 bytes
 };
 constexpr int MAX_STEPS = 24;
@@ -290,12 +297,14 @@ __device__ __forceinline__ void producer_loop(const Smem& s, const Program& prog
       const Step sp = prog.step[st];
       const uint32_t tile_bytes = (uint32_t)sp.n_pad * 128u;
       const unsigned char* src = prog.blob[st] + sp.w_off;
-      for (int t = 0; t < 2 * sp.nkb; ++t, t_parity ^= 1u) {
+      const int n_tiles = sp.single ? sp.nkb : 2 * sp.nkb;
+      for (int t = 0; t < n_tiles; ++t, t_parity ^= 1u) {
         mbar_wait_cluster_relaxed(&s.c->w_empty[stage], phase ^ 1u);     // released by the MMA warps of both CTAs
         mbar_arrive_expect_tx(&s.c->w_full[stage], tile_bytes);          // this CTA's copy of the tile
+        const int blob_tile = sp.single ? 2 * t : (t ^ 1);  // ring order per K block: lo tile, then hi tile (blob: hi, lo); single: hi only
         if (t_parity == rank)
-          bulk_g2s_multicast(s.w + stage * W_STAGE_BYTES, src + (size_t)(t ^ 1) * tile_bytes, tile_bytes, &s.c->w_full[stage],
-                             (uint16_t)((1u << CLUSTER) - 1u));  // ring order per K block: lo tile, then hi tile (blob: hi, lo)
+          bulk_g2s_multicast(s.w + stage * W_STAGE_BYTES, src + (size_t)blob_tile * tile_bytes, tile_bytes, &s.c->w_full[stage],
+                             (uint16_t)((1u << CLUSTER) - 1u));
         if (++stage == W_STAGES) { stage = 0; phase ^= 1u; }
       }
     }
@@ -339,6 +348,41 @@ __device__ __forceinline__ void mma_loop(const Smem& s, const Program& prog, lon
       const uint32_t idesc = umma_idesc(sp.n_pad);
       long long t_wait_a = 0, t_wait_w = 0;  // bring-up trace only (dead code otherwise)
       for (int kb = 0; kb < sp.nkb; ++kb) {
+        if (sp.single) {
+          // single-pass step: one weight stage (the hi tile) and four MMAs A_hi W_hi per K block; same split of the last K block
+          const uint32_t st_w = stage, ph_w = phase;
+          if (++stage == W_STAGES) { stage = 0; phase ^= 1u; }
+          mbar_wait(&s.c->w_full[st_w], ph_w);
+          mbar_wait(&s.c->a_ready[kb], (a_phase >> kb) & 1u);
+          a_phase ^= (1u << kb);
+          tc_fence_after();
+          const uint32_t a_s = a_addr + (uint32_t)kb * 64u;
+          const uint32_t lo_w = umma_desc_lo(w_base + st_w * W_STAGE_BYTES);
+          if (elect_one()) {
+            if (trace && it == TRACE_ITER && blockIdx.x == 0) trace[st * 8 + kb] = clock64();
+            if (kb + 1 < sp.nkb) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) umma_ts_f16(d_addr, a_s + ks * 16, umma_desc_at(lo_w, ks * 32), idesc, (kb | ks) ? 1u : 0u);
+            } else {
+              const uint32_t n0 = sp.n_pad < 64 ? (uint32_t)sp.n_pad : 64u;
+              const uint32_t id0 = umma_idesc(n0);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) umma_ts_f16(d_addr, a_s + ks * 16, umma_desc_at(lo_w, ks * 32), id0, (kb | ks) ? 1u : 0u);
+              umma_commit(&s.c->d_q[buf][0]);
+              if (sp.n_pad > 64) {
+                const uint32_t id1 = umma_idesc((uint32_t)sp.n_pad - 64u);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                  umma_ts_f16(d_addr + 64u, a_s + ks * 16, umma_desc_at(lo_w, 8192 + ks * 32), id1, (kb | ks) ? 1u : 0u);
+              }
+              umma_commit(&s.c->d_q[buf][1]);
+              if (trace && it == TRACE_ITER && blockIdx.x == 0) trace[st * 8 + 7] = clock64();
+            }
+            umma_commit_multicast(&s.c->w_empty[st_w], (uint16_t)((1u << CLUSTER) - 1u));
+          }
+          __syncwarp();
+          continue;
+        }
         // this K block's two weight stages (lo tile first: it is consumed - and released - first).  They are checked BEFORE the
         // activations: the weights are normally long there (the checks cost ~100 cycles of barrier round trip each), whereas the
         // a_ready -> first MMA latency sits on the critical epilogue -> MMA -> epilogue chain of every layer.
@@ -510,6 +554,22 @@ __device__ __forceinline__ void epi_store_a16(const EpiCtx& e, uint32_t col0, in
     r[8 + u] = *reinterpret_cast<const uint32_t*>(&ll);
   }
   tmem_st16(e.tmem_base + e.lane_addr + col0 + (uint32_t)col, r);
+}
+// The same 16 activation values for a SINGLE-PASS consumer step (Step::single): only the packed fp16 hi half, at the columns
+// where the full layout has it (the 8 lo columns keep stale data that no MMA of that step reads): half the conversions, half the
+// tcgen05.st traffic.
+__device__ __forceinline__ void epi_store_a16_hi(const EpiCtx& e, uint32_t col0, int col, const float (&v)[CW]) {
+  uint32_t r[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const __half2 hh = __floats2half2_rn(v[2 * u], v[2 * u + 1]);
+    r[u] = *reinterpret_cast<const uint32_t*>(&hh);
+  }
+  tmem_st8(e.tmem_base + e.lane_addr + col0 + (uint32_t)col, r);
+}
+__device__ __forceinline__ void epi_store_a16(const EpiCtx& e, uint32_t col0, int col, const float (&v)[CW], bool hi_only) {
+  if (hi_only) epi_store_a16_hi(e, col0, col, v);
+  else epi_store_a16(e, col0, col, v);
 }
 // this warp's 16 columns of K-block kb are written: publish to the MMA warp (one arrival per epilogue warp, 16 per block)
 __device__ __forceinline__ void epi_signal_a(const Smem& s, int kb) {

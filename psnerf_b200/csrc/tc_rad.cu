@@ -8,6 +8,12 @@
 //   s19..s21 appearance layers 1..3 (ReLU);   s22 appearance layer 4 (N = 3) -> tanh * 0.5 + 0.5
 // plus the fp32 logit head (alpha) folded into s7's epilogue.  The same kernel with only s0..s7, s10..s17 is the
 // gradient (surface normal) kernel.  Algorithmic work: 2,509,824 FLOP per sample.
+//
+// Mixed program (PSN_PREC_TC_MIXED, radiance only): s0..s7 stay three-pass - alpha and the sigma' stash need the split product
+// (a 2- or 1-pass geo forward misses the 1e-4 gate on alpha: tools/precision_study.py) - but everything the appearance MLP
+// consumes tolerates plain fp16 operands: s8..s22 run ONE pass A_hi W_hi (Step::single), their producers write only the hi
+// half of the A operand.  rgb moves by 6e-6 rel-L2 per sample / 1e-6 per rendered pixel (same tool); the gradient OUTPUT
+// (surface normals) is never taken from this program - tc_gradient always runs the three-pass one.
 #include "tc_mlp.cuh"
 #include "stage1_simt.cuh"
 #include "launch.cuh"
@@ -49,6 +55,7 @@ struct TcRadArgs {
   int octaves_view, pe_view_dim;
   uint4* scratch;
   int with_app;  // 1: radiance (23 steps), 0: gradient only (16 steps)
+  int mixed;     // 1: steps s8.. are single-pass (radiance only)
 };
 
 #define PSN_INV_SQRT2 0.70710678118654752440f
@@ -108,6 +115,7 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
   do {                                                                                                              \
     if (TRACE && trace && it == TRACE_ITER && blockIdx.x == 0 && row == 0 && sub == 0) trace[(slot) + tstep] = clock64(); \
   } while (0)
+    const bool ho = g.mixed != 0;  // operands of the single-pass steps: hi half only
     uint4* stash = g.scratch + (size_t)blockIdx.x * SCR_U4_PER_CTA;
     float4* parked = reinterpret_cast<float4*>(stash + SCR_STASH_U4);
     for (long long it = 0; it < iters; ++it) {
@@ -139,6 +147,7 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
         const bool pre_skip = (l + 1 == g.skip);
         const int n_out = g.n_out[l];
         const float cc = pre_skip ? PSN_SOFTPLUS_C * PSN_INV_SQRT2 : PSN_SOFTPLUS_C;
+        const bool ho_l = ho && l == 7;  // h_7 feeds the (single-pass) feature head s8
         epi_for_chunks_pf<Bias16>(s, e, [&](int col, Bias16& b) { load_bias16(bias, col, b); },
                                   [&](int pass, int col, float (&v)[CW], const Bias16& b) {
           add16(v, b.b);
@@ -173,7 +182,7 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
               if (k >= 0) v[i] = (k < g.pe_dim ? s.pe[k * TILE_M + row] : 0.f) * PSN_INV_SQRT2;
             }
           }
-          epi_store_a16(e, e.d_col0(), col, v);
+          epi_store_a16(e, e.d_col0(), col, v, ho_l);
           epi_signal_a(s, pass);
         });
         PSN_RAD_MARK(192);
@@ -186,7 +195,7 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
         epi_for_chunks_pf<Bias16>(s, e, [&](int col, Bias16& b) { load_bias16(g.bias_feat, col, b); },
                                   [&](int pass, int col, float (&v)[CW], const Bias16& b) {
           add16(v, b.b);
-          epi_store_a16(e, e.d_col0(), col, v);
+          epi_store_a16(e, e.d_col0(), col, v, ho);
           epi_signal_a(s, pass);
         });
         PSN_RAD_MARK(192);
@@ -215,7 +224,7 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
               v[8 * t + 4 * h + 2] = (w.z * PSN_INV_U16) * sg[4 * h + 2]; v[8 * t + 4 * h + 3] = (w.w * PSN_INV_U16) * sg[4 * h + 3];
             }
           }
-          epi_store_a16(e, e.d_col0(), col, v);
+          epi_store_a16(e, e.d_col0(), col, v, ho);
           epi_signal_a(s, pass);
         });
         PSN_RAD_MARK(192);
@@ -257,7 +266,7 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
             for (int i = 0; i < CW; ++i)
               if (col + i >= nprev) v[i] = 0.f;
           }
-          epi_store_a16(e, e.d_col0(), col, v);
+          epi_store_a16(e, e.d_col0(), col, v, ho);
           epi_signal_a(s, pass);
         });
         PSN_RAD_MARK(192);
@@ -314,7 +323,7 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
             else if (k < o_g + 3) val = (k == o_g ? gr[0] : (k == o_g + 1 ? gr[1] : gr[2]));
             v[i] = val;
           }
-          epi_store_a16(e, e.a_col0(), sub * CW, v);
+          epi_store_a16(e, e.a_col0(), sub * CW, v, ho);
           epi_signal_a(s, 0);
         }
         // ---- s18: appearance layer 0 (rest) + parked + bias, ReLU ------------------------------------------------------------
@@ -330,7 +339,7 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
           add16(v, o.b);
 #pragma unroll
           for (int i = 0; i < CW; ++i) v[i] = fmaxf(v[i], 0.f);
-          epi_store_a16(e, e.d_col0(), col, v);
+          epi_store_a16(e, e.d_col0(), col, v, ho);
           epi_signal_a(s, pass);
         });
         PSN_RAD_MARK(192);
@@ -345,7 +354,7 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
             add16(v, b.b);
 #pragma unroll
             for (int i = 0; i < CW; ++i) v[i] = fmaxf(v[i], 0.f);
-            epi_store_a16(e, e.d_col0(), col, v);
+            epi_store_a16(e, e.d_col0(), col, v, ho);
             epi_signal_a(s, pass);
           });
           PSN_RAD_MARK(192);
@@ -382,7 +391,7 @@ static void put_step(Program& p, int i, const psn_mlp* net, int idx) {
   p.blob[i] = net->tc_blob;
 }
 
-static int make_tc_rad(const psn_mlp* geo, const psn_mlp* app, void* scratch, TcRadArgs* a) {
+static int make_tc_rad(const psn_mlp* geo, const psn_mlp* app, void* scratch, TcRadArgs* a, int mixed = 0) {
   PSN_REQUIRE(geo && geo->kind == PSN_NET_GEO && geo->tc_ok, PSN_ERR_SHAPE, "geo net is not packed for the tensor-core path");
   memset(a, 0, sizeof(*a));
   int n = 0;
@@ -410,6 +419,9 @@ static int make_tc_rad(const psn_mlp* geo, const psn_mlp* app, void* scratch, Tc
     PSN_REQUIRE(a->pe_view_dim <= PE_K, PSN_ERR_SHAPE, "tensor path: view encoding wider than %d", PE_K);
   }
   a->prog.n_steps = n;
+  a->mixed = (mixed && app) ? 1 : 0;
+  if (a->mixed)
+    for (int i = 8; i < n; ++i) a->prog.step[i].single = 1;  // s8.. : feature head, reverse sweep, appearance MLP
   a->bias_feat = geo->fwd[8].bias;
   a->w_row = geo->w_logit_row;
   a->b_logit = geo->logit_head.bias;
@@ -447,10 +459,10 @@ static int launch_tc_rad(const TcRadArgs& a, const PointGen& gen, long long M, c
 }
 
 int tc_radiance(const psn_mlp* geo, const psn_mlp* app, const PointGen& gen, long long M, float* rgb, float* alpha, void* stash,
-                cudaStream_t st) {
+                int mixed, cudaStream_t st) {
   PSN_REQUIRE(app, PSN_ERR_ARG, "tc_radiance: app net is null");
   TcRadArgs a;
-  int rc = make_tc_rad(geo, app, stash, &a);
+  int rc = make_tc_rad(geo, app, stash, &a, mixed);
   if (rc) return rc;
   if (M == 0) return PSN_OK;
   return launch_tc_rad(a, gen, M, nullptr, rgb, alpha, nullptr, st);
@@ -470,10 +482,10 @@ using namespace psn;
 
 // Bring-up tool: clock64() timeline of one tile of the radiance kernel (explicit points / view directions): trace is int64[256].
 extern "C" int psn_tc_debug_trace_rad(const psn_mlp* geo, const psn_mlp* app, const float* pts, const float* views, int64_t M,
-                                      float* rgb, float* alpha, void* stash, long long* trace, void* stream) {
+                                      float* rgb, float* alpha, void* stash, long long* trace, int mixed, void* stream) {
   PSN_REQUIRE(geo && app && pts && views && rgb && alpha && stash && trace, PSN_ERR_ARG, "psn_tc_debug_trace_rad: bad argument");
   TcRadArgs a;
-  int rc = make_tc_rad(geo, app, stash, &a);
+  int rc = make_tc_rad(geo, app, stash, &a, mixed);
   if (rc) return rc;
   PointGen gen;
   memset(&gen, 0, sizeof(gen));

@@ -11,8 +11,9 @@ _DEFAULT_PRECISION = [B.PREC_FP32]
 
 
 def set_default_precision(name):
-    """'fp32' (FFMA kernels) or 'tc' (tcgen05, fp16 hi/lo split operands, fp32 accumulate)."""
-    _DEFAULT_PRECISION[0] = {"fp32": B.PREC_FP32, "tc": B.PREC_TC}[name]
+    """'fp32' (FFMA kernels), 'tc' (tcgen05, fp16 hi/lo split operands, fp32 accumulate) or 'tc_mixed' (EXPERIMENTAL: 'tc' with
+    the appearance side of the radiance program in single fp16 passes, include/psnerf_b200.h)."""
+    _DEFAULT_PRECISION[0] = B.PRECISIONS[name]
 
 
 def tc_available():

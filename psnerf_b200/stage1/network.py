@@ -76,11 +76,11 @@ class NeuralNetwork(nn.Module):
         self.num_layers_app = len(app_widths)
         for l in range(self.num_layers_app - 1):
             setattr(self, "lina%d" % l, WNLinear(_fresh_linear(app_widths[l], app_widths[l + 1])))
-        self.precision = None  # None = engine default; 'fp32' | 'tc' per module
+        self.precision = None  # None = engine default; 'fp32' | 'tc' | 'tc_mixed' per module
 
     # ---- packing -------------------------------------------------------------------------------------------
     def _prec(self):
-        return None if self.precision is None else {"fp32": B.PREC_FP32, "tc": B.PREC_TC}[self.precision]
+        return None if self.precision is None else B.PRECISIONS[self.precision]
 
     def _packed(self):
         def build():

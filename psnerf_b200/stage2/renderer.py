@@ -137,7 +137,7 @@ class PSNetwork(nn.Module):
         self.precision = None
 
     def _prec(self):
-        return engine.default_precision() if self.precision is None else {"fp32": B.PREC_FP32, "tc": B.PREC_TC}[self.precision]
+        return engine.default_precision() if self.precision is None else B.PRECISIONS[self.precision]
 
     def forward(self, input, albedo_new=None, basis_new=None, noise=None):
         """Inference (no autograd graph) unless the module is in train() mode, gradients are enabled and a parameter / the

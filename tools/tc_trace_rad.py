@@ -18,6 +18,7 @@ torch.manual_seed(0)
 m = NeuralNetwork(cfg).cuda().eval()
 g, a = m._packed()
 M = 148 * 128 * 8
+MIXED = 1 if "--mixed" in sys.argv else 0  # the PSN_PREC_TC_MIXED program (s8.. single-pass)
 pts = (torch.rand(M, 3, device="cuda") * 2.4 - 1.2).contiguous()
 views = torch.nn.functional.normalize(torch.randn(M, 3, device="cuda"), dim=-1).contiguous()
 rgb = torch.empty(M, 3, device="cuda")
@@ -28,7 +29,7 @@ lib = B.load()
 for _ in range(2):
     B.check(lib.psn_tc_debug_trace_rad(g.handle, a.handle, C.c_void_p(pts.data_ptr()), C.c_void_p(views.data_ptr()), M,
                                        C.c_void_p(rgb.data_ptr()), C.c_void_p(alpha.data_ptr()), C.c_void_p(stash.data_ptr()),
-                                       C.c_void_p(trace.data_ptr()), engine._stream()), "trace")
+                                       C.c_void_p(trace.data_ptr()), MIXED, engine._stream()), "trace")
 torch.cuda.synchronize()
 t = trace.cpu().tolist()
 t0 = t[0]
