@@ -298,7 +298,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--precision", default="auto", choices=["auto", "tc", "fp32"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "tc", "tc_mixed", "fp32"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ref-crop", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -420,13 +420,17 @@ def main():
                                     % traffic_src,
                     "peak_source": peaks["src"], "flops_per_row": MFLOP_RAD * 1e6,
                     "issued_frac": (3.0 * tf / peaks["tflops"]) if precision == "tc" else None}
+            if precision == "tc_mixed":  # three passes for the 8 softplus layers (0.918 MFLOP), one for the remaining 1.592 MFLOP
+                roof["issued_frac"] = (3.0 * 0.918 + 1.0 * (MFLOP_RAD - 0.918)) / MFLOP_RAD * tf / peaks["tflops"]
             occ = kern.get("occ_march")
             if occ:
                 tfo = occ["rows_per_launch"] * MFLOP_OCC * 1e6 / (occ["ms_per_launch"] * 1e-3) / 1e12
                 roof["second_kernel"] = {"kernel": "occ_march", "achieved": tfo, "frac": tfo / peaks["tflops"], "flops_per_row": MFLOP_OCC * 1e6}
         line = {"metric": "Msamples/sec (rays x samples x lights)", "value": value, "unit": "Msamples/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f16x3-split operands, f32 accumulate" if precision == "tc" else "f32", "data": "synthetic",
+                "vs_baseline": None, "dtype": {"tc": "f16x3-split operands, f32 accumulate", "fp32": "f32",
+                                            "tc_mixed": "f16x3-split operands (softplus stack) + f16 single pass (appearance side), f32 accumulate"}[precision],
+                "data": "synthetic",
                 "config": {"workload": "stage1-unisurf-render 512x512x128spp (BASELINE configs[1]): %d march steps + 8 secant, %d+%d samples/ray, "
                                        "lights=1" % (MARCH, S_IN, S_OUT),
                            "views_per_step": n_views, "rays_per_gpu_per_step": n_views * n_local, "parallelism": "ray-shard x%d" % world,

@@ -264,8 +264,8 @@ typedef struct psn_adam_tensor {
   float* exp_avg_sq;
   int64_t numel;
 } psn_adam_tensor;
-typedef struct psn_adam_hyper {
-  float lr, beta1, beta2, eps, weight_decay;
+typedef struct psn_adam_hyper { /* doubles, as torch holds them: (float)(1 - beta2) of the DOUBLE 0.999 is what torch multiplies with */
+  double lr, beta1, beta2, eps, weight_decay;
   int64_t step;
 } psn_adam_hyper;
 int psn_adam_step(const psn_adam_tensor* tensors, int n_tensors, const psn_adam_hyper* hyper, void* stream);

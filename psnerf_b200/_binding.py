@@ -43,7 +43,7 @@ class AdamTensor(C.Structure):
 
 
 class AdamHyper(C.Structure):
-    _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float),
+    _fields_ = [("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double), ("weight_decay", C.c_double),
                 ("step", C.c_int64)]
 
 

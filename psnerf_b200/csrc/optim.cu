@@ -10,7 +10,8 @@
 // SparseAdam (torch/optim/_functional.py sparse_adam()), only for the rows present in the (coalesced) sparse gradient:
 //     m += (1 - beta1)(g - m) ;  v += (1 - beta2)(g g - v) ;  p -= lr sqrt(1 - beta2^t) / (1 - beta1^t) * m / (sqrt(v) + eps)
 // The two differ in where eps sits relative to the bias correction; both are kept as the reference's optimizers have them.
-// The bias corrections are evaluated on the host in double, as torch does, and enter the kernels as fp32 scalars.
+// The hyper-parameters arrive as doubles and every derived scalar (1 - beta, the bias corrections, lr / bc1) is evaluated on the
+// host in double before it is rounded to fp32, as torch does: (float)(1 - 0.999) is 1.3e-5 away from 1.f - (float)0.999.
 #include "launch.cuh"
 #include "internal.cuh"
 
@@ -110,8 +111,8 @@ __global__ void __launch_bounds__(128) k_sparse_adam(float* __restrict__ param, 
 static int check_hyper(const psn_adam_hyper* h, const char* who) {
   PSN_REQUIRE(h, PSN_ERR_ARG, "%s: null hyper-parameters", who);
   PSN_REQUIRE(h->step >= 1, PSN_ERR_ARG, "%s: step must be >= 1 (the count AFTER this update), got %lld", who, (long long)h->step);
-  PSN_REQUIRE(h->lr >= 0.f && h->eps >= 0.f && h->weight_decay >= 0.f, PSN_ERR_ARG, "%s: negative lr / eps / weight_decay", who);
-  PSN_REQUIRE(h->beta1 >= 0.f && h->beta1 < 1.f && h->beta2 >= 0.f && h->beta2 < 1.f, PSN_ERR_ARG, "%s: betas must be in [0, 1)", who);
+  PSN_REQUIRE(h->lr >= 0.0 && h->eps >= 0.0 && h->weight_decay >= 0.0, PSN_ERR_ARG, "%s: negative lr / eps / weight_decay", who);
+  PSN_REQUIRE(h->beta1 >= 0.0 && h->beta1 < 1.0 && h->beta2 >= 0.0 && h->beta2 < 1.0, PSN_ERR_ARG, "%s: betas must be in [0, 1)", who);
   return PSN_OK;
 }
 
@@ -123,16 +124,16 @@ extern "C" int psn_adam_step(const psn_adam_tensor* tensors, int n_tensors, cons
   int rc = check_hyper(h, "psn_adam_step");
   if (rc) return rc;
   PSN_REQUIRE(n_tensors >= 0 && (tensors || n_tensors == 0), PSN_ERR_ARG, "psn_adam_step: bad tensor list");
-  const double bc1 = 1.0 - pow((double)h->beta1, (double)h->step);
-  const double bc2 = 1.0 - pow((double)h->beta2, (double)h->step);
+  const double bc1 = 1.0 - pow(h->beta1, (double)h->step);
+  const double bc2 = 1.0 - pow(h->beta2, (double)h->step);
   AdamScalars s;
-  s.beta1 = h->beta1;
-  s.beta2 = h->beta2;
-  s.one_m_beta1 = 1.f - h->beta1;
-  s.one_m_beta2 = 1.f - h->beta2;
-  s.eps = h->eps;
-  s.weight_decay = h->weight_decay;
-  s.step_size = (float)((double)h->lr / bc1);
+  s.beta1 = (float)h->beta1;
+  s.beta2 = (float)h->beta2;
+  s.one_m_beta1 = (float)(1.0 - h->beta1);
+  s.one_m_beta2 = (float)(1.0 - h->beta2);
+  s.eps = (float)h->eps;
+  s.weight_decay = (float)h->weight_decay;
+  s.step_size = (float)(h->lr / bc1);
   s.inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
   cudaStream_t st = (cudaStream_t)stream;
   for (int i = 0; i < n_tensors; ++i) {
@@ -177,16 +178,17 @@ extern "C" int psn_sparse_adam_step(float* param, float* exp_avg, float* exp_avg
   int rc = check_hyper(h, "psn_sparse_adam_step");
   if (rc) return rc;
   PSN_REQUIRE(R >= 0 && D >= 1 && K >= 0, PSN_ERR_ARG, "psn_sparse_adam_step: bad shape R=%lld D=%d K=%lld", (long long)R, D, (long long)K);
-  PSN_REQUIRE(h->weight_decay == 0.f, PSN_ERR_ARG, "psn_sparse_adam_step: SparseAdam has no weight decay");
+  PSN_REQUIRE(h->weight_decay == 0.0, PSN_ERR_ARG, "psn_sparse_adam_step: SparseAdam has no weight decay");
   PSN_REQUIRE(K <= 65536, PSN_ERR_SHAPE, "psn_sparse_adam_step: %lld gradient rows > 65536 (coalesce on the caller's side)", (long long)K);
   if (K == 0 || R == 0) return PSN_OK;
   PSN_REQUIRE(param && exp_avg && exp_avg_sq && rows && grad_values, PSN_ERR_ARG, "psn_sparse_adam_step: null pointer");
-  const double bc1 = 1.0 - pow((double)h->beta1, (double)h->step);
-  const double bc2 = 1.0 - pow((double)h->beta2, (double)h->step);
-  const float step_size = (float)((double)h->lr * sqrt(bc2) / bc1);
+  const double bc1 = 1.0 - pow(h->beta1, (double)h->step);
+  const double bc2 = 1.0 - pow(h->beta2, (double)h->step);
+  const float step_size = (float)(h->lr * sqrt(bc2) / bc1);
   const long long total = (long long)K * D;
   k_sparse_adam<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-      param, exp_avg, exp_avg_sq, R, D, (const long long*)rows, grad_values, K, 1.f - h->beta1, 1.f - h->beta2, h->eps, step_size);
+      param, exp_avg, exp_avg_sq, R, D, (const long long*)rows, grad_values, K, (float)(1.0 - h->beta1), (float)(1.0 - h->beta2), (float)h->eps,
+      step_size);
   count_launch();
   PSN_CUDA_CHECK(cudaGetLastError());
   return PSN_OK;
