@@ -18,6 +18,12 @@ def _step_int(s):
     return int(s.item()) if torch.is_tensor(s) else int(s)
 
 
+def _bump(tensors):
+    """The kernels write through raw pointers: tell autograd (and everything keyed on Tensor._version, e.g. the packed-weight cache
+    of engine.packed_handles and saved-tensor checks) that these tensors were modified in place."""
+    torch.autograd.graph.increment_version(tensors)
+
+
 def _check_param(p, who):
     if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
         raise RuntimeError("psnerf_b200.optim.%s: parameters must be contiguous fp32 CUDA tensors (got %s %s)"
@@ -63,6 +69,7 @@ class Adam(torch.optim.Optimizer):
                 hyper = B.AdamHyper(group["lr"], group["betas"][0], group["betas"][1], group["eps"], group["weight_decay"], step)
                 with torch.cuda.device(dev):
                     B.check(lib.psn_adam_step(arr, len(items), C.byref(hyper), engine._stream()), "psn_adam_step")
+                _bump([t for p, _, st in items for t in (p, st["exp_avg"], st["exp_avg_sq"])])
         return loss
 
 
@@ -102,4 +109,5 @@ class SparseAdam(torch.optim.Optimizer):
                     B.check(lib.psn_sparse_adam_step(p.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.shape[0],
                                                      p.shape[1], rows.data_ptr(), vals.data_ptr(), rows.numel(), C.byref(hyper),
                                                      engine._stream()), "psn_sparse_adam_step")
+                _bump([p, st["exp_avg"], st["exp_avg_sq"]])
         return loss

@@ -64,6 +64,7 @@ def test_adam_skips_params_without_grad_and_counts_steps_per_param():
         o1.step()
         o2.step()
     assert o1.state[a]["step"] == 4 and o1.state[b]["step"] == 2
+    assert a._version >= 4 and b._version >= 2  # in-place updates are visible to autograd and to the packed-weight cache
     _close(a.detach().cpu().numpy(), a2.detach().cpu().numpy())
     _close(b.detach().cpu().numpy(), b2.detach().cpu().numpy())
 

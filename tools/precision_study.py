@@ -139,28 +139,32 @@ def main():
         pix = synth.pixel_grid_xmajor(R, R)
         K, pose = synth.intrinsics(R, R), synth.look_at_pose(20.0, 10.0)
         sd = sds["trained"]
-        ref = O.unisurf_render(sd, cfg_r, pix, K, pose, it=100000)
+        ref = O.unisurf_render(sd, cfg_r, pix, K, pose, it=100000, return_aux=True)
         real_geo, real_grad, real_app = O.geo_forward, O.geo_gradient, O.network_forward
         print("\nunisurf %dx%d, trained weights: mask flips, rgb relL2 / maxabs, normal maxabs (rays hit in both)" % (R, R))
-        for s in ["3pass", "1pass", "mixed"]:
+        for s in ["3pass", "1pass", "mixed", "a_hi|mixed", "w_hi|mixed"]:  # "X|Y": occupancy queries (march, secant) under X, radiance under Y
             def net(sd_, mcfg_, pp, ray_d=None, only_occupancy=False, return_logits=False, return_addocc=False, _s=s):
-                al, gg, rgb = field(sd_, mcfg_, pp.reshape(-1, 3), ray_d if ray_d is not None else torch.ones_like(pp).reshape(-1, 3), _s)
+                _occ_s, _rad_s = _s.split("|") if "|" in _s else (_s, _s)
+                al, gg, rgb = field(sd_, mcfg_, pp.reshape(-1, 3), ray_d if ray_d is not None else torch.ones_like(pp).reshape(-1, 3),
+                                    _occ_s if only_occupancy else _rad_s)
                 if only_occupancy:
                     return al.reshape(*pp.shape[:-1], 1)
                 if ray_d is not None:
                     return (rgb, al.reshape(-1, 1)) if return_addocc else rgb
                 raise NotImplementedError
             O.network_forward = net
-            O.geo_gradient = lambda sd_, pp, mcfg_, _s=("3pass" if s == "mixed" else s): field(sd_, mcfg_, pp, torch.ones_like(pp), _s)[1].unsqueeze(1)  # normals: gradient-mode launch
+            O.geo_gradient = lambda sd_, pp, mcfg_, _s=("3pass" if "mixed" in s else s): field(sd_, mcfg_, pp, torch.ones_like(pp), _s)[1].unsqueeze(1)  # normals: gradient-mode launch
             try:
-                out = O.unisurf_render(sd, cfg_r, pix, K, pose, it=100000)
+                out = O.unisurf_render(sd, cfg_r, pix, K, pose, it=100000, return_aux=True)
             finally:
                 O.geo_forward, O.geo_gradient, O.network_forward = real_geo, real_grad, real_app
             flips = int((out["mask_pred"] != ref["mask_pred"]).sum())
             both = (out["mask_pred"] & ref["mask_pred"]).reshape(-1)
             e = err(out["rgb"], ref["rgb"])
+            dd = (out["aux"]["d_i"] - ref["aux"]["d_i"]).abs() if "aux" in out else None
             en = float((out["normal_pred"][0][both] - ref["normal_pred"][0][both]).abs().max()) if both.any() else 0.0
-            print("%-17s flips %d / %d   rgb %.2e / %.2e   normal %.2e" % (s, flips, R * R, *e, en))
+            fin = torch.isfinite(dd)
+            print("%-17s flips %d / %d   rgb %.2e / %.2e   normal %.2e   depth maxabs %.2e" % (s, flips, R * R, *e, en, float(dd[fin].max()) if fin.any() else 0.0))
 
 
 if __name__ == "__main__":
