@@ -159,6 +159,26 @@ def cpu_baseline_quick():
             "sample": "16x16 centre crop of the 512x512x128spp view, 1 pass, oracle port (torch CPU fp32, %d threads)" % cores}
 
 
+def ncu_traffic(precision, root=None):
+    """DRAM read + write bytes of ONE launch of the radiance kernel on this workload, from the newest committed ncu summary under
+    profiles/ that holds a capture of k_tc_rad taken at this precision (captures carry a "precision" tag; untagged ones are 'tc')."""
+    pdir = os.path.join(root or ROOT, "profiles")
+    try:
+        cands = sorted(f for f in os.listdir(pdir) if "_ncu_v" in f and f.endswith(".json"))
+    except OSError:
+        return None, None
+    for name in reversed(cands):
+        try:
+            with open(os.path.join(pdir, name)) as f:
+                caps = [c for c in json.load(f) if "k_tc_rad" in c.get("kernel", "") and c.get("precision", "tc") == precision]
+            if caps:
+                big = max(caps, key=lambda c: c["metrics"]["gpu__time_duration.sum"]["value"])
+                return big["dram_bytes_total"], name
+        except Exception:
+            continue
+    return None, None
+
+
 def _time_cuda(fn, reps=2):
     fn()
     torch.cuda.synchronize()
@@ -324,7 +344,8 @@ def main():
     lib = B.load()
     precision = args.precision
     if precision == "auto":
-        precision = "tc" if engine.tc_available() else "fp32"
+        # the fastest program that holds the parity gate (tests/test_gpu_tc_mixed.py); the full-split 'tc' render is timed next to it
+        precision = "tc_mixed" if engine.tc_available() else "fp32"
     cfg, net, rend = build_model(dev, precision)
     N = H * W
     S = S_IN + S_OUT
@@ -401,22 +422,11 @@ def main():
         roof = None
         if rad:
             tf = rad["rows_per_launch"] * MFLOP_RAD * 1e6 / (rad["ms_per_launch"] * 1e-3) / 1e12
-            traffic, traffic_src = None, None  # dram read+write bytes per launch of this kernel on this workload (committed ncu capture)
-            try:
-                cands = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if "_ncu_v" in f and f.endswith(".json"))
-                for name in reversed(cands):  # newest summary that holds a capture of the radiance kernel
-                    with open(os.path.join(ROOT, "profiles", name)) as f:
-                        caps = [c for c in json.load(f) if "k_tc_rad" in c["kernel"]]
-                    if caps and precision == "tc":
-                        big = max(caps, key=lambda c: c["metrics"]["gpu__time_duration.sum"]["value"])
-                        traffic, traffic_src = big["dram_bytes_total"], name
-                        break
-            except Exception:
-                pass
+            traffic, traffic_src = ncu_traffic(precision)  # dram read+write bytes per launch of this kernel on this workload
             roof = {"bound": "tensor", "kernel": "radiance (geo fwd + analytic normal + app MLP), %s path" % precision,
                     "achieved": tf, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": tf / peaks["tflops"], "traffic": traffic,
-                    "traffic_note": "ncu --set full, profiles/%s: the unorm16 sigma' stash + fp32 parked partial of the analytic-normal pass "
-                                    "(5 KB/sample written, re-read from L2; algorithmic I/O is 20 B/sample); DRAM stays below 15 %% of peak"
+                    "traffic_note": "ncu capture summarised in profiles/%s: the unorm16 sigma' stash + fp32 parked partial of the analytic-normal "
+                                    "pass (5 KB/sample written, re-read from L2; algorithmic I/O is 20 B/sample); DRAM stays below 15 %% of peak"
                                     % traffic_src,
                     "peak_source": peaks["src"], "flops_per_row": MFLOP_RAD * 1e6,
                     "issued_frac": (3.0 * tf / peaks["tflops"]) if precision == "tc" else None}
@@ -441,7 +451,19 @@ def main():
                         "h2d_bytes_per_step": n_views * n_local * 2 * 8, "d2h_bytes_per_step": n_views * n_local * 7 * 4},
                 "roofline": roof, "kernels": kern}
         if world == 1 and not args.no_extras:
-            line["other_workloads"] = extra_workloads(dev, precision, rend, views[0], peaks)
+            x_prec = "tc" if precision == "tc_mixed" else precision  # the other workloads have no mixed program: plain 'tc'
+            net.precision = x_prec
+            extras = {}
+            if precision == "tc_mixed":
+                try:  # the same headline step with every product in the three-pass split ('tc'), for comparison
+                    ms_tc = _time_cuda(lambda: step(False), reps=2)
+                    extras["headline_step_full_split_tc"] = {"ms_per_step": ms_tc, "Msamples_per_s": units / (ms_tc / 1e3) / 1e6,
+                                                             "note": "--precision tc: feature head, reverse sweep and appearance MLP in three passes too"}
+                except Exception as e:
+                    extras["headline_step_full_split_tc"] = {"error": repr(e)[:300]}
+            extras.update(extra_workloads(dev, x_prec, rend, views[0], peaks))
+            net.precision = precision
+            line["other_workloads"] = extras
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_quick()
         emit(line)

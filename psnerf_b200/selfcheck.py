@@ -27,7 +27,7 @@ def run_smoke(verbose=True):
     pix, K, pose = synth.pixel_grid_xmajor(h, w), synth.intrinsics(h, w), synth.look_at_pose(15.0, 10.0)
     ref = O.unisurf_render(sd, cfg, pix, K, pose, it=100000)
     rend = Renderer(net, cfg, device=dev)
-    for prec in precisions:
+    for prec in precisions + (["tc_mixed"] if "tc" in precisions else []):  # tc_mixed: the radiance program bench.py runs by default
         net.precision = prec
         out = rend(pix.to(dev), K, pose, None, "unisurf", add_noise=False, eval_=True, it=100000)
         agree = out["mask_pred"].cpu() == ref["mask_pred"]

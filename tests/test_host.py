@@ -144,6 +144,16 @@ def test_arange_pixels_is_xmajor():
     assert torch.equal(loc, lo) and torch.equal(sc, so)
 
 
+def test_bench_traffic_lookup_matches_precision():
+    """roofline.traffic comes from the committed ncu capture of the radiance kernel AT THE BENCHED PRECISION."""
+    import bench
+    t_tc, src_tc = bench.ncu_traffic("tc")
+    t_mx, src_mx = bench.ncu_traffic("tc_mixed")
+    assert src_tc and src_mx and src_tc != src_mx and "tc_mixed" in src_mx
+    assert 1e11 < t_tc < 3e11 and 1e11 < t_mx < 3e11
+    assert bench.ncu_traffic("fp32") == (None, None)
+
+
 def test_bench_reference_arm_prints_one_json_line():
     """bench.py --impl reference (the CPU arm the driver times next to the GPU arm): exactly one JSON line on stdout with the
     contract keys; library chatter must not reach stdout."""
