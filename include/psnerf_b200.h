@@ -14,7 +14,7 @@
  *    PSN_PREC_TC_MIXED = the same kernels, except that the radiance program (psn_radiance, psn_render_unisurf) keeps the split
  *    product only for the eight softplus layers that decide alpha and runs the feature head, the reverse sweep that feeds the
  *    appearance MLP and the appearance MLP itself as single fp16 passes (rgb within 1e-5 rel-L2 of PSN_PREC_TC; alpha, depth,
- *    masks and the surface-normal output are bit-identical to PSN_PREC_TC).  EXPERIMENTAL: opt-in, not the default.
+ *    masks and the surface-normal output are bit-identical to PSN_PREC_TC).  Opt-in (the library default is PSN_PREC_FP32; bench.py runs it).
  *  - No CPU fallback exists: every entry point fails with PSN_ERR_CUDA without a sm_100 device.
  */
 #ifndef PSNERF_B200_H

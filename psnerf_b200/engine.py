@@ -11,8 +11,8 @@ _DEFAULT_PRECISION = [B.PREC_FP32]
 
 
 def set_default_precision(name):
-    """'fp32' (FFMA kernels), 'tc' (tcgen05, fp16 hi/lo split operands, fp32 accumulate) or 'tc_mixed' (EXPERIMENTAL: 'tc' with
-    the appearance side of the radiance program in single fp16 passes, include/psnerf_b200.h)."""
+    """'fp32' (FFMA kernels), 'tc' (tcgen05, fp16 hi/lo split operands, fp32 accumulate) or 'tc_mixed' ('tc' with the appearance
+    side of the radiance program in single fp16 passes: rgb within 1e-5 of 'tc', everything else bit-identical)."""
     _DEFAULT_PRECISION[0] = B.PRECISIONS[name]
 
 
