@@ -10,7 +10,7 @@
 // gradient (surface normal) kernel.  Algorithmic work: 2,509,824 FLOP per sample.
 //
 // Mixed program (PSN_PREC_TC_MIXED, radiance only): s0..s7 stay three-pass - alpha and the sigma' stash need the split product
-// (a 2- or 1-pass geo forward misses the 1e-4 gate on alpha: tools/precision_study.py) - but everything the appearance MLP
+// (a 2- or 1-pass geo forward misses the 1e-4 gate on alpha: tests/precision_study.py) - but everything the appearance MLP
 // consumes tolerates plain fp16 operands: s8..s22 run ONE pass A_hi W_hi (Step::single), their producers write only the hi
 // half of the A operand.  rgb moves by 6e-6 rel-L2 per sample / 1e-6 per rendered pixel (same tool); the gradient OUTPUT
 // (surface normals) is never taken from this program - tc_gradient always runs the three-pass one.

@@ -14,7 +14,7 @@ tests/test_gpu_stage1.py: rel-L2 5e-5, max-abs 1e-4):
     mixed   geo layers 0-7 3pass (alpha and the sigma' stash need it), fp32 logit head, then feature head, reverse sweep and
             appearance net all 1pass - what a radiance-mode k_tc_rad could run when only rgb / alpha leave the kernel
 
-    python tools/precision_study.py [--points 4096] [--render 24]"""
+    python tests/precision_study.py [--points 4096] [--render 24]"""
 import argparse
 import os
 import sys
@@ -167,34 +167,43 @@ def main():
             print("%-17s flips %d / %d   rgb %.2e / %.2e   normal %.2e   depth maxabs %.2e" % (s, flips, R * R, *e, en, float(dd[fin].max()) if fin.any() else 0.0))
 
 
-if __name__ == "__main__":
-    main()
-
-
-def study_stage2(points=1024, lights=16):
-    """visibility_net (126 -> 256 x 8 -> 1, ReLU, cat[y, x] after the skip layer; renderer.py:17-49,193) under the same schemes.
-    Gates of tests/test_gpu_stage2.py (tc): visibility max-abs 5e-4, rgb max-abs 1e-4 (rgb = brdf * intensity * cos * vis)."""
-    conf, sds = util.stage2_state_dicts()
+def visibility_errors(sd, conf, points=1024, lights=16):
+    """{scheme: (relL2, maxabs)} of visibility_net (126 -> 256 x 8 -> 1, ReLU, cat[y, x] after the skip layer; renderer.py:17-49,193)
+    against its fp32 evaluation."""
     nf = int(conf["brdf.net.n_freqs_xyz"])
     skip = int(conf["visibility.net.mlp_skip_at"])
     g = torch.Generator().manual_seed(3)
     surf = torch.nn.functional.normalize(torch.randn(points, 3, generator=g), dim=-1) * (0.5 + 0.5 * torch.rand(points, 1, generator=g))
     lt = synth.lights(lights)
     x = torch.cat([O.embed(surf, nf).tile(lights, 1), O.embed(lt[:, None].expand(-1, points, -1).reshape(-1, 3), nf)], -1)
+    n = 0
+    while ("visibility_net.linears.%d.bias" % n) in sd:
+        n += 1
+    outs = {}
+    for s in ["fp32", "3pass", "a_hi", "w_hi", "1pass"]:
+        y = x
+        for li in range(n):
+            y = mm(y, sd["visibility_net.linears.%d.weight" % li], s) + sd["visibility_net.linears.%d.bias" % li]
+            if li != n - 1:
+                y = torch.relu(y)
+            if li == skip:
+                y = torch.cat([y, x], -1)
+        outs[s] = y
+    res = {s: err(outs[s], outs["fp32"]) for s in ["3pass", "a_hi", "w_hi", "1pass"]}
+    res["max"] = float(outs["fp32"].abs().max())
+    return res
+
+
+def study_stage2(points=1024, lights=16):
+    """Gates of tests/test_gpu_stage2.py (tc): visibility max-abs 5e-4, rgb max-abs 1e-4 (rgb = brdf * intensity * cos * vis)."""
+    conf, sds = util.stage2_state_dicts()
     print("\nstage-2 visibility_net, %d points x %d lights: relL2 / maxabs of the visibility" % (points, lights))
     for wname, sd in sds.items():
-        n = 0
-        while ("visibility_net.linears.%d.bias" % n) in sd:
-            n += 1
-        outs = {}
-        for s in ["fp32", "3pass", "a_hi", "w_hi", "1pass"]:
-            y = x
-            for li in range(n):
-                y = mm(y, sd["visibility_net.linears.%d.weight" % li], s) + sd["visibility_net.linears.%d.bias" % li]
-                if li != n - 1:
-                    y = torch.relu(y)
-                if li == skip:
-                    y = torch.cat([y, x], -1)
-            outs[s] = y
+        r = visibility_errors(sd, conf, points, lights)
         for s in ["3pass", "a_hi", "w_hi", "1pass"]:
-            print("%-8s %-17s %.2e / %.2e   (|vis| max %.2f)" % (wname, s, *err(outs[s], outs["fp32"]), float(outs["fp32"].abs().max())))
+            print("%-8s %-17s %.2e / %.2e   (|vis| max %.2f)" % (wname, s, *r[s], r["max"]))
+
+
+if __name__ == "__main__":
+    main()
+    study_stage2()

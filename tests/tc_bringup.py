@@ -1,5 +1,5 @@
 """Bring-up report of the tcgen05 geo stack: per-layer activation error vs the CPU oracle (prints, no asserts).
-Run on the GPU box:  python tools/tc_bringup.py"""
+Run on the GPU box:  python tests/tc_bringup.py"""
 import ctypes as C
 import os
 import sys

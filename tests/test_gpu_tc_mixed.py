@@ -1,5 +1,5 @@
 """PSN_PREC_TC_MIXED ('tc_mixed'): the radiance program with the appearance side in single fp16 passes (tc_rad.cu header,
-tools/precision_study.py).  Opt-in (the default tensor-core precision stays 'tc').
+tests/precision_study.py).  Opt-in (the default tensor-core precision stays 'tc').
 
 What must hold: alpha, depth, masks and surface normals are BIT-IDENTICAL to 'tc' (the same three-pass programs produce them);
 rgb stays inside the 'tc' gate against the reference fixtures (rel-L2 5e-5 / max-abs 1e-4; the CPU emulation predicts 6e-6 / 2e-5

@@ -3,7 +3,7 @@
 # PSN_NCU=1 adds the `ncu --set full` capture of the stage-1 tensor kernels.
 mkdir -p gpurun_out
 echo "== bringup std" > gpurun_out/bringup.log
-timeout 240 python tools/tc_bringup.py >> gpurun_out/bringup.log 2>&1; echo "rc=$?" >> gpurun_out/bringup.log
+timeout 240 python tests/tc_bringup.py >> gpurun_out/bringup.log 2>&1; echo "rc=$?" >> gpurun_out/bringup.log
 cat gpurun_out/bringup.log
 (time timeout 900 python -m pytest tests -m gpu -x -q) > gpurun_out/pytest_gpu.log 2>&1; tail -5 gpurun_out/pytest_gpu.log
 timeout 120 python tools/tc_trace.py > gpurun_out/trace.log 2>&1; cat gpurun_out/trace.log
