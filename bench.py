@@ -318,7 +318,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--precision", default="auto", choices=["auto", "tc", "tc_mixed", "fp32"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "tc", "tc_mixed", "tc_two_level", "fp32"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ref-crop", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -430,7 +430,7 @@ def main():
                                     % traffic_src,
                     "peak_source": peaks["src"], "flops_per_row": MFLOP_RAD * 1e6,
                     "issued_frac": (3.0 * tf / peaks["tflops"]) if precision == "tc" else None}
-            if precision == "tc_mixed":  # three passes for the 8 softplus layers (0.918 MFLOP), one for the remaining 1.592 MFLOP
+            if precision in ("tc_mixed", "tc_two_level"):  # three passes for the 8 softplus layers (0.918 MFLOP), one for the remaining 1.592 MFLOP
                 roof["issued_frac"] = (3.0 * 0.918 + 1.0 * (MFLOP_RAD - 0.918)) / MFLOP_RAD * tf / peaks["tflops"]
             occ = kern.get("occ_march")
             if occ:
@@ -439,7 +439,8 @@ def main():
         line = {"metric": "Msamples/sec (rays x samples x lights)", "value": value, "unit": "Msamples/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": {"tc": "f16x3-split operands, f32 accumulate", "fp32": "f32",
-                                            "tc_mixed": "f16x3-split operands (softplus stack) + f16 single pass (appearance side), f32 accumulate"}[precision],
+                                            "tc_mixed": "f16x3-split operands (softplus stack) + f16 single pass (appearance side), f32 accumulate",
+                                            "tc_two_level": "tc_mixed + two-level march (f16 single pass, f16x3 near the threshold)"}[precision],
                 "data": "synthetic",
                 "config": {"workload": "stage1-unisurf-render 512x512x128spp (BASELINE configs[1]): %d march steps + 8 secant, %d+%d samples/ray, "
                                        "lights=1" % (MARCH, S_IN, S_OUT),
@@ -451,10 +452,10 @@ def main():
                         "h2d_bytes_per_step": n_views * n_local * 2 * 8, "d2h_bytes_per_step": n_views * n_local * 7 * 4},
                 "roofline": roof, "kernels": kern}
         if world == 1 and not args.no_extras:
-            x_prec = "tc" if precision == "tc_mixed" else precision  # the other workloads have no mixed program: plain 'tc'
+            x_prec = "tc" if precision in ("tc_mixed", "tc_two_level") else precision  # the other workloads have no mixed program: plain 'tc'
             net.precision = x_prec
             extras = {}
-            if precision == "tc_mixed":
+            if precision in ("tc_mixed", "tc_two_level"):
                 try:  # the same headline step with every product in the three-pass split ('tc'), for comparison
                     ms_tc = _time_cuda(lambda: step(False), reps=2)
                     extras["headline_step_full_split_tc"] = {"ms_per_step": ms_tc, "Msamples_per_s": units / (ms_tc / 1e3) / 1e6,

@@ -15,6 +15,11 @@
  *    product only for the eight softplus layers that decide alpha and runs the feature head, the reverse sweep that feeds the
  *    appearance MLP and the appearance MLP itself as single fp16 passes (rgb within 1e-5 rel-L2 of PSN_PREC_TC; alpha, depth,
  *    masks and the surface-normal output are bit-identical to PSN_PREC_TC).  Opt-in (the library default is PSN_PREC_FP32; bench.py runs it).
+ *    PSN_PREC_TC_TWOLEVEL = PSN_PREC_TC_MIXED plus a two-level surface march (psn_raymarch, psn_render_unisurf): all proposal
+ *    points go through a single-pass copy of the occupancy program, and the three-pass program re-evaluates only the points the
+ *    scan can tell apart (within 0.02 of the threshold, next to a sign change, and their neighbours: < 1 % of them), so the
+ *    crossing index, the bracket values and therefore every output are those of PSN_PREC_TC_MIXED.  EXPERIMENTAL: written after
+ *    the round's GPU budget was spent; validated by CPU emulation only (tests/precision_study.py march_refine_study).
  *  - No CPU fallback exists: every entry point fails with PSN_ERR_CUDA without a sm_100 device.
  */
 #ifndef PSNERF_B200_H
@@ -35,6 +40,7 @@ extern "C" {
 #define PSN_PREC_FP32 0
 #define PSN_PREC_TC 1
 #define PSN_PREC_TC_MIXED 2
+#define PSN_PREC_TC_TWOLEVEL 3
 
 #define PSN_NET_GEO 0 /* stage1/model/network.py:37-66 lin0..lin8 (softplus beta=100, skip concat /sqrt2) */
 #define PSN_NET_APP 1 /* stage1/model/network.py:71-79 lina0..lina4 (ReLU, tanh*0.5+0.5)               */

@@ -12,8 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PSNERF_B200_LIB") or os.path.join(_HERE, "lib", "libpsnerf_b200.so")  # env override: bring-up builds
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "psnerf_b200.h")
 
-PREC_FP32, PREC_TC, PREC_TC_MIXED = 0, 1, 2
-PRECISIONS = {"fp32": PREC_FP32, "tc": PREC_TC, "tc_mixed": PREC_TC_MIXED}
+PREC_FP32, PREC_TC, PREC_TC_MIXED, PREC_TC_TWOLEVEL = 0, 1, 2, 3
+PRECISIONS = {"fp32": PREC_FP32, "tc": PREC_TC, "tc_mixed": PREC_TC_MIXED, "tc_two_level": PREC_TC_TWOLEVEL}
 NET_GEO, NET_APP, NET_S2 = 0, 1, 2
 OUT_ALPHA, OUT_NEG_LOGIT, OUT_LOGIT = 0, 1, 2
 

@@ -26,7 +26,7 @@ static int gradient_any(const psn_mlp* geo, const PointGen& gen, long long M, co
 static int radiance_any(const psn_mlp* geo, const psn_mlp* app, const PointGen& gen, long long M, float* rgb, float* alpha,
                         void* stash, int precision, cudaStream_t st) {
   ProfScope prof(PSN_PROF_RADIANCE, M, st);
-  if (prec_is_tc(precision)) return tc_radiance(geo, app, gen, M, rgb, alpha, stash, precision == PSN_PREC_TC_MIXED, st);
+  if (prec_is_tc(precision)) return tc_radiance(geo, app, gen, M, rgb, alpha, stash, prec_is_mixed(precision) ? 1 : 0, st);
   return simt_radiance(geo, app, gen, M, rgb, alpha, stash, st);
 }
 
@@ -34,8 +34,16 @@ static size_t stash_bytes(int precision) { return prec_is_tc(precision) ? tc_sta
 
 static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
+// Two-level march: at most 1/8 of the proposal points on the refine list (measured: < 1 %); beyond that the whole march falls back
+// to the full program on the device (RefineList::count[2]), so the cap bounds memory, not correctness.
+static long long refine_cap(long long N, int S) {
+  const long long c = N * S / 8;
+  return c < 4096 ? 4096 : c;
+}
+static const float kRefineMargin = 0.02f;  // >= 20 x the largest |cheap - full| occupancy difference seen (tests/precision_study.py)
+
 static size_t march_ws_bytes(long long N, int S) {
-  return align256((size_t)N * S * 4) + 8 * align256((size_t)N * 4) + 1024;
+  return align256((size_t)N * S * 4) + 8 * align256((size_t)N * 4) + 1024 + 4 * align256((size_t)refine_cap(N, S) * 4) + 512;
 }
 static const long long kShadowChunkPairs = 1 << 21;  // (light, point) pairs per shadow chunk (1 GB of occupancies at S=128)
 
@@ -143,7 +151,40 @@ static int raymarch_impl(const psn_mlp* geo, const float* origin, const float* d
   gen.near_ = near_;
   gen.S = n_steps;
   gen.o[0] = origin[0]; gen.o[1] = origin[1]; gen.o[2] = origin[2];
-  if ((rc = occupancy_any(geo, gen, N * n_steps, nullptr, PSN_OUT_ALPHA, occ, precision, st))) return rc;
+  if (precision == PSN_PREC_TC_TWOLEVEL && n_steps >= 4 && N * n_steps < (1LL << 31)) {
+    // Level 1: every proposal point through the single-pass program.  Level 2: the full program on the points the scan below can
+    // tell apart (k_march_refine_select), written back over the level-1 values.  The scan reads signs everywhere and values only
+    // at the crossing, so crossing index and bracket values - hence every output - equal those of the full evaluation.
+    RefineList rl;
+    rl.cap = (int)refine_cap(N, n_steps);
+    rl.count = w.take<int>(64);
+    rl.ray = w.take<int>(rl.cap);
+    rl.depth = w.take<float>(rl.cap);
+    rl.pos = w.take<int>(rl.cap);
+    float* refined = w.take<float>(rl.cap);
+    PSN_REQUIRE(w.ok, PSN_ERR_WORKSPACE, "two-level ray marching: workspace too small (need %zu bytes)", w.used);
+    {
+      ProfScope prof(PSN_PROF_OCC_MARCH, N * n_steps, st);
+      if ((rc = tc_occupancy_cheap(geo, gen, N * n_steps, PSN_OUT_ALPHA, occ, st))) return rc;
+    }
+    PSN_CUDA_CHECK(cudaMemsetAsync(rl.count, 0, 4 * sizeof(int), st));
+    if ((rc = launch_march_refine_select(occ, far, N, n_steps, near_, tau, kRefineMargin, rl, st))) return rc;
+    PointGen g3;
+    memset(&g3, 0, sizeof(g3));
+    g3.kind = GEN_INDEXED_DEPTH;
+    g3.dirs = dirs;
+    g3.index = rl.ray;
+    g3.depth = rl.depth;
+    g3.o[0] = origin[0]; g3.o[1] = origin[1]; g3.o[2] = origin[2];
+    {
+      ProfScope prof(PSN_PROF_OCC_OTHER, 0, st);
+      if ((rc = tc_occupancy(geo, g3, 0, rl.count, PSN_OUT_ALPHA, refined, st))) return rc;
+      if ((rc = launch_march_refine_scatter(rl, refined, occ, st))) return rc;
+      if ((rc = tc_occupancy(geo, gen, 0, rl.count + 2, PSN_OUT_ALPHA, occ, st))) return rc;  // list overflow: the whole march again (0 points normally)
+    }
+  } else {
+    if ((rc = occupancy_any(geo, gen, N * n_steps, nullptr, PSN_OUT_ALPHA, occ, precision, st))) return rc;
+  }
   PSN_CUDA_CHECK(cudaMemsetAsync(s.count, 0, sizeof(int), st));
   if ((rc = launch_march_scan(occ, far, N, n_steps, near_, tau, s, depth, st))) return rc;
   PointGen g2;

@@ -10,6 +10,9 @@ struct SecantState {
   float *d_low, *d_high, *f_low, *f_high, *d_pred;  // [N] per slot
 };
 struct SurfList { int* count; int* ray; float* depth; };
+// Two-level march: the proposal points the full program has to re-evaluate.  count[0] = entries (clamped to cap), count[1] = raw
+// number of selected points, count[2] = points of the whole-march fallback (N * S if the list overflowed, else 0).
+struct RefineList { int* count; int* ray; float* depth; int* pos; int cap; };
 
 // stage1_simt.cu
 int simt_occupancy(const psn_mlp* geo, const PointGen& gen, long long M, const int* M_dev, int out_kind, float* out,
@@ -24,13 +27,16 @@ int make_geo_dev(const psn_mlp* net, GeoDev* g);
 // tc_*.cu (tcgen05 path)
 int tc_occupancy(const psn_mlp* geo, const PointGen& gen, long long M, const int* M_dev, int out_kind, float* out,
                  cudaStream_t st);
+int tc_occupancy_cheap(const psn_mlp* geo, const PointGen& gen, long long M, int out_kind, float* out, cudaStream_t st);
 int tc_infer_occ(const psn_mlp* geo, const PointGen& gen, long long M, float* out, cudaStream_t st);
 int tc_gradient(const psn_mlp* geo, const PointGen& gen, long long M, const int* M_dev, float* grad, void* stash,
                 cudaStream_t st);
 int tc_radiance(const psn_mlp* geo, const psn_mlp* app, const PointGen& gen, long long M, float* rgb, float* alpha,
                 void* stash, int mixed, cudaStream_t st);
-// PSN_PREC_TC and PSN_PREC_TC_MIXED both select the tcgen05 kernels; they differ only in the radiance program (tc_rad.cu)
-inline bool prec_is_tc(int precision) { return precision == PSN_PREC_TC || precision == PSN_PREC_TC_MIXED; }
+// PSN_PREC_TC, _TC_MIXED and _TC_TWOLEVEL all select the tcgen05 kernels; MIXED and TWOLEVEL run the mixed radiance program
+// (tc_rad.cu), TWOLEVEL additionally the two-level surface march (api_stage1.cu raymarch_impl)
+inline bool prec_is_tc(int precision) { return precision >= PSN_PREC_TC && precision <= PSN_PREC_TC_TWOLEVEL; }
+inline bool prec_is_mixed(int precision) { return precision == PSN_PREC_TC_MIXED || precision == PSN_PREC_TC_TWOLEVEL; }
 int tc_shadow(const psn_mlp* geo, const PointGen& gen, long long pairs, float box, float* vis, cudaStream_t st);
 size_t tc_stash_bytes();
 
@@ -40,6 +46,9 @@ int launch_sphere_far(const float* dirs, long long N, const float* o, float r, f
 int launch_march_scan(const float* occ, const float* far, long long N, int S, float near_, float tau, SecantState s,
                       float* depth, cudaStream_t st);
 int launch_secant_update(SecantState s, const float* occ_mid, float tau, long long N, cudaStream_t st);
+int launch_march_refine_select(const float* occ, const float* far, long long N, int S, float near_, float tau, float margin,
+                               RefineList rl, cudaStream_t st);
+int launch_march_refine_scatter(RefineList rl, const float* refined, float* occ, cudaStream_t st);
 int launch_march_finalize(SecantState s, float* depth, long long N, cudaStream_t st);
 int launch_sample_plan(const float* d_i, const float* far, long long N, const psn_unisurf_params& prm, const float* noise,
                        float* sample_depth, uint8_t* mask, SurfList sl, cudaStream_t st);

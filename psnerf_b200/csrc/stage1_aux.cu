@@ -86,6 +86,46 @@ __global__ void k_march_scan(const float* __restrict__ occ, const float* __restr
   depth[ray] = first_free ? CUDART_INF_F : 0.f;  // masked rays are overwritten by k_march_finalize
 }
 
+// Two-level march, selection: one thread per proposal point.  A point is "visible" to k_march_scan beyond its sign if it can be
+// the crossing or its successor; it must be re-evaluated by the full program if its level-1 value is within `margin` of the
+// threshold (sign not trusted) or its sign differs from a neighbour's (crossing candidate) - or if that holds for one of its two
+// neighbours (a refined neighbour may change sign, which makes this point a crossing candidate).
+__device__ __forceinline__ bool refine_seed(const float* __restrict__ v, int j, int S, float tau, float margin) {
+  const float c = v[j] - tau;
+  bool sel = fabsf(c) < margin;
+  if (j > 0) sel |= (c < 0.f) != (v[j - 1] - tau < 0.f);
+  if (j + 1 < S) sel |= (c < 0.f) != (v[j + 1] - tau < 0.f);
+  return sel;
+}
+__global__ void k_march_refine_select(const float* __restrict__ occ, const float* __restrict__ far, long long N, int S, float near_,
+                                      float tau, float margin, RefineList rl) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * S) return;
+  const long long ray = i / S;
+  const int s = (int)(i - ray * S);
+  const float* v = occ + ray * S;
+  bool need = refine_seed(v, s, S, tau, margin);
+  if (!need && s > 0) need = refine_seed(v, s - 1, S, tau, margin);
+  if (!need && s + 1 < S) need = refine_seed(v, s + 1, S, tau, margin);
+  if (!need) return;
+  const int slot = atomicAdd(&rl.count[1], 1);
+  if (slot < rl.cap) {
+    rl.ray[slot] = (int)ray;
+    rl.depth[slot] = lerp_depth(near_, far[ray], linspace01(s, S));  // the depth GEN_MARCH gives this point
+    rl.pos[slot] = (int)i;
+  }
+}
+__global__ void k_march_refine_close(RefineList rl, int total) {
+  const int raw = rl.count[1];
+  rl.count[0] = raw < rl.cap ? raw : rl.cap;
+  rl.count[2] = raw > rl.cap ? total : 0;
+}
+__global__ void k_march_refine_scatter(RefineList rl, const float* __restrict__ refined, float* __restrict__ occ) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= rl.count[0]) return;
+  occ[rl.pos[slot]] = refined[slot];
+}
+
 __global__ void k_secant_update(SecantState st, const float* __restrict__ occ_mid, float tau) {
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= *st.count) return;
@@ -303,6 +343,22 @@ int launch_march_scan(const float* occ, const float* far, long long N, int S, fl
 int launch_secant_update(SecantState s, const float* occ_mid, float tau, long long N, cudaStream_t st) {
   psn::count_launch();
   k_secant_update<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(s, occ_mid, tau);
+  PSN_CUDA_CHECK(cudaGetLastError());
+  return PSN_OK;
+}
+int launch_march_refine_select(const float* occ, const float* far, long long N, int S, float near_, float tau, float margin,
+                               RefineList rl, cudaStream_t st) {
+  const long long total = N * S;
+  psn::count_launch();
+  k_march_refine_select<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(occ, far, N, S, near_, tau, margin, rl);
+  psn::count_launch();
+  k_march_refine_close<<<1, 1, 0, st>>>(rl, (int)total);
+  PSN_CUDA_CHECK(cudaGetLastError());
+  return PSN_OK;
+}
+int launch_march_refine_scatter(RefineList rl, const float* refined, float* occ, cudaStream_t st) {
+  psn::count_launch();
+  k_march_refine_scatter<<<(unsigned)((rl.cap + 255) / 256), 256, 0, st>>>(rl, refined, occ);
   PSN_CUDA_CHECK(cudaGetLastError());
   return PSN_OK;
 }

@@ -3,6 +3,9 @@
 //   MODE_SHADOW : a 128-row tile is one shadow ray; box mask + transmittance are reduced in the epilogue and only
 //                 vis[pair] is written (rendering.py:378-408), no per-sample HBM traffic at all.
 // Algorithmic work per sample: 2 * 459,008 FLOP (the 256 unused feature rows of the last layer are not computed).
+// CHEAP = true is the first level of the two-level surface march (PSN_PREC_TC_TWOLEVEL, api_stage1.cu): every layer in ONE pass
+// A_hi W_hi (Step::single, hi-only operand stores).  Its values are only trusted away from the occupancy threshold; the
+// CHEAP = false instantiations are what every other caller runs.
 #include "tc_mlp.cuh"
 #include "stage1_simt.cuh"
 #include "launch.cuh"
@@ -24,7 +27,7 @@ struct TcGeoArgs {
 
 constexpr int MODE_OUT = 0, MODE_SHADOW = 1, MODE_DEBUG = 2;  // MODE_DEBUG = MODE_OUT + layer dump / clock64 trace hooks
 
-template <int MODE>
+template <int MODE, bool CHEAP = false>
 __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 k_tc_occ(TcGeoArgs g, PointGen gen, long long M_host, const int* M_dev, int out_kind, float* out, float box, int dump_layer,
          float* dump, long long* trace) {
@@ -62,7 +65,7 @@ k_tc_occ(TcGeoArgs g, PointGen gen, long long M_host, const int* M_dev, int out_
           const int k = sub * CW + i;
           v[i] = k < g.pe_dim ? s.pe[k * TILE_M + row] : 0.f;
         }
-        epi_store_a16(e, e.a_col0(), sub * CW, v);
+        epi_store_a16(e, e.a_col0(), sub * CW, v, CHEAP);
         epi_signal_a(s, 0);
       }
       float part = 0.f;  // partial logit over this thread's 64 columns
@@ -94,7 +97,7 @@ k_tc_occ(TcGeoArgs g, PointGen gen, long long M_host, const int* M_dev, int out_
                 if (k >= 0) v[i] = (k < g.pe_dim ? s.pe[k * TILE_M + row] : 0.f) * 0.70710678118654752440f;
               }
             }
-            epi_store_a16(e, e.d_col0(), col, v);
+            epi_store_a16(e, e.d_col0(), col, v, CHEAP);
             epi_signal_a(s, pass);
             if (tr) trace[64 + sub * 40 + l * 5 + 1 + pass] = clock64();
           } else {
@@ -212,18 +215,18 @@ static int make_tc_geo(const psn_mlp* geo, TcGeoArgs* a) {
   return PSN_OK;
 }
 
-template <int MODE>
+template <int MODE, bool CHEAP = false>
 static int launch_tc_occ(const TcGeoArgs& a, const PointGen& gen, long long M, const int* M_dev, int out_kind, float* out, float box,
                          int dump_layer, float* dump, cudaStream_t st, long long* trace = nullptr) {
-  PSN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_occ<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  PSN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_occ<MODE, CHEAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   {
-    const int rcr = check_launch_regs((const void*)k_tc_occ<MODE>, "k_tc_occ");
+    const int rcr = check_launch_regs((const void*)k_tc_occ<MODE, CHEAP>, "k_tc_occ");
     if (rcr) return rcr;
   }
   const long long tiles = M_dev ? (long long)num_ctas() : (M + TILE_M - 1) / TILE_M;
-  const int grid = tc_grid((const void*)k_tc_occ<MODE>, tiles);
+  const int grid = tc_grid((const void*)k_tc_occ<MODE, CHEAP>, tiles);
   count_launch();
-  k_tc_occ<MODE><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(a, gen, M, M_dev, out_kind, out, box, dump_layer, dump, trace);
+  k_tc_occ<MODE, CHEAP><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(a, gen, M, M_dev, out_kind, out, box, dump_layer, dump, trace);
   PSN_CUDA_CHECK(cudaGetLastError());
   return PSN_OK;
 }
@@ -234,6 +237,16 @@ int tc_occupancy(const psn_mlp* geo, const PointGen& gen, long long M, const int
   if (rc) return rc;
   if (M == 0 && !M_dev) return PSN_OK;
   return launch_tc_occ<MODE_OUT>(a, gen, M, M_dev, out_kind, out, 0.f, -1, nullptr, st);
+}
+
+// Single-pass evaluation of the same stack (first level of the two-level march): NOT within the parity tolerance on its own.
+int tc_occupancy_cheap(const psn_mlp* geo, const PointGen& gen, long long M, int out_kind, float* out, cudaStream_t st) {
+  TcGeoArgs a;
+  int rc = make_tc_geo(geo, &a);
+  if (rc) return rc;
+  if (M == 0) return PSN_OK;
+  for (int l = 0; l < 8; ++l) a.prog.step[l].single = 1;
+  return launch_tc_occ<MODE_OUT, true>(a, gen, M, nullptr, out_kind, out, 0.f, -1, nullptr, st);
 }
 
 // pairs shadow rays of gen.S == 128 steps each; vis[pair]

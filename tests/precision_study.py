@@ -207,3 +207,71 @@ def study_stage2(points=1024, lights=16):
 if __name__ == "__main__":
     main()
     study_stage2()
+
+
+def alpha_only(sd, mcfg, p, scheme):
+    """Occupancy probability of the geo net under `scheme` (what k_tc_occ computes: forward stack + fp32 logit head)."""
+    layers = O.stage1_weights(sd, "lin", O.count_layers(sd, "lin"))
+    nl = len(layers)
+    pe = O.positional_encoding(p / mcfg["rescale"], mcfg["octaves_pe"])
+    x = pe
+    inv = float(1.0 / np.sqrt(2))
+    for l, (W, b) in enumerate(layers[:nl - 1]):
+        if l in mcfg["skips"]:
+            x = torch.cat([x, pe], -1) * inv
+        x = O.softplus100(mm(x, W, scheme) + b)
+    W, b = layers[nl - 1]
+    logit = mm(x, W[:1], "fp32") + b[:1]
+    return torch.sigmoid(logit[:, 0] * -10.0)
+
+
+def march_refine_study(R=32, n_steps=256, margin=0.02, cheap="1pass"):
+    """Two-level surface march: every proposal point with the CHEAP program, then the full three-pass program only where the scan
+    (rendering.py:443-470) can see the difference - points within `margin` of the threshold, points next to a sign change of the
+    cheap values, and their neighbours.  The scan reads nothing else (signs everywhere, values only at the crossing), so the
+    merged values must give the SAME crossing index and bracket values as the full evaluation, on every ray."""
+    cfg, sds = util.stage1_state_dicts()
+    mcfg = cfg["model"]
+    pix = synth.pixel_grid_xmajor(R, R)
+    K, pose = synth.intrinsics(R, R), synth.look_at_pose(20.0, 10.0)
+    print("\ntwo-level march, %dx%d rays x %d steps, cheap = %s, margin = %g" % (R, R, n_steps, cheap, margin))
+    all_same = True
+    for wname, sd in sds.items():
+        ray0, rayd = O.pixels_to_rays(pix, K, pose)
+        N = ray0.shape[1]
+        far = O.sphere_intersection(ray0[:, 0], rayd, r=2.0)[0][..., 1]
+        t = torch.linspace(0, 1, steps=n_steps).view(1, 1, n_steps, 1)
+        d_prop = 2.0 * (1.0 - t) + far.view(1, -1, 1, 1) * t
+        p_prop = (ray0.unsqueeze(2) + rayd.unsqueeze(2) * d_prop).reshape(-1, 3)
+        full = torch.cat([alpha_only(sd, mcfg, c, "3pass") for c in torch.split(p_prop, 65536)]).view(N, n_steps) - 0.5
+        chp = torch.cat([alpha_only(sd, mcfg, c, cheap) for c in torch.split(p_prop, 65536)]).view(N, n_steps) - 0.5
+        unsure = chp.abs() < margin
+        flip = torch.zeros_like(unsure)
+        flip[:, 1:] |= torch.sign(chp[:, 1:]) != torch.sign(chp[:, :-1])
+        flip[:, :-1] |= torch.sign(chp[:, :-1]) != torch.sign(chp[:, 1:])
+        sel = unsure | flip
+        grow = sel.clone()
+        grow[:, 1:] |= sel[:, :-1]
+        grow[:, :-1] |= sel[:, 1:]
+        merged = torch.where(grow, full, chp)
+
+        def scan(val):
+            sign = torch.cat([torch.sign(val[:, :-1] * val[:, 1:]), torch.ones(N, 1)], dim=-1)
+            cost = sign * torch.arange(n_steps, 0, -1).float()
+            values, idx = torch.min(cost, -1)
+            ar = torch.arange(N)
+            mask = (values < 0) & (val[ar, idx] < 0) & (val[:, 0] < 0)
+            idx2 = torch.clamp(idx + 1, max=n_steps - 1)
+            return mask, idx, val[ar, idx], val[ar, idx2], val[:, 0] < 0
+
+        m_f, i_f, lo_f, hi_f, ff_f = scan(full)
+        m_m, i_m, lo_m, hi_m, ff_m = scan(merged)
+        m_c, i_c, _, _, _ = scan(chp)
+        same = bool(torch.equal(m_f, m_m) and torch.equal(ff_f, ff_m) and torch.equal(i_f[m_f], i_m[m_f])
+                    and torch.equal(lo_f[m_f], lo_m[m_f]) and torch.equal(hi_f[m_f], hi_m[m_f]))
+        print("%-8s refined %.3f %% of the points (%d of %d); hit rays %d; merged scan identical to the full one: %s; "
+              "cheap alone: %d masks / %d crossing indices differ; max |cheap - full| = %.2e"
+              % (wname, 100.0 * float(grow.float().mean()), int(grow.sum()), grow.numel(), int(m_f.sum()), same,
+                 int((m_c != m_f).sum()), int((i_c[m_f & m_c] != i_f[m_f & m_c]).sum()), float((chp - full).abs().max())))
+        all_same = all_same and same and int(m_f.sum()) > 0
+    return all_same

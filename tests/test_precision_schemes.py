@@ -44,3 +44,9 @@ def test_stage2_visibility_mlp_needs_the_split_too():
     assert out["3pass"][0] < 5e-6
     for scheme in ("a_hi", "w_hi", "1pass"):
         assert out[scheme][0] > 2e-4, (scheme, out[scheme])
+
+
+def test_two_level_march_reproduces_the_full_scan():
+    """PSN_PREC_TC_TWOLEVEL: single-pass values everywhere, the full program only where the scan can tell the difference (< 2 % of
+    the points here): crossing index and bracket values of every ray equal those of the full evaluation."""
+    assert P.march_refine_study(R=16, n_steps=128, margin=0.02)
