@@ -288,6 +288,8 @@ __device__ __forceinline__ void teardown(uint32_t tmem_base) {
 
 // ---- producer: stream every weight tile of `iters` tile-iterations through the ring (warp 0, lane 0) ------------------
 // Both CTAs of the pair run this loop over the same tile sequence; tile t is fetched (multicast) by CTA (t & 1).
+// ALLOW_SINGLE = false compiles the Step::single handling out (kernels whose programs never contain single-pass steps).
+template <bool ALLOW_SINGLE = true>
 __device__ __forceinline__ void producer_loop(const Smem& s, const Program& prog, long long iters) {
   uint32_t stage = 0, phase = 0;
   const uint32_t rank = cluster_ctarank();
@@ -297,11 +299,12 @@ __device__ __forceinline__ void producer_loop(const Smem& s, const Program& prog
       const Step sp = prog.step[st];
       const uint32_t tile_bytes = (uint32_t)sp.n_pad * 128u;
       const unsigned char* src = prog.blob[st] + sp.w_off;
-      const int n_tiles = sp.single ? sp.nkb : 2 * sp.nkb;
+      const bool single = ALLOW_SINGLE && sp.single;
+      const int n_tiles = single ? sp.nkb : 2 * sp.nkb;
       for (int t = 0; t < n_tiles; ++t, t_parity ^= 1u) {
         mbar_wait_cluster_relaxed(&s.c->w_empty[stage], phase ^ 1u);     // released by the MMA warps of both CTAs
         mbar_arrive_expect_tx(&s.c->w_full[stage], tile_bytes);          // this CTA's copy of the tile
-        const int blob_tile = sp.single ? 2 * t : (t ^ 1);  // ring order per K block: lo tile, then hi tile (blob: hi, lo); single: hi only
+        const int blob_tile = single ? 2 * t : (t ^ 1);  // ring order per K block: lo tile, then hi tile (blob: hi, lo); single: hi only
         if (t_parity == rank)
           bulk_g2s_multicast(s.w + stage * W_STAGE_BYTES, src + (size_t)blob_tile * tile_bytes, tile_bytes, &s.c->w_full[stage],
                              (uint16_t)((1u << CLUSTER) - 1u));
@@ -333,6 +336,7 @@ constexpr uint64_t UMMA_DESC_HI = ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
 __device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
 __device__ __forceinline__ uint64_t umma_desc_at(uint32_t lo, uint32_t bytes) { return UMMA_DESC_HI | (uint64_t)(lo + (bytes >> 4)); }
 
+template <bool ALLOW_SINGLE = true>
 __device__ __forceinline__ void mma_loop(const Smem& s, const Program& prog, long long iters, uint32_t tmem_base,
                                          long long* trace = nullptr) {
   uint32_t stage = 0, phase = 0;   // weight ring
@@ -348,7 +352,7 @@ __device__ __forceinline__ void mma_loop(const Smem& s, const Program& prog, lon
       const uint32_t idesc = umma_idesc(sp.n_pad);
       long long t_wait_a = 0, t_wait_w = 0;  // bring-up trace only (dead code otherwise)
       for (int kb = 0; kb < sp.nkb; ++kb) {
-        if (sp.single) {
+        if (ALLOW_SINGLE && sp.single) {
           // single-pass step: one weight stage (the hi tile) and four MMAs A_hi W_hi per K block; same split of the last K block
           const uint32_t st_w = stage, ph_w = phase;
           if (++stage == W_STAGES) { stage = 0; phase ^= 1u; }

@@ -91,8 +91,8 @@ k_tc_vis(TcVisArgs g, float* __restrict__ vis) {
   const long long iters = chunk;
   if (warp < EPI_WARP0) {
     regs_shrink_control();
-    if (warp == 0 && lane == 0) producer_loop(s, g.prog, iters);
-    if (warp == 1) mma_loop(s, g.prog, iters, tmem_base);
+    if (warp == 0 && lane == 0) producer_loop<false>(s, g.prog, iters);  // no single-pass steps in this program
+    if (warp == 1) mma_loop<false>(s, g.prog, iters, tmem_base);
     __syncwarp();
   } else {
     regs_grow_epilogue();
