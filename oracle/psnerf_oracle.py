@@ -722,10 +722,32 @@ def merge_output(res, total_pixels, batch_size):
     return out
 
 
-def psnr(a, b):
-    """10 log10(1/mse), 100 dB when identical (stage2/utils/metrics.py:38-51)."""
-    mse = float(torch.mean((a.double() - b.double()) ** 2))
+def psnr(a, b, mask=None):
+    """10 log10(1/mse) over the (masked) pixels, 100 dB when identical (stage2/utils/metrics.py:38-51)."""
+    a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+    if mask is not None:
+        m = torch.as_tensor(mask).bool()
+        a, b = a[m], b[m]
+    mse = float(torch.mean((a - b) ** 2))
     return 100.0 if mse == 0 else 10.0 * math.log10(1.0 / mse)
+
+
+def mae(n1, n2, mask=None, normalize=True):
+    """Mean angular error in degrees between two normal maps, and the per-pixel errors (stage2/utils/metrics.py:16-36): fp32
+    normalisation by (|n| + 1e-5) with zero vectors kept zero, fp64 dot product clipped to [-1, 1]."""
+    v1, v2 = np.array(n1, dtype=np.float32, copy=True), np.array(n2, dtype=np.float32, copy=True)
+    if normalize:
+        l1 = np.linalg.norm(v1.astype(np.float64), axis=-1)
+        l2 = np.linalg.norm(v2.astype(np.float64), axis=-1)
+        v1 /= l1[..., None] + 1e-5
+        v2 /= l2[..., None] + 1e-5
+        v1[l1 == 0] = 0
+        v2[l2 == 0] = 0
+    dot = (v1.astype(np.float64) * v2.astype(np.float64)).sum(-1).clip(-1, 1)
+    if mask is not None:
+        dot = dot[np.asarray(mask).astype(bool)]
+    ang = np.arccos(dot) * 180.0 / math.pi
+    return ang.mean(), ang
 
 
 # ----------------------------------------------------------------------------------------------

@@ -432,6 +432,38 @@ def make_stage2_general():
     np.savez_compressed(os.path.join(HERE, "stage2_general.npz"), **out)
 
 
+def metrics_case():
+    g = torch.Generator().manual_seed(77)
+    a = torch.rand(9, 11, 3, generator=g).numpy()
+    b = (torch.rand(9, 11, 3, generator=g) * 0.1).numpy() + a * 0.9
+    m = (torch.rand(9, 11, generator=g) > 0.4).numpy()
+    n1 = torch.randn(9, 11, 3, generator=g).numpy()
+    n2 = n1 + 0.2 * torch.randn(9, 11, 3, generator=g).numpy()
+    n1[0, 0] = 0  # a zero normal (background pixel)
+    return a, b, m, n1, n2
+
+
+def make_metrics():
+    """PSNR / MAE of the REAL stage2/utils/metrics.py:16-51 (its skimage / lpips / trimesh imports, unused by these two functions,
+    are shimmed with empty modules)."""
+    import importlib.util
+    import types
+    for name in ("skimage", "skimage.metrics", "lpips", "trimesh", "trimesh.proximity", "trimesh.sample"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["skimage.metrics"].structural_similarity = None
+    spec = importlib.util.spec_from_file_location("psnerf_ref_metrics", os.path.join(ref_loader.REF, "stage2/utils/metrics.py"))
+    met = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(met)
+    a, b, m, n1, n2 = metrics_case()
+    mae_all, ang_all = met.MAE(n1, n2)
+    mae_m, ang_m = met.MAE(n1, n2, m)
+    mae_raw, _ = met.MAE(n1 / 3.0, n2, m, normalize=False)
+    out = {"psnr": np.array(met.PSNR(a, b)), "psnr_masked": np.array(met.PSNR(a, b, m)), "psnr_same": np.array(met.PSNR(a, a)),
+           "mae": np.array(mae_all), "ang": ang_all, "mae_masked": np.array(mae_m), "ang_masked": ang_m, "mae_raw": np.array(mae_raw)}
+    np.savez_compressed(os.path.join(HERE, "metrics.npz"), **out)
+
+
 if __name__ == "__main__":
     make_stage1_net()
     make_stage1_render()
@@ -442,5 +474,6 @@ if __name__ == "__main__":
     make_stage1_phong()
     make_stage2_losses()
     make_stage2_general()
-    for f in ("stage1_net", "stage1_render", "stage2_shade", "stage2_grads", "stage2_edit", "stage1_grads", "stage1_phong", "stage2_loss", "stage2_general"):
+    make_metrics()
+    for f in ("stage1_net", "stage1_render", "stage2_shade", "stage2_grads", "stage2_edit", "stage1_grads", "stage1_phong", "stage2_loss", "stage2_general", "metrics"):
         print(f, os.path.getsize(os.path.join(HERE, f + ".npz")) // 1024, "KB")

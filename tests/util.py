@@ -138,3 +138,15 @@ def general_chunk_outputs(chunk):
     m = chunk["uv"].shape[1]
     return {"mask": chunk["object_mask"].reshape(-1), "flag": chunk["object_mask"].float(), "rgb": chunk["points"] * 2,
             "per_light": chunk["visibility"].permute(2, 0, 1)[..., None].expand(2, 1, m, 3).contiguous(), "none": None}
+
+
+def metrics_case():
+    """Same inputs as tests/golden/make_golden.py:metrics_case."""
+    g = torch.Generator().manual_seed(77)
+    a = torch.rand(9, 11, 3, generator=g).numpy()
+    b = (torch.rand(9, 11, 3, generator=g) * 0.1).numpy() + a * 0.9
+    m = (torch.rand(9, 11, generator=g) > 0.4).numpy()
+    n1 = torch.randn(9, 11, 3, generator=g).numpy()
+    n2 = n1 + 0.2 * torch.randn(9, 11, 3, generator=g).numpy()
+    n1[0, 0] = 0
+    return a, b, m, n1, n2
