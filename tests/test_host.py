@@ -135,6 +135,45 @@ def test_fused_optimizers_host_contract(lib_built):
         optim.Adam(list(e.parameters())).step()
 
 
+@pytest.mark.parametrize("case", list(util.TRAINER_CASES))
+def test_stage1_trainer_equals_reference_trainer(case):
+    """psnerf_b200.stage1.Trainer (train_step / compute_loss / process_data_dict) against the REAL stage1/model/training.py run
+    around the same stub renderer (tests/golden/stage1_trainer.npz): the same pixels are sampled under the same seed, every loss
+    term agrees, and so do the parameters after two optimizer steps."""
+    from psnerf_b200.stage1 import Trainer
+    g = util.golden("stage1_trainer")
+    over, it = util.TRAINER_CASES[case]
+    stub = util.StubRenderer()
+    opt = torch.optim.Adam(stub.parameters(), lr=1e-2)
+    t = Trainer(stub, opt, util.trainer_cfg(over), device=torch.device("cpu"))
+    torch.manual_seed(123)
+    for k in range(2):
+        ld = t.train_step(util.trainer_data(), it=it + k)
+        assert sorted(ld.keys()) == list(g[case + "_keys"])
+        for key, val in ld.items():
+            np.testing.assert_allclose(val.detach().numpy(), g["%s_s%d_%s" % (case, k, key)], rtol=2e-6, atol=1e-7)
+    assert np.array_equal(stub.calls[0][3].numpy(), g[case + "_pix"])
+    assert stub.calls[0][0] == "unisurf" and stub.calls[0][1] == it and stub.calls[0][2] is False and stub.training
+    np.testing.assert_allclose(stub.w.detach().numpy(), g[case + "_w"], rtol=1e-6)
+    with pytest.raises(NotImplementedError):
+        t.render_visdata(None, 0, "x.png")
+
+
+def test_get_tensor_values_and_full_grid_branch():
+    """get_tensor_values reads pixel round(x (W-1)/W) (the reference's W / H normalisation); n_training_points >= H W takes every pixel."""
+    from psnerf_b200.stage1 import Trainer, get_tensor_values
+    img = torch.arange(2 * 6 * 10, dtype=torch.float32).view(1, 2, 6, 10)
+    pix = torch.tensor([[[0.0, 0.0], [9.0, 5.0], [4.0, 2.0], [7.0, 3.0]]])
+    got = get_tensor_values(img, pix)
+    xs = torch.round(pix[0, :, 0] * 9 / 10).long()
+    ys = torch.round(pix[0, :, 1] * 5 / 6).long()
+    assert torch.equal(got[0], img[0][:, ys, xs].t())
+    stub = util.StubRenderer()
+    t = Trainer(stub, torch.optim.SGD(stub.parameters(), lr=0.0), util.trainer_cfg(dict(n_training_points=10 ** 6)), device=torch.device("cpu"))
+    ld = t.compute_loss(util.trainer_data(h=6, w=8), it=0)
+    assert stub.calls[0][3].shape == (1, 48, 2) and torch.isfinite(ld["loss"])
+
+
 def test_arange_pixels_is_xmajor():
     from psnerf_b200.stage1 import arange_pixels
     import psnerf_oracle as O
