@@ -141,3 +141,26 @@ def flat_params(model):
         for l in m.linears:
             out += [l.weight, l.bias]
     return out
+
+
+def train_step(model, loss, model_input, ground_truth, sg_optimizer, loss_n=None, light_optimizer=None, light_para=None):
+    """One iteration of TrainRunner.run (stage2/trainer.py:394-410): forward, MainLoss (+ NormalLoss when normal_train), zero_grad,
+    backward, optimizer steps.  The light optimizer (SparseAdam over the light tables, trainer.py:165) is zeroed and stepped only while
+    the light-direction table still requires grad (train_fix may freeze it, trainer.py:359-360).  Returns (loss_output, loss_normal)."""
+    model_outputs = model(model_input)
+    loss_output = loss(model_outputs, ground_truth, model_input)
+    total = loss_output["loss"]
+    loss_normal = None
+    if loss_n is not None:
+        loss_normal = loss_n(model_outputs)
+        total = total + loss_normal["loss"]
+    step_lights = light_optimizer is not None and (light_para is None or light_para.weight.requires_grad)
+    sg_optimizer.zero_grad()
+    if step_lights:
+        light_optimizer.zero_grad()
+    total.backward()
+    sg_optimizer.step()
+    if step_lights:
+        light_optimizer.step()
+    loss_output["loss"] = total
+    return loss_output, loss_normal

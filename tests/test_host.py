@@ -174,6 +174,48 @@ def test_get_tensor_values_and_full_grid_branch():
     assert stub.calls[0][3].shape == (1, 48, 2) and torch.isfinite(ld["loss"])
 
 
+def test_stage2_train_step_order_of_operations():
+    """psnerf_b200.stage2.train_step = trainer.py:394-410: losses summed, both optimizers zeroed before and stepped after ONE backward,
+    the light optimizer left alone once the light table is frozen."""
+    from psnerf_b200.stage2 import train_step
+    w = torch.nn.Parameter(torch.tensor([1.0, 2.0]))
+    table = torch.nn.Embedding(4, 3)
+    log = []
+
+    class Opt(torch.optim.SGD):
+        def __init__(self, params, name):
+            super().__init__(params, lr=0.1)
+            self.name = name
+
+        def zero_grad(self, set_to_none=True):
+            log.append(self.name + ".zero")
+            super().zero_grad(set_to_none)
+
+        def step(self, closure=None):
+            log.append(self.name + ".step")
+            return super().step(closure)
+
+    def model(inp):
+        log.append("forward")
+        return {"y": (w * inp["x"]).sum() + table.weight.sum() * 0.0 + table.weight[1, 0]}
+
+    def loss(out, gt, inp):
+        return {"loss": (out["y"] - gt["y"]) ** 2, "sg_rgb_loss": out["y"].detach()}
+
+    def loss_n(out):
+        return {"loss": out["y"] * 0.5}
+
+    sg, lo = Opt([w], "sg"), Opt(table.parameters(), "light")
+    y = 3.0 + float(table.weight[1, 0])  # before the step
+    lo_out, ln_out = train_step(model, loss, {"x": torch.tensor([1.0, 1.0])}, {"y": torch.tensor(0.0)}, sg, loss_n, lo, table)
+    assert log == ["forward", "sg.zero", "light.zero", "sg.step", "light.step"]
+    assert float(w[0]) != 1.0 and ln_out is not None and abs(float(lo_out["loss"]) - ((y - 0.0) ** 2 + 0.5 * y)) < 1e-3 * max(1.0, abs(y))
+    table.weight.requires_grad_(False)
+    del log[:]
+    train_step(model, loss, {"x": torch.tensor([1.0, 1.0])}, {"y": torch.tensor(0.0)}, sg, None, lo, table)
+    assert log == ["forward", "sg.zero", "sg.step"]
+
+
 def test_arange_pixels_is_xmajor():
     from psnerf_b200.stage1 import arange_pixels
     import psnerf_oracle as O
