@@ -6,6 +6,7 @@
   occupancy_grid_logits<- stage1/model/extracting.py:84-96,137-155 (dense -logit grid for mesh export)
   render_envmap_view   <- stage2/eval.py:173-231          (envmap relighting: RGB-intensity light grid, sum over lights)
   extract_and_shade    <- SURVEY.md §8f-1: stage-1 surface extraction feeding stage-2 shading directly, no .npy hand-off
+  save_shape_view / load_shape_view <- shape_extract.py:144-162 / stage2/datasets/dataset.py:100-114: the .npy hand-off, kept as an option
   *_sharded            <- SURVEY.md §8e: rays of a view dealt over the ranks, one all_gather of pixels at the end
 
 All functions take / return torch tensors; `view` dicts carry the camera: stage 1 {camera_mat, world_mat}, stage 2
@@ -125,3 +126,44 @@ def render_stage1_view_sharded(renderer, h, w, camera_mat, world_mat, rank, worl
     out = renderer(p_all[:, idx].to(dev), camera_mat, world_mat, None, "unisurf", add_noise=False, eval_=True, it=it)
     local = torch.cat([out["rgb"][0], out["normal_pred"][0], out["acc_map"][0].unsqueeze(-1)], -1)
     return sharding.gather_pixels(local, h * w, rank, world)
+
+
+# ---- the on-disk hand-off between the stages (optional: extract_and_shade needs none of it) ------------------------------------
+def save_shape_view(out_dir, view_number, shape, h, w):
+    """Write one view of `extract_shape` in the layout stage1/shape_extract.py:144-162 produces and stage2/datasets/dataset.py:100-114
+    reads: points/view_XX.npy, normal/view_XX.npy (float32 [h,w,3]), mask/view_XX.npy (bool [h,w]) and, when the shadow pass ran,
+    visibility/view_XX.npy (float32; the reference reshapes the x-major [L, h*w] array as (L, h, w) and swaps the last two axes,
+    which is only a transpose to row-major for square images - reproduced as is).  view_number is 1-based like the file names."""
+    import os
+
+    import numpy as np
+    name = "view_%02d.npy" % view_number
+    for sub in ("points", "normal", "mask") + (("visibility",) if "visibility" in shape else ()):
+        os.makedirs(os.path.join(out_dir, sub), exist_ok=True)
+    mask = to_hw(shape["mask"].reshape(1, -1, 1)[0], h, w).cpu().numpy()[..., 0]
+    np.save(os.path.join(out_dir, "points", name), to_hw(shape["points"][0], h, w).cpu().numpy().astype(np.float32))
+    np.save(os.path.join(out_dir, "normal", name), to_hw(shape["normal"][0], h, w).cpu().numpy().astype(np.float32))
+    np.save(os.path.join(out_dir, "mask", name), mask.astype(bool))
+    if "visibility" in shape:
+        vis = shape["visibility"].cpu().numpy()
+        L = vis.shape[0]
+        np.save(os.path.join(out_dir, "visibility", name), vis.reshape(L, h, w).transpose(0, 2, 1).astype(np.float32))
+
+
+def load_shape_view(shape_dir, view_number, with_visibility=False):
+    """Read one view back the way the stage-2 dataset does (dataset.py:100-114): row-major pixel order, points / normal [1,N,3],
+    surface_mask bool [1,N], visibility [L,N] - the model_input entries PSNetwork.forward consumes next to uv / pose / intrinsics."""
+    import os
+
+    import numpy as np
+    name = "view_%02d.npy" % view_number
+    def load(sub, dtype):  # C-ordered copy: a file written from a transposed view comes back Fortran-ordered
+        return torch.from_numpy(np.ascontiguousarray(np.load(os.path.join(shape_dir, sub, name)).astype(dtype)))
+
+    pts = load("points", np.float32)
+    out = {"points": pts.view(1, -1, 3), "normal": load("normal", np.float32).view(1, -1, 3),
+           "surface_mask": load("mask", bool).view(1, -1), "img_res": list(pts.shape[:2])}
+    if with_visibility:
+        vis = load("visibility", np.float32)
+        out["visibility"] = vis.reshape(vis.shape[0], -1)
+    return out

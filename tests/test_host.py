@@ -216,6 +216,36 @@ def test_stage2_train_step_order_of_operations():
     assert log == ["forward", "sg.zero", "sg.step"]
 
 
+def test_shape_files_round_trip_in_the_reference_layout(tmp_path):
+    """points / normal / mask / visibility .npy files of one view: written from the x-major stage-1 arrays as shape_extract.py:144-162
+    does, read back row-major as dataset.py:100-114 does - pixel (y, x) of the file is ray x*h + y of the renderer."""
+    from psnerf_b200 import pipeline
+    h, w, L = 6, 6, 3
+    g = torch.Generator().manual_seed(4)
+    n = h * w
+    shape = {"points": torch.randn(1, n, 3, generator=g), "normal": torch.randn(1, n, 3, generator=g),
+             "mask": torch.rand(1, n, generator=g) > 0.5, "visibility": torch.rand(L, n, generator=g)}
+    pipeline.save_shape_view(str(tmp_path), 7, shape, h, w)
+    pts = np.load(tmp_path / "points" / "view_07.npy")
+    msk = np.load(tmp_path / "mask" / "view_07.npy")
+    vis = np.load(tmp_path / "visibility" / "view_07.npy")
+    assert pts.shape == (h, w, 3) and pts.dtype == np.float32 and msk.shape == (h, w) and msk.dtype == bool and vis.shape == (L, h, w)
+    for (y, x) in [(0, 0), (2, 5), (5, 1)]:
+        ray = x * h + y
+        assert np.array_equal(pts[y, x], shape["points"][0, ray].numpy()) and msk[y, x] == bool(shape["mask"][0, ray])
+        assert np.array_equal(vis[:, y, x], shape["visibility"][:, ray].numpy())
+    back = pipeline.load_shape_view(str(tmp_path), 7, with_visibility=True)
+    assert back["points"].shape == (1, n, 3) and back["surface_mask"].dtype == torch.bool and back["visibility"].shape == (L, n)
+    assert back["img_res"] == [h, w]
+    row_major = torch.arange(n).view(w, h).t().reshape(-1)  # ray index of row-major pixel k
+    assert torch.equal(back["points"][0], shape["points"][0][row_major])
+    assert torch.equal(back["normal"][0], shape["normal"][0][row_major])
+    assert torch.equal(back["surface_mask"][0], shape["mask"][0][row_major])
+    assert torch.equal(back["visibility"], shape["visibility"][:, row_major])
+    pipeline.save_shape_view(str(tmp_path), 8, {k: v for k, v in shape.items() if k != "visibility"}, h, w)
+    assert not (tmp_path / "visibility" / "view_08.npy").exists()
+
+
 def test_arange_pixels_is_xmajor():
     from psnerf_b200.stage1 import arange_pixels
     import psnerf_oracle as O
