@@ -1,0 +1,29 @@
+#!/bin/bash
+# First GPU call of the next round (gpurun --timeout 1500 -- 'bash tools/r2_bringup.sh'): everything that was prepared without a GPU.
+#   1. the full GPU suite (includes tc_mixed, the fused optimizers and the Trainer end-to-end test)
+#   2. the two-level march (PSN_PREC_TC_TWOLEVEL) - gated tests under a timeout (a protocol error would hang, not fail)
+#   3. bench lines for tc / tc_mixed / tc_two_level (no extras) and the default bench
+#   4. the ncu launch list of the default bench command and a --set full capture of the two tensor kernels at tc_mixed
+mkdir -p gpurun_out
+(time timeout 900 python -m pytest tests -m gpu -x -q) > gpurun_out/r2_pytest_gpu.log 2>&1; tail -4 gpurun_out/r2_pytest_gpu.log
+PSNERF_B200_TEST_TWOLEVEL=1 timeout -k 5 180 python -m pytest tests/test_gpu_tc_two_level.py -x -q > gpurun_out/r2_two_level.log 2>&1
+rc=$?; echo "two-level rc=$rc" | tee -a gpurun_out/r2_two_level.log; tail -4 gpurun_out/r2_two_level.log
+for p in tc tc_mixed $([ $rc -eq 0 ] && echo tc_two_level); do
+  timeout -k 5 120 python bench.py --precision $p --steps 4 --warmup 3 --no-extras --no-cpu-baseline > gpurun_out/r2_bench_$p.json 2> gpurun_out/r2_bench_$p.err
+  python - <<PY
+import json
+try:
+    d = json.load(open("gpurun_out/r2_bench_$p.json")); k = d["kernels"]
+    print("$p", "step %.1f ms" % d["ms_per_step"], "march %.1f" % k["occ_march"]["ms_per_launch"], "rad %.1f" % k["radiance"]["ms_per_launch"], "clk", d["clocks"]["sm_mhz"])
+except Exception as e:
+    print("$p failed:", e)
+PY
+done
+timeout 400 python bench.py > gpurun_out/r2_bench_default.json 2> gpurun_out/r2_bench_default.err; tail -c 600 gpurun_out/r2_bench_default.json
+timeout 300 python tools/tc_trace_rad.py --mixed > gpurun_out/r2_trace_rad_mixed.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launch_list.csv \
+  python bench.py --steps 2 --warmup 3 --no-extras --no-cpu-baseline > gpurun_out/r2_launch_list.log 2>&1
+if [ -n "$PSN_NCU" ]; then
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_tc_(occ|rad)" -c 4 -o gpurun_out/r2_prof_s1 \
+    python tools/profile_step.py --steps 1 --precision tc_mixed > gpurun_out/r2_ncu_s1.log 2>&1; tail -3 gpurun_out/r2_ncu_s1.log
+fi
