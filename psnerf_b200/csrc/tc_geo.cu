@@ -82,7 +82,7 @@ k_tc_occ(TcGeoArgs g, PointGen gen, long long M_host, const int* M_dev, int out_
           if (tr && pass == 0) trace[64 + sub * 40 + l * 5] = clock64();
           add16(v, b.b);
 #pragma unroll
-          for (int i = 0; i < CW; ++i) v[i] = softplus_scaled(v[i], cc);
+          for (int i = 0; i < CW; ++i) v[i] = CHEAP ? softplus_scaled_cheap(v[i], cc) : softplus_scaled(v[i], cc);
           if (MODE == MODE_DEBUG) {
             if (dump && dump_layer == l && idx < M) {  // bring-up hook: the MMA-produced columns only
 #pragma unroll

@@ -621,6 +621,15 @@ __device__ __forceinline__ float softplus_scaled(float zs, float c) {
   const float e = ex2_approx(fminf(zs, 40.f));
   return c * fmaxf(zs, lg2_approx(1.f + e));
 }
+// First level of the two-level march only (k_tc_occ<.., CHEAP>): softplus = c (max(zs, 0) + lg2(1 + u)), u = 2^-|zs| in (0, 1], with
+// lg2(1 + u) ~ u (C1 + C2 u + C3 u^2) (no constant term; max error 7.7e-4, i.e. 5e-6 on the activation): ONE MUFU and the same six
+// issue slots as the two-MUFU form.  The values this produces are only trusted away from the occupancy threshold
+// (tests/precision_study.py: max |cheap - full| = 1e-3 on alpha against a refine margin of 0.02).
+__device__ __forceinline__ float softplus_scaled_cheap(float zs, float c) {
+  const float u = ex2_approx(-fabsf(zs));
+  const float q = fmaf(fmaf(0.165381165f, u, -0.589203729f), u, 1.42459315f);
+  return c * fmaf(q, u, fmaxf(zs, 0.f));
+}
 // same, also returning sigma'(z) = sigmoid(100 z) = e / (1 + e)
 __device__ __forceinline__ float softplus_scaled_d(float zs, float c, float* dsig) {
   const float e = ex2_approx(fminf(zs, 40.f));

@@ -209,8 +209,23 @@ if __name__ == "__main__":
     study_stage2()
 
 
+POLY3 = (1.42459315, -0.589203729, 0.165381165)  # lg2(1 + u) ~ u (C1 + C2 u + C3 u^2) on (0, 1]: tc_mlp.cuh softplus_scaled_cheap
+
+
+def softplus_poly3(z):
+    """softplus(beta = 100) the way the CHEAP occupancy program evaluates it: one ex2 and a cubic for lg2(1 + 2^-|t|)."""
+    t = (z * (100.0 / np.log(2.0))).float()
+    u = torch.exp2(-t.abs())
+    q = (POLY3[2] * u + POLY3[1]) * u + POLY3[0]
+    return (float(np.log(2.0) / 100.0) * (q * u + torch.clamp(t, min=0.0))).float()
+
+
 def alpha_only(sd, mcfg, p, scheme):
-    """Occupancy probability of the geo net under `scheme` (what k_tc_occ computes: forward stack + fp32 logit head)."""
+    """Occupancy probability of the geo net under `scheme` (what k_tc_occ computes: forward stack + fp32 logit head);
+    "1pass_poly3" = the CHEAP program (single fp16 pass + softplus_poly3)."""
+    act = O.softplus100
+    if scheme == "1pass_poly3":
+        scheme, act = "1pass", softplus_poly3
     layers = O.stage1_weights(sd, "lin", O.count_layers(sd, "lin"))
     nl = len(layers)
     pe = O.positional_encoding(p / mcfg["rescale"], mcfg["octaves_pe"])
@@ -219,13 +234,13 @@ def alpha_only(sd, mcfg, p, scheme):
     for l, (W, b) in enumerate(layers[:nl - 1]):
         if l in mcfg["skips"]:
             x = torch.cat([x, pe], -1) * inv
-        x = O.softplus100(mm(x, W, scheme) + b)
+        x = act(mm(x, W, scheme) + b)
     W, b = layers[nl - 1]
     logit = mm(x, W[:1], "fp32") + b[:1]
     return torch.sigmoid(logit[:, 0] * -10.0)
 
 
-def march_refine_study(R=32, n_steps=256, margin=0.02, cheap="1pass"):
+def march_refine_study(R=32, n_steps=256, margin=0.02, cheap="1pass_poly3"):
     """Two-level surface march: every proposal point with the CHEAP program, then the full three-pass program only where the scan
     (rendering.py:443-470) can see the difference - points within `margin` of the threshold, points next to a sign change of the
     cheap values, and their neighbours.  The scan reads nothing else (signs everywhere, values only at the crossing), so the
