@@ -3,6 +3,7 @@
 #   1. the full GPU suite (includes tc_mixed, the fused optimizers and the Trainer end-to-end test)
 #   2. the two-level march (PSN_PREC_TC_TWOLEVEL) - gated tests under a timeout (a protocol error would hang, not fail)
 #   3. bench lines for tc / tc_mixed / tc_two_level (no extras) and the default bench
+#   3b. the H16 variant of the mixed radiance program (PSNERF_B200_RAD_H16=1): mixed tests + bench A/B
 #   4. the ncu launch list of the default bench command and a --set full capture of the two tensor kernels at tc_mixed
 mkdir -p gpurun_out
 (time timeout 900 python -m pytest tests -m gpu -x -q) > gpurun_out/r2_pytest_gpu.log 2>&1; tail -4 gpurun_out/r2_pytest_gpu.log
@@ -19,6 +20,13 @@ except Exception as e:
     print("$p failed:", e)
 PY
 done
+# H16 variant of the mixed radiance program (sigma' rebuilt from the fp16 activations in the reverse layers): same tests, then A/B
+PSNERF_B200_RAD_H16=1 timeout -k 5 180 python -m pytest tests/test_gpu_tc_mixed.py -x -q > gpurun_out/r2_h16.log 2>&1
+rch=$?; echo "h16 rc=$rch" | tee -a gpurun_out/r2_h16.log; tail -3 gpurun_out/r2_h16.log
+if [ $rch -eq 0 ]; then
+  PSNERF_B200_RAD_H16=1 timeout -k 5 120 python bench.py --precision tc_mixed --steps 4 --warmup 3 --no-extras --no-cpu-baseline > gpurun_out/r2_bench_tc_mixed_h16.json 2> gpurun_out/r2_bench_tc_mixed_h16.err
+  python -c "import json; d=json.load(open('gpurun_out/r2_bench_tc_mixed_h16.json')); print('tc_mixed+h16 step %.1f ms rad %.1f' % (d['ms_per_step'], d['kernels']['radiance']['ms_per_launch']))"
+fi
 timeout 400 python bench.py > gpurun_out/r2_bench_default.json 2> gpurun_out/r2_bench_default.err; tail -c 600 gpurun_out/r2_bench_default.json
 timeout 300 python tools/tc_trace_rad.py --mixed > gpurun_out/r2_trace_rad_mixed.log 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launch_list.csv \
