@@ -240,6 +240,18 @@ struct Step {
                    // writes only the hi half of the A operand (epi_store_a16 hi_only); 0: the three-pass split product
   uint16_t n_pad;  // N (multiple of 16, <= 256); a tile is n_pad x 128 bytes
 };
+// The same 8 bytes as the loops that never see single-pass steps read them (ALLOW_SINGLE = false: `single` is 0 there, so nkb and
+// single together are the 16-bit K-block count).  Keeps the code of those kernels what it was before Step::single existed.
+struct StepNoSingle {
+  uint32_t w_off;
+  uint16_t nkb;
+  uint16_t n_pad;
+};
+static_assert(sizeof(StepNoSingle) == sizeof(Step), "Step views must overlay");
+template <bool ALLOW_SINGLE> struct StepView { using type = Step; };
+template <> struct StepView<false> { using type = StepNoSingle; };
+__device__ __forceinline__ bool step_is_single(const Step& s) { return s.single != 0; }
+__device__ __forceinline__ bool step_is_single(const StepNoSingle&) { return false; }
 constexpr int MAX_STEPS = 24;
 struct Program {
   Step step[MAX_STEPS];
@@ -296,10 +308,10 @@ __device__ __forceinline__ void producer_loop(const Smem& s, const Program& prog
   uint32_t t_parity = 0;
   for (long long it = 0; it < iters; ++it) {
     for (int st = 0; st < prog.n_steps; ++st) {
-      const Step sp = prog.step[st];
+      const typename StepView<ALLOW_SINGLE>::type sp = reinterpret_cast<const typename StepView<ALLOW_SINGLE>::type&>(prog.step[st]);
       const uint32_t tile_bytes = (uint32_t)sp.n_pad * 128u;
       const unsigned char* src = prog.blob[st] + sp.w_off;
-      const bool single = ALLOW_SINGLE && sp.single;
+      const bool single = ALLOW_SINGLE && step_is_single(sp);
       const int n_tiles = single ? sp.nkb : 2 * sp.nkb;
       for (int t = 0; t < n_tiles; ++t, t_parity ^= 1u) {
         mbar_wait_cluster_relaxed(&s.c->w_empty[stage], phase ^ 1u);     // released by the MMA warps of both CTAs
@@ -345,14 +357,14 @@ __device__ __forceinline__ void mma_loop(const Smem& s, const Program& prog, lon
   const uint32_t w_base = smem_u32(s.w);
   for (long long it = 0; it < iters; ++it) {
     for (int st = 0; st < prog.n_steps; ++st, ++step_ctr) {
-      const Step sp = prog.step[st];
+      const typename StepView<ALLOW_SINGLE>::type sp = reinterpret_cast<const typename StepView<ALLOW_SINGLE>::type&>(prog.step[st]);
       const uint32_t buf = step_ctr & 1u;
       const uint32_t d_addr = tmem_base + buf * 256u;           // accumulator of this step
       const uint32_t a_addr = tmem_base + (buf ^ 1u) * 256u;    // its A operand = the previous step's accumulator, converted in place
       const uint32_t idesc = umma_idesc(sp.n_pad);
       long long t_wait_a = 0, t_wait_w = 0;  // bring-up trace only (dead code otherwise)
       for (int kb = 0; kb < sp.nkb; ++kb) {
-        if (ALLOW_SINGLE && sp.single) {
+        if (ALLOW_SINGLE && step_is_single(sp)) {
           // single-pass step: one weight stage (the hi tile) and four MMAs A_hi W_hi per K block; same split of the last K block
           const uint32_t st_w = stage, ph_w = phase;
           if (++stage == W_STAGES) { stage = 0; phase ^= 1u; }
