@@ -41,8 +41,8 @@ k_tc_occ(TcGeoArgs g, PointGen gen, long long M_host, const int* M_dev, int out_
 
   if (warp < EPI_WARP0) {
     regs_shrink_control();
-    if (warp == 0 && lane == 0) producer_loop(s, g.prog, iters);
-    if (warp == 1) mma_loop(s, g.prog, iters, tmem_base, MODE == MODE_DEBUG ? trace : nullptr);
+    if (warp == 0 && lane == 0) producer_loop<CHEAP>(s, g.prog, iters);  // single-pass steps exist only in the CHEAP program
+    if (warp == 1) mma_loop<CHEAP>(s, g.prog, iters, tmem_base, MODE == MODE_DEBUG ? trace : nullptr);
     __syncwarp();
   } else {
     regs_grow_epilogue();
