@@ -215,8 +215,7 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
             epi_signal_a(s, pass);
             scr_st<HINT>(&stash[(size_t)(l * 32 + (col >> 3)) * TILE_M + row], hw[0], pol);
             scr_st<HINT>(&stash[(size_t)(l * 32 + (col >> 3) + 1) * TILE_M + row], hw[1], pol);
-            return;
-          }
+          } else {
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
             float sg[8];
@@ -250,6 +249,7 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
           }
           epi_store_a16(e, e.d_col0(), col, v, ho_l);
           epi_signal_a(s, pass);
+          }
         });
         PSN_RAD_MARK(192);
         ++tstep;
