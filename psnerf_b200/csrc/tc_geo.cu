@@ -81,6 +81,16 @@ k_tc_occ(TcGeoArgs g, PointGen gen, long long M_host, const int* M_dev, int out_
                                   [&](int pass, int col, float (&v)[CW], const Bias16& b) {
           if (tr && pass == 0) trace[64 + sub * 40 + l * 5] = clock64();
           add16(v, b.b);
+          if (CHEAP && l < 7 && !(pre_skip && col + CW > n_out)) {
+            // level-1 march program, ordinary chunk: activation in packed fp16, result = the hi-only operand columns
+            const __half2 c2 = __float2half2_rn(cc);
+            uint32_t r8[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) r8[u] = softplus_scaled_cheap_h2(v[2 * u], v[2 * u + 1], c2);
+            tmem_st8(e.tmem_base + e.lane_addr + e.d_col0() + (uint32_t)col, r8);
+            epi_signal_a(s, pass);
+            return;
+          }
 #pragma unroll
           for (int i = 0; i < CW; ++i) v[i] = CHEAP ? softplus_scaled_cheap(v[i], cc) : softplus_scaled(v[i], cc);
           if (MODE == MODE_DEBUG) {

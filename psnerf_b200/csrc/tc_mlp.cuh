@@ -666,6 +666,20 @@ __device__ __forceinline__ float softplus_scaled_cheap(float zs, float c) {
   const float q = fmaf(fmaf(0.165381165f, u, -0.589203729f), u, 1.42459315f);
   return c * fmaf(q, u, fmaxf(zs, 0.f));
 }
+// The same activation for TWO pre-scaled accumulators entirely in packed fp16 arithmetic (ex2.approx.f16x2, HFMA2, HMNMX2): the result
+// is directly one 32-bit column of the single-pass A operand, so neither a second MUFU nor a conversion follows.  An fp16 epilogue
+// adds about as much error as the fp16 operands themselves (emulated: max |cheap - full| = 1.5e-3 on alpha, margin 0.02).
+__device__ __forceinline__ uint32_t softplus_scaled_cheap_h2(float zs0, float zs1, __half2 c2) {
+  const __half2 zs = __floats2half2_rn(zs0, zs1);
+  const __half2 na = __hneg2(__habs2(zs));
+  uint32_t ub;
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(ub) : "r"(*reinterpret_cast<const uint32_t*>(&na)));
+  const __half2 u = *reinterpret_cast<const __half2*>(&ub);
+  __half2 q = __hfma2(__float2half2_rn(0.165381165f), u, __float2half2_rn(-0.589203729f));
+  q = __hfma2(q, u, __float2half2_rn(1.42459315f));
+  const __half2 r = __hmul2(__hfma2(q, u, __hmax2(zs, __float2half2_rn(0.f))), c2);
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
 // same, also returning sigma'(z) = sigmoid(100 z) = e / (1 + e)
 __device__ __forceinline__ float softplus_scaled_d(float zs, float c, float* dsig) {
   const float e = ex2_approx(fminf(zs, 40.f));

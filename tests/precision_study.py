@@ -220,12 +220,28 @@ def softplus_poly3(z):
     return (float(np.log(2.0) / 100.0) * (q * u + torch.clamp(t, min=0.0))).float()
 
 
+def softplus_poly3_h2(z):
+    """The same activation in packed fp16 arithmetic (tc_mlp.cuh softplus_scaled_cheap_h2): the accumulator is rounded to fp16 and every
+    operation after it rounds to fp16 again (the fused HFMA2s round once; rounding twice here errs on the pessimistic side)."""
+    def h(t):
+        return torch.as_tensor(t, dtype=torch.float32).half().float()
+
+    zs = h(z * (100.0 / np.log(2.0)))
+    u = h(torch.exp2(-zs.abs()))
+    q = h(h(h(POLY3[2]) * u) + h(POLY3[1]))
+    q = h(h(q * u) + h(POLY3[0]))
+    r = h(h(q * u) + torch.clamp(zs, min=0.0))
+    return h(r * h(float(np.log(2.0) / 100.0)))
+
+
 def alpha_only(sd, mcfg, p, scheme):
     """Occupancy probability of the geo net under `scheme` (what k_tc_occ computes: forward stack + fp32 logit head);
     "1pass_poly3" = the CHEAP program (single fp16 pass + softplus_poly3)."""
-    act = O.softplus100
+    act = act_last = O.softplus100
     if scheme == "1pass_poly3":
-        scheme, act = "1pass", softplus_poly3
+        scheme, act, act_last = "1pass", softplus_poly3, softplus_poly3
+    elif scheme == "1pass_h2":  # the CHEAP program as built: layers 0-6 in packed fp16, layer 7 (feeds the fp32 logit head) in fp32
+        scheme, act, act_last = "1pass", softplus_poly3_h2, softplus_poly3
     layers = O.stage1_weights(sd, "lin", O.count_layers(sd, "lin"))
     nl = len(layers)
     pe = O.positional_encoding(p / mcfg["rescale"], mcfg["octaves_pe"])
@@ -234,13 +250,13 @@ def alpha_only(sd, mcfg, p, scheme):
     for l, (W, b) in enumerate(layers[:nl - 1]):
         if l in mcfg["skips"]:
             x = torch.cat([x, pe], -1) * inv
-        x = act(mm(x, W, scheme) + b)
+        x = (act if l < nl - 2 else act_last)(mm(x, W, scheme) + b)
     W, b = layers[nl - 1]
     logit = mm(x, W[:1], "fp32") + b[:1]
     return torch.sigmoid(logit[:, 0] * -10.0)
 
 
-def march_refine_study(R=32, n_steps=256, margin=0.02, cheap="1pass_poly3"):
+def march_refine_study(R=32, n_steps=256, margin=0.02, cheap="1pass_h2"):
     """Two-level surface march: every proposal point with the CHEAP program, then the full three-pass program only where the scan
     (rendering.py:443-470) can see the difference - points within `margin` of the threshold, points next to a sign change of the
     cheap values, and their neighbours.  The scan reads nothing else (signs everywhere, values only at the crossing), so the
