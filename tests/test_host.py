@@ -246,6 +246,39 @@ def test_shape_files_round_trip_in_the_reference_layout(tmp_path):
     assert not (tmp_path / "visibility" / "view_08.npy").exists()
 
 
+@pytest.mark.skipif(not __import__("os").path.exists("/root/reference/stage1/model/checkpoints.py"),
+                    reason="needs the reference checkout (authoring container only)")
+def test_reference_checkpoint_io_round_trips_the_drop_in_modules(tmp_path):
+    """The reference's OWN CheckpointIO (stage1/model/checkpoints.py, loaded by path, unmodified) saves and restores the drop-in
+    NeuralNetwork and the fused Adam exactly as it does its own classes (stage1/train.py:66-72): same 'model' / 'optimizer' entries,
+    scalars passed through."""
+    import importlib.util
+    from psnerf_b200 import optim
+    from psnerf_b200.stage1 import NeuralNetwork
+    spec = importlib.util.spec_from_file_location("psnerf_ref_checkpoints", "/root/reference/stage1/model/checkpoints.py")
+    ck = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ck)
+    torch.manual_seed(3)
+    net = NeuralNetwork(synth.stage1_cfg())
+    opt = optim.Adam(net.parameters(), lr=1e-4)
+    for p in list(net.parameters())[:2]:  # give the optimizer some state without running a CUDA step
+        opt.state[p] = {"step": 5, "exp_avg": torch.full_like(p, 0.25), "exp_avg_sq": torch.full_like(p, 0.5)}
+    io = ck.CheckpointIO(str(tmp_path), model=net, optimizer=opt)
+    io.save("model.pt", epoch_it=7, it=1234, loss_val_best=0.5)
+    raw = torch.load(tmp_path / "model.pt", weights_only=False)
+    assert set(raw) == {"model", "optimizer", "epoch_it", "it", "loss_val_best"}
+    assert set(raw["model"]) == set(net.state_dict()) and len(raw["optimizer"]["state"]) == 2
+    torch.manual_seed(4)
+    net2 = NeuralNetwork(synth.stage1_cfg())
+    opt2 = optim.Adam(net2.parameters(), lr=1e-4)
+    scalars = ck.CheckpointIO(str(tmp_path), model=net2, optimizer=opt2).load("model.pt")
+    assert scalars == {"epoch_it": 7, "it": 1234, "loss_val_best": 0.5}
+    for (k, a), b in zip(net.state_dict().items(), net2.state_dict().values()):
+        assert torch.equal(a, b), k
+    p0 = list(net2.parameters())[0]
+    assert opt2.state[p0]["step"] == 5 and float(opt2.state[p0]["exp_avg"].mean()) == 0.25
+
+
 def test_arange_pixels_is_xmajor():
     from psnerf_b200.stage1 import arange_pixels
     import psnerf_oracle as O
