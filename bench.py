@@ -453,15 +453,30 @@ def main():
                 "roofline": roof, "kernels": kern}
         if world == 1 and not args.no_extras:
             x_prec = "tc" if precision in ("tc_mixed", "tc_two_level") else precision  # the other workloads have no mixed program: plain 'tc'
-            net.precision = x_prec
             extras = {}
+            res_bench = None
             if precision in ("tc_mixed", "tc_two_level"):
-                try:  # the same headline step with every product in the three-pass split ('tc'), for comparison
+                try:
+                    res_bench = step(False).clone()  # [rays, 7] = rgb, normal, acc of the benched precision
+                except Exception:
+                    res_bench = None
+            net.precision = x_prec
+            if precision in ("tc_mixed", "tc_two_level"):
+                try:  # the same headline step with every product in the three-pass split ('tc'): time and output difference
                     ms_tc = _time_cuda(lambda: step(False), reps=2)
                     extras["headline_step_full_split_tc"] = {"ms_per_step": ms_tc, "Msamples_per_s": units / (ms_tc / 1e3) / 1e6,
                                                              "note": "--precision tc: feature head, reverse sweep and appearance MLP in three passes too"}
+                    if res_bench is not None:
+                        res_tc = step(False)
+                        extras["headline_step_full_split_tc"]["benched_vs_full_split"] = {
+                            "rgb_max_abs_diff": float((res_bench[:, :3] - res_tc[:, :3]).abs().max()),
+                            "normal_identical": bool(torch.equal(res_bench[:, 3:6], res_tc[:, 3:6])),
+                            "acc_identical": bool(torch.equal(res_bench[:, 6], res_tc[:, 6])),
+                            "gate": "north star: 1e-4 relative; tests/test_gpu_tc_mixed.py holds rgb to 2e-5 of 'tc' and alpha / normals bit-identical"}
+                        del res_tc
                 except Exception as e:
                     extras["headline_step_full_split_tc"] = {"error": repr(e)[:300]}
+            del res_bench
             extras.update(extra_workloads(dev, x_prec, rend, views[0], peaks))
             net.precision = precision
             line["other_workloads"] = extras
