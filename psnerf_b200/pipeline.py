@@ -7,7 +7,7 @@
   render_envmap_view   <- stage2/eval.py:173-231          (envmap relighting: RGB-intensity light grid, sum over lights)
   extract_and_shade    <- SURVEY.md §8f-1: stage-1 surface extraction feeding stage-2 shading directly, no .npy hand-off
   save_shape_view / load_shape_view <- shape_extract.py:144-162 / stage2/datasets/dataset.py:100-114: the .npy hand-off, kept as an option
-  *_sharded            <- SURVEY.md §8e: rays of a view dealt over the ranks, one all_gather of pixels at the end
+  *_sharded            <- SURVEY.md §8e: rays of a view dealt over the ranks (stage 2: balanced by surface pixels), one all_gather at the end
 
 All functions take / return torch tensors; `view` dicts carry the camera: stage 1 {camera_mat, world_mat}, stage 2
 {intrinsics, pose}.  The pixel order conventions of the reference are preserved (stage 1: x-major, undone by to_hw;
@@ -126,6 +126,40 @@ def render_stage1_view_sharded(renderer, h, w, camera_mat, world_mat, rank, worl
     out = renderer(p_all[:, idx].to(dev), camera_mat, world_mat, None, "unisurf", add_noise=False, eval_=True, it=it)
     local = torch.cat([out["rgb"][0], out["normal_pred"][0], out["acc_map"][0].unsqueeze(-1)], -1)
     return sharding.gather_pixels(local, h * w, rank, world)
+
+
+PER_PIXEL_INPUTS = ("uv", "object_mask", "gt_normal", "normal", "depth", "points", "surface_mask", "visibility")
+
+
+@torch.no_grad()
+def render_stage2_view_sharded(model, model_input, light_dirs, rank, world, light_batch=96, light_intensity=None, group=None):
+    """BASELINE config 4: the pixels of one stage-2 view dealt over the ranks with the SURFACE pixels balanced
+    (sharding.shard_indices_by_mask), every rank shades its share under all lights, ONE all_gather returns the full view on every
+    rank.  Output: the per-pixel entries of render_stage2_view in the reference's shapes - sg_rgb_values / visibility [L,N,3],
+    normal_pred / sg_diffuse_albedo_values [1,N,3]."""
+    smask = model_input["surface_mask"]
+    N = smask.shape[1]
+    dev = model_input["points"].device
+
+    def indices_of(r):
+        return sharding.shard_indices_by_mask(smask[0], r, world)
+
+    idx = indices_of(rank).to(dev)
+    sub = dict(model_input)
+    for k in PER_PIXEL_INPUTS:
+        if k in model_input and torch.is_tensor(model_input[k]) and model_input[k].dim() >= 2 and model_input[k].shape[1] == N:
+            sub[k] = torch.index_select(model_input[k], 1, idx)
+    out = render_stage2_view(model, sub, light_dirs, light_batch, light_intensity)
+    L = light_dirs.shape[0]
+    n_loc = idx.numel()
+    rgb = out["sg_rgb_values"].reshape(L, n_loc, 3)
+    vis = out["visibility"].reshape(L, n_loc, 3)
+    local = torch.cat([rgb.permute(1, 0, 2).reshape(n_loc, L * 3), vis.permute(1, 0, 2).reshape(n_loc, L * 3),
+                       out["normal_pred"].reshape(n_loc, 3), out["sg_diffuse_albedo_values"].reshape(n_loc, 3)], -1).contiguous()
+    full = sharding.gather_rows(local, N, rank, world, indices_of, group=group)
+    return {"sg_rgb_values": full[:, :L * 3].reshape(N, L, 3).permute(1, 0, 2).contiguous(),
+            "visibility": full[:, L * 3:2 * L * 3].reshape(N, L, 3).permute(1, 0, 2).contiguous(),
+            "normal_pred": full[:, 6 * L:6 * L + 3].reshape(1, N, 3), "sg_diffuse_albedo_values": full[:, 6 * L + 3:].reshape(1, N, 3)}
 
 
 # ---- the on-disk hand-off between the stages (optional: extract_and_shade needs none of it) ------------------------------------

@@ -18,6 +18,36 @@ def shard_counts(n_rays, world, tile=128):
     return [int(shard_indices(n_rays, r, world, tile).numel()) for r in range(world)]
 
 
+def shard_indices_by_mask(mask, rank, world, tile=128):
+    """Pixel ids owned by `rank` when the work sits on the masked pixels (stage 2: cost grows with the surface points, not with the
+    pixels): masked and unmasked pixels are dealt separately, tiles of `tile` round-robin, so every rank shades the
+    same number of surface points (to within one tile) whatever the silhouette looks like.  Sorted, identical on every rank."""
+    m = mask.reshape(-1).bool().cpu()
+    ids = torch.arange(m.numel())
+    parts = []
+    for sel in (ids[m], ids[~m]):
+        parts.append(sel[((torch.arange(sel.numel()) // tile) % world) == rank])
+    return torch.cat(parts).sort().values
+
+
+def gather_rows(local, n_rows, rank, world, indices_of, group=None):
+    """local: [n_local, C] values of the rows indices_of(rank) -> full [n_rows, C] on every rank.  ONE collective (all_gather on
+    equally padded shards), then an index scatter; indices_of(r) must give every rank the same answer for every r."""
+    if world == 1:
+        return local
+    idx = [indices_of(r) for r in range(world)]
+    pad = max(int(i.numel()) for i in idx)
+    C = local.shape[1]
+    buf = local.new_zeros(pad, C)
+    buf[: local.shape[0]] = local
+    out = local.new_empty(world * pad, C)
+    dist.all_gather_into_tensor(out, buf, group=group)
+    full = local.new_empty(n_rows, C)
+    for r in range(world):
+        full[idx[r].to(local.device)] = out[r * pad: r * pad + idx[r].numel()]
+    return full
+
+
 def gather_pixels(local, n_rays, rank, world, tile=128, group=None):
     """local: [n_local, C] rendered values of this rank's rays -> full [n_rays, C] image on every rank.
     One collective (all_gather on equally padded shards), then an index scatter to undo the tile interleave."""

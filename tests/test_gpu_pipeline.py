@@ -71,6 +71,30 @@ def test_sharded_render_single_rank_is_identity():
     assert torch.equal(full[:, :3], one["rgb"][0])
 
 
+def test_stage2_sharded_view_matches_unsharded():
+    """render_stage2_view_sharded with the real PSNetwork: a single rank reproduces render_stage2_view bit for bit, and the two
+    surface-balanced shards of a 2-rank deal, rendered one after the other on this GPU, reassemble to the same view."""
+    from psnerf_b200 import sharding
+    *_, conf, sd2, ps = _models("fp32")
+    inp = synth.stage2_input(14, 12, 1, all_surface=False, seed=9, mask_frac=0.5)
+    inp = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in inp.items()}
+    lights = synth.lights(5).cuda()
+    want = pipeline.render_stage2_view(ps, inp, lights, light_batch=2)
+    one = pipeline.render_stage2_view_sharded(ps, inp, lights, 0, 1, light_batch=2)
+    n = inp["uv"].shape[1]
+    for k in ("sg_rgb_values", "visibility", "normal_pred", "sg_diffuse_albedo_values"):
+        assert torch.equal(one[k], want[k].reshape(one[k].shape)), k
+    full = torch.zeros(5, n, 3, device="cuda")
+    for r in range(2):
+        idx = sharding.shard_indices_by_mask(inp["surface_mask"][0], r, 2, tile=16).cuda()
+        sub = dict(inp)
+        for k in pipeline.PER_PIXEL_INPUTS:
+            if k in inp and torch.is_tensor(inp[k]) and inp[k].dim() >= 2 and inp[k].shape[1] == n:
+                sub[k] = torch.index_select(inp[k], 1, idx)
+        full[:, idx] = pipeline.render_stage2_view(ps, sub, lights, light_batch=2)["sg_rgb_values"]
+    assert util.max_abs(full.cpu(), want["sg_rgb_values"].cpu()) < 1e-6
+
+
 @pytest.mark.parametrize("prec", ["fp32", "tc"])
 def test_envmap_relighting_matches_oracle_loop(prec):
     """stage2/eval.py:173-231: ragged light batches over a small lat-long grid, RGB intensities, sum + clip / mean."""
