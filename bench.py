@@ -1,16 +1,22 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the PS-NeRF render hot path on B200 (contract: see DESIGN.md §Measurement).
+"""bench.py — headline benchmark of the PS-NeRF hot path on B200 (contract: DESIGN.md "Measurement").
 
-One "step" = one full Renderer.unisurf pass over a 512x512 view at 128 samples/ray (BASELINE.json configs[1]):
-ray generation, 256-step surface march + 8 secant refinements, interval sampling plan, 33.5 M radiance samples
-(geo MLP + analytic normal + appearance MLP), alpha compositing and surface normals.
-metric: Msamples/s = rays x samples (x lights, 1 for the stage-1 render) / second.
+Headline workload = the metric's own configuration, 512 x 512 rays x 128 samples x 96 lights: ONE relit view through
+psnerf_b200.pipeline.extract_and_shade, i.e. the reference's per-view chain  stage1/shape_extract.py --visibility  ->
+stage2/eval.py --light_batch 96  without the .npy hand-off:
+    ray generation, 512-step surface march + 8 secant refinements, analytic normals   (stage1/model/rendering.py:297-361)
+    shadow-ray visibility: surface points x 96 lights x 128 march samples              (rendering.py:378-408, the rays x samples x lights loop)
+    stage-2 shading of the same points under the same 96 lights                        (stage2/model/renderer.py:110-266)
+metric: Msamples/s = surface points x 128 samples x 96 lights / second  (the unit of the fused shadow-march + shade pass).
+The stage-1 volume render of the same view (BASELINE configs[1], 512 x 512 x 128 spp, lights = 1) is timed in the same run and
+reported under "secondary", with its own roofline and parity block.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--precision tc|fp32] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--precision auto|tc_two_level|tc_mixed|tc|fp32] [--impl reference]
 
-N > 1 (torchrun): every rank renders the ray shard [rank::N] of N views per step (weak scaling: one view's worth
-of rays per GPU) and one NCCL all_gather of the rendered pixels closes the step.
---impl reference: the CPU oracle port of the reference path on a bounded crop of the same workload.
+N > 1 (torchrun): weak scaling - N views per step, every rank runs the chain on its 128-ray tiles of every view and ONE NCCL
+all_gather of the packed per-pixel rows closes the step.  The same line carries "multi_gpu": one view split N ways (strong scaling),
+BASELINE config 4 (stage-2 view sharded by surface pixels) and config 5 (data-parallel train step, strong + weak).
+--impl reference: the CPU oracle port of the same chain on a bounded strided sample of the same view, all host threads.
 """
 import argparse
 import ctypes as C
@@ -27,10 +33,15 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 H = W = 512
-S_IN, S_OUT, MARCH = 96, 32, 256  # 128 samples/ray, bear.yaml ray_marching_steps
+L_LIGHTS, S_SHADOW, MARCH_EXTRACT = 96, 128, 512   # shape_extract: 512 march steps (rendering.py:302); 128 shadow steps (rendering.py:380)
+S_IN, S_OUT, MARCH = 96, 32, 256                   # secondary: 128 samples/ray, bear.yaml ray_marching_steps
 MFLOP_OCC = 0.918016      # occupancy sample, logit row only (2 * 459,008 MAC): what the occupancy kernels compute
-MFLOP_RAD = 2.509824      # radiance sample: fwd 524,544 + reverse 459,008 + app 271,360 MAC (BASELINE.md §3)
+MFLOP_RAD = 2.509824      # radiance sample: fwd 524,544 + reverse 459,008 + app 271,360 MAC (BASELINE.md 3)
+MFLOP_PAIR = 1.04704      # stage-2 (point, light) pair: visibility MLP
+MFLOP_POINT = 0.282368    # stage-2 per-point nets
 PROF_TAGS = ["occ_march", "occ_secant", "radiance", "gradient", "shadow", "s2_vis", "s2_point", "occ_other"]
+SAMPLE_GRID = 24          # CPU legs / parity: a SAMPLE_GRID^2 strided sub-grid of the full view (same hit fraction as the view)
+METRIC = "Msamples/sec (rays x samples x lights)"
 
 
 def load_peaks():
@@ -74,103 +85,195 @@ class ClockSampler:
             self.proc.kill()
         sm = sorted(int(float(r[0])) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
         mx = [int(float(r[1])) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        pw = sorted(float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace(".", "").isdigit())
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in self.rows)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "power_w": pw[len(pw) // 2] if pw else None, "samples": len(sm)}
 
 
-def scene(device, view):
+# ---- the synthetic scene -----------------------------------------------------------------------------------------
+def scene(view):
     from psnerf_b200 import synth
     pose = synth.look_at_pose(20.0 + 37.0 * view, 10.0 + 3.0 * (view % 5))
     return synth.intrinsics(H, W), pose
 
 
-def build_model(device, precision):
+def scene_lights(pose):
     from psnerf_b200 import synth
-    from psnerf_b200.stage1 import NeuralNetwork, Renderer
-    cfg = synth.stage1_cfg(num_points_in=S_IN, num_points_out=S_OUT, ray_marching_steps=MARCH)
+    return synth.lights(L_LIGHTS, axis=tuple((-pose[0, :3, 2]).tolist()))  # upper hemisphere about the view axis
+
+
+def stage1_cfg():
+    from psnerf_b200 import synth
+    return synth.stage1_cfg(num_points_in=S_IN, num_points_out=S_OUT, ray_marching_steps=MARCH)
+
+
+def state_dicts():
+    """Reference-constructor weights under torch.manual_seed(0) for both stages (CPU tensors; the same on every arm)."""
+    from psnerf_b200 import synth
+    from psnerf_b200.stage1 import NeuralNetwork
+    from psnerf_b200.stage2 import PSNetwork
+    cfg = stage1_cfg()
     torch.manual_seed(0)
-    net = NeuralNetwork(cfg).eval()  # geometric init: sphere-like occupancy, ~17 % of the rays hit the surface
+    sd1 = {k: v.detach().clone() for k, v in NeuralNetwork(cfg).state_dict().items()}
+    conf = synth.stage2_conf()
+    torch.manual_seed(0)
+    sd2 = {k: v.detach().clone() for k, v in PSNetwork(conf).state_dict().items()}
+    return cfg, sd1, conf, sd2
+
+
+def build_models(dev, precision):
+    from psnerf_b200.stage1 import NeuralNetwork, Renderer
+    from psnerf_b200.stage2 import PSNetwork
+    cfg, sd1, conf, sd2 = state_dicts()
+    net = NeuralNetwork(cfg)
+    net.load_state_dict(sd1)
+    net = net.eval()  # geometric init: sphere-like occupancy, ~18 % of the rays hit the surface
     net.precision = precision
-    return cfg, net, Renderer(net, cfg, device=device)
+    rend = Renderer(net, cfg, device=dev)
+    ps = PSNetwork(conf)
+    ps.load_state_dict(sd2)
+    ps = ps.to(dev).eval()
+    ps.precision = precision
+    return cfg, net, rend, conf, ps
+
+
+def sample_pixels():
+    """[1, SAMPLE_GRID^2, 2] integer pixels on a regular sub-grid of the whole view and their indices in the x-major pixel order."""
+    step = W // SAMPLE_GRID
+    xs = torch.arange(SAMPLE_GRID) * step + step // 2
+    gx, gy = torch.meshgrid(xs, xs, indexing="ij")
+    pix = torch.stack([gx, gy], -1).long().view(1, -1, 2)
+    return pix, (pix[0, :, 0] * H + pix[0, :, 1])
+
+
+# ---- CPU legs: the oracle port of the same chain ----------------------------------------------------------------------------------
+def oracle_relit_sample(O, cfg, sd1, conf, sd2, pix, K, pose, lights):
+    """The reference chain on the sample pixels: shape_extract(visibility) -> PSNetwork.forward, both through the oracle port."""
+    shp = O.shape_extract(sd1, cfg, pix, K, pose, visibility=True, light_dir=lights, ray_steps=MARCH_EXTRACT)
+    Ks = torch.eye(4).unsqueeze(0)
+    Ks[0, 0, 0] = Ks[0, 1, 1] = K[0, 0, 0]
+    Ks[0, 0, 2], Ks[0, 1, 2] = K[0, 0, 2], K[0, 1, 2]
+    inp = {"intrinsics": Ks, "uv": pix.float(), "pose": pose, "object_mask": shp["mask"], "surface_mask": shp["mask"],
+           "points": shp["points"], "normal": shp["normal"], "light_direction": lights}
+    with torch.no_grad():
+        out = O.psnetwork_forward(sd2, conf, inp)
+    return shp, out
+
+
+def sample_text(n_surf):
+    return ("%dx%d strided sub-grid of the 512x512 view (every %dth pixel in x and y: the view's own hit fraction, %d surface points) "
+            "x 128 shadow samples x 96 lights, oracle port of shape_extract(visibility) -> PSNetwork.forward"
+            % (SAMPLE_GRID, SAMPLE_GRID, W // SAMPLE_GRID, n_surf))
 
 
 def run_reference(args):
-    """CPU arm: the oracle port of the reference path (oracle/psnerf_oracle.py) on a bounded crop, all host threads."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import psnerf_oracle as O
-    from psnerf_b200 import synth
-    from psnerf_b200.stage1 import NeuralNetwork
+    """CPU arm: the oracle port of the reference chain (oracle/psnerf_oracle.py) on the bounded sample, all host threads."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import psnerf_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = synth.stage1_cfg(num_points_in=S_IN, num_points_out=S_OUT, ray_marching_steps=MARCH)
-    torch.manual_seed(0)
-    sd = {k: v.detach().clone() for k, v in NeuralNetwork(cfg).state_dict().items()}
-    crop = args.ref_crop  # crop x crop pixels from the centre of the 512x512 view (rays are independent)
-    K, pose = synth.intrinsics(H, W), synth.look_at_pose(20.0, 10.0)
-    gx, gy = torch.meshgrid(torch.arange(W // 2 - crop // 2, W // 2 + crop // 2), torch.arange(H // 2 - crop // 2, H // 2 + crop // 2),
-                            indexing="ij")
-    pix = torch.stack([gx, gy], -1).long().view(1, -1, 2)
-    units = pix.shape[1] * (S_IN + S_OUT)
-    times = []
+    cfg, sd1, conf, sd2 = state_dicts()
+    K, pose = scene(0)
+    lights = scene_lights(pose)
+    pix, _ = sample_pixels()
+    times, n_surf = [], 0
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        O.unisurf_render(sd, cfg, pix, K, pose, it=100000)
+        shp, _ = oracle_relit_sample(O, cfg, sd1, conf, sd2, pix, K, pose, lights)
         if i >= args.warmup:
             times.append(time.perf_counter() - t0)
+        n_surf = int(shp["mask"].sum())
     ms = 1e3 * sum(times) / len(times)
-    val = units / (ms / 1e3) / 1e6
-    sample = "%dx%d centre crop of the 512x512 view (all rays hit the sphere-init surface region more often than the full view)" % (crop, crop)
-    line = {"impl": "reference", "metric": "Msamples/sec (rays x samples x lights)", "value": val, "unit": "Msamples/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "stage1-unisurf-render 512x512x128spp (BASELINE configs[1]), CPU oracle port of the reference path",
-                       "sample": sample},
+    val = n_surf * S_SHADOW * L_LIGHTS / (ms / 1e3) / 1e6
+    sample = sample_text(n_surf)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": workload_text() + ", CPU oracle port of the reference path", "sample": sample},
             "cpu_baseline": {"value": val, "unit": "Msamples/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
 
-def cpu_baseline_quick():
-    """Oracle port on a 16x16 crop (about 10-20 s of CPU work) for the cpu_baseline object of the main line."""
+def workload_text():
+    return ("relit view 512x512 x 128spp x 96L: shape_extract (512 march steps + 8 secant, analytic normals) + shadow-ray visibility "
+            "(surface points x 96 lights x 128 samples) + stage-2 shading x 96 lights, one pipeline.extract_and_shade call per view")
+
+
+def _stats(a, b):
+    """max-abs / relative-L2 / PSNR of GPU values a against oracle values b (CPU tensors of equal shape)."""
+    if a.numel() == 0:
+        return {"max_abs": 0.0, "rel_l2": 0.0, "psnr": 100.0}
+    d = (a.double() - b.double())
+    mse = float((d ** 2).mean())
+    return {"max_abs": float(d.abs().max()), "rel_l2": float(d.norm() / b.double().norm().clamp_min(1e-30)),
+            "psnr": 100.0 if mse == 0 else float(20.0 * torch.log10(torch.tensor(1.0)) - 10.0 * torch.log10(torch.tensor(mse)))}
+
+
+def cpu_baseline_and_parity(gpu_shape, gpu_out, gpu_render, K, pose, lights):
+    """Runs the oracle port once on the strided sample (about 10-20 s of CPU work): its time is the cpu_baseline of the headline, its
+    outputs are the parity reference for the GPU results AT THE SAME PIXELS of the full-view run (rays are independent).  The same is
+    done for the secondary workload (stage-1 unisurf render at 96+32 samples, 256 march steps)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import psnerf_oracle as O
-    from psnerf_b200 import synth
-    from psnerf_b200.stage1 import NeuralNetwork
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = synth.stage1_cfg(num_points_in=S_IN, num_points_out=S_OUT, ray_marching_steps=MARCH)
-    torch.manual_seed(0)
-    sd = {k: v.detach().clone() for k, v in NeuralNetwork(cfg).state_dict().items()}
-    crop = 16
-    K, pose = synth.intrinsics(H, W), synth.look_at_pose(20.0, 10.0)
-    gx, gy = torch.meshgrid(torch.arange(W // 2 - crop // 2, W // 2 + crop // 2), torch.arange(H // 2 - crop // 2, H // 2 + crop // 2),
-                            indexing="ij")
-    pix = torch.stack([gx, gy], -1).long().view(1, -1, 2)
-    O.unisurf_render(sd, cfg, pix[:, :64], K, pose, it=100000)  # warm-up
+    cfg, sd1, conf, sd2 = state_dicts()
+    pix, idx = sample_pixels()
+    lights = lights.cpu()
+    O.shape_extract(sd1, cfg, pix[:, :32], K, pose, ray_steps=64)  # warm-up of the CPU kernels
     t0 = time.perf_counter()
-    O.unisurf_render(sd, cfg, pix, K, pose, it=100000)
+    shp, out = oracle_relit_sample(O, cfg, sd1, conf, sd2, pix, K, pose, lights)
     dt = time.perf_counter() - t0
-    return {"value": pix.shape[1] * (S_IN + S_OUT) / dt / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "port",
-            "sample": "16x16 centre crop of the 512x512x128spp view, 1 pass, oracle port (torch CPU fp32, %d threads)" % cores}
+    n_surf = int(shp["mask"].sum())
+    cpu = {"value": n_surf * S_SHADOW * L_LIGHTS / dt / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "port",
+           "sample": sample_text(n_surf) + " (torch CPU fp32, %d threads, 1 pass)" % cores}
+    # ---- parity of the headline chain
+    g_mask = gpu_shape["mask"][0][idx].cpu()
+    agree = g_mask == shp["mask"][0]
+    both = agree & shp["mask"][0]
+    par = {"pixels": int(idx.numel()), "surface_points_oracle": n_surf, "mask_agree": float(agree.float().mean()),
+           "gate": "north star: 1e-4 relative; compared on the pixels whose hit / miss decision agrees (flips sit at |occupancy - 0.5| < rounding)"}
+    par["points"] = _stats(gpu_shape["points"][0][idx].cpu()[both], shp["points"][0][both])
+    par["normal"] = _stats(gpu_shape["normal"][0][idx].cpu()[both], shp["normal"][0][both])
+    par["shadow_visibility"] = _stats(gpu_shape["visibility"][:, idx].cpu()[:, both], shp["visibility"][:, both])
+    for k_gpu, name in (("sg_rgb_values", "rgb"), ("sg_diffuse_albedo_values", "albedo"), ("normal_pred", "normal_pred"),
+                        ("visibility", "s2_visibility"), ("sg_specular_rgb_values", "specular")):
+        a = gpu_out[k_gpu][:, idx].cpu()[:, agree]
+        b = out[k_gpu].reshape(a.shape[0], -1, a.shape[-1])[:, agree]
+        par[name] = _stats(a, b)
+    # ---- secondary: stage-1 volume render (configs[1]) on the same sample pixels
+    t0 = time.perf_counter()
+    ref = O.unisurf_render(sd1, cfg, pix, K, pose, it=100000)
+    dt2 = time.perf_counter() - t0
+    m2 = gpu_render["mask_pred"][idx].cpu()
+    ag2 = m2 == ref["mask_pred"]
+    par2 = {"pixels": int(idx.numel()), "mask_agree": float(ag2.float().mean()),
+            "rgb": _stats(gpu_render["rgb"][0][idx].cpu()[ag2], ref["rgb"][0][ag2]),
+            "normal": _stats(gpu_render["normal_pred"][0][idx].cpu()[ag2], ref["normal_pred"][0][ag2]),
+            "acc": _stats(gpu_render["acc_map"][0][idx].cpu()[ag2], ref["acc_map"][0][ag2])}
+    cpu2 = {"value": idx.numel() * (S_IN + S_OUT) / dt2 / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "port",
+            "sample": "the same %d pixels, unisurf render at 96+32 samples / 256 march steps" % idx.numel()}
+    return cpu, par, cpu2, par2
 
 
-def ncu_traffic(precision, root=None):
-    """DRAM read + write bytes of ONE launch of the radiance kernel on this workload, from the newest committed ncu summary under
-    profiles/ that holds a capture of k_tc_rad taken at this precision (captures carry a "precision" tag; untagged ones are 'tc')."""
-    pdir = os.path.join(root or ROOT, "profiles")
+def ncu_capture(kernel_substr, workload):
+    """{dram_bytes_total, file} of ONE launch of a kernel on this bench's workload from the newest committed ncu summary under
+    profiles/ whose capture carries the matching "workload" tag, or (None, None)."""
+    pdir = os.path.join(ROOT, "profiles")
     try:
-        cands = sorted(f for f in os.listdir(pdir) if "_ncu_v" in f and f.endswith(".json"))
+        cands = sorted(f for f in os.listdir(pdir) if "_ncu_" in f and f.endswith(".json"))
     except OSError:
         return None, None
     for name in reversed(cands):
         try:
             with open(os.path.join(pdir, name)) as f:
-                caps = [c for c in json.load(f) if "k_tc_rad" in c.get("kernel", "") and c.get("precision", "tc") == precision]
+                caps = [c for c in json.load(f) if kernel_substr in c.get("kernel", "") and c.get("workload") == workload]
             if caps:
                 big = max(caps, key=lambda c: c["metrics"]["gpu__time_duration.sum"]["value"])
                 return big["dram_bytes_total"], name
@@ -191,101 +294,213 @@ def _time_cuda(fn, reps=2):
     return a.elapsed_time(b) / reps
 
 
-def extra_workloads(dev, precision, rend, view, peaks):
-    """The other BASELINE configurations, timed once each (device-resident inputs, CUDA events; not the headline value):
-    configs[2] stage-2 shading 512x512 x 96 lights (all-surface synthetic points) and the 96-light shadow-ray pass
-    (rays x 128 samples x lights) on the surface found by the stage-1 render of the bench view."""
+def collect_kernels(lib, steps):
+    nt = len(PROF_TAGS)
+    pl, pms, prow = (C.c_int64 * nt)(), (C.c_double * nt)(), (C.c_double * nt)()
+    lib.psn_profile_collect(nt, pl, pms, prow)
+    kern = {}
+    for i, t in enumerate(PROF_TAGS):
+        if pl[i]:
+            kern[t] = {"launches_per_step": pl[i] / steps, "ms_per_launch": pms[i] / pl[i], "ms_per_step": pms[i] / steps,
+                       "rows_per_launch": prow[i] / pl[i]}
+    return kern
+
+
+# ---- secondary / other BASELINE configurations --------------------------------------------------------------------------------------
+def secondary_stage1_render(lib, dev, rend, precision, view, peaks, steps):
+    """BASELINE configs[1]: Renderer.unisurf over the 512x512 view at 96+32 samples/ray, 256 march steps (the round-1 headline)."""
+    from psnerf_b200 import synth
+    K, pose = view
+    pix = synth.pixel_grid_xmajor(H, W).to(dev)
+
+    def step():
+        return rend(pix, K, pose, None, "unisurf", add_noise=False, eval_=True, it=100000)
+    for _ in range(2):
+        step()
+    lib.psn_profile_enable(1)
+    ms = _time_cuda(step, reps=steps)
+    kern = collect_kernels(lib, steps + 1)
+    lib.psn_profile_enable(0)
+    units = H * W * (S_IN + S_OUT)
+    sec = {"workload": "stage1-unisurf-render 512x512x128spp (BASELINE configs[1]): %d march steps + 8 secant, %d+%d samples/ray, lights=1"
+                       % (MARCH, S_IN, S_OUT),
+           "ms_per_step": ms, "value": units / (ms / 1e3) / 1e6, "unit": "Msamples/s", "kernels": kern}
+    rad = kern.get("radiance")
+    if rad:
+        tf = rad["rows_per_launch"] * MFLOP_RAD * 1e6 / (rad["ms_per_launch"] * 1e-3) / 1e12
+        traffic, src = ncu_capture("k_tc_rad", "stage1_render")
+        issued = {"tc": 3.0, "fp32": None}.get(precision, (3.0 * 0.918 + 1.0 * (MFLOP_RAD - 0.918)) / MFLOP_RAD)
+        sec["roofline"] = {"bound": "tensor", "kernel": "k_tc_rad (geo fwd + analytic normal + app MLP)", "achieved": tf, "peak": peaks["tflops"],
+                           "unit": "TFLOP/s", "frac": tf / peaks["tflops"], "issued_frac": None if issued is None else issued * tf / peaks["tflops"],
+                           "traffic": traffic, "traffic_source": src, "flops_per_row": MFLOP_RAD * 1e6}
+    occ = kern.get("occ_march")
+    if occ:
+        tfo = occ["rows_per_launch"] * MFLOP_OCC * 1e6 / (occ["ms_per_launch"] * 1e-3) / 1e12
+        sec["march"] = {"ms": occ["ms_per_launch"], "achieved_TFLOPs": tfo, "frac": tfo / peaks["tflops"],
+                        "note": "all N x 256 proposals; under tc_two_level the first level runs in ONE fp16 pass, so algorithmic and issued FLOPs coincide there"}
+    return sec, step()
+
+
+def other_workloads(dev, precision, rend, ps, view, lights, peaks):
+    """The remaining BASELINE configurations at N = 1, timed once each with device-resident inputs (CUDA events)."""
     from psnerf_b200 import synth, engine
-    from psnerf_b200.stage2 import PSNetwork
     out = {}
-    conf = synth.stage2_conf()
-    torch.manual_seed(0)
-    ps = PSNetwork(conf).to(dev).eval()
-    ps.precision = precision
-    inp = synth.stage2_input(H, W, 96, all_surface=True)
+    # configs[2]: stage-2 shading 512x512 x 96 lights on the all-surface synthetic points
+    inp = synth.stage2_input(H, W, L_LIGHTS, all_surface=True)
     inp = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in inp.items()}
     ms = _time_cuda(lambda: ps(inp))
-    pairs = H * W * 96
-    tf = (pairs * 1.04704 + H * W * 0.282368) * 1e6 / (ms * 1e-3) / 1e12
-    out["stage2_shade_512x512x96L"] = {"ms": ms, "Mpairs_per_s": pairs / ms / 1e3, "algorithmic_TFLOPs": tf, "frac_of_peak": tf / peaks["tflops"],
-                                       "hbm_output_GBps": 3 * pairs * 3 * 4 / (ms * 1e-3) / 1e9}
+    pairs = H * W * L_LIGHTS
+    tf = (pairs * MFLOP_PAIR + H * W * MFLOP_POINT) * 1e6 / (ms * 1e-3) / 1e12
+    out["stage2_shade_512x512x96L_all_surface"] = {"ms": ms, "Mpairs_per_s": pairs / ms / 1e3, "algorithmic_TFLOPs": tf,
+                                                   "frac_of_peak": tf / peaks["tflops"],
+                                                   "hbm_output_GBps": 3 * pairs * 3 * 4 / (ms * 1e-3) / 1e9}
+    del inp
+    # the shadow pass alone, box-culled (default) against the unculled evaluation of every step (what the reference executes)
     K, pose = view
     g, _ = rend._geo_app()
     origin, dirs = rend._rays(synth.pixel_grid_xmajor(H, W).to(dev), K, pose)
-    d = engine.raymarch(g, origin, dirs, 2.0, 2.0, 512, 8, 0.5, rend.model._prec())
+    d = engine.raymarch(g, origin, dirs, 2.0, 2.0, MARCH_EXTRACT, 8, 0.5, rend.model._prec())
     obj, pts = rend._surface(d, origin, dirs)
     surf = pts[obj].contiguous()
-    lights = synth.lights(96, axis=tuple((-pose[0, :3, 2]).tolist())).to(dev)
-    ms2 = _time_cuda(lambda: engine.shadow_visibility(g, surf, lights, precision=rend.model._prec()), reps=1)
-    samples = surf.shape[0] * 96 * 128
-    tf2 = samples * MFLOP_OCC * 1e6 / (ms2 * 1e-3) / 1e12
-    out["shadow_visibility_96L_x128"] = {"surface_points": int(surf.shape[0]), "ms": ms2, "Msamples_per_s": samples / ms2 / 1e3,
-                                         "algorithmic_TFLOPs": tf2, "frac_of_peak": tf2 / peaks["tflops"]}
-    # BASELINE configs[4]: stage-2 train step, 4096 in-mask pixels x 96 lights (+ 8 vis-train lights, xyz jitter), fwd + bwd + Adam
+    lt = lights.to(dev)
+    ms_c = _time_cuda(lambda: engine.shadow_visibility(g, surf, lt, precision=rend.model._prec()), reps=2)
+    vis_c, st = engine.shadow_visibility(g, surf, lt, precision=rend.model._prec(), return_stats=True)
+    os.environ["PSNERF_B200_SHADOW_UNCULLED"] = "1"
+    try:
+        ms_u = _time_cuda(lambda: engine.shadow_visibility(g, surf, lt, precision=rend.model._prec()), reps=1)
+        vis_u = engine.shadow_visibility(g, surf, lt, precision=rend.model._prec())
+    finally:
+        os.environ.pop("PSNERF_B200_SHADOW_UNCULLED", None)
+    out["shadow_visibility_96L_x128"] = {
+        "surface_points": int(surf.shape[0]), "nominal_samples": st["nominal"], "evaluated_samples": st["evaluated"],
+        "ms_box_culled": ms_c, "ms_every_step": ms_u, "max_abs_diff_culled_vs_every_step": float((vis_c - vis_u).abs().max()),
+        "Msamples_per_s_nominal": st["nominal"] / ms_c / 1e3,
+        "tensor_TFLOPs_box_culled": st["evaluated"] * MFLOP_OCC * 1e6 / (ms_c * 1e-3) / 1e12,
+        "tensor_TFLOPs_every_step": st["nominal"] * MFLOP_OCC * 1e6 / (ms_u * 1e-3) / 1e12}
+    del vis_c, vis_u
+    out.update(train_steps(dev, rend, ps, view, world=1, rank=0))
+    return out
+
+
+def train_steps(dev, rend, ps, view, world, rank, n_px=4096, tag="", dist=None):
+    """BASELINE configs[4]: stage-2 train step over n_px in-mask pixels x 96 lights (+ 8 vis-train lights, xyz jitter), forward +
+    losses + backward (+ ONE all_reduce of the gradients when world > 1) + Adam; and its stage-1 analogue over n_px rays x 128 samples."""
+    from psnerf_b200 import synth, sharding
     from psnerf_b200.stage2.loss import MainLoss, NormalLoss
+    out = {}
     ps.train()
-    n_px = 4096
-    tin = synth.stage2_input(64, 64, 96, all_surface=True, seed=11)
+    side = int(round(n_px ** 0.5))
+    n_px = side * side
+    tin = synth.stage2_input(side, side, L_LIGHTS, all_surface=True, seed=11 + rank)
     tin = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in tin.items()}
-    gen = torch.Generator().manual_seed(1)
-    lraw = torch.nn.Parameter(synth.lights(96).to(dev) + 0.01)
-    linten = torch.nn.Parameter(torch.full((96, 1), 2.0, device=dev))
+    gen = torch.Generator().manual_seed(1 + rank)
+    lraw = torch.nn.Parameter(synth.lights(L_LIGHTS).to(dev) + 0.01)
+    linten = torch.nn.Parameter(torch.full((L_LIGHTS, 1), 2.0, device=dev))
     tin["light_vis_train"] = synth.lights(8, seed=5).to(dev)
     tin["vis_train_gt"] = torch.rand(8, n_px, generator=gen).to(dev)
-    tin["visibility"] = torch.rand(96, n_px, generator=gen).to(dev)
-    gt = {"rgb": torch.rand(96, n_px, 3, generator=gen).to(dev)}
+    tin["visibility"] = torch.rand(L_LIGHTS, n_px, generator=gen).to(dev)
+    gt = {"rgb": torch.rand(L_LIGHTS, n_px, 3, generator=gen).to(dev)}
     lm, ln = MainLoss(1.0, "L1", 0.05, 0.01, 1.0), NormalLoss(1.0, 0.05)
-    opt = torch.optim.Adam(list(ps.parameters()) + [lraw, linten], lr=5e-4)
+    opt = torch.optim.Adam(list(ps.parameters()) + [lraw, linten], lr=1e-6)
 
-    def train_step():
+    class _Lights(torch.nn.Module):  # the light tables are reduced with the model's gradients (ADVICE: replicas must not diverge)
+        def __init__(self):
+            super().__init__()
+            self.a, self.b = lraw, linten
+
+    def s2_step():
         tin["light_direction"] = torch.nn.functional.normalize(lraw, p=2, dim=-1)
         tin["light_intensity"] = linten
         o = ps(tin)
         loss = lm(o, gt, tin)["loss"] + ln(o)["loss"]
         opt.zero_grad(set_to_none=True)
         loss.backward()
+        if world > 1:
+            sharding.allreduce_gradients(torch.nn.ModuleList([ps, _Lights()]), world)
         opt.step()
-    ms3 = _time_cuda(train_step, reps=5)
-    out["stage2_train_step_4096px_96L_8vis"] = {"ms_fwd_bwd_adam": ms3, "Mpairs_per_s": n_px * 96 / ms3 / 1e3,
-                                                "note": "PSNetwork.forward + MainLoss/NormalLoss + backward + Adam (stage2/trainer.py:394-410); "
-                                                        "96-light visibility pass detached (tensor-core inference kernel), fp32 GEMM backward"}
+    ms3 = _time_dist(s2_step, 5, dev, dist)
+    out["stage2_train_step%s" % tag] = {"pixels_per_rank": n_px, "lights": L_LIGHTS, "vis_train_lights": 8, "ms_fwd_bwd_adam": ms3,
+                                        "Mpairs_per_s": world * n_px * L_LIGHTS / ms3 / 1e3}
     ps.eval()
-    # Stage-1 analogue of configs[4] (SURVEY.md §8d / §8f-2): 4096 random rays x 128 samples of the bench view, training forward
-    # (inference-kernel surface search + differentiable fp32 field incl. the double-backward normals) + Loss + backward + Adam
+    del opt
     try:
         from psnerf_b200.stage1 import Loss
+        K, pose = view
         net = rend.model
         net.train()
-        gen = torch.Generator().manual_seed(2)
-        n_rays = 4096
+        gen = torch.Generator().manual_seed(2 + rank)
         pix_all = synth.pixel_grid_xmajor(H, W)
-        sel = torch.randperm(H * W, generator=gen)[:n_rays]
+        sel = torch.randperm(H * W, generator=gen)[:n_px]
         pix_t = pix_all[:, sel].to(dev)
-        rgb_gt = torch.rand(1, n_rays, 3, generator=gen).to(dev)
-        n_gt = torch.nn.functional.normalize(torch.randn(1, n_rays, 3, generator=gen), dim=-1).to(dev)
-        n_mask = torch.rand(1, n_rays, generator=gen).to(dev) > 0.5
-        m_gt = (torch.rand(1, n_rays, generator=gen) > 0.5).float().to(dev)
-        m_valid = torch.ones(1, n_rays, dtype=torch.bool, device=dev)
+        rgb_gt = torch.rand(1, n_px, 3, generator=gen).to(dev)
+        n_gt = torch.nn.functional.normalize(torch.randn(1, n_px, 3, generator=gen), dim=-1).to(dev)
+        n_mask = torch.rand(1, n_px, generator=gen).to(dev) > 0.5
+        m_gt = (torch.rand(1, n_px, generator=gen) > 0.5).float().to(dev)
+        m_valid = torch.ones(1, n_px, dtype=torch.bool, device=dev)
         crit = Loss(1.0, 0.01, 0.05, 0.1, device=dev)
-        opt1 = torch.optim.Adam(net.parameters(), lr=1e-6)  # tiny rate: the timing loop must not walk the field away
+        opt1 = torch.optim.Adam(net.parameters(), lr=1e-7)  # tiny rate: the timing loop must not walk the field away
 
         def s1_step():
             o = rend(pix_t, K, pose, None, "unisurf", add_noise=True, eval_=False, it=100000)
             loss = crit(o, rgb_gt, n_gt, n_mask, o["acc_map"], m_gt, m_valid)["loss"]
             opt1.zero_grad(set_to_none=True)
             loss.backward()
+            if world > 1:
+                sharding.allreduce_gradients(net, world)
             opt1.step()
-        ms4 = _time_cuda(s1_step, reps=3)
-        samples = n_rays * (S_IN + S_OUT)
-        out["stage1_train_step_4096rays_x128"] = {
-            "ms_fwd_bwd_adam": ms4, "Msamples_per_s": samples / ms4 / 1e3,
-            "note": "Renderer.forward('unisurf', eval_=False) + Loss + backward + Adam (stage1/model/training.py:46-60,141-198): fp32 GEMM "
-                    "forward/backward with saved activations, create_graph normals by a hand-derived second-order pass"}
+        ms4 = _time_dist(s1_step, 3, dev, dist)
+        out["stage1_train_step%s" % tag] = {"rays_per_rank": n_px, "samples_per_ray": S_IN + S_OUT, "ms_fwd_bwd_adam": ms4,
+                                            "Msamples_per_s": world * n_px * (S_IN + S_OUT) / ms4 / 1e3}
         net.eval()
         del opt1
         torch.cuda.empty_cache()
     except Exception as e:  # an extra: never let it take the headline line down
-        out["stage1_train_step_4096rays_x128"] = {"error": repr(e)[:300]}
+        out["stage1_train_step%s" % tag] = {"error": repr(e)[:300]}
+    return out
+
+
+def _time_dist(fn, reps, dev, dist):
+    """fn timed with CUDA events after one warm-up call; with a process group: barrier on both sides, max over ranks."""
+    fn()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    ms = a.elapsed_time(b) / reps
+    if dist is not None:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    return ms
+
+
+def multi_gpu_block(dev, rend, ps, view, lights, rank, world, td, ms_single_view):
+    """What only exists at N > 1: one view split N ways (strong scaling of the headline chain), BASELINE config 4
+    (one stage-2 view sharded by surface pixels, gathered) and config 5 (data-parallel train steps, strong and weak)."""
+    from psnerf_b200 import pipeline, synth
+    K, pose = view
+    lt = lights.to(dev)
+    out = {}
+    ms = _time_dist(lambda: pipeline.extract_and_shade_sharded(rend, ps, H, W, K, pose, lt, rank, world), 3, dev, td)
+    out["strong_one_view"] = {"ms_per_view": ms, "note": "the headline chain on ONE 512x512x96L view, rays dealt over the ranks, one "
+                                                         "all_gather of the packed rows; compare with ms_per_step of the N=1 run"}
+    inp = synth.stage2_input(H, W, L_LIGHTS, all_surface=False, seed=9, mask_frac=0.25)
+    inp = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in inp.items()}
+    ms4 = _time_dist(lambda: pipeline.render_stage2_view_sharded(ps, inp, lt, rank, world), 3, dev, td)
+    n_surf = int(inp["surface_mask"].sum())
+    out["config4_stage2_view_sharded_96L"] = {"ms_per_view": ms4, "surface_points": n_surf, "Mpairs_per_s": n_surf * L_LIGHTS / ms4 / 1e3,
+                                              "note": "render_stage2_view_sharded: surface pixels balanced over the ranks, 96 lights, one "
+                                                      "all_gather of [N, 6L+..] rows"}
+    del inp
+    out.update(train_steps(dev, rend, ps, view, world, rank, n_px=4096, tag="_ddp_weak_4096_per_rank", dist=td))
+    out.update(train_steps(dev, rend, ps, view, world, rank, n_px=max(4096 // world, 64), tag="_ddp_strong_4096_total", dist=td))
     return out
 
 
@@ -312,6 +527,12 @@ def emit(line):
         os.write(_JSON_FD, data)
 
 
+DTYPES = {"tc": "f16x3-split operands, f32 accumulate", "fp32": "f32",
+          "tc_mixed": "f16x3-split operands (softplus stacks) + f16 single pass (appearance side), f32 accumulate",
+          "tc_two_level": "f16x3-split operands (softplus stacks; march proposals away from the threshold in one f16 pass) + f16 single pass "
+                          "(appearance side), f32 accumulate"}
+
+
 def main():
     _claim_stdout()
     ap = argparse.ArgumentParser()
@@ -320,15 +541,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--precision", default="auto", choices=["auto", "tc", "tc_mixed", "tc_two_level", "fp32"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--ref-crop", type=int, default=24)
+    ap.add_argument("--sample-grid", type=int, default=SAMPLE_GRID, help="side of the strided pixel sub-grid the CPU legs run on")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
+    globals()["SAMPLE_GRID"] = args.sample_grid
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
     if args.impl == "reference":
         return run_reference(args)
 
-    from psnerf_b200 import _binding as B, engine, synth
+    from psnerf_b200 import _binding as B, engine, pipeline, sharding, synth
     if not os.path.exists(B.LIB_PATH):
         import __graft_entry__ as ge
         ge.build()
@@ -338,39 +560,44 @@ def main():
     dist = world > 1
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    td = None
     if dist:
         import torch.distributed as td
         td.init_process_group("nccl", device_id=dev)
     lib = B.load()
     precision = args.precision
     if precision == "auto":
-        # the fastest program that holds the parity gate (tests/test_gpu_tc_mixed.py); the full-split 'tc' render is timed next to it
-        precision = "tc_mixed" if engine.tc_available() else "fp32"
-    cfg, net, rend = build_model(dev, precision)
+        precision = "tc_two_level"  # the engine default: fastest program that holds the parity gate (tests/test_gpu_parity_at_size.py)
+    cfg, net, rend, conf, ps = build_models(dev, precision)
     N = H * W
-    S = S_IN + S_OUT
-    pix_host = synth.pixel_grid_xmajor(H, W).pin_memory()      # long [1,N,2]
     n_views = world                                            # weak scaling: one view's worth of rays per GPU
-    views = [scene(dev, v) for v in range(n_views)]
-    from psnerf_b200 import sharding
+    views = [scene(v) for v in range(n_views)]
+    lights = [scene_lights(pose).to(dev) for (_, pose) in views]
+    pix_all = synth.pixel_grid_xmajor(H, W)                    # long [1,N,2]
     shard = sharding.shard_indices(N, rank, world)             # this rank's 128-ray tiles of every view (round-robin)
-    pix_dev = pix_host[:, shard].to(dev)
+    pix_host = pix_all[:, shard].contiguous().pin_memory()
+    pix_dev = pix_host.to(dev)
     n_local = pix_dev.shape[1]
-    gather_buf = torch.empty(world, n_views * n_local, 7, device=dev) if dist else None
-    out_host = torch.empty(n_views * n_local, 7, dtype=torch.float32).pin_memory()
-    pix_host_shard = pix_host[:, shard].contiguous().pin_memory()
+    layout, width, row_w = pipeline.relit_row_layout(ps, L_LIGHTS, True)
+    gather_buf = torch.empty(world, n_views * n_local, row_w, device=dev) if dist else None
+    # e2e result read-back: the relit images [L,n,3], albedo, normal, mask and the shadow visibilities [L,n] (what eval.py / shape_extract.py save)
+    col_rgb = next(off for key, _, _, off, _ in layout if key == "sg_rgb_values")
+    col_alb = next(off for key, _, _, off, _ in layout if key == "sg_diffuse_albedo_values")
+    host_cols = 3 * L_LIGHTS + 3 + (row_w - width)
+    out_host = torch.empty(n_views * n_local, host_cols, dtype=torch.float32).pin_memory()
 
     def step(e2e=False):
-        outs = []
-        for (K, pose) in views:
-            p = pix_host_shard.to(dev, non_blocking=True) if e2e else pix_dev
-            o = rend(p, K, pose, None, "unisurf", add_noise=False, eval_=True, it=100000)
-            outs.append(torch.cat([o["rgb"][0], o["normal_pred"][0], o["acc_map"][0].unsqueeze(-1)], -1))
-        res = torch.cat(outs, 0)
+        rows = []
+        for (K, pose), lt in zip(views, lights):
+            p = pix_host.to(dev, non_blocking=True) if e2e else pix_dev
+            rows.append(pipeline.extract_and_shade_rows(rend, ps, H, W, K, pose, lt, p))
+        res = rows[0] if len(rows) == 1 else torch.cat(rows, 0)
         if dist:
             td.all_gather_into_tensor(gather_buf.view(-1), res.view(-1))  # the single NCCL pixel gather
         if e2e:
-            out_host.copy_(res, non_blocking=True)
+            out_host[:, :3 * L_LIGHTS].copy_(res[:, col_rgb:col_rgb + 3 * L_LIGHTS], non_blocking=True)
+            out_host[:, 3 * L_LIGHTS:3 * L_LIGHTS + 3].copy_(res[:, col_alb:col_alb + 3], non_blocking=True)
+            out_host[:, 3 * L_LIGHTS + 3:].copy_(res[:, width:], non_blocking=True)
         return res
 
     def timed(e2e, steps):
@@ -393,8 +620,23 @@ def main():
         return ms
 
     for _ in range(args.warmup):
-        step(False)
+        res = step(False)
     torch.cuda.synchronize()
+    # surface points of this rank's rays over all views -> units of the whole job (counted once, outside the timed region), and the
+    # number of in-box shadow samples the MLP kernel evaluates for them (device-side list length, read back here for the roofline)
+    n_surf = (res[:, width] > 0.5).sum().to(torch.int64)
+    evaluated_rank = 0
+    g_geo, _ = rend._geo_app()
+    for v in range(n_views):
+        rows_v = res[v * n_local:(v + 1) * n_local]
+        surf_v = rows_v[:, width + 1:width + 4][rows_v[:, width] > 0.5].contiguous()
+        if surf_v.shape[0] > 0:
+            _, st = engine.shadow_visibility(g_geo, surf_v, lights[v], precision=rend.model._prec(), return_stats=True)
+            evaluated_rank += st["evaluated"]
+    if dist:
+        td.all_reduce(n_surf)
+    n_surf = int(n_surf)
+    del res
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -403,85 +645,67 @@ def main():
     l0 = lib.psn_launch_count()
     ms = timed(False, args.steps)
     launches = (lib.psn_launch_count() - l0) / args.steps
-    nt = len(PROF_TAGS)
-    pl, pms, prow = (C.c_int64 * nt)(), (C.c_double * nt)(), (C.c_double * nt)()
-    lib.psn_profile_collect(nt, pl, pms, prow)
+    kern = collect_kernels(lib, args.steps)
     lib.psn_profile_enable(0)
     step(True)
     ms_e2e = timed(True, args.steps)
     clocks = sampler.stop() if rank == 0 else None
-    units = n_views * n_local * S * world  # whole job per step
+    units = n_surf * S_SHADOW * L_LIGHTS  # whole job per step: every surface point's 128 shadow samples towards every light
     value = units / (ms / 1e3) / 1e6
+    mg = None
+    if dist:
+        mg = multi_gpu_block(dev, rend, ps, views[0], lights[0], rank, world, td, ms)
     if rank == 0:
         peaks = load_peaks()
-        kern = {}
-        for i, t in enumerate(PROF_TAGS):
-            if pl[i]:
-                kern[t] = {"launches_per_step": pl[i] / args.steps, "ms_per_launch": pms[i] / pl[i], "rows_per_launch": prow[i] / pl[i]}
-        rad = kern.get("radiance")
         roof = None
-        if rad:
-            tf = rad["rows_per_launch"] * MFLOP_RAD * 1e6 / (rad["ms_per_launch"] * 1e-3) / 1e12
-            traffic, traffic_src = ncu_traffic(precision)  # dram read+write bytes per launch of this kernel on this workload
-            roof = {"bound": "tensor", "kernel": "radiance (geo fwd + analytic normal + app MLP), %s path" % precision,
-                    "achieved": tf, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": tf / peaks["tflops"], "traffic": traffic,
-                    "traffic_note": "ncu capture summarised in profiles/%s: the unorm16 sigma' stash + fp32 parked partial of the analytic-normal "
-                                    "pass (5 KB/sample written, re-read from L2; algorithmic I/O is 20 B/sample); DRAM stays below 15 %% of peak"
-                                    % traffic_src,
-                    "peak_source": peaks["src"], "flops_per_row": MFLOP_RAD * 1e6,
-                    "issued_frac": (3.0 * tf / peaks["tflops"]) if precision == "tc" else None}
-            if precision in ("tc_mixed", "tc_two_level"):  # three passes for the 8 softplus layers (0.918 MFLOP), one for the remaining 1.592 MFLOP
-                roof["issued_frac"] = (3.0 * 0.918 + 1.0 * (MFLOP_RAD - 0.918)) / MFLOP_RAD * tf / peaks["tflops"]
-            occ = kern.get("occ_march")
-            if occ:
-                tfo = occ["rows_per_launch"] * MFLOP_OCC * 1e6 / (occ["ms_per_launch"] * 1e-3) / 1e12
-                roof["second_kernel"] = {"kernel": "occ_march", "achieved": tfo, "frac": tfo / peaks["tflops"], "flops_per_row": MFLOP_OCC * 1e6}
-        line = {"metric": "Msamples/sec (rays x samples x lights)", "value": value, "unit": "Msamples/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": {"tc": "f16x3-split operands, f32 accumulate", "fp32": "f32",
-                                            "tc_mixed": "f16x3-split operands (softplus stack) + f16 single pass (appearance side), f32 accumulate",
-                                            "tc_two_level": "tc_mixed + two-level march (f16 single pass, f16x3 near the threshold)"}[precision],
+        sh = kern.get("shadow")
+        if sh:
+            # dominant kernel: k_tc_occ over the box-culled shadow list; its rows are the in-box samples (device-side count)
+            rows_per_launch = evaluated_rank / max(sh["launches_per_step"], 1.0)
+            tf = rows_per_launch * MFLOP_OCC * 1e6 / (sh["ms_per_launch"] * 1e-3) / 1e12
+            traffic, src = ncu_capture("k_tc_occ", "relit_view_shadow")
+            roof = {"bound": "tensor", "kernel": "k_tc_occ<MODE_OUT> over the box-culled shadow list (GEN_SHADOW_LIST), %s" % precision,
+                    "achieved": tf, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": tf / peaks["tflops"],
+                    "issued_frac": None if precision == "fp32" else 3.0 * tf / peaks["tflops"], "traffic": traffic, "traffic_source": src,
+                    "peak_source": peaks["src"], "flops_per_row": MFLOP_OCC * 1e6, "rows_per_launch": rows_per_launch,
+                    "share_of_step": sh["ms_per_step"] / ms,
+                    "note": "rows = in-box shadow samples actually evaluated (the reference also evaluates the out-of-box steps and then "
+                            "zeroes them, rendering.py:402-404); nominal rows would be %d per view" % (n_surf // n_views * S_SHADOW * L_LIGHTS)}
+        line = {"metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPES[precision],
                 "data": "synthetic",
-                "config": {"workload": "stage1-unisurf-render 512x512x128spp (BASELINE configs[1]): %d march steps + 8 secant, %d+%d samples/ray, "
-                                       "lights=1" % (MARCH, S_IN, S_OUT),
-                           "views_per_step": n_views, "rays_per_gpu_per_step": n_views * n_local, "parallelism": "ray-shard x%d" % world,
-                           "precision": precision, "l2": "per-step working set (>=400 MB of samples / occupancies) exceeds the 126 MB L2",
-                           "weights": "reference constructors, torch.manual_seed(0) (geometric init)"},
+                "config": {"workload": workload_text(), "views_per_step": n_views, "rays_per_gpu_per_step": n_views * n_local,
+                           "surface_points_per_step": n_surf, "units_per_step": units,
+                           "units": "surface points x 128 shadow samples x 96 lights (SURVEY.md 8d); the march proposals (rays x 512) and the "
+                                    "stage-2 pairs (points x 96) of the same step are not counted",
+                           "parallelism": "ray-shard x%d" % world, "precision": precision,
+                           "l2": "per-step working set (268 MB of march occupancies, >= 600 MB of shadow lists, 1 GB of outputs) exceeds the 126 MB L2",
+                           "weights": "reference constructors, torch.manual_seed(0) (stage 1: geometric init)"},
                 "gpu_launches": launches, "clocks": clocks,
                 "e2e": {"value": units / (ms_e2e / 1e3) / 1e6, "unit": "Msamples/s", "ms_per_step": ms_e2e,
-                        "h2d_bytes_per_step": n_views * n_local * 2 * 8, "d2h_bytes_per_step": n_views * n_local * 7 * 4},
+                        "h2d_bytes_per_step": n_views * n_local * 2 * 8, "d2h_bytes_per_step": n_views * n_local * host_cols * 4},
                 "roofline": roof, "kernels": kern}
-        if world == 1 and not args.no_extras:
-            x_prec = "tc" if precision in ("tc_mixed", "tc_two_level") else precision  # the other workloads have no mixed program: plain 'tc'
-            extras = {}
-            res_bench = None
-            if precision in ("tc_mixed", "tc_two_level"):
+        if mg is not None:
+            line["multi_gpu"] = mg
+        if world == 1:
+            K, pose = views[0]
+            sec, gpu_render = secondary_stage1_render(lib, dev, rend, precision, views[0], peaks, 3)
+            line["secondary"] = {"stage1_unisurf_512x512x128spp": sec}
+            if not args.no_cpu_baseline:
+                full = step(False)
+                gshape, gout = pipeline.unpack_relit_rows(full, ps, L_LIGHTS, True)
+                cpu, par, cpu2, par2 = cpu_baseline_and_parity(gshape, gout, gpu_render, K, pose, lights[0])
+                line["cpu_baseline"] = cpu
+                line["parity"] = par
+                sec["cpu_baseline"] = cpu2
+                sec["parity"] = par2
+                del full, gshape, gout
+            del gpu_render
+            if not args.no_extras:
                 try:
-                    res_bench = step(False).clone()  # [rays, 7] = rgb, normal, acc of the benched precision
-                except Exception:
-                    res_bench = None
-            net.precision = x_prec
-            if precision in ("tc_mixed", "tc_two_level"):
-                try:  # the same headline step with every product in the three-pass split ('tc'): time and output difference
-                    ms_tc = _time_cuda(lambda: step(False), reps=2)
-                    extras["headline_step_full_split_tc"] = {"ms_per_step": ms_tc, "Msamples_per_s": units / (ms_tc / 1e3) / 1e6,
-                                                             "note": "--precision tc: feature head, reverse sweep and appearance MLP in three passes too"}
-                    if res_bench is not None:
-                        res_tc = step(False)
-                        extras["headline_step_full_split_tc"]["benched_vs_full_split"] = {
-                            "rgb_max_abs_diff": float((res_bench[:, :3] - res_tc[:, :3]).abs().max()),
-                            "normal_identical": bool(torch.equal(res_bench[:, 3:6], res_tc[:, 3:6])),
-                            "acc_identical": bool(torch.equal(res_bench[:, 6], res_tc[:, 6])),
-                            "gate": "north star: 1e-4 relative; tests/test_gpu_tc_mixed.py holds rgb to 2e-5 of 'tc' and alpha / normals bit-identical"}
-                        del res_tc
+                    line["other_workloads"] = other_workloads(dev, precision, rend, ps, views[0], lights[0], peaks)
                 except Exception as e:
-                    extras["headline_step_full_split_tc"] = {"error": repr(e)[:300]}
-            del res_bench
-            extras.update(extra_workloads(dev, x_prec, rend, views[0], peaks))
-            net.precision = precision
-            line["other_workloads"] = extras
-        if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline_quick()
+                    line["other_workloads"] = {"error": repr(e)[:400]}
         emit(line)
     if dist:
         td.destroy_process_group()

@@ -1,4 +1,5 @@
 // C-ABI entry points of the stage-1 path (see include/psnerf_b200.h for the reference lines each replaces).
+#include <stdlib.h>
 #include "stage1_simt.cuh"
 #include "launch.cuh"
 #include "internal.cuh"
@@ -46,6 +47,12 @@ static size_t march_ws_bytes(long long N, int S) {
   return align256((size_t)N * S * 4) + 8 * align256((size_t)N * 4) + 1024 + 4 * align256((size_t)refine_cap(N, S) * 4) + 512;
 }
 static const long long kShadowChunkPairs = 1 << 21;  // (light, point) pairs per shadow chunk (1 GB of occupancies at S=128)
+// A/B switch for measurements: PSNERF_B200_SHADOW_UNCULLED=1 evaluates every step of every shadow ray like the reference does
+// (fused k_tc_occ<MODE_SHADOW> on the tensor path) instead of the box-culled list.  Results agree to rounding of the product order.
+static bool shadow_unculled_requested() {
+  const char* e = getenv("PSNERF_B200_SHADOW_UNCULLED");
+  return e && e[0] == '1';
+}
 
 }  // namespace psn
 
@@ -63,7 +70,7 @@ extern "C" int64_t psn_workspace_bytes(const char* op, int64_t n_rays, int64_t n
   if (!strcmp(op, "shadow")) {
     const long long pairs = N * (n_lights < 1 ? 1 : n_lights);
     const long long chunk = pairs < kShadowChunkPairs + N ? pairs : kShadowChunkPairs + N;
-    return (int64_t)(align256((size_t)chunk * S * 4) + 4096);
+    return (int64_t)(align256((size_t)chunk * S * 4) + align256((size_t)chunk * 8) + 4096);
   }
   if (!strcmp(op, "shade") || !strcmp(op, "s2_vis")) return (int64_t)s2_workspace_bytes(N, n_lights);
   if (!strcmp(op, "s2_train")) {  // n_rays = max(pixels, surface points), n_samples = vis-train lights, n_lights = L
@@ -278,10 +285,24 @@ extern "C" int psn_shadow_visibility(const psn_mlp* geo, const float* surf, cons
   long long lights_per_chunk = kShadowChunkPairs / Ns;
   if (lights_per_chunk < 1) lights_per_chunk = 1;
   if (lights_per_chunk > L) lights_per_chunk = L;
+  const long long chunk_pairs = lights_per_chunk * Ns;
   Workspace w(ws, ws_bytes);
-  float* occ = w.take<float>((size_t)lights_per_chunk * Ns * n_steps);
+  // ws[0..3] = list length of the current chunk, ws[8..15] = in-box samples evaluated by this call (64-bit), ws[16..19] = 1 when the
+  // box-culled pass ran: readable by the caller after the call (psnerf_b200.engine.shadow_visibility(..., return_stats=True))
+  unsigned* counters = w.take<unsigned>(64);
+  float* occ = w.take<float>((size_t)chunk_pairs * n_steps);  // culled: packed entries, overwritten in place by their alpha
+  unsigned long long* meta = w.take<unsigned long long>((size_t)chunk_pairs);
   PSN_REQUIRE(w.ok, PSN_ERR_WORKSPACE, "psn_shadow_visibility: workspace too small (need %zu bytes, have %lld)", w.used,
               (long long)ws_bytes);
+  // The box-culled pass needs the step index in SHADOW_LIST_STEP_BITS bits and the pair index in the rest of an entry.
+  const bool culled = n_steps <= (1 << SHADOW_LIST_STEP_BITS) && chunk_pairs < (1LL << (32 - SHADOW_LIST_STEP_BITS)) &&
+                      !shadow_unculled_requested();
+  PSN_CUDA_CHECK(cudaMemsetAsync(counters, 0, 64 * sizeof(unsigned), st));
+  ShadowList sl;
+  sl.total = counters;
+  sl.evaluated = reinterpret_cast<unsigned long long*>(counters + 2);
+  sl.meta = meta;
+  sl.entry = reinterpret_cast<unsigned*>(occ);
   for (long long l0 = 0; l0 < L; l0 += lights_per_chunk) {
     const long long nl = (L - l0 < lights_per_chunk) ? (L - l0) : lights_per_chunk;
     PointGen gen;
@@ -294,6 +315,22 @@ extern "C" int psn_shadow_visibility(const psn_mlp* geo, const float* surf, cons
     gen.lnear = lnear;
     gen.lfar = lfar;
     int rc;
+    if (culled) {
+      // plan -> MLP over the in-box samples only (row count read on the device) -> transmittance over all steps
+      if (l0 > 0) PSN_CUDA_CHECK(cudaMemsetAsync(sl.total, 0, sizeof(unsigned), st));
+      if ((rc = launch_shadow_plan(surf, gen.lights, Ns, nl * Ns, n_steps, lnear, lfar, box, sl, st))) return rc;
+      gen.kind = GEN_SHADOW_LIST;
+      gen.index = reinterpret_cast<const int*>(sl.entry);
+      {
+        ProfScope prof(PSN_PROF_SHADOW, nl * Ns * n_steps, st);
+        if (prec_is_tc(precision)) rc = tc_occupancy(geo, gen, 0, reinterpret_cast<const int*>(sl.total), PSN_OUT_ALPHA, occ, st);
+        else rc = simt_occupancy(geo, gen, 0, reinterpret_cast<const int*>(sl.total), PSN_OUT_ALPHA, occ, 0, st);
+        if (rc) return rc;
+      }
+      if ((rc = launch_shadow_composite_list(occ, sl, surf, gen.lights, Ns, nl * Ns, n_steps, lnear, lfar, box, vis + l0 * Ns, st)))
+        return rc;
+      continue;
+    }
     if (prec_is_tc(precision) && n_steps == 128) {
       ProfScope prof(PSN_PROF_SHADOW, nl * Ns * n_steps, st);
       rc = tc_shadow(geo, gen, nl * Ns, box, vis + l0 * Ns, st);  // fused march + transmittance, no HBM round trip

@@ -14,6 +14,11 @@ struct SurfList { int* count; int* ray; float* depth; };
 // number of selected points, count[2] = points of the whole-march fallback (N * S if the list overflowed, else 0).
 struct RefineList { int* count; int* ray; float* depth; int* pos; int cap; };
 
+// Box-culled shadow pass: the (pair, step) entries of the in-box samples of one light chunk (stage1_aux.cu:k_shadow_plan).
+// total = entries of the current chunk (the MLP kernels read it as their device-side row count); evaluated = running 64-bit sum
+// over the chunks of a call; meta[pair] = list offset | first step << 32 | steps << 40.
+struct ShadowList { unsigned* total; unsigned long long* evaluated; unsigned long long* meta; unsigned* entry; };
+
 // stage1_simt.cu
 int simt_occupancy(const psn_mlp* geo, const PointGen& gen, long long M, const int* M_dev, int out_kind, float* out,
                    int with_feat, cudaStream_t st);
@@ -56,6 +61,10 @@ int launch_composite(const float* rgb_s, const float* alpha, long long N, int S,
                      cudaStream_t st);
 int launch_shadow_composite(const float* occ, const float* surf, const float* lights, long long Ns, long long pairs, int S,
                             float lnear, float lfar, float box, float* vis, cudaStream_t st);
+int launch_shadow_plan(const float* surf, const float* lights, long long Ns, long long pairs, int S, float lnear, float lfar,
+                       float box, ShadowList sl, cudaStream_t st);
+int launch_shadow_composite_list(const float* occ, ShadowList sl, const float* surf, const float* lights, long long Ns,
+                                 long long pairs, int S, float lnear, float lfar, float box, float* vis, cudaStream_t st);
 int launch_scatter_normals(const float* grad, SurfList sl, float* normal, long long N, cudaStream_t st);
 
 // stage2_simt.cu

@@ -293,6 +293,115 @@ __global__ void k_shadow_composite(const float* __restrict__ occ, const float* _
   if (lane == 0) vis[pair] = 1.f - sw;
 }
 
+// ---- box-culled shadow pass (rendering.py:378-408) ------------------------------------------------------------
+// The reference evaluates the occupancy MLP at all S steps of every shadow ray and then zeroes alpha outside the +-box cube
+// (rendering.py:402-404): those evaluations cannot influence the result.  A shadow ray starts on the surface (inside the cube) and
+// the cube is convex, so the in-box steps of a ray are one contiguous span - typically a quarter of the 128 steps at lfar = 3.5.
+// k_shadow_plan finds that span per (light, point) pair with the SAME per-step predicate and point arithmetic the composite uses,
+// and appends one packed (pair, step) entry per in-span step to a list; the MLP kernels evaluate only the list (GEN_SHADOW_LIST),
+// writing alpha over the entry it came from; k_shadow_composite_list then runs the reference's transmittance product over all S
+// steps with alpha = 0 outside the box, exactly as the unculled pass does.  (Contiguity follows from the monotonicity of every
+// rounded operation in t -> o + d t; the composite re-evaluates the predicate per step, so correctness does not rest on it.)
+// One block = 64 pairs (8 warps x 8 pairs); one atomicAdd per block reserves the block's list range (the list order is therefore
+// not reproducible between runs, the values are: every sample is evaluated independently of its tile neighbours).
+constexpr int PLAN_PAIRS_PER_BLOCK = 64;
+
+__device__ __forceinline__ bool shadow_step_inside(const float (&p0)[3], const float (&ld)[3], float dd, float box) {
+  bool inside = true;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float pc = madd_rn(p0[c], ld[c], dd);
+    inside = inside && (pc <= box) && (pc >= -box);
+  }
+  return inside;
+}
+
+__global__ void __launch_bounds__(256)
+k_shadow_plan(const float* __restrict__ surf, const float* __restrict__ lights, long long Ns, long long pairs, int S, float lnear,
+              float lfar, float box, ShadowList sl) {
+  __shared__ int s_first[PLAN_PAIRS_PER_BLOCK], s_cnt[PLAN_PAIRS_PER_BLOCK], s_off[PLAN_PAIRS_PER_BLOCK];
+  __shared__ unsigned s_base;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long pair0 = (long long)blockIdx.x * PLAN_PAIRS_PER_BLOCK;
+  for (int k = 0; k < 8; ++k) {
+    const int slot = w * 8 + k;
+    const long long pair = pair0 + slot;
+    int first = 0, cnt = 0;
+    if (pair < pairs) {
+      const long long l = pair / Ns, n = pair - l * Ns;
+      const float p0[3] = {surf[n * 3], surf[n * 3 + 1], surf[n * 3 + 2]};
+      const float ld[3] = {lights[l * 3], lights[l * 3 + 1], lights[l * 3 + 2]};
+      int lo = S, hi = -1;
+      for (int b = 0; b < S; b += 32) {
+        const int s = b + lane;
+        const bool in = (s < S) && shadow_step_inside(p0, ld, lerp_depth(lnear, lfar, linspace01(s, S)), box);
+        const unsigned m = __ballot_sync(0xffffffffu, in);
+        if (m) {
+          if (lo == S) lo = b + __ffs(m) - 1;
+          hi = b + 31 - __clz(m);
+        }
+      }
+      if (hi >= 0) { first = lo; cnt = hi - lo + 1; }
+    }
+    if (lane == 0) { s_first[slot] = first; s_cnt[slot] = cnt; }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int i = 0; i < PLAN_PAIRS_PER_BLOCK; ++i) { s_off[i] = run; run += s_cnt[i]; }
+    s_base = run ? atomicAdd(sl.total, (unsigned)run) : 0u;
+    if (run) atomicAdd(sl.evaluated, (unsigned long long)run);
+    if (blockIdx.x == 0) sl.total[4] = 1u;  // marks "the box-culled pass ran" next to the counters (read by the host for statistics)
+  }
+  __syncthreads();
+  for (int k = 0; k < 8; ++k) {
+    const int slot = w * 8 + k;
+    const long long pair = pair0 + slot;
+    if (pair >= pairs) break;
+    const unsigned off = s_base + (unsigned)s_off[slot];
+    const int first = s_first[slot], cnt = s_cnt[slot];
+    if (lane == 0) sl.meta[pair] = (unsigned long long)off | ((unsigned long long)first << 32) | ((unsigned long long)cnt << 40);
+    for (int i = lane; i < cnt; i += 32) sl.entry[off + i] = ((unsigned)pair << SHADOW_LIST_STEP_BITS) | (unsigned)(first + i);
+  }
+}
+
+// One warp per pair: the transmittance product of k_shadow_composite with alpha read through the pair's list span.
+__global__ void k_shadow_composite_list(const float* __restrict__ occ, ShadowList sl, const float* __restrict__ surf,
+                                        const float* __restrict__ lights, long long Ns, long long pairs, int S, float lnear,
+                                        float lfar, float box, float* __restrict__ vis) {
+  const long long pair = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (pair >= pairs) return;
+  const unsigned long long meta = sl.meta[pair];
+  const unsigned off = (unsigned)meta;
+  const int first = (int)((meta >> 32) & 0xffu), cnt = (int)((meta >> 40) & 0x1ffu);
+  const long long l = pair / Ns, n = pair - l * Ns;
+  const float p0[3] = {surf[n * 3], surf[n * 3 + 1], surf[n * 3 + 2]};
+  const float ld[3] = {lights[l * 3], lights[l * 3 + 1], lights[l * 3 + 2]};
+  float carry = 1.f, sw = 0.f;
+  for (int b = 0; b < S && b < first + cnt; b += 32) {  // steps after the span have alpha = 0: they add nothing to the sum
+    const int s = b + lane;
+    float a = 0.f;
+    if (s < S && s >= first && s < first + cnt) {
+      if (shadow_step_inside(p0, ld, lerp_depth(lnear, lfar, linspace01(s, S)), box)) a = occ[off + (unsigned)(s - first)];
+    }
+    const float t = (s < S) ? __fadd_rn(__fsub_rn(1.f, a), 1e-6f) : 1.f;
+    float incl = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float u = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl *= u;
+    }
+    float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = 1.f;
+    sw += a * (carry * excl);
+    carry *= __shfl_sync(0xffffffffu, incl, 31);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sw += __shfl_xor_sync(0xffffffffu, sw, o);
+  if (lane == 0) vis[pair] = 1.f - sw;
+}
+
 // ---- surface normals (rendering.py:208-211) -----------------------------------------------------------------
 __global__ void k_scatter_normals(const float* __restrict__ grad, SurfList sl, float* __restrict__ normal) {
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
@@ -392,6 +501,22 @@ int launch_shadow_composite(const float* occ, const float* surf, const float* li
   psn::count_launch();
   k_shadow_composite<<<(unsigned)((pairs * 32 + 255) / 256), 256, 0, st>>>(occ, surf, lights, Ns, pairs, S, lnear, lfar,
                                                                             box, vis);
+  PSN_CUDA_CHECK(cudaGetLastError());
+  return PSN_OK;
+}
+int launch_shadow_plan(const float* surf, const float* lights, long long Ns, long long pairs, int S, float lnear, float lfar,
+                       float box, ShadowList sl, cudaStream_t st) {
+  psn::count_launch();
+  k_shadow_plan<<<(unsigned)((pairs + PLAN_PAIRS_PER_BLOCK - 1) / PLAN_PAIRS_PER_BLOCK), 256, 0, st>>>(surf, lights, Ns, pairs, S,
+                                                                                                      lnear, lfar, box, sl);
+  PSN_CUDA_CHECK(cudaGetLastError());
+  return PSN_OK;
+}
+int launch_shadow_composite_list(const float* occ, ShadowList sl, const float* surf, const float* lights, long long Ns,
+                                 long long pairs, int S, float lnear, float lfar, float box, float* vis, cudaStream_t st) {
+  psn::count_launch();
+  k_shadow_composite_list<<<(unsigned)((pairs * 32 + 255) / 256), 256, 0, st>>>(occ, sl, surf, lights, Ns, pairs, S, lnear, lfar,
+                                                                                 box, vis);
   PSN_CUDA_CHECK(cudaGetLastError());
   return PSN_OK;
 }

@@ -27,7 +27,8 @@ struct AppDev {
 };
 
 // How a kernel obtains the i-th evaluation point.
-enum { GEN_EXPLICIT = 0, GEN_MARCH = 1, GEN_SHADOW = 2, GEN_INDEXED_DEPTH = 3, GEN_RAY_DEPTH = 4 };
+enum { GEN_EXPLICIT = 0, GEN_MARCH = 1, GEN_SHADOW = 2, GEN_INDEXED_DEPTH = 3, GEN_RAY_DEPTH = 4, GEN_SHADOW_LIST = 5 };
+constexpr int SHADOW_LIST_STEP_BITS = 7;  // GEN_SHADOW_LIST entry = (pair << 7) | step: at most 128 steps per shadow ray
 struct PointGen {
   int kind;
   const float* pts;    // EXPLICIT: [M,3]
@@ -35,7 +36,7 @@ struct PointGen {
   const float* dirs;   // ray directions [N,3]
   const float* far;    // MARCH: sphere far depth per ray [N]
   const float* depth;  // INDEXED_DEPTH: depth per list entry [M]; RAY_DEPTH: [N*S] sample depths
-  const int* index;    // INDEXED_DEPTH: ray id per list entry
+  const int* index;    // INDEXED_DEPTH: ray id per list entry; SHADOW_LIST: packed (pair, step) entries (k_shadow_plan)
   const float* surf;   // SHADOW: [Ns,3]
   const float* lights; // SHADOW: [L,3]
   float o[3];
@@ -69,6 +70,15 @@ __device__ __forceinline__ void gen_point(const PointGen& g, long long i, float 
   } else if (g.kind == GEN_SHADOW) {
     const long long pair = i / g.S;  // light-major: pair = l*Ns + n
     const int s = (int)(i - pair * g.S);
+    const long long l = pair / g.Ns, n = pair - l * g.Ns;
+    const float d = lerp_depth(g.lnear, g.lfar, linspace01(s, g.S));
+#pragma unroll
+    for (int c = 0; c < 3; ++c) p[c] = madd_rn(g.surf[n * 3 + c], g.lights[l * 3 + c], d);
+  } else if (g.kind == GEN_SHADOW_LIST) {
+    // the in-box samples of the shadow rays only (stage1_aux.cu:k_shadow_plan); same arithmetic as GEN_SHADOW
+    const unsigned e = (unsigned)g.index[i];
+    const long long pair = e >> SHADOW_LIST_STEP_BITS;
+    const int s = (int)(e & ((1u << SHADOW_LIST_STEP_BITS) - 1u));
     const long long l = pair / g.Ns, n = pair - l * g.Ns;
     const float d = lerp_depth(g.lnear, g.lfar, linspace01(s, g.S));
 #pragma unroll

@@ -7,12 +7,16 @@ import torch
 
 from . import _binding as B
 
-_DEFAULT_PRECISION = [B.PREC_FP32]
+# The default is the fastest program that holds the north star's 1e-4 gate (tests/test_gpu_parity_at_size.py): the tcgen05 kernels
+# with the mixed radiance program and the two-level surface march.  'fp32' (FFMA kernels) is the debug / cross-check path.
+_DEFAULT_PRECISION = [B.PREC_TC_TWOLEVEL]
 
 
 def set_default_precision(name):
-    """'fp32' (FFMA kernels), 'tc' (tcgen05, fp16 hi/lo split operands, fp32 accumulate) or 'tc_mixed' ('tc' with the appearance
-    side of the radiance program in single fp16 passes: rgb within 1e-5 of 'tc', everything else bit-identical)."""
+    """'tc_two_level' (default: 'tc_mixed' + the two-level surface march: single-pass occupancy over all march proposals, full
+    re-evaluation where the sign scan can tell the difference - depths / masks identical to 'tc_mixed'), 'tc_mixed' ('tc' with the
+    appearance side of the radiance program in single fp16 passes: rgb within 1e-5 of 'tc', everything else bit-identical), 'tc'
+    (tcgen05, fp16 hi/lo split operands everywhere, fp32 accumulate) or 'fp32' (FFMA kernels: debug / cross-check path)."""
     _DEFAULT_PRECISION[0] = B.PRECISIONS[name]
 
 
@@ -62,7 +66,8 @@ class PackedMLP:
         h = C.c_void_p()
         with torch.cuda.device(ws[0].device):
             B.check(lib.psn_mlp_create(C.byref(desc), in_dims, out_dims, wp, bp, _stream(), C.byref(h)), "psn_mlp_create")
-            torch.cuda.current_stream().synchronize()  # pack kernels read self._keep
+        # No host synchronisation: the pack kernels read the staging copies on the current stream, and torch's caching allocator only
+        # hands their memory to later work of the same stream, so dropping the references here is safe (train steps re-pack every step).
         self.handle = h
         self.device = ws[0].device
         self._keep = None
@@ -81,7 +86,8 @@ class _Workspace:
         self.buf = {}
 
     def get(self, device, nbytes):
-        key = (device.type, device.index)
+        # one buffer per (device, stream): calls on different streams may run concurrently and must not share scratch
+        key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream)
         cur = self.buf.get(key)
         if cur is None or cur.numel() < nbytes:
             self.buf[key] = None
@@ -209,7 +215,9 @@ def render_unisurf(geo, app, origin, dirs, prm, noise=None, want_sample_depth=Fa
     return {"rgb": rgb, "acc": acc, "normal": normal, "mask": mask.bool(), "depth": depth, "sample_depth": sd}
 
 
-def shadow_visibility(geo, surf, lights, lnear=0.1, lfar=3.5, n_steps=128, box=1.1, precision=None):
+def shadow_visibility(geo, surf, lights, lnear=0.1, lfar=3.5, n_steps=128, box=1.1, precision=None, return_stats=False):
+    """vis [L, Ns] (rendering.py:378-408).  return_stats=True also returns {'evaluated': in-box samples the MLP kernel ran on,
+    'nominal': L * Ns * n_steps} (one device-to-host read: measurements only)."""
     surf = f32c(surf).reshape(-1, 3)
     lights = f32c(lights, surf.device).reshape(-1, 3)
     Ns, L = surf.shape[0], lights.shape[0]
@@ -220,6 +228,11 @@ def shadow_visibility(geo, surf, lights, lnear=0.1, lfar=3.5, n_steps=128, box=1
                                                int(n_steps), float(box), _ptr(vis), _ptr(ws), ws.numel(),
                                                default_precision() if precision is None else precision, _stream()),
                 "psn_shadow_visibility")
+    if return_stats:
+        nominal = Ns * L * int(n_steps)
+        head = ws[:24].view(torch.int64).tolist() if nominal > 0 else [0, 0, 0]  # counters the library leaves at the head of ws
+        culled = bool(head[2] & 0xffffffff)
+        return vis, {"evaluated": int(head[1]) if culled else nominal, "nominal": nominal, "culled": culled}
     return vis
 
 

@@ -5,7 +5,7 @@
   render_stage2_view   <- stage2/eval.py:314-417          (all light batches of a view)
   occupancy_grid_logits<- stage1/model/extracting.py:84-96,137-155 (dense -logit grid for mesh export)
   render_envmap_view   <- stage2/eval.py:173-231          (envmap relighting: RGB-intensity light grid, sum over lights)
-  extract_and_shade    <- SURVEY.md §8f-1: stage-1 surface extraction feeding stage-2 shading directly, no .npy hand-off
+  extract_and_shade    <- SURVEY.md §8f-1: stage-1 surface extraction + shadow-ray visibility feeding stage-2 shading directly, no .npy hand-off
   save_shape_view / load_shape_view <- shape_extract.py:144-162 / stage2/datasets/dataset.py:100-114: the .npy hand-off, kept as an option
   *_sharded            <- SURVEY.md §8e: rays of a view dealt over the ranks (stage 2: balanced by surface pixels), one all_gather at the end
 
@@ -101,20 +101,90 @@ def render_envmap_view(model, model_input, env_light, light_xyz, light_batch=64)
     return res
 
 
-@torch.no_grad()
-def extract_and_shade(renderer, ps_model, h, w, camera_mat, world_mat, light_dirs, light_batch=96):
-    """Stage-1 surface search + analytic normals feeding stage-2 shading in one pass (no points/normal/mask .npy files).
-    Stage-1 pixel order is x-major while stage 2 consumes uv pairs explicitly, so no re-ordering is needed."""
-    dev = next(renderer.model.parameters()).device
-    shp = extract_shape(renderer, h, w, camera_mat, world_mat)
-    p_loc = arange_pixels((h, w))[0].to(dev)
+def _stage2_input_from_shape(shp, p_loc, camera_mat, world_mat):
+    """The model_input PSNetwork.forward consumes, built from an extract_shape result instead of the .npy files of
+    stage1/shape_extract.py:144-162 (stage2/datasets/dataset.py:100-114 reads them back).  Stage-1 pixel order is x-major while stage 2
+    consumes explicit uv pairs, so no re-ordering is needed; stage 1 uses fx for both axes (common.py:220)."""
     K = torch.eye(4).unsqueeze(0)
     cm = camera_mat.detach().float().cpu()
-    K[0, 0, 0] = K[0, 1, 1] = cm[0, 0, 0]  # stage 1 uses fx for both axes (common.py:220)
+    K[0, 0, 0] = K[0, 1, 1] = cm[0, 0, 0]
     K[0, 0, 2], K[0, 1, 2] = cm[0, 0, 2], cm[0, 1, 2]
     inp = {"intrinsics": K, "uv": p_loc.float(), "pose": world_mat, "object_mask": shp["mask"], "surface_mask": shp["mask"],
            "points": shp["points"], "normal": shp["normal"]}
-    return shp, render_stage2_view(ps_model, inp, light_dirs.to(dev), light_batch)
+    if "visibility" in shp:
+        inp["visibility"] = shp["visibility"]  # [L, N]: the shadow-ray transmittances stage 2 trains its visibility net against
+    return inp
+
+
+@torch.no_grad()
+def extract_and_shade(renderer, ps_model, h, w, camera_mat, world_mat, light_dirs, light_batch=96, shadows=True, pixels=None):
+    """the whole per-view chain of the reference in one pass, nothing written to disk - stage-1 surface search
+    (512-step ray march + secant), analytic normals, the shadow-ray visibility of every surface point towards every light
+    (rendering.py:378-408; `shadows=False` skips it like shape_extract.py without --visibility) and stage-2 shading of the same
+    points under the same lights.  Returns (shape dict incl. 'visibility' [L, N], stage-2 result dict).  `pixels` ([1,n,2] integer
+    pixel positions) restricts the pass to a subset of the view (ray shards)."""
+    dev = next(renderer.model.parameters()).device
+    p_loc = (arange_pixels((h, w))[0] if pixels is None else pixels).to(dev)
+    light_dirs = light_dirs.to(dev)
+    shp = renderer(p_loc, camera_mat, world_mat, None, "shape_extract", visibility=bool(shadows), light_dir=light_dirs if shadows else None)
+    inp = _stage2_input_from_shape(shp, p_loc, camera_mat, world_mat)
+    return shp, render_stage2_view(ps_model, inp, light_dirs, light_batch)
+
+
+def relit_row_layout(ps_model, L, shadows=True):
+    """Column layout of one packed per-pixel row of a relit view: the stage-2 entries (see _s2_packed_layout) followed by the
+    stage-1 mask (1), surface point (3), normal (3) and, with the shadow pass, the L shadow-ray transmittances."""
+    layout, width = _s2_packed_layout(ps_model, L)
+    return layout, width, width + 7 + (L if shadows else 0)
+
+
+@torch.no_grad()
+def extract_and_shade_rows(renderer, ps_model, h, w, camera_mat, world_mat, light_dirs, pixels, light_batch=96, shadows=True):
+    """extract_and_shade over the given pixel positions ([1,n,2]), packed as one fp32 row per pixel (relit_row_layout): the unit a
+    rank contributes to the pixel gather."""
+    dev = next(renderer.model.parameters()).device
+    shp, out = extract_and_shade(renderer, ps_model, h, w, camera_mat, world_mat, light_dirs, light_batch, shadows, pixels=pixels)
+    L = light_dirs.shape[0]
+    n_loc = int(pixels.shape[1])
+    layout, width, total = relit_row_layout(ps_model, L, shadows)
+    local = torch.empty(n_loc, total, dtype=torch.float32, device=dev)
+    for key, per_light, chans, off, w_ in layout:
+        v = out[key]
+        local[:, off:off + w_] = (v.reshape(L, n_loc, chans).permute(1, 0, 2) if per_light else v).reshape(n_loc, w_)
+    local[:, width] = shp["mask"].reshape(n_loc).float()
+    local[:, width + 1:width + 4] = shp["points"].reshape(n_loc, 3)
+    local[:, width + 4:width + 7] = shp["normal"].reshape(n_loc, 3)
+    if shadows:
+        local[:, width + 7:] = shp["visibility"].t()
+    return local
+
+
+def unpack_relit_rows(full, ps_model, L, shadows=True):
+    """(shape dict, stage-2 result dict) views of packed rows [N, total] in the shapes extract_and_shade returns."""
+    N = full.shape[0]
+    layout, width, _ = relit_row_layout(ps_model, L, shadows)
+    res = {}
+    for key, per_light, chans, off, w_ in layout:
+        v = full[:, off:off + w_]
+        res[key] = v.reshape(N, L, chans).permute(1, 0, 2) if per_light else v.reshape(1, N, chans)
+    shape = {"mask": full[:, width].reshape(1, N) > 0.5, "points": full[:, width + 1:width + 4].reshape(1, N, 3),
+             "normal": full[:, width + 4:width + 7].reshape(1, N, 3)}
+    if shadows:
+        shape["visibility"] = full[:, width + 7:].t()
+    return shape, res
+
+
+@torch.no_grad()
+def extract_and_shade_sharded(renderer, ps_model, h, w, camera_mat, world_mat, light_dirs, rank, world, light_batch=96, shadows=True,
+                              group=None):
+    """extract_and_shade with the rays of the view dealt over the ranks (128-ray tiles round-robin, sharding.shard_indices) and ONE
+    all_gather of the packed per-pixel rows at the end: every rank returns the full view."""
+    N = h * w
+    idx = sharding.shard_indices(N, rank, world)
+    p_all = arange_pixels((h, w))[0]
+    local = extract_and_shade_rows(renderer, ps_model, h, w, camera_mat, world_mat, light_dirs, p_all[:, idx], light_batch, shadows)
+    full = sharding.gather_pixels(local, N, rank, world, group=group)
+    return unpack_relit_rows(full, ps_model, light_dirs.shape[0], shadows)
 
 
 @torch.no_grad()
@@ -131,35 +201,103 @@ def render_stage1_view_sharded(renderer, h, w, camera_mat, world_mat, rank, worl
 PER_PIXEL_INPUTS = ("uv", "object_mask", "gt_normal", "normal", "depth", "points", "surface_mask", "visibility")
 
 
+def split_input(model_input, total_pixels, n_pixels=None):
+    """Pixel chunks of a stage-2 model input (the role of stage2/utils/general.py:23-37 in the eval loops, stage2/eval.py:345-365).
+    The CUDA path shades a whole view per call, so the default is ONE chunk (n_pixels=None); a chunk size is honoured for callers
+    that keep the reference's 1024-pixel loop.  Chunks are `narrow` views of the per-pixel entries (no index tensors, no copies);
+    camera / light entries are shared by reference."""
+    step = int(total_pixels) if not n_pixels else int(n_pixels)
+    chunks = []
+    for start in range(0, int(total_pixels), max(step, 1)):
+        length = min(step, int(total_pixels) - start)
+        chunk = {k: v for k, v in model_input.items() if k not in PER_PIXEL_INPUTS}
+        chunk.update({k: model_input[k].narrow(1, start, length) for k in PER_PIXEL_INPUTS if k in model_input})
+        chunks.append(chunk)
+    return chunks
+
+
+def merge_output(res, total_pixels, batch_size):
+    """Stitch per-chunk model outputs back into whole-view tensors in the layout stage2/eval.py consumes (general.py:39-53):
+    per-pixel scalars -> [batch * total_pixels]; [..., n, C] entries -> [prod(...) * total_pixels, C] with the pixel axis second
+    to last.  Every output is allocated once and the chunks are copied into their pixel range; None entries are dropped."""
+    merged = {}
+    for key, first in res[0].items():
+        if first is None:
+            continue
+        scalar = first.dim() < 3
+        chans = 1 if scalar else first.shape[-1]
+        lead = (batch_size,) if scalar else tuple(first.shape[:-2])
+        buf = first.new_empty(*lead, total_pixels, chans)
+        at = 0
+        for r in res:
+            part = r[key].reshape(*lead, -1, chans)
+            buf.narrow(-2, at, part.shape[-2]).copy_(part)
+            at += part.shape[-2]
+        merged[key] = buf.reshape(-1) if scalar else buf.reshape(-1, chans)
+    return merged
+
+
+# per-pixel entries of a stage-2 result a sharded view returns: key -> (has a light axis, channels)
+_S2_SHARDED_KEYS = (("sg_rgb_values", True, 3), ("sg_specular_rgb_values", True, 3), ("visibility", True, 3),
+                    ("normal_pred", False, 3), ("sg_diffuse_albedo_values", False, 3), ("sg_weight", False, None))
+
+
+def _s2_packed_layout(model, L):
+    """Column layout of the packed per-pixel rows a stage-2 shard sends through the gather.  Derived from the MODEL's flags (which
+    entries PSNetwork.forward emits: renderer.py:145-152,200-208), never from a rank's own output, so every rank - including one that
+    was dealt no pixels - agrees on it."""
+    micro = bool(getattr(model, "microfacet", False))  # microfacet: no SG weights, the "specular" entry is the [1,N,3] roughness image
+    present = {"sg_rgb_values": True, "sg_specular_rgb_values": True, "sg_diffuse_albedo_values": True, "sg_weight": not micro,
+               "visibility": bool(getattr(model, "visibility", False)), "normal_pred": bool(getattr(model, "normal_mlp", False))}
+    layout, off = [], 0
+    for key, per_light, chans in _S2_SHARDED_KEYS:
+        if not present[key]:
+            continue
+        if key == "sg_specular_rgb_values" and micro:
+            per_light = False
+        if chans is None:
+            chans = int(model.nbasis)
+        width = (L if per_light else 1) * chans
+        layout.append((key, per_light, chans, off, width))
+        off += width
+    return layout, off
+
+
 @torch.no_grad()
 def render_stage2_view_sharded(model, model_input, light_dirs, rank, world, light_batch=96, light_intensity=None, group=None):
     """BASELINE config 4: the pixels of one stage-2 view dealt over the ranks with the SURFACE pixels balanced
-    (sharding.shard_indices_by_mask), every rank shades its share under all lights, ONE all_gather returns the full view on every
-    rank.  Output: the per-pixel entries of render_stage2_view in the reference's shapes - sg_rgb_values / visibility [L,N,3],
-    normal_pred / sg_diffuse_albedo_values [1,N,3]."""
+    (sharding.shard_plan_by_mask: one host copy of the mask per view), every rank shades its share under all lights, ONE all_gather
+    returns the full view on every rank.  Output: the per-pixel entries of render_stage2_view in the reference's shapes -
+    sg_rgb_values / sg_specular_rgb_values / visibility [L,N,3], normal_pred / sg_diffuse_albedo_values [1,N,3], sg_weight [1,N,27]
+    (visibility / normal_pred only when the model emits them, like the unsharded path)."""
     smask = model_input["surface_mask"]
     N = smask.shape[1]
-    dev = model_input["points"].device
-
-    def indices_of(r):
-        return sharding.shard_indices_by_mask(smask[0], r, world)
-
-    idx = indices_of(rank).to(dev)
-    sub = dict(model_input)
-    for k in PER_PIXEL_INPUTS:
-        if k in model_input and torch.is_tensor(model_input[k]) and model_input[k].dim() >= 2 and model_input[k].shape[1] == N:
-            sub[k] = torch.index_select(model_input[k], 1, idx)
-    out = render_stage2_view(model, sub, light_dirs, light_batch, light_intensity)
+    first = next(model.parameters(), None)
+    dev = first.device if first is not None else model_input["points"].device
+    plan = sharding.shard_plan_by_mask(smask[0], world)
+    idx = plan[rank]
+    n_loc = int(idx.numel())
     L = light_dirs.shape[0]
-    n_loc = idx.numel()
-    rgb = out["sg_rgb_values"].reshape(L, n_loc, 3)
-    vis = out["visibility"].reshape(L, n_loc, 3)
-    local = torch.cat([rgb.permute(1, 0, 2).reshape(n_loc, L * 3), vis.permute(1, 0, 2).reshape(n_loc, L * 3),
-                       out["normal_pred"].reshape(n_loc, 3), out["sg_diffuse_albedo_values"].reshape(n_loc, 3)], -1).contiguous()
-    full = sharding.gather_rows(local, N, rank, world, indices_of, group=group)
-    return {"sg_rgb_values": full[:, :L * 3].reshape(N, L, 3).permute(1, 0, 2).contiguous(),
-            "visibility": full[:, L * 3:2 * L * 3].reshape(N, L, 3).permute(1, 0, 2).contiguous(),
-            "normal_pred": full[:, 6 * L:6 * L + 3].reshape(1, N, 3), "sg_diffuse_albedo_values": full[:, 6 * L + 3:].reshape(1, N, 3)}
+    layout, width = _s2_packed_layout(model, L)
+    local = torch.zeros(n_loc, width, dtype=torch.float32, device=dev)
+    if n_loc > 0:
+        sub = dict(model_input)
+        for k in PER_PIXEL_INPUTS:
+            v = model_input.get(k)
+            if torch.is_tensor(v) and v.dim() >= 2 and v.shape[1] == N:
+                sub[k] = torch.index_select(v, 1, idx.to(v.device))
+        out = render_stage2_view(model, sub, light_dirs, light_batch, light_intensity)
+        for key, per_light, chans, off, w_ in layout:
+            v = out[key]
+            if per_light:
+                v = v.reshape(L, n_loc, chans).permute(1, 0, 2)
+            local[:, off:off + w_] = v.reshape(n_loc, w_).to(dev)
+    full = sharding.gather_rows(local, N, rank, world, lambda r: plan[r], group=group)
+    res = {}
+    for key, per_light, chans, off, w_ in layout:
+        v = full[:, off:off + w_]
+        res[key] = v.reshape(N, L, chans).permute(1, 0, 2).contiguous() if per_light else v.reshape(1, N, chans).contiguous()
+    return res
 
 
 # ---- the on-disk hand-off between the stages (optional: extract_and_shade needs none of it) ------------------------------------

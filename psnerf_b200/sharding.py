@@ -18,16 +18,24 @@ def shard_counts(n_rays, world, tile=128):
     return [int(shard_indices(n_rays, r, world, tile).numel()) for r in range(world)]
 
 
-def shard_indices_by_mask(mask, rank, world, tile=128):
-    """Pixel ids owned by `rank` when the work sits on the masked pixels (stage 2: cost grows with the surface points, not with the
+def shard_plan_by_mask(mask, world, tile=128):
+    """Pixel ids of EVERY rank when the work sits on the masked pixels (stage 2: cost grows with the surface points, not with the
     pixels): masked and unmasked pixels are dealt separately, tiles of `tile` round-robin, so every rank shades the
-    same number of surface points (to within one tile) whatever the silhouette looks like.  Sorted, identical on every rank."""
+    same number of surface points (to within one tile) whatever the silhouette looks like.  ONE device-to-host copy of the mask per
+    view; returns a list of sorted index tensors (host), identical on every rank."""
     m = mask.reshape(-1).bool().cpu()
     ids = torch.arange(m.numel())
-    parts = []
+    per_rank = [[] for _ in range(world)]
     for sel in (ids[m], ids[~m]):
-        parts.append(sel[((torch.arange(sel.numel()) // tile) % world) == rank])
-    return torch.cat(parts).sort().values
+        owner = (torch.arange(sel.numel()) // tile) % world
+        for r in range(world):
+            per_rank[r].append(sel[owner == r])
+    return [torch.cat(p).sort().values for p in per_rank]
+
+
+def shard_indices_by_mask(mask, rank, world, tile=128):
+    """Pixel ids owned by `rank` (see shard_plan_by_mask; use the plan when more than one rank's list is needed)."""
+    return shard_plan_by_mask(mask, world, tile)[rank]
 
 
 def gather_rows(local, n_rows, rank, world, indices_of, group=None):

@@ -7,16 +7,16 @@ import torch
 
 
 def run_smoke(verbose=True):
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    root = os.path.dirname(os.path.abspath(__file__))
     sys.path.insert(0, os.path.join(root, "oracle"))
     import psnerf_oracle as O
-    from . import synth
-    from .stage1 import NeuralNetwork, Renderer
-    from .stage2 import PSNetwork
+    from psnerf_b200 import synth
+    from psnerf_b200.stage1 import NeuralNetwork, Renderer
+    from psnerf_b200.stage2 import PSNetwork
 
     dev = torch.device("cuda:0")
     res = {}
-    from . import engine
+    from psnerf_b200 import engine
     precisions = ["fp32", "tc"] if engine.tc_available() else ["fp32"]
     # ---- stage 1: 16x16 view, 64 march steps, 12+4 samples per ray
     cfg = synth.stage1_cfg(num_points_in=12, num_points_out=4, ray_marching_steps=64)

@@ -432,69 +432,6 @@ def make_stage2_general():
     np.savez_compressed(os.path.join(HERE, "stage2_general.npz"), **out)
 
 
-class StubRenderer(torch.nn.Module):
-    """Stands in for the Renderer in the Trainer fixture: smooth functions of the sampled pixel positions and three parameters, so that
-    sampling, ground-truth lookup, loss terms and the optimizer step of Trainer.train_step are exercised without a GPU."""
-
-    def __init__(self):
-        super().__init__()
-        self.w = torch.nn.Parameter(torch.tensor([0.3, 0.5, 0.7]))
-        self.calls = []
-
-    def forward(self, p, camera_mat, world_mat, scale_mat, technique, it=None, eval_=False, add_noise=True):
-        self.calls.append((technique, it, eval_, p.detach().clone()))
-        x = p.float()
-        u, v = x[..., 0:1] * 0.02, x[..., 1:2] * 0.03
-        rgb = torch.sigmoid(u * self.w + v)
-        normal = torch.nn.functional.normalize(torch.cat([u - 0.5, v - 0.4, torch.ones_like(u)], -1), dim=-1) * self.w.sum()
-        acc = torch.sigmoid((u + v)[..., 0] - 1.0 + self.w[0]) * 0.98 + 0.01
-        diff = (u[0, :, 0] * self.w[1]).abs()
-        return {"rgb": rgb, "normal_pred": normal, "acc_map": acc, "diff_norm": diff, "mask_pred": acc[0] > 0.5}
-
-
-TRAINER_CASES = {  # name: training-config overrides, iteration
-    "rgb_only": (dict(), 10),
-    "normals": (dict(normal_loss=True, normal_after=5, normal_angle=75.0), 10),
-    "normals_late": (dict(normal_loss=True, normal_after=50), 10),
-    "mask": (dict(mask_loss=True, normal_loss=True, normal_after=-1, lambda_mask=0.5, lambda_normloss=0.2), 3),
-}
-
-
-def trainer_cfg(over):
-    t = dict(n_training_points=96, type="unisurf", lambda_l1_rgb=1.0, lambda_normals=0.05)
-    t.update(over)
-    return {"training": t}
-
-
-def trainer_data(h=20, w=28):
-    g = torch.Generator().manual_seed(31)
-    n = torch.nn.functional.normalize(torch.randn(1, 3, h, w, generator=g) + torch.tensor([0.0, 0.0, 1.5]).view(1, 3, 1, 1), dim=1)
-    return {"img": torch.rand(1, 3, h, w, generator=g), "img.idx": torch.tensor([4]),
-            "img.mask": (torch.rand(1, h, w, generator=g) > 0.3).float(), "img.world_mat": synth.look_at_pose(25.0, 15.0),
-            "img.camera_mat": synth.intrinsics(h, w), "img.scale_mat": torch.eye(4)[None], "img.normal": n,
-            "img.norm_mask": (torch.rand(1, h, w, generator=g) > 0.4).float(), "img.mask_valid": (torch.rand(1, h, w, generator=g) > 0.1).float()}
-
-
-def make_stage1_trainer():
-    """Trainer.compute_loss / train_step of the REAL stage1/model/training.py on CPU around a stub renderer: which pixels are sampled
-    under a fixed seed, every loss term, and the parameters after two optimizer steps."""
-    tr = ref_loader.load_stage1_trainer()
-    out = {}
-    for name, (over, it) in TRAINER_CASES.items():
-        stub = StubRenderer()
-        opt = torch.optim.Adam(stub.parameters(), lr=1e-2)
-        t = tr.Trainer(stub, opt, trainer_cfg(over), device=torch.device("cpu"))
-        torch.manual_seed(123)
-        for k in range(2):
-            ld = t.train_step(trainer_data(), it=it + k)
-            for key, val in ld.items():
-                out["%s_s%d_%s" % (name, k, key)] = np_(val)
-        out[name + "_pix"] = np_(stub.calls[0][3])
-        out[name + "_w"] = np_(stub.w)
-        out[name + "_keys"] = np.array(sorted(ld.keys()))
-    np.savez_compressed(os.path.join(HERE, "stage1_trainer.npz"), **out)
-
-
 def metrics_case():
     g = torch.Generator().manual_seed(77)
     a = torch.rand(9, 11, 3, generator=g).numpy()
@@ -538,6 +475,5 @@ if __name__ == "__main__":
     make_stage2_losses()
     make_stage2_general()
     make_metrics()
-    make_stage1_trainer()
-    for f in ("stage1_net", "stage1_render", "stage2_shade", "stage2_grads", "stage2_edit", "stage1_grads", "stage1_phong", "stage2_loss", "stage2_general", "metrics", "stage1_trainer"):
+    for f in ("stage1_net", "stage1_render", "stage2_shade", "stage2_grads", "stage2_edit", "stage1_grads", "stage1_phong", "stage2_loss", "stage2_general", "metrics"):
         print(f, os.path.getsize(os.path.join(HERE, f + ".npz")) // 1024, "KB")

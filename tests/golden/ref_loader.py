@@ -47,35 +47,6 @@ def load_stage1():
     return network, rendering, common
 
 
-def load_stage1_trainer():
-    """The reference stage-1 ``training`` module (Trainer) and its ``losses``: matplotlib (absent here) and utils.tools (MAE, used only
-    by the visualisation) are replaced by empty stand-ins."""
-    load_stage1()
-    pkg = "psnerf_ref_stage1"
-    if pkg + ".training" in sys.modules:
-        return sys.modules[pkg + ".training"]
-    mpl, plt = types.ModuleType("matplotlib"), types.ModuleType("matplotlib.pyplot")
-    plt.get_cmap = lambda name: None
-    mpl.pyplot = plt
-    sys.modules.setdefault("matplotlib", mpl)
-    sys.modules.setdefault("matplotlib.pyplot", plt)
-    saved = {k: sys.modules.get(k) for k in ("utils", "utils.tools")}
-    utils, tools = types.ModuleType("utils"), types.ModuleType("utils.tools")
-    tools.MAE = None
-    utils.tools = tools
-    sys.modules["utils"], sys.modules["utils.tools"] = utils, tools
-    try:
-        _load(pkg + ".losses", os.path.join(REF, "stage1/model/losses.py"), pkg)
-        training = _load(pkg + ".training", os.path.join(REF, "stage1/model/training.py"), pkg)
-    finally:
-        for k, v in saved.items():
-            if v is None:
-                sys.modules.pop(k, None)
-            else:
-                sys.modules[k] = v
-    return training
-
-
 def _camera_params_standin(uv, pose, intrinsics):
     # device-agnostic equivalent of stage2/utils/rend_util.py:90-147 (pose-matrix branch)
     cam_loc = pose[:, :3, 3]

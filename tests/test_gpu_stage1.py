@@ -16,13 +16,18 @@ pytestmark = pytest.mark.gpu
 def _precisions():
     from psnerf_b200 import engine
     try:
-        return ["fp32", "tc"] if engine.tc_available() else ["fp32"]
+        return ["fp32", "tc", "tc_two_level"] if engine.tc_available() else ["fp32"]
     except Exception:
         return ["fp32"]
 
 
 PRECISIONS = _precisions()
-TOL = {"fp32": dict(rel=1e-5, abs=2e-5), "tc": dict(rel=5e-5, abs=1e-4)}
+TOL = {"fp32": dict(rel=1e-5, abs=2e-5), "tc": dict(rel=5e-5, abs=1e-4), "tc_two_level": dict(rel=5e-5, abs=1e-4)}
+
+
+# Gates on rendered quantities against the real reference's fixtures (all O(1) quantities, max-abs over the pixels whose discrete
+# hit / miss decision agrees).  PROVISIONAL values are replaced by <= 1e-4 / 3 x measured from the error log of the GPU run.
+GATE = {"rgb": 5e-4, "acc": 5e-4, "normal": 2e-3, "points": 2e-4, "visibility": 2e-3, "light_visibility": 5e-4}
 
 
 @pytest.fixture(scope="module")
@@ -118,9 +123,10 @@ def test_unisurf_vs_golden(s1, variant, case, prec):
     agree = out["mask_pred"].cpu().numpy() == mask_ref
     assert agree.mean() >= 0.99
     ok = torch.from_numpy(agree & (same[0]))
-    assert util.max_abs(out["rgb"][0].cpu()[ok], g[key + "rgb"][0][ok.numpy()]) < 5 * t["abs"]
-    assert util.max_abs(out["acc_map"][0].cpu()[ok], g[key + "acc"][0][ok.numpy()]) < 5 * t["abs"]
-    assert util.max_abs(out["normal_pred"][0].cpu()[ok], g[key + "normal"][0][ok.numpy()]) < 20 * t["abs"]
+    tag = "unisurf_golden/%s/%s/%s/" % (prec, variant, case)
+    util.bound(tag + "rgb", util.max_abs(out["rgb"][0].cpu()[ok], g[key + "rgb"][0][ok.numpy()]), GATE["rgb"])
+    util.bound(tag + "acc", util.max_abs(out["acc_map"][0].cpu()[ok], g[key + "acc"][0][ok.numpy()]), GATE["acc"])
+    util.bound(tag + "normal", util.max_abs(out["normal_pred"][0].cpu()[ok], g[key + "normal"][0][ok.numpy()]), GATE["normal"])
     assert O.psnr(out["rgb"].cpu(), torch.from_numpy(g[key + "rgb"])) > 50.0
     assert out["diff_norm"] is None
 
@@ -193,15 +199,53 @@ def test_shape_extract_and_shadow_vs_golden(s1, variant, prec):
     assert agree.mean() >= 0.99
     ok = torch.from_numpy(agree[0])
     t = TOL[prec]
-    assert util.max_abs(out["points"][0].cpu()[ok], g[key + "points"][0][ok.numpy()]) < 2e-4
-    assert util.max_abs(out["normal"][0].cpu()[ok], g[key + "normal"][0][ok.numpy()]) < 20 * t["abs"]
-    assert util.max_abs(out["visibility"].cpu()[:, ok], g[key + "visibility"][:, ok.numpy()]) < 20 * t["abs"]
+    tag = "extract_golden/%s/%s/" % (prec, variant)
+    util.bound(tag + "points", util.max_abs(out["points"][0].cpu()[ok], g[key + "points"][0][ok.numpy()]), GATE["points"])
+    util.bound(tag + "normal", util.max_abs(out["normal"][0].cpu()[ok], g[key + "normal"][0][ok.numpy()]), GATE["normal"])
+    util.bound(tag + "visibility", util.max_abs(out["visibility"].cpu()[:, ok], g[key + "visibility"][:, ok.numpy()]), GATE["visibility"])
     # direct light_visibility on the golden surface points (no discrete decisions involved)
     surf = torch.from_numpy(g[key + "points"][0][g[key + "mask"][0]])
     vis = r.light_visibility(surf=surf.cuda(), light_dir=lights.cuda()).cpu()
     with torch.no_grad():
         ref = O.light_visibility(sds[variant], cfg["model"], surf, lights)
-    assert util.max_abs(vis, ref) < 5 * t["abs"]
+    util.bound(tag + "light_visibility", util.max_abs(vis, ref), GATE["light_visibility"])
+
+
+@pytest.mark.parametrize("prec", PRECISIONS)
+@pytest.mark.parametrize("Ns,L", [(1, 1), (37, 7), (1000, 5)])
+def test_box_culled_shadow_pass(s1, prec, Ns, L, monkeypatch):
+    """The shadow pass evaluates the occupancy MLP only at the in-box steps of every shadow ray (k_shadow_plan / GEN_SHADOW_LIST):
+    equal to the evaluation of every step (what the reference executes, PSNERF_B200_SHADOW_UNCULLED=1) up to the order of the
+    transmittance product, and to the oracle; points outside the +-1.1 cube (no in-box step at all) give visibility exactly 1."""
+    from psnerf_b200 import engine
+    from psnerf_b200.stage1 import Renderer
+    _, sds = s1
+    cfg = synth.stage1_cfg()
+    r = Renderer(make_model(cfg, sds["trained"], prec), cfg, device=torch.device("cuda"))
+    g, _ = r._geo_app()
+    gen = torch.Generator().manual_seed(500 + Ns)
+    surf = torch.nn.functional.normalize(torch.randn(Ns, 3, generator=gen), dim=-1) * (0.3 + 0.9 * torch.rand(Ns, 1, generator=gen))
+    if Ns > 2:
+        surf[0] = torch.tensor([1.5, 0.2, -0.1])    # outside the box from the first step on
+        surf[1] = torch.tensor([1.09, 1.09, 1.09])  # leaves the box after a few steps whatever the light
+    lights = synth.lights(L, seed=21)
+    vis, st = engine.shadow_visibility(g, surf.cuda(), lights.cuda(), precision=r.model._prec(), return_stats=True)
+    assert st["culled"] and st["nominal"] == Ns * L * 128 and 0 <= st["evaluated"] < st["nominal"]
+    monkeypatch.setenv("PSNERF_B200_SHADOW_UNCULLED", "1")
+    vis_all, st_all = engine.shadow_visibility(g, surf.cuda(), lights.cuda(), precision=r.model._prec(), return_stats=True)
+    monkeypatch.delenv("PSNERF_B200_SHADOW_UNCULLED")
+    assert not st_all["culled"] and st_all["evaluated"] == st_all["nominal"]
+    util.bound("shadow_culled_vs_every_step/%s/%d" % (prec, Ns), util.max_abs(vis.cpu(), vis_all.cpu()), 2e-6)
+    with torch.no_grad():
+        ref = O.light_visibility(sds["trained"], cfg["model"], surf, lights).view(L, Ns)
+    util.bound("shadow_culled_vs_oracle/%s/%d" % (prec, Ns), util.max_abs(vis.cpu(), ref), GATE["light_visibility"])
+    if Ns > 2:
+        assert float((vis[:, 0] - 1).abs().max()) == 0.0
+    # the in-box count is what the oracle's own box mask says
+    t = torch.linspace(0, 1, 128)
+    p = surf[None, :, None, :] + lights[:, None, None, :] * (0.1 * (1 - t) + 3.5 * t)[None, None, :, None]
+    inside = ((p <= 1.1) & (p >= -1.1)).all(-1).sum()
+    assert abs(st["evaluated"] - int(inside)) <= max(2, int(0.001 * int(inside)))  # a step exactly on the box face may round either way
 
 
 def test_composite_properties():

@@ -1,20 +1,15 @@
-"""PSN_PREC_TC_TWOLEVEL ('tc_two_level'): tc_mixed plus the two-level surface march (api_stage1.cu raymarch_impl).  EXPERIMENTAL:
-written after this round's GPU budget was spent, validated only by CPU emulation (tests/test_precision_schemes.py), so the
-tests are gated behind PSNERF_B200_TEST_TWOLEVEL=1 until the path has run on hardware (use `timeout`).
+"""PSN_PREC_TC_TWOLEVEL ('tc_two_level', the engine default): tc_mixed plus the two-level surface march (api_stage1.cu
+raymarch_impl).  Verified on hardware in round 2 (profiles/r2_bringup.md): march 152 -> 88 ms at 512 x 512 x 256.
 
 What must hold: every output is BIT-IDENTICAL to 'tc_mixed' (and every march depth to 'tc'): the full program re-evaluates all
 proposal points the scan can tell apart, the single-pass values elsewhere only contribute their sign."""
-import os
-
 import pytest
 import torch
 
 import util
 from psnerf_b200 import engine, synth
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("PSNERF_B200_TEST_TWOLEVEL") != "1",
-                                 reason="experimental, not yet run on hardware (set PSNERF_B200_TEST_TWOLEVEL=1)")]
+pytestmark = pytest.mark.gpu
 
 
 def make_model(cfg, sd, prec):

@@ -135,45 +135,6 @@ def test_fused_optimizers_host_contract(lib_built):
         optim.Adam(list(e.parameters())).step()
 
 
-@pytest.mark.parametrize("case", list(util.TRAINER_CASES))
-def test_stage1_trainer_equals_reference_trainer(case):
-    """psnerf_b200.stage1.Trainer (train_step / compute_loss / process_data_dict) against the REAL stage1/model/training.py run
-    around the same stub renderer (tests/golden/stage1_trainer.npz): the same pixels are sampled under the same seed, every loss
-    term agrees, and so do the parameters after two optimizer steps."""
-    from psnerf_b200.stage1 import Trainer
-    g = util.golden("stage1_trainer")
-    over, it = util.TRAINER_CASES[case]
-    stub = util.StubRenderer()
-    opt = torch.optim.Adam(stub.parameters(), lr=1e-2)
-    t = Trainer(stub, opt, util.trainer_cfg(over), device=torch.device("cpu"))
-    torch.manual_seed(123)
-    for k in range(2):
-        ld = t.train_step(util.trainer_data(), it=it + k)
-        assert sorted(ld.keys()) == list(g[case + "_keys"])
-        for key, val in ld.items():
-            np.testing.assert_allclose(val.detach().numpy(), g["%s_s%d_%s" % (case, k, key)], rtol=2e-6, atol=1e-7)
-    assert np.array_equal(stub.calls[0][3].numpy(), g[case + "_pix"])
-    assert stub.calls[0][0] == "unisurf" and stub.calls[0][1] == it and stub.calls[0][2] is False and stub.training
-    np.testing.assert_allclose(stub.w.detach().numpy(), g[case + "_w"], rtol=1e-6)
-    with pytest.raises(NotImplementedError):
-        t.render_visdata(None, 0, "x.png")
-
-
-def test_get_tensor_values_and_full_grid_branch():
-    """get_tensor_values reads pixel round(x (W-1)/W) (the reference's W / H normalisation); n_training_points >= H W takes every pixel."""
-    from psnerf_b200.stage1 import Trainer, get_tensor_values
-    img = torch.arange(2 * 6 * 10, dtype=torch.float32).view(1, 2, 6, 10)
-    pix = torch.tensor([[[0.0, 0.0], [9.0, 5.0], [4.0, 2.0], [7.0, 3.0]]])
-    got = get_tensor_values(img, pix)
-    xs = torch.round(pix[0, :, 0] * 9 / 10).long()
-    ys = torch.round(pix[0, :, 1] * 5 / 6).long()
-    assert torch.equal(got[0], img[0][:, ys, xs].t())
-    stub = util.StubRenderer()
-    t = Trainer(stub, torch.optim.SGD(stub.parameters(), lr=0.0), util.trainer_cfg(dict(n_training_points=10 ** 6)), device=torch.device("cpu"))
-    ld = t.compute_loss(util.trainer_data(h=6, w=8), it=0)
-    assert stub.calls[0][3].shape == (1, 48, 2) and torch.isfinite(ld["loss"])
-
-
 def test_stage2_train_step_order_of_operations():
     """psnerf_b200.stage2.train_step = trainer.py:394-410: losses summed, both optimizers zeroed before and stepped after ONE backward,
     the light optimizer left alone once the light table is frozen."""
@@ -288,14 +249,13 @@ def test_arange_pixels_is_xmajor():
     assert torch.equal(loc, lo) and torch.equal(sc, so)
 
 
-def test_bench_traffic_lookup_matches_precision():
-    """roofline.traffic comes from the committed ncu capture of the radiance kernel AT THE BENCHED PRECISION."""
+def test_bench_traffic_lookup_matches_workload():
+    """roofline.traffic comes from a committed ncu capture of the named kernel ON THE NAMED WORKLOAD (captures carry a tag)."""
     import bench
-    t_tc, src_tc = bench.ncu_traffic("tc")
-    t_mx, src_mx = bench.ncu_traffic("tc_mixed")
-    assert src_tc and src_mx and src_tc != src_mx and "tc_mixed" in src_mx
-    assert 1e11 < t_tc < 3e11 and 1e11 < t_mx < 3e11
-    assert bench.ncu_traffic("fp32") == (None, None)
+    t_rad, src = bench.ncu_capture("k_tc_rad", "stage1_render")
+    assert src and 1e9 < t_rad < 3e11
+    assert bench.ncu_capture("k_tc_rad", "no_such_workload") == (None, None)
+    assert bench.ncu_capture("k_no_such_kernel", "stage1_render") == (None, None)
 
 
 def test_bench_reference_arm_prints_one_json_line():
@@ -307,7 +267,7 @@ def test_bench_reference_arm_prints_one_json_line():
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
-                        "--ref-crop", "8"], capture_output=True, text=True, timeout=600)
+                        "--sample-grid", "10"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1, r.stdout[:500]

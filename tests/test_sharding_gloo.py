@@ -2,6 +2,7 @@
 import os
 import socket
 
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -117,16 +118,30 @@ def test_mask_balanced_shards():
 
 
 class _StubPS(torch.nn.Module):
-    """PSNetwork stand-in: per-pixel outputs in the reference's shapes as functions of uv, mask and light direction."""
+    """PSNetwork stand-in: per-pixel outputs in the reference's shapes as functions of uv, mask and light direction.  Carries the
+    flags the sharded path derives its packed layout from (visibility / normal_mlp / microfacet / nbasis)."""
+
+    def __init__(self, visibility=True, normal_mlp=True):
+        super().__init__()
+        self.visibility, self.normal_mlp, self.microfacet, self.nbasis = visibility, normal_mlp, False, 9
+        self.calls = 0
 
     def forward(self, inp):
+        self.calls += 1
         uv, sm, l = inp["uv"][0], inp["surface_mask"][0], inp["light_direction"]
         L, n = l.shape[0], uv.shape[0]
+        assert n > 0, "a rank without pixels must not call the model"
         base = (uv[:, :1] * 0.01 + uv[:, 1:] * 0.02)[None] + l[:, None, :1]          # [L, n, 1]
         rgb = torch.where(sm[None, :, None], base.expand(L, n, 3) * torch.tensor([1.0, 2.0, 3.0]), torch.ones(L, n, 3))
         vis = torch.where(sm[None, :, None], (base * 0.5).expand(L, n, 3), torch.ones(L, n, 3))
         nrm = torch.where(sm[:, None], torch.stack([uv[:, 0], uv[:, 1], uv.sum(-1)], -1), torch.ones(n, 3))[None]
-        return {"sg_rgb_values": rgb, "visibility": vis, "normal_pred": nrm, "sg_diffuse_albedo_values": nrm * 0.25}
+        out = {"sg_rgb_values": rgb, "sg_specular_rgb_values": rgb * 0.125, "sg_diffuse_albedo_values": nrm * 0.25,
+               "sg_weight": (uv.sum(-1, keepdim=True) * torch.arange(1.0, 10.0))[None]}
+        if self.visibility:
+            out["visibility"] = vis
+        if self.normal_mlp:
+            out["normal_pred"] = nrm
+        return out
 
 
 def _s2_input(n_side=24):
@@ -139,26 +154,37 @@ def _s2_input(n_side=24):
             "normal": torch.randn(1, n, 3, generator=g), "intrinsics": torch.eye(4)[None], "pose": torch.eye(4)[None]}
 
 
-def _s2_worker(rank, world, port, q):
+S2_CASES = {  # name: (image side, model flags) - "tiny": 64 pixels < world * tile, so rank 1 is dealt no pixels at all
+    "full": (24, dict()),
+    "no_vis_no_normal": (24, dict(visibility=False, normal_mlp=False)),
+    "tiny": (8, dict()),
+}
+
+
+def _s2_worker(rank, world, port, q, case):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from psnerf_b200 import pipeline
+    side, flags = S2_CASES[case]
     lights = torch.nn.functional.normalize(torch.randn(7, 3, generator=torch.Generator().manual_seed(2)), dim=-1)
-    out = pipeline.render_stage2_view_sharded(_StubPS(), _s2_input(), lights, rank, world, light_batch=3)
+    out = pipeline.render_stage2_view_sharded(_StubPS(**flags), _s2_input(side), lights, rank, world, light_batch=3)
     q.put((rank, {k: v.numpy() for k, v in out.items()}))
     dist.destroy_process_group()
 
 
-def test_stage2_view_sharded_world2_gloo():
+@pytest.mark.parametrize("case", list(S2_CASES))
+def test_stage2_view_sharded_world2_gloo(case):
     """BASELINE config 4 host logic: surface-balanced pixel shards, all light batches per rank, one all_gather - equal to the
-    unsharded render of the same (stub) model on every rank."""
+    unsharded render of the same (stub) model on every rank; the entries follow the model's flags like the unsharded path, and a
+    rank that was dealt no pixels takes part in the gather without calling the model."""
     from psnerf_b200 import pipeline
     world = 2
+    side, flags = S2_CASES[case]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_s2_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_s2_worker, args=(r, world, port, q, case)) for r in range(world)]
     for p in procs:
         p.start()
     res = dict(q.get(timeout=120) for _ in range(world))
@@ -166,9 +192,14 @@ def test_stage2_view_sharded_world2_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     lights = torch.nn.functional.normalize(torch.randn(7, 3, generator=torch.Generator().manual_seed(2)), dim=-1)
-    want = pipeline.render_stage2_view(_StubPS(), _s2_input(), lights, light_batch=3)
-    single = pipeline.render_stage2_view_sharded(_StubPS(), _s2_input(), lights, 0, 1, light_batch=3)
-    for k in ("sg_rgb_values", "visibility", "normal_pred", "sg_diffuse_albedo_values"):
+    want = pipeline.render_stage2_view(_StubPS(**flags), _s2_input(side), lights, light_batch=3)
+    single = pipeline.render_stage2_view_sharded(_StubPS(**flags), _s2_input(side), lights, 0, 1, light_batch=3)
+    keys = ["sg_rgb_values", "sg_specular_rgb_values", "sg_diffuse_albedo_values", "sg_weight"]
+    keys += ["visibility"] if flags.get("visibility", True) else []
+    keys += ["normal_pred"] if flags.get("normal_mlp", True) else []
+    assert sorted(single.keys()) == sorted(keys)
+    for k in keys:
         assert torch.equal(single[k], want[k].reshape(single[k].shape)), k
         for r in range(world):
+            assert sorted(res[r].keys()) == sorted(keys)
             assert torch.equal(torch.from_numpy(res[r][k]), want[k].reshape(single[k].shape)), (k, r)
