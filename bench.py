@@ -247,6 +247,22 @@ def cpu_baseline_and_parity(gpu_shape, gpu_out, gpu_render, K, pose, lights):
         a = gpu_out[k_gpu][:, idx].cpu()[:, agree]
         b = out[k_gpu].reshape(a.shape[0], -1, a.shape[-1])[:, agree]
         par[name] = _stats(a, b)
+    # ---- stage 2 on IDENTICAL inputs: the oracle's PSNetwork.forward fed with the GPU's own surface (points / normals / mask) at the
+    # sample pixels, so that only the shading kernels are compared (the chain above also carries the 2^9-frequency encoding of the
+    # ~1e-5 surface-point differences between the two stage-1 results)
+    Ks = torch.eye(4).unsqueeze(0)
+    Ks[0, 0, 0] = Ks[0, 1, 1] = K[0, 0, 0]
+    Ks[0, 0, 2], Ks[0, 1, 2] = K[0, 0, 2], K[0, 1, 2]
+    gm = gpu_shape["mask"][:, idx].cpu()
+    inp_same = {"intrinsics": Ks, "uv": pix.float(), "pose": pose, "object_mask": gm, "surface_mask": gm,
+                "points": gpu_shape["points"][:, idx].cpu(), "normal": gpu_shape["normal"][:, idx].cpu(), "light_direction": lights}
+    with torch.no_grad():
+        same = O.psnetwork_forward(sd2, conf, inp_same)
+    par["stage2_identical_inputs"] = {}
+    for k_gpu, name in (("sg_rgb_values", "rgb"), ("sg_diffuse_albedo_values", "albedo"), ("normal_pred", "normal_pred"),
+                        ("visibility", "s2_visibility"), ("sg_specular_rgb_values", "specular")):
+        a = gpu_out[k_gpu][:, idx].cpu()
+        par["stage2_identical_inputs"][name] = _stats(a, same[k_gpu].reshape(a.shape))
     # ---- secondary: stage-1 volume render (configs[1]) on the same sample pixels
     t0 = time.perf_counter()
     ref = O.unisurf_render(sd1, cfg, pix, K, pose, it=100000)
@@ -594,10 +610,9 @@ def main():
         res = rows[0] if len(rows) == 1 else torch.cat(rows, 0)
         if dist:
             td.all_gather_into_tensor(gather_buf.view(-1), res.view(-1))  # the single NCCL pixel gather
-        if e2e:
-            out_host[:, :3 * L_LIGHTS].copy_(res[:, col_rgb:col_rgb + 3 * L_LIGHTS], non_blocking=True)
-            out_host[:, 3 * L_LIGHTS:3 * L_LIGHTS + 3].copy_(res[:, col_alb:col_alb + 3], non_blocking=True)
-            out_host[:, 3 * L_LIGHTS + 3:].copy_(res[:, width:], non_blocking=True)
+        if e2e:  # one contiguous device buffer -> one DMA into pinned host memory
+            packed = torch.cat([res[:, col_rgb:col_rgb + 3 * L_LIGHTS], res[:, col_alb:col_alb + 3], res[:, width:]], 1)
+            out_host.copy_(packed, non_blocking=True)
         return res
 
     def timed(e2e, steps):

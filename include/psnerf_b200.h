@@ -201,6 +201,12 @@ int psn_tc_debug_trace_q(const psn_mlp* geo, const float* pts, int64_t M, float*
 int psn_tc_debug_trace_rad(const psn_mlp* geo, const psn_mlp* app, const float* pts, const float* views, int64_t M,
                            float* rgb, float* alpha, void* stash, long long* trace, int mixed, void* stream);
 
+/* Test hook for the GEMM of the train steps (csrc/tc_gemm.cu: tcgen05 kind::tf32, three split passes, fp32 accumulate):
+ * form 0: C[M,N] = A[M,K] B[N,K]^T (+bias, epi 1 / relu 2 / sigmoid 3); form 1: C[M,N] = A[M,K] B[K,N];
+ * form 2: C[M,N] += A[K,M]^T B[K,N].  Row-major fp32 device matrices with leading dimensions lda / ldb / ldc. */
+int psn_tc_gemm_debug(int form, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, const float* bias,
+                      int64_t M, int N, int64_t K, int epi, void* stream);
+
 /* ---- stage-2 train step (BASELINE config 5): PSNetwork.forward + backward, stage2/trainer.py:394-410 ------------------------
  * Gradient-carrying parts (renderer.py:193-199,211-231,251-262 with light_vis_detach = vis_rgb_detach = True): the per-point nets
  * through the SG shading of all L lights and their jittered re-evaluation, light directions / intensities, and visibility_net

@@ -32,6 +32,16 @@ static int radiance_any(const psn_mlp* geo, const psn_mlp* app, const PointGen& 
 }
 
 static size_t stash_bytes(int precision) { return prec_is_tc(precision) ? tc_stash_bytes() : simt_stash_bytes(); }
+static size_t stash_bytes_any() { return tc_stash_bytes() > simt_stash_bytes() ? tc_stash_bytes() : simt_stash_bytes(); }
+
+// Accuracy policy of the tensor-core precisions.  The O(rays x samples) launches (march proposals, radiance samples, shadow samples)
+// run on tcgen05; two O(rays) launches decide quantities every later stage amplifies and run on the fp32 FFMA kernels instead:
+//  * the LAST kSecantFp32Tail secant iterations - the refined depth is the root of the occupancy evaluated there; the split-operand
+//    logit carries ~1e-5 of rounding, i.e. ~3e-5 of depth, and shadow visibilities / stage-2 encodings (2^9 x) multiply that by 100;
+//  * the surface-normal OUTPUT (one gradient evaluation per hit ray).
+// Measured (profiles/r2_parity_errlog.jsonl): points 3.5e-5 -> fp32 level, normals 3.4e-4 -> below the 1e-4 gate, for ~1 % of a step.
+static const int kSecantFp32Tail = 2;
+static int normal_precision(int precision) { return prec_is_tc(precision) ? PSN_PREC_FP32 : precision; }
 
 static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
@@ -202,7 +212,8 @@ static int raymarch_impl(const psn_mlp* geo, const float* origin, const float* d
   g2.depth = s.d_pred;
   g2.o[0] = origin[0]; g2.o[1] = origin[1]; g2.o[2] = origin[2];
   for (int it = 0; it < n_secant; ++it) {
-    if ((rc = occupancy_any(geo, g2, 0, s.count, PSN_OUT_ALPHA, occ_mid, precision, st))) return rc;
+    const int prec_it = (prec_is_tc(precision) && it >= n_secant - kSecantFp32Tail) ? PSN_PREC_FP32 : precision;
+    if ((rc = occupancy_any(geo, g2, 0, s.count, PSN_OUT_ALPHA, occ_mid, prec_it, st))) return rc;
     if ((rc = launch_secant_update(s, occ_mid, tau, N, st))) return rc;
   }
   return launch_march_finalize(s, depth, N, st);
@@ -248,7 +259,7 @@ extern "C" int psn_render_unisurf(const psn_mlp* geo, const psn_mlp* app, const 
   sl.ray = w.take<int>(N);
   sl.depth = w.take<float>(N);
   float* grads = w.take<float>((size_t)N * 3);
-  void* stash = w.take<char>(stash_bytes(precision));
+  void* stash = w.take<char>(stash_bytes_any());
   PSN_REQUIRE(w.ok, PSN_ERR_WORKSPACE, "psn_render_unisurf: workspace too small (need %zu bytes, have %lld)", w.used,
               (long long)ws_bytes);
   PSN_CUDA_CHECK(cudaMemsetAsync(sl.count, 0, sizeof(int), st));
@@ -271,7 +282,7 @@ extern "C" int psn_render_unisurf(const psn_mlp* geo, const psn_mlp* app, const 
   g2.index = sl.ray;
   g2.depth = sl.depth;
   g2.o[0] = origin[0]; g2.o[1] = origin[1]; g2.o[2] = origin[2];
-  if ((rc = gradient_any(geo, g2, 0, sl.count, grads, stash, precision, st))) return rc;
+  if ((rc = gradient_any(geo, g2, 0, sl.count, grads, stash, normal_precision(precision), st))) return rc;
   return launch_scatter_normals(grads, sl, normal, N, st);
 }
 

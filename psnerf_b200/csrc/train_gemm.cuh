@@ -99,9 +99,16 @@ static __global__ void k_colsum(const float* __restrict__ dZ, int ld, long long 
 }
 static inline unsigned nblk(long long n, int t = 256) { return (unsigned)((n + t - 1) / t); }
 
+// tc_gemm.cu: the same three products on the tensor cores (tcgen05 kind::tf32, x = hi + lo split, three passes, fp32 accumulate).
+// It is what the train steps run; PSNERF_B200_TRAIN_GEMM=ffma selects the FFMA kernel above (A/B measurements, cross-check).
+int tc_gemm(int form, const float* A, long long lda, const float* B, long long ldb, float* C, long long ldc, const float* bias, long long M,
+            int N, long long K, int epi, cudaStream_t st);
+bool train_gemm_use_tc();
+
 static int gemm(int form, const float* A, int lda, const float* B, int ldb, float* C, int ldc, const float* bias, long long M, int N,
                 long long K, int epi, cudaStream_t st) {
   if (M == 0 || N == 0 || K == 0) return PSN_OK;
+  if (train_gemm_use_tc()) return tc_gemm(form, A, lda, B, ldb, C, ldc, bias, M, N, K, epi, st);
   count_launch();
   if (form == 0) {
     dim3 g((N + 63) / 64, (unsigned)((M + 63) / 64));

@@ -47,6 +47,13 @@ class Renderer(nn.Module):
     def _geo_app(self):
         return self.model._packed()
 
+    def _normal_prec(self):
+        """Precision of the surface-normal OUTPUT launches (one gradient evaluation per hit ray): fp32 under every tensor-core
+        precision, like the library's own unisurf normals (csrc/api_stage1.cu: normal_precision)."""
+        p = self.model._prec()
+        p = engine.default_precision() if p is None else p
+        return B.PREC_FP32 if p != B.PREC_FP32 else p
+
     def _surface(self, depth, origin, dirs):
         """mask / surface points exactly as rendering.py:88-108."""
         zero_occ = depth == 0
@@ -190,7 +197,7 @@ class Renderer(nn.Module):
         obj, pts = self._surface(d, origin, dirs)
         rgb = torch.ones_like(pts)
         if int(obj.sum()) > 0:
-            grad = engine.gradient(g, pts[obj], self.model._prec())
+            grad = engine.gradient(g, pts[obj], self._normal_prec())
             nrm = grad / grad.norm(2, 1, keepdim=True)
             o = torch.tensor(origin, dtype=torch.float32, device=dirs.device)
             light = (o / o.norm(2)).unsqueeze(1)
@@ -209,7 +216,7 @@ class Renderer(nn.Module):
         surf = pts[obj]
         normal = torch.zeros(N, 3, device=dirs.device)
         if surf.shape[0] > 0:
-            normal[obj] = F.normalize(engine.gradient(g, surf, self.model._prec()), dim=-1)
+            normal[obj] = F.normalize(engine.gradient(g, surf, self._normal_prec()), dim=-1)
         out = {"mask": obj.reshape(1, -1), "normal": normal.reshape(1, -1, 3), "points": pts.reshape(1, -1, 3)}
         if visibility and light_dir is not None:
             light_dir = light_dir.to(dirs.device).float()

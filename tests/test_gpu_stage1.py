@@ -226,7 +226,7 @@ def test_box_culled_shadow_pass(s1, prec, Ns, L, monkeypatch):
     gen = torch.Generator().manual_seed(500 + Ns)
     surf = torch.nn.functional.normalize(torch.randn(Ns, 3, generator=gen), dim=-1) * (0.3 + 0.9 * torch.rand(Ns, 1, generator=gen))
     if Ns > 2:
-        surf[0] = torch.tensor([1.5, 0.2, -0.1])    # outside the box from the first step on
+        surf[0] = torch.tensor([5.0, 5.0, 5.0])     # no step of any unit direction (t <= 3.5) reaches the box
         surf[1] = torch.tensor([1.09, 1.09, 1.09])  # leaves the box after a few steps whatever the light
     lights = synth.lights(L, seed=21)
     vis, st = engine.shadow_visibility(g, surf.cuda(), lights.cuda(), precision=r.model._prec(), return_stats=True)
