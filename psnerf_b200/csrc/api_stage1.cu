@@ -35,12 +35,13 @@ static size_t stash_bytes(int precision) { return prec_is_tc(precision) ? tc_sta
 static size_t stash_bytes_any() { return tc_stash_bytes() > simt_stash_bytes() ? tc_stash_bytes() : simt_stash_bytes(); }
 
 // Accuracy policy of the tensor-core precisions.  The O(rays x samples) launches (march proposals, radiance samples, shadow samples)
-// run on tcgen05; two O(rays) launches decide quantities every later stage amplifies and run on the fp32 FFMA kernels instead:
-//  * the LAST kSecantFp32Tail secant iterations - the refined depth is the root of the occupancy evaluated there; the split-operand
-//    logit carries ~1e-5 of rounding, i.e. ~3e-5 of depth, and shadow visibilities / stage-2 encodings (2^9 x) multiply that by 100;
+// run on tcgen05; two O(rays) computations decide quantities every later stage amplifies and run on the fp32 FFMA kernels instead:
+//  * the secant refinement - its result is the root of the occupancy AS EVALUATED; the split-operand logit carries ~1e-5 of rounding
+//    (48 truncating tensor-core accumulations per layer), which near the root is as large as the bracket values themselves: wrong-signed
+//    updates push the bracket ~3e-5 off the fp32 root (measured, profiles/r2_parity_errlog_*.jsonl), and the shadow visibilities
+//    (x 100) and the 2^9-frequency encodings of stage 2 multiply that;
 //  * the surface-normal OUTPUT (one gradient evaluation per hit ray).
-// Measured (profiles/r2_parity_errlog.jsonl): points 3.5e-5 -> fp32 level, normals 3.4e-4 -> below the 1e-4 gate, for ~1 % of a step.
-static const int kSecantFp32Tail = 2;
+// Cost: 8 x 1.3 ms + 3 ms per 512 x 512 view (2 % of the relit-view step), in ONE launch each.
 static int normal_precision(int precision) { return prec_is_tc(precision) ? PSN_PREC_FP32 : precision; }
 
 static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
@@ -59,6 +60,10 @@ static size_t march_ws_bytes(long long N, int S) {
 static const long long kShadowChunkPairs = 1 << 21;  // (light, point) pairs per shadow chunk (1 GB of occupancies at S=128)
 // A/B switch for measurements: PSNERF_B200_SHADOW_UNCULLED=1 evaluates every step of every shadow ray like the reference does
 // (fused k_tc_occ<MODE_SHADOW> on the tensor path) instead of the box-culled list.  Results agree to rounding of the product order.
+static bool secant_unfused_requested() {
+  const char* e = getenv("PSNERF_B200_SECANT_UNFUSED");
+  return e && e[0] == '1';
+}
 static bool shadow_unculled_requested() {
   const char* e = getenv("PSNERF_B200_SHADOW_UNCULLED");
   return e && e[0] == '1';
@@ -211,10 +216,17 @@ static int raymarch_impl(const psn_mlp* geo, const float* origin, const float* d
   g2.index = s.ray;
   g2.depth = s.d_pred;
   g2.o[0] = origin[0]; g2.o[1] = origin[1]; g2.o[2] = origin[2];
-  for (int it = 0; it < n_secant; ++it) {
-    const int prec_it = (prec_is_tc(precision) && it >= n_secant - kSecantFp32Tail) ? PSN_PREC_FP32 : precision;
-    if ((rc = occupancy_any(geo, g2, 0, s.count, PSN_OUT_ALPHA, occ_mid, prec_it, st))) return rc;
-    if ((rc = launch_secant_update(s, occ_mid, tau, N, st))) return rc;
+  // All n_secant iterations in ONE launch of the fp32 kernel, the bracket kept on chip (k_geo_secant); the tensor precisions use it
+  // too (accuracy policy above).  PSNERF_B200_SECANT_UNFUSED=1 runs one evaluation launch + one update kernel per iteration
+  // instead (bit-identical: A/B tests).
+  if (!secant_unfused_requested()) {
+    ProfScope prof(PSN_PROF_OCC_SECANT, 0, st);
+    if ((rc = simt_secant(geo, g2, s, n_secant, tau, st))) return rc;
+  } else {
+    for (int it = 0; it < n_secant; ++it) {
+      if ((rc = occupancy_any(geo, g2, 0, s.count, PSN_OUT_ALPHA, occ_mid, PSN_PREC_FP32, st))) return rc;
+      if ((rc = launch_secant_update(s, occ_mid, tau, N, st))) return rc;
+    }
   }
   return launch_march_finalize(s, depth, N, st);
 }

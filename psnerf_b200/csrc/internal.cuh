@@ -22,6 +22,7 @@ struct ShadowList { unsigned* total; unsigned long long* evaluated; unsigned lon
 // stage1_simt.cu
 int simt_occupancy(const psn_mlp* geo, const PointGen& gen, long long M, const int* M_dev, int out_kind, float* out,
                    int with_feat, cudaStream_t st);
+int simt_secant(const psn_mlp* geo, const PointGen& gen, const SecantState& sec, int n_iter, float tau, cudaStream_t st);
 int simt_gradient(const psn_mlp* geo, const PointGen& gen, long long M, const int* M_dev, float* grad, void* stash,
                   cudaStream_t st);
 int simt_radiance(const psn_mlp* geo, const psn_mlp* app, const PointGen& gen, long long M, float* rgb, float* alpha,

@@ -1,6 +1,7 @@
 // Stage-1 fp32 FFMA kernels: occupancy / infer_occ / gradient / radiance over 64-row tiles, persistent CTAs.
 #include "stage1_simt.cuh"
 #include "launch.cuh"
+#include "internal.cuh"
 
 namespace psn {
 
@@ -63,6 +64,75 @@ k_geo_occ(GeoDev g, PointGen gen, long long M_host, const int* M_dev, int out_ki
           }
         }
       }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// secant refinement (rendering.py:525-555): n_iter evaluations per tile of 64 masked rays, the bracket stays in shared memory
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT, 1)
+k_geo_secant(GeoDev g, PointGen gen, SecantState sec, int n_iter, float tau) {
+  extern __shared__ __align__(16) float smem[];
+  float* PE = smem;
+  float* X = PE + PE_ROWS * LDX;
+  float* WS = X + 256 * LDX;
+  float* P = WS + WRING_FLOATS;   // [3][TM]
+  float* ST = P + 3 * TM;         // d_low, d_high, f_low, f_high, d_pred, dir x / y / z, z (logit): [9][TM]
+  const long long M = (long long)*sec.count;
+  const long long n_tiles = (M + TM - 1) / TM;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long base = tile * TM;
+    const int r = threadIdx.x;
+    const bool live = r < TM && base + r < M;
+    if (r < TM) {
+      float d_low = 0.f, d_high = 0.f, f_low = -1.f, f_high = 1.f, d_pred = 0.f, dx = 0.f, dy = 0.f, dz = 0.f;
+      if (live) {
+        const long long slot = base + r, ray = sec.ray[slot];
+        d_low = sec.d_low[slot]; d_high = sec.d_high[slot]; f_low = sec.f_low[slot]; f_high = sec.f_high[slot];
+        d_pred = sec.d_pred[slot];
+        dx = gen.dirs[ray * 3]; dy = gen.dirs[ray * 3 + 1]; dz = gen.dirs[ray * 3 + 2];
+      }
+      ST[r] = d_low; ST[TM + r] = d_high; ST[2 * TM + r] = f_low; ST[3 * TM + r] = f_high; ST[4 * TM + r] = d_pred;
+      ST[5 * TM + r] = dx; ST[6 * TM + r] = dy; ST[7 * TM + r] = dz;
+    }
+    __syncthreads();
+    for (int it = 0; it < n_iter; ++it) {
+      if (r < TM) {  // p_mid = ray0 + d_pred * ray_direction (the arithmetic of GEN_INDEXED_DEPTH)
+        const float d = ST[4 * TM + r];
+        P[r] = madd_rn(gen.o[0], ST[5 * TM + r], d);
+        P[TM + r] = madd_rn(gen.o[1], ST[6 * TM + r], d);
+        P[2 * TM + r] = madd_rn(gen.o[2], ST[7 * TM + r], d);
+      }
+      __syncthreads();
+      encode_points(P, PE, g.octaves, g.rescale);
+      __syncthreads();
+      geo_forward<false>(g, PE, X, WS, nullptr);
+      {
+        float acc[8][1];
+        dense<1>(g.logit, X, WS, acc);
+        if (tx == 0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) ST[8 * TM + ty * 8 + i] = acc[i][0];
+        }
+      }
+      __syncthreads();
+      if (r < TM) {  // f_mid = occupancy - tau with the PSN_OUT_ALPHA expression of k_geo_occ, then the update of k_secant_update
+        const float f_mid = sigmoidf_(ST[8 * TM + r] * -10.0f) - tau;
+        float d_low = ST[r], d_high = ST[TM + r], f_low = ST[2 * TM + r], f_high = ST[3 * TM + r];
+        const float d_pred = ST[4 * TM + r];
+        if (f_mid < 0.f) { d_low = d_pred; f_low = f_mid; } else { d_high = d_pred; f_high = f_mid; }
+        ST[r] = d_low; ST[TM + r] = d_high; ST[2 * TM + r] = f_low; ST[3 * TM + r] = f_high;
+        ST[4 * TM + r] = __fadd_rn(__fdiv_rn(__fmul_rn(-f_low, __fsub_rn(d_high, d_low)), __fsub_rn(f_high, f_low)), d_low);
+      }
+      __syncthreads();
+    }
+    if (live) {
+      const long long slot = base + r;
+      sec.d_low[slot] = ST[r]; sec.d_high[slot] = ST[TM + r]; sec.f_low[slot] = ST[2 * TM + r]; sec.f_high[slot] = ST[3 * TM + r];
+      sec.d_pred[slot] = ST[4 * TM + r];
     }
     __syncthreads();
   }
@@ -280,6 +350,20 @@ int simt_occupancy(const psn_mlp* geo, const PointGen& gen, long long M, const i
   const int grid = (int)(tiles < num_ctas() ? tiles : num_ctas());
   psn::count_launch();
   k_geo_occ<<<grid, NT, smem_occ(), st>>>(g, gen, M, M_dev, out_kind, out, with_feat);
+  PSN_CUDA_CHECK(cudaGetLastError());
+  return PSN_OK;
+}
+
+// n_iter secant iterations over the masked rays of `sec` in ONE launch (count read on the device)
+int simt_secant(const psn_mlp* geo, const PointGen& gen, const SecantState& sec, int n_iter, float tau, cudaStream_t st) {
+  GeoDev g;
+  int rc = make_geo_dev(geo, &g);
+  if (rc) return rc;
+  if (n_iter <= 0) return PSN_OK;
+  const size_t smem = smem_occ() + 9 * TM * 4;
+  PSN_CUDA_CHECK(cudaFuncSetAttribute(k_geo_secant, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  psn::count_launch();
+  k_geo_secant<<<num_ctas(), NT, smem, st>>>(g, gen, sec, n_iter, tau);
   PSN_CUDA_CHECK(cudaGetLastError());
   return PSN_OK;
 }

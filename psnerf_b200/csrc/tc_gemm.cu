@@ -319,11 +319,15 @@ int tc_gemm(int form, const float* A, long long lda, const float* B, long long l
   a.k_per_split = K;
   const int ctas = num_ctas();
   if (form == 2) {
-    // K = samples: enough splits to fill the machine, at least 8 K blocks each
+    // K = samples.  Enough splits to fill the machine, each at least 8 K blocks long - and at most 1024 samples: every MMA adds its
+    // partial sum into the fp32 accumulator with truncation, so a long chain on one accumulator loses accuracy linearly in its
+    // length (3 x 128 instructions per 1024 samples ~ 1e-5); the partial tiles are combined by fp32 atomics instead.
     const long long tiles = a.m_tiles * a.n_chunks;
     long long splits = (ctas + tiles - 1) / tiles;
     const long long max_splits = (K + 8 * BK - 1) / (8 * BK);
+    const long long min_splits = (K + 1023) / 1024;
     if (splits > max_splits) splits = max_splits;
+    if (splits < min_splits) splits = min_splits;
     if (splits < 1) splits = 1;
     a.k_per_split = ((K + splits - 1) / splits + BK - 1) / BK * BK;
     a.k_splits = (int)((K + a.k_per_split - 1) / a.k_per_split);

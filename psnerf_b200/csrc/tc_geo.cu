@@ -2,6 +2,8 @@
 //   MODE_OUT    : one value per sample (alpha / logits) - ray-march proposals, secant points, explicit queries
 //   MODE_SHADOW : a 128-row tile is one shadow ray; box mask + transmittance are reduced in the epilogue and only
 //                 vis[pair] is written (rendering.py:378-408), no per-sample HBM traffic at all.
+//   MODE_FEAT   : NeuralNetwork.infer_occ (network.py:85-95): a ninth step, the feature head, follows the stack; out[M, 1 + 256] =
+//                 [logit, feature] per sample.
 // Algorithmic work per sample: 2 * 459,008 FLOP (the 256 unused feature rows of the last layer are not computed).
 // CHEAP = true is the first level of the two-level surface march (PSN_PREC_TC_TWOLEVEL, api_stage1.cu): every layer in ONE pass
 // A_hi W_hi (Step::single, hi-only operand stores).  Its values are only trusted away from the occupancy threshold; the
@@ -19,13 +21,15 @@ struct TcGeoArgs {
   const float* bias[8];
   const float* w_row;     // [256] logit row
   const float* b_logit;   // [>=1]
+  const float* bias_feat; // MODE_FEAT: bias of the feature head (rows 1.. of the last Linear)
+  int n_feat;             // MODE_FEAT: feature width (256)
   int n_out[8];           // valid output columns per layer (217 for the pre-skip layer)
   int skip;               // layer whose input is cat[x, pe]/sqrt2
   int octaves, pe_dim;
   float rescale;
 };
 
-constexpr int MODE_OUT = 0, MODE_SHADOW = 1, MODE_DEBUG = 2;  // MODE_DEBUG = MODE_OUT + layer dump / clock64 trace hooks
+constexpr int MODE_OUT = 0, MODE_SHADOW = 1, MODE_DEBUG = 2, MODE_FEAT = 3;  // MODE_DEBUG = MODE_OUT + layer dump / clock64 trace hooks
 
 template <int MODE, bool CHEAP = false>
 __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1)
@@ -99,7 +103,17 @@ k_tc_occ(TcGeoArgs g, PointGen gen, long long M_host, const int* M_dev, int out_
               for (int i = 0; i < CW; ++i) dump[idx * 256 + col + i] = v[i];
             }
           }
-          if (l < 7) {
+          if (MODE == MODE_FEAT && l == 7) {  // h_7 feeds both the fp32 logit row and the feature-head step
+            const float4* w4 = reinterpret_cast<const float4*>(g.w_row + col);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float4 w = __ldg(w4 + t);
+              part = fmaf(v[4 * t], w.x, part); part = fmaf(v[4 * t + 1], w.y, part);
+              part = fmaf(v[4 * t + 2], w.z, part); part = fmaf(v[4 * t + 3], w.w, part);
+            }
+            epi_store_a16(e, e.d_col0(), col, v, false);
+            epi_signal_a(s, pass);
+          } else if (l < 7) {
             if (pre_skip && col + CW > n_out) {  // columns n_out.. of the skip layer's input are pe/sqrt2 (network.py:90-91)
 #pragma unroll
               for (int i = 0; i < CW; ++i) {
@@ -122,13 +136,28 @@ k_tc_occ(TcGeoArgs g, PointGen gen, long long M_host, const int* M_dev, int out_
         });
         e.step_ctr++;
       }
+      if (MODE == MODE_FEAT) {  // step 8: feature head, no activation (network.py:95 returns the raw last Linear)
+        const int stride = 1 + g.n_feat;
+        epi_for_chunks_pf<Bias16>(s, e, [&](int col, Bias16& b) { load_bias16(g.bias_feat, col, b); },
+                                  [&](int pass, int col, float (&v)[CW], const Bias16& b) {
+          add16(v, b.b);
+          if (idx < M) {
+#pragma unroll
+            for (int i = 0; i < CW; ++i)
+              if (col + i < g.n_feat) out[idx * stride + 1 + col + i] = v[i];
+          }
+        });
+        e.step_ctr++;
+      }
       tc_fence_before();  // order this tile's last TMEM reads before the next tile's operand stores / MMAs
       s.stage[sub * TILE_M + row].x = part;
       named_bar_sync(1, EPI_THREADS);
       if (sub == 0) {
         const float z = ((s.stage[row].x + s.stage[TILE_M + row].x) + (s.stage[2 * TILE_M + row].x + s.stage[3 * TILE_M + row].x)) +
                         __ldg(g.b_logit);
-        if (MODE != MODE_SHADOW) {
+        if (MODE == MODE_FEAT) {
+          if (idx < M) out[idx * (1 + g.n_feat)] = z;
+        } else if (MODE != MODE_SHADOW) {
           if (idx < M) {
             float o = z;
             if (out_kind == PSN_OUT_ALPHA) o = 1.f / (1.f + __expf(10.f * z));
@@ -249,6 +278,22 @@ int tc_occupancy(const psn_mlp* geo, const PointGen& gen, long long M, const int
   return launch_tc_occ<MODE_OUT>(a, gen, M, M_dev, out_kind, out, 0.f, -1, nullptr, st);
 }
 
+// NeuralNetwork.infer_occ: [M, 1 + feat] = logit and feature vector (network.py:85-95), the stack plus the feature-head step
+int tc_infer_occ(const psn_mlp* geo, const PointGen& gen, long long M, float* out, cudaStream_t st) {
+  TcGeoArgs a;
+  int rc = make_tc_geo(geo, &a);
+  if (rc) return rc;
+  if (M == 0) return PSN_OK;
+  a.prog.n_steps = 9;
+  a.prog.step[8].w_off = geo->tc_step[TCG_FEAT].w_off;
+  a.prog.step[8].nkb = geo->tc_step[TCG_FEAT].nkb;
+  a.prog.step[8].n_pad = geo->tc_step[TCG_FEAT].n_pad;
+  a.prog.blob[8] = geo->tc_blob;
+  a.bias_feat = geo->fwd[8].bias;
+  a.n_feat = geo->fwd[8].N;
+  return launch_tc_occ<MODE_FEAT>(a, gen, M, nullptr, PSN_OUT_LOGIT, out, 0.f, -1, nullptr, st);
+}
+
 // Single-pass evaluation of the same stack (first level of the two-level march): NOT within the parity tolerance on its own.
 int tc_occupancy_cheap(const psn_mlp* geo, const PointGen& gen, long long M, int out_kind, float* out, cudaStream_t st) {
   TcGeoArgs a;
@@ -272,6 +317,9 @@ int tc_shadow(const psn_mlp* geo, const PointGen& gen, long long pairs, float bo
 }  // namespace psn
 
 using namespace psn;
+
+// sm_100a builds always carry the tcgen05 kernels (engine.tc_available()).
+extern "C" int psn_has_tensor_path(void) { return 1; }
 
 // Bring-up / test hook: run the tensor-core geo stack on explicit points and dump the activations that layer `layer`
 // hands to the next one (fp32, before the fp16 hi/lo split): out[M, 256].

@@ -55,3 +55,29 @@ def test_unisurf_equals_tc_mixed(variant, case):
         outs[prec] = r(pix.cuda(), K.cuda(), pose.cuda(), None, "unisurf", add_noise=False, eval_=True, it=it)
     for k in ("rgb", "mask_pred", "acc_map", "normal_pred"):
         assert torch.equal(outs["tc_mixed"][k], outs["tc_two_level"][k]), k
+
+
+@pytest.mark.parametrize("variant", ["init", "trained"])
+@pytest.mark.parametrize("prec", ["fp32", "tc", "tc_two_level"])
+def test_fused_secant_equals_one_launch_per_iteration(variant, prec, monkeypatch):
+    """Renderer.secant (rendering.py:525-555) runs as ONE launch of the fp32 occupancy kernel with the bracket kept on chip (under
+    every precision: csrc/api_stage1.cu accuracy policy); PSNERF_B200_SECANT_UNFUSED=1 runs one evaluation launch + one update
+    kernel per iteration: same bits."""
+    from psnerf_b200.stage1 import Renderer
+    _, sds = util.stage1_state_dicts()
+    cfg = synth.stage1_cfg(ray_marching_steps=128)
+    h, w = 37, 29  # 1073 rays: several tiles, a ragged last one
+    pix, K, pose = synth.pixel_grid_xmajor(h, w), synth.intrinsics(h, w), synth.look_at_pose(40.0, -15.0)
+    r = Renderer(make_model(cfg, sds[variant], prec), cfg, device=torch.device("cuda"))
+    g, _ = r._geo_app()
+    origin, dirs = r._rays(pix, K, pose)
+    fused = engine.raymarch(g, origin, dirs, 2.0, 2.0, 128, 8, 0.5, r.model._prec())
+    monkeypatch.setenv("PSNERF_B200_SECANT_UNFUSED", "1")
+    unfused = engine.raymarch(g, origin, dirs, 2.0, 2.0, 128, 8, 0.5, r.model._prec())
+    assert int(torch.isfinite(fused).sum()) > 50
+    assert torch.equal(fused, unfused)
+    for n_sec in (0, 1, 3):
+        monkeypatch.delenv("PSNERF_B200_SECANT_UNFUSED", raising=False)
+        a = engine.raymarch(g, origin, dirs, 2.0, 2.0, 128, n_sec, 0.5, r.model._prec())
+        monkeypatch.setenv("PSNERF_B200_SECANT_UNFUSED", "1")
+        assert torch.equal(a, engine.raymarch(g, origin, dirs, 2.0, 2.0, 128, n_sec, 0.5, r.model._prec())), n_sec
