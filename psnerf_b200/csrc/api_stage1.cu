@@ -57,6 +57,7 @@ static const float kRefineMargin = 0.02f;  // >= 20 x the largest |cheap - full|
 static size_t march_ws_bytes(long long N, int S) {
   return align256((size_t)N * S * 4) + 8 * align256((size_t)N * 4) + 1024 + 4 * align256((size_t)refine_cap(N, S) * 4) + 512;
 }
+static const int kShadowLead = 8;  // in-box steps of every shadow ray evaluated before its transmittance decides about the rest (<= 32)
 static const long long kShadowChunkPairs = 1 << 21;  // (light, point) pairs per shadow chunk (1 GB of occupancies at S=128)
 // A/B switch for measurements: PSNERF_B200_SHADOW_UNCULLED=1 evaluates every step of every shadow ray like the reference does
 // (fused k_tc_occ<MODE_SHADOW> on the tensor path) instead of the box-culled list.  Results agree to rounding of the product order.
@@ -85,7 +86,7 @@ extern "C" int64_t psn_workspace_bytes(const char* op, int64_t n_rays, int64_t n
   if (!strcmp(op, "shadow")) {
     const long long pairs = N * (n_lights < 1 ? 1 : n_lights);
     const long long chunk = pairs < kShadowChunkPairs + N ? pairs : kShadowChunkPairs + N;
-    return (int64_t)(align256((size_t)chunk * S * 4) + align256((size_t)chunk * 8) + 4096);
+    return (int64_t)(align256((size_t)chunk * S * 4) + align256((size_t)chunk * 8) + align256((size_t)chunk * 4) + 4096);
   }
   if (!strcmp(op, "shade") || !strcmp(op, "s2_vis")) return (int64_t)s2_workspace_bytes(N, n_lights);
   if (!strcmp(op, "s2_train")) {  // n_rays = max(pixels, surface points), n_samples = vis-train lights, n_lights = L
@@ -315,6 +316,7 @@ extern "C" int psn_shadow_visibility(const psn_mlp* geo, const float* surf, cons
   unsigned* counters = w.take<unsigned>(64);
   float* occ = w.take<float>((size_t)chunk_pairs * n_steps);  // culled: packed entries, overwritten in place by their alpha
   unsigned long long* meta = w.take<unsigned long long>((size_t)chunk_pairs);
+  unsigned* off_b = w.take<unsigned>((size_t)chunk_pairs);
   PSN_REQUIRE(w.ok, PSN_ERR_WORKSPACE, "psn_shadow_visibility: workspace too small (need %zu bytes, have %lld)", w.used,
               (long long)ws_bytes);
   // The box-culled pass needs the step index in SHADOW_LIST_STEP_BITS bits and the pair index in the rest of an entry.
@@ -325,7 +327,10 @@ extern "C" int psn_shadow_visibility(const psn_mlp* geo, const float* surf, cons
   sl.total = counters;
   sl.evaluated = reinterpret_cast<unsigned long long*>(counters + 2);
   sl.meta = meta;
+  sl.off_b = off_b;
   sl.entry = reinterpret_cast<unsigned*>(occ);
+  sl.lead = n_steps < kShadowLead ? n_steps : kShadowLead;
+  sl.cap_a = (unsigned)(chunk_pairs * sl.lead);  // list A never exceeds lead entries per pair; B takes the rest of the buffer
   for (long long l0 = 0; l0 < L; l0 += lights_per_chunk) {
     const long long nl = (L - l0 < lights_per_chunk) ? (L - l0) : lights_per_chunk;
     PointGen gen;
@@ -339,16 +344,22 @@ extern "C" int psn_shadow_visibility(const psn_mlp* geo, const float* surf, cons
     gen.lfar = lfar;
     int rc;
     if (culled) {
-      // plan -> MLP over the in-box samples only (row count read on the device) -> transmittance over all steps
-      if (l0 > 0) PSN_CUDA_CHECK(cudaMemsetAsync(sl.total, 0, sizeof(unsigned), st));
+      // plan A -> MLP on the first `lead` in-box steps of every pair -> plan B -> MLP on the remaining steps of the pairs that are
+      // still alive -> transmittance over all steps; the row counts of both MLP launches are read on the device
+      PSN_CUDA_CHECK(cudaMemsetAsync(sl.total, 0, 2 * sizeof(unsigned), st));
       if ((rc = launch_shadow_plan(surf, gen.lights, Ns, nl * Ns, n_steps, lnear, lfar, box, sl, st))) return rc;
       gen.kind = GEN_SHADOW_LIST;
-      gen.index = reinterpret_cast<const int*>(sl.entry);
-      {
-        ProfScope prof(PSN_PROF_SHADOW, nl * Ns * n_steps, st);
-        if (prec_is_tc(precision)) rc = tc_occupancy(geo, gen, 0, reinterpret_cast<const int*>(sl.total), PSN_OUT_ALPHA, occ, st);
-        else rc = simt_occupancy(geo, gen, 0, reinterpret_cast<const int*>(sl.total), PSN_OUT_ALPHA, occ, 0, st);
-        if (rc) return rc;
+      for (int which = 0; which < 2; ++which) {
+        float* occ_w = occ + (which ? sl.cap_a : 0u);
+        gen.index = reinterpret_cast<const int*>(occ_w);
+        const int* rows = reinterpret_cast<const int*>(sl.total + which);
+        {
+          ProfScope prof(PSN_PROF_SHADOW, which ? 0 : nl * Ns * n_steps, st);
+          if (prec_is_tc(precision)) rc = tc_occupancy(geo, gen, 0, rows, PSN_OUT_ALPHA, occ_w, st);
+          else rc = simt_occupancy(geo, gen, 0, rows, PSN_OUT_ALPHA, occ_w, 0, st);
+          if (rc) return rc;
+        }
+        if (which == 0 && (rc = launch_shadow_plan_b(occ, nl * Ns, sl, st))) return rc;
       }
       if ((rc = launch_shadow_composite_list(occ, sl, surf, gen.lights, Ns, nl * Ns, n_steps, lnear, lfar, box, vis + l0 * Ns, st)))
         return rc;

@@ -14,10 +14,20 @@ struct SurfList { int* count; int* ray; float* depth; };
 // number of selected points, count[2] = points of the whole-march fallback (N * S if the list overflowed, else 0).
 struct RefineList { int* count; int* ray; float* depth; int* pos; int cap; };
 
-// Box-culled shadow pass: the (pair, step) entries of the in-box samples of one light chunk (stage1_aux.cu:k_shadow_plan).
-// total = entries of the current chunk (the MLP kernels read it as their device-side row count); evaluated = running 64-bit sum
-// over the chunks of a call; meta[pair] = list offset | first step << 32 | steps << 40.
-struct ShadowList { unsigned* total; unsigned long long* evaluated; unsigned long long* meta; unsigned* entry; };
+// Box-culled shadow pass: the (pair, step) entries of the in-box samples of one light chunk (stage1_aux.cu:k_shadow_plan*).
+// Two lists: A = the first `lead` in-box steps of every pair, B = the remaining in-box steps of the pairs whose transmittance after
+// list A is still above the death threshold.  total[0] / total[1] = entries of A / B (the MLP kernels read them as their device-side
+// row counts); evaluated = running 64-bit sum over the chunks of a call; meta[pair] = offset in A | first step << 32 | in-box steps
+// << 40; off_b[pair] = offset in B or 0xffffffff (no B entries); entry = A region [0, cap_a) followed by the B region.
+struct ShadowList {
+  unsigned* total;
+  unsigned long long* evaluated;
+  unsigned long long* meta;
+  unsigned* off_b;
+  unsigned* entry;
+  unsigned cap_a;
+  int lead;
+};
 
 // stage1_simt.cu
 int simt_occupancy(const psn_mlp* geo, const PointGen& gen, long long M, const int* M_dev, int out_kind, float* out,
@@ -64,6 +74,7 @@ int launch_shadow_composite(const float* occ, const float* surf, const float* li
                             float lnear, float lfar, float box, float* vis, cudaStream_t st);
 int launch_shadow_plan(const float* surf, const float* lights, long long Ns, long long pairs, int S, float lnear, float lfar,
                        float box, ShadowList sl, cudaStream_t st);
+int launch_shadow_plan_b(const float* occ, long long pairs, ShadowList sl, cudaStream_t st);
 int launch_shadow_composite_list(const float* occ, ShadowList sl, const float* surf, const float* lights, long long Ns,
                                  long long pairs, int S, float lnear, float lfar, float box, float* vis, cudaStream_t st);
 int launch_scatter_normals(const float* grad, SurfList sl, float* normal, long long N, cudaStream_t st);

@@ -298,13 +298,18 @@ __global__ void k_shadow_composite(const float* __restrict__ occ, const float* _
 // (rendering.py:402-404): those evaluations cannot influence the result.  A shadow ray starts on the surface (inside the cube) and
 // the cube is convex, so the in-box steps of a ray are one contiguous span - typically a quarter of the 128 steps at lfar = 3.5.
 // k_shadow_plan finds that span per (light, point) pair with the SAME per-step predicate and point arithmetic the composite uses,
-// and appends one packed (pair, step) entry per in-span step to a list; the MLP kernels evaluate only the list (GEN_SHADOW_LIST),
-// writing alpha over the entry it came from; k_shadow_composite_list then runs the reference's transmittance product over all S
-// steps with alpha = 0 outside the box, exactly as the unculled pass does.  (Contiguity follows from the monotonicity of every
-// rounded operation in t -> o + d t; the composite re-evaluates the predicate per step, so correctness does not rest on it.)
+// and appends one packed (pair, step) entry per step to a list; the MLP kernels evaluate only the lists (GEN_SHADOW_LIST), writing
+// alpha over the entry it came from; k_shadow_composite_list then runs the reference's transmittance product over all S steps with
+// alpha = 0 outside the box, exactly as the unculled pass does.  (Contiguity follows from the monotonicity of every rounded
+// operation in t -> o + d t; the composite re-evaluates the predicate per step, so correctness does not rest on it.)
+// Second cull - dead rays.  vis = 1 - sum_j alpha_j T_j with T_j the transmittance in front of step j, so everything behind step k
+// contributes at most T_k.  Rays that enter the object (lights below the local horizon) reach T < 1e-7 within a few steps but stay
+// inside the cube for another 60-80.  The span is therefore evaluated in two lists: A = its first `lead` steps for every pair,
+// B = the rest, only for the pairs with T after list A >= kShadowDeadT (k_shadow_plan_b).  The dropped terms change vis by < 1e-7.
 // One block = 64 pairs (8 warps x 8 pairs); one atomicAdd per block reserves the block's list range (the list order is therefore
 // not reproducible between runs, the values are: every sample is evaluated independently of its tile neighbours).
 constexpr int PLAN_PAIRS_PER_BLOCK = 64;
+constexpr float kShadowDeadT = 1e-7f;
 
 __device__ __forceinline__ bool shadow_step_inside(const float (&p0)[3], const float (&ld)[3], float dd, float box) {
   bool inside = true;
@@ -316,10 +321,23 @@ __device__ __forceinline__ bool shadow_step_inside(const float (&p0)[3], const f
   return inside;
 }
 
+// Reserve `mine[slot]` entries per pair slot of this block in list `which`; returns the block's base offset through s_off / s_base.
+__device__ __forceinline__ void plan_reserve(const int* s_cnt, int* s_off, unsigned* s_base, ShadowList sl, int which) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int i = 0; i < PLAN_PAIRS_PER_BLOCK; ++i) { s_off[i] = run; run += s_cnt[i]; }
+    *s_base = run ? atomicAdd(sl.total + which, (unsigned)run) : 0u;
+    if (run) atomicAdd(sl.evaluated, (unsigned long long)run);
+    if (blockIdx.x == 0) sl.total[4] = 1u;  // marks "the box-culled pass ran" next to the counters (read by the host for statistics)
+  }
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(256)
 k_shadow_plan(const float* __restrict__ surf, const float* __restrict__ lights, long long Ns, long long pairs, int S, float lnear,
               float lfar, float box, ShadowList sl) {
-  __shared__ int s_first[PLAN_PAIRS_PER_BLOCK], s_cnt[PLAN_PAIRS_PER_BLOCK], s_off[PLAN_PAIRS_PER_BLOCK];
+  __shared__ int s_first[PLAN_PAIRS_PER_BLOCK], s_cnt[PLAN_PAIRS_PER_BLOCK], s_lead[PLAN_PAIRS_PER_BLOCK], s_off[PLAN_PAIRS_PER_BLOCK];
   __shared__ unsigned s_base;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long pair0 = (long long)blockIdx.x * PLAN_PAIRS_PER_BLOCK;
@@ -343,29 +361,64 @@ k_shadow_plan(const float* __restrict__ surf, const float* __restrict__ lights, 
       }
       if (hi >= 0) { first = lo; cnt = hi - lo + 1; }
     }
-    if (lane == 0) { s_first[slot] = first; s_cnt[slot] = cnt; }
+    if (lane == 0) { s_first[slot] = first; s_cnt[slot] = cnt; s_lead[slot] = cnt < sl.lead ? cnt : sl.lead; }
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int run = 0;
-    for (int i = 0; i < PLAN_PAIRS_PER_BLOCK; ++i) { s_off[i] = run; run += s_cnt[i]; }
-    s_base = run ? atomicAdd(sl.total, (unsigned)run) : 0u;
-    if (run) atomicAdd(sl.evaluated, (unsigned long long)run);
-    if (blockIdx.x == 0) sl.total[4] = 1u;  // marks "the box-culled pass ran" next to the counters (read by the host for statistics)
-  }
-  __syncthreads();
+  plan_reserve(s_lead, s_off, &s_base, sl, 0);
   for (int k = 0; k < 8; ++k) {
     const int slot = w * 8 + k;
     const long long pair = pair0 + slot;
     if (pair >= pairs) break;
     const unsigned off = s_base + (unsigned)s_off[slot];
-    const int first = s_first[slot], cnt = s_cnt[slot];
-    if (lane == 0) sl.meta[pair] = (unsigned long long)off | ((unsigned long long)first << 32) | ((unsigned long long)cnt << 40);
-    for (int i = lane; i < cnt; i += 32) sl.entry[off + i] = ((unsigned)pair << SHADOW_LIST_STEP_BITS) | (unsigned)(first + i);
+    const int first = s_first[slot], cnt = s_cnt[slot], lead = s_lead[slot];
+    if (lane == 0) {
+      sl.meta[pair] = (unsigned long long)off | ((unsigned long long)first << 32) | ((unsigned long long)cnt << 40);
+      sl.off_b[pair] = 0xffffffffu;
+    }
+    for (int i = lane; i < lead; i += 32) sl.entry[off + i] = ((unsigned)pair << SHADOW_LIST_STEP_BITS) | (unsigned)(first + i);
   }
 }
 
-// One warp per pair: the transmittance product of k_shadow_composite with alpha read through the pair's list span.
+// After the MLP ran on list A: pairs with more in-box steps than `lead` whose transmittance is still >= kShadowDeadT get their
+// remaining steps appended to list B.  occ = the alpha values of list A (written over its entries).
+__global__ void __launch_bounds__(256) k_shadow_plan_b(const float* __restrict__ occ, long long pairs, ShadowList sl) {
+  __shared__ int s_cnt[PLAN_PAIRS_PER_BLOCK], s_off[PLAN_PAIRS_PER_BLOCK];
+  __shared__ unsigned s_base;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long pair0 = (long long)blockIdx.x * PLAN_PAIRS_PER_BLOCK;
+  for (int k = 0; k < 8; ++k) {
+    const int slot = w * 8 + k;
+    const long long pair = pair0 + slot;
+    int rest = 0;
+    if (pair < pairs) {
+      const unsigned long long meta = sl.meta[pair];
+      const int cnt = (int)((meta >> 40) & 0x1ffu);
+      if (cnt > sl.lead) {
+        const unsigned off = (unsigned)meta;
+        float t = lane < sl.lead ? __fadd_rn(__fsub_rn(1.f, occ[off + lane]), 1e-6f) : 1.f;  // lead <= 32
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t *= __shfl_xor_sync(0xffffffffu, t, o);
+        if (t >= kShadowDeadT) rest = cnt - sl.lead;
+      }
+    }
+    if (lane == 0) s_cnt[slot] = rest;
+  }
+  plan_reserve(s_cnt, s_off, &s_base, sl, 1);
+  for (int k = 0; k < 8; ++k) {
+    const int slot = w * 8 + k;
+    const long long pair = pair0 + slot;
+    if (pair >= pairs) break;
+    const int rest = s_cnt[slot];
+    if (rest == 0) continue;
+    const unsigned off = s_base + (unsigned)s_off[slot];
+    const int first = (int)((sl.meta[pair] >> 32) & 0xffu);
+    if (lane == 0) sl.off_b[pair] = off;
+    unsigned* dst = sl.entry + sl.cap_a;
+    for (int i = lane; i < rest; i += 32) dst[off + i] = ((unsigned)pair << SHADOW_LIST_STEP_BITS) | (unsigned)(first + sl.lead + i);
+  }
+}
+
+// One warp per pair: the transmittance product of k_shadow_composite with alpha read through the pair's list spans (occ = the entry
+// buffer after both MLP launches).  Steps of a dead pair behind list A keep alpha = 0.
 __global__ void k_shadow_composite_list(const float* __restrict__ occ, ShadowList sl, const float* __restrict__ surf,
                                         const float* __restrict__ lights, long long Ns, long long pairs, int S, float lnear,
                                         float lfar, float box, float* __restrict__ vis) {
@@ -373,17 +426,21 @@ __global__ void k_shadow_composite_list(const float* __restrict__ occ, ShadowLis
   const int lane = threadIdx.x & 31;
   if (pair >= pairs) return;
   const unsigned long long meta = sl.meta[pair];
-  const unsigned off = (unsigned)meta;
+  const unsigned off = (unsigned)meta, off_b = sl.off_b[pair];
   const int first = (int)((meta >> 32) & 0xffu), cnt = (int)((meta >> 40) & 0x1ffu);
+  const int lead = cnt < sl.lead ? cnt : sl.lead;
+  const int last = off_b != 0xffffffffu ? first + cnt : first + lead;  // steps >= last have alpha = 0: they add nothing to the sum
+  const float* occ_b = occ + sl.cap_a;
   const long long l = pair / Ns, n = pair - l * Ns;
   const float p0[3] = {surf[n * 3], surf[n * 3 + 1], surf[n * 3 + 2]};
   const float ld[3] = {lights[l * 3], lights[l * 3 + 1], lights[l * 3 + 2]};
   float carry = 1.f, sw = 0.f;
-  for (int b = 0; b < S && b < first + cnt; b += 32) {  // steps after the span have alpha = 0: they add nothing to the sum
+  for (int b = 0; b < S && b < last; b += 32) {
     const int s = b + lane;
     float a = 0.f;
-    if (s < S && s >= first && s < first + cnt) {
-      if (shadow_step_inside(p0, ld, lerp_depth(lnear, lfar, linspace01(s, S)), box)) a = occ[off + (unsigned)(s - first)];
+    if (s < S && s >= first && s < last) {
+      if (shadow_step_inside(p0, ld, lerp_depth(lnear, lfar, linspace01(s, S)), box))
+        a = s < first + lead ? occ[off + (unsigned)(s - first)] : occ_b[off_b + (unsigned)(s - first - lead)];
     }
     const float t = (s < S) ? __fadd_rn(__fsub_rn(1.f, a), 1e-6f) : 1.f;
     float incl = t;
@@ -509,6 +566,12 @@ int launch_shadow_plan(const float* surf, const float* lights, long long Ns, lon
   psn::count_launch();
   k_shadow_plan<<<(unsigned)((pairs + PLAN_PAIRS_PER_BLOCK - 1) / PLAN_PAIRS_PER_BLOCK), 256, 0, st>>>(surf, lights, Ns, pairs, S,
                                                                                                       lnear, lfar, box, sl);
+  PSN_CUDA_CHECK(cudaGetLastError());
+  return PSN_OK;
+}
+int launch_shadow_plan_b(const float* occ, long long pairs, ShadowList sl, cudaStream_t st) {
+  psn::count_launch();
+  k_shadow_plan_b<<<(unsigned)((pairs + PLAN_PAIRS_PER_BLOCK - 1) / PLAN_PAIRS_PER_BLOCK), 256, 0, st>>>(occ, pairs, sl);
   PSN_CUDA_CHECK(cudaGetLastError());
   return PSN_OK;
 }

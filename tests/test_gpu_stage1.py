@@ -214,9 +214,10 @@ def test_shape_extract_and_shadow_vs_golden(s1, variant, prec):
 @pytest.mark.parametrize("prec", PRECISIONS)
 @pytest.mark.parametrize("Ns,L", [(1, 1), (37, 7), (1000, 5)])
 def test_box_culled_shadow_pass(s1, prec, Ns, L, monkeypatch):
-    """The shadow pass evaluates the occupancy MLP only at the in-box steps of every shadow ray (k_shadow_plan / GEN_SHADOW_LIST):
-    equal to the evaluation of every step (what the reference executes, PSNERF_B200_SHADOW_UNCULLED=1) up to the order of the
-    transmittance product, and to the oracle; points outside the +-1.1 cube (no in-box step at all) give visibility exactly 1."""
+    """The shadow pass evaluates the occupancy MLP only at the in-box steps of every shadow ray (k_shadow_plan / GEN_SHADOW_LIST), and
+    past the first 8 of them only while the ray's transmittance is still >= 1e-7 (k_shadow_plan_b): equal to the evaluation of every
+    step (what the reference executes, PSNERF_B200_SHADOW_UNCULLED=1) up to the order of the transmittance product and the < 1e-7 of
+    the dropped tail, and to the oracle; points outside the +-1.1 cube (no in-box step at all) give visibility exactly 1."""
     from psnerf_b200 import engine
     from psnerf_b200.stage1 import Renderer
     _, sds = s1
