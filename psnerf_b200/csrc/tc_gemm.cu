@@ -99,15 +99,22 @@ __device__ __forceinline__ void k_range(const Args& a, const TileIt& it, long lo
 }
 
 // ---- loaders: 256 threads fill one stage (A_hi, A_lo, B_hi, B_lo) for K block [kb, kb + 32) ----------------------------------------
-// rows x 32 tile of an operand whose k index is CONTIGUOUS in memory (value(r, k) = P[(row0 + r) * ld + kb + k])
-__device__ __forceinline__ void load_k_contig(unsigned char* hi, unsigned char* lo, const float* __restrict__ P, long long ld, long long row0,
-                                              long long n_rows_valid, int rows, long long kb, long long k_end, int t, bool vec_ok) {
-  // thread t: 16-byte chunk (t & 7) of rows (t >> 3) + 32 j
+// Every thread first ISSUES all of its global loads for both operands (4 float4 of A, up to 8 of B: the latency of one HBM / L2
+// round trip per K block instead of twelve), then splits and stores.
+struct Frag { float4 v; };
+// rows x 32 tile of an operand whose k index is CONTIGUOUS in memory (value(r, k) = P[(row0 + r) * ld + kb + k]):
+// thread t owns the 16-byte chunk (t & 7) of rows (t >> 3) + 32 j
+template <int NIT>
+__device__ __forceinline__ void fetch_k_contig(Frag (&f)[NIT], const float* __restrict__ P, long long ld, long long row0, long long n_rows_valid,
+                                               int rows, long long kb, long long k_end, int t, bool vec_ok) {
   const int c = t & 7;
-  for (int r = t >> 3; r < rows; r += LOAD_THREADS / 8) {
+  const long long gk = kb + 4 * c;
+#pragma unroll
+  for (int j = 0; j < NIT; ++j) {
+    const int r = (t >> 3) + 32 * j;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    const long long gr = row0 + r, gk = kb + 4 * c;
-    if (gr < n_rows_valid && gk < k_end) {
+    const long long gr = row0 + r;
+    if (r < rows && gr < n_rows_valid && gk < k_end) {
       const float* src = P + gr * ld + gk;
       if (vec_ok && gk + 3 < k_end) v = __ldg(reinterpret_cast<const float4*>(src));
       else {
@@ -117,6 +124,17 @@ __device__ __forceinline__ void load_k_contig(unsigned char* hi, unsigned char* 
         if (gk + 3 < k_end) v.w = __ldg(src + 3);
       }
     }
+    f[j].v = v;
+  }
+}
+template <int NIT>
+__device__ __forceinline__ void store_k_contig(const Frag (&f)[NIT], unsigned char* hi, unsigned char* lo, int rows, int t) {
+  const int c = t & 7;
+#pragma unroll
+  for (int j = 0; j < NIT; ++j) {
+    const int r = (t >> 3) + 32 * j;
+    if (r >= rows) break;
+    const float4 v = f[j].v;
     const float4 h = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
     const float4 l = make_float4(to_tf32(v.x - h.x), to_tf32(v.y - h.y), to_tf32(v.z - h.z), to_tf32(v.w - h.w));
     const uint32_t off = (uint32_t)r * 128u + (((uint32_t)c ^ ((uint32_t)r & 7u)) << 4);
@@ -124,26 +142,43 @@ __device__ __forceinline__ void load_k_contig(unsigned char* hi, unsigned char* 
     *reinterpret_cast<float4*>(lo + off) = l;
   }
 }
-// rows x 32 tile of an operand whose ROW index is contiguous in memory (value(r, k) = P[(kb + k) * ld + row0 + r]): transposing write
-__device__ __forceinline__ void load_row_contig(unsigned char* hi, unsigned char* lo, const float* __restrict__ P, long long ld, long long row0,
-                                                long long n_rows_valid, int rows, long long kb, long long k_end, int t, bool vec_ok) {
-  // thread t: rows 4 (t % (rows/4)) .. +3 at k = t / (rows/4) + step; consecutive threads read consecutive float4 of one memory row
+// rows x 32 tile of an operand whose ROW index is contiguous in memory (value(r, k) = P[(kb + k) * ld + row0 + r]): transposing
+// write.  Item idx = t + 256 j: rows 4 (idx % (rows/4)) .. +3 at k = idx / (rows/4); consecutive threads read consecutive float4 of
+// one memory row.
+template <int NIT>
+__device__ __forceinline__ void fetch_row_contig(Frag (&f)[NIT], const float* __restrict__ P, long long ld, long long row0, long long n_rows_valid,
+                                                 int rows, long long kb, long long k_end, int t, bool vec_ok) {
   const int quads = rows >> 2;
-  for (int idx = t; idx < quads * BK; idx += LOAD_THREADS) {
-    const int q = idx % quads, k = idx / quads;
-    const long long gk = kb + k, gr = row0 + 4 * q;
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
-    if (gk < k_end && gr < n_rows_valid) {
-      const float* src = P + gk * ld + gr;
-      if (vec_ok && gr + 3 < n_rows_valid) {
-        const float4 f = __ldg(reinterpret_cast<const float4*>(src));
-        v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
-      } else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (gr + i < n_rows_valid) v[i] = __ldg(src + i);
+  for (int j = 0; j < NIT; ++j) {
+    const int idx = t + LOAD_THREADS * j;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (idx < quads * BK) {
+      const int q = idx % quads, k = idx / quads;
+      const long long gk = kb + k, gr = row0 + 4 * q;
+      if (gk < k_end && gr < n_rows_valid) {
+        const float* src = P + gk * ld + gr;
+        if (vec_ok && gr + 3 < n_rows_valid) v = __ldg(reinterpret_cast<const float4*>(src));
+        else {
+          v.x = __ldg(src);
+          if (gr + 1 < n_rows_valid) v.y = __ldg(src + 1);
+          if (gr + 2 < n_rows_valid) v.z = __ldg(src + 2);
+          if (gr + 3 < n_rows_valid) v.w = __ldg(src + 3);
+        }
       }
     }
+    f[j].v = v;
+  }
+}
+template <int NIT>
+__device__ __forceinline__ void store_row_contig(const Frag (&f)[NIT], unsigned char* hi, unsigned char* lo, int rows, int t) {
+  const int quads = rows >> 2;
+#pragma unroll
+  for (int j = 0; j < NIT; ++j) {
+    const int idx = t + LOAD_THREADS * j;
+    if (idx >= quads * BK) break;
+    const int q = idx % quads, k = idx / quads;
+    const float v[4] = {f[j].v.x, f[j].v.y, f[j].v.z, f[j].v.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float h = to_tf32(v[i]);
@@ -177,6 +212,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_gemm(Args a) {
     // ---- epilogue: TMEM lanes 32 warp .. +31 = tile rows; 16 columns at a time ----------------------------------------------------
     uint32_t acc_phase = 0;  // bit b = parity to wait for on acc_full[b]
     long long it_ctr = 0;
+    const bool c_vec = ((reinterpret_cast<uintptr_t>(a.C) | (uintptr_t)(a.ldc * 4)) & 15u) == 0;  // 16-byte stores (bn is a multiple of 16)
     for (long long t = blockIdx.x; t < total; t += gridDim.x, ++it_ctr) {
       const TileIt it = tile_at<FORM>(a, t);
       const uint32_t buf = (uint32_t)(it_ctr & 1);
@@ -191,19 +227,34 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_gemm(Args a) {
         tmem_ld16(taddr + (uint32_t)c, v);
         if (row < a.M) {
           float* dst = a.C + row * a.ldc + col0 + c;
+          if (FORM == 2) {
+            if (c_vec && col0 + c + 15 < a.N) {  // 16-byte reductions (sm_90+): a quarter of the atomic traffic of the split-K sum
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int n = col0 + c + i;
-            if (n < a.N) {
+              for (int q = 0; q < 4; ++q)
+                atomicAdd(reinterpret_cast<float4*>(dst) + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (col0 + c + i < a.N) atomicAdd(dst + i, v[i]);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int n = col0 + c + i;
               float x = v[i];
-              if (FORM == 2) {
-                atomicAdd(dst + i, x);
-              } else {
-                if (a.epi >= 1) x += __ldg(a.bias + n);
-                if (a.epi == 2) x = fmaxf(x, 0.f);
-                if (a.epi == 3) x = 1.f / (1.f + expf(-x));
-                dst[i] = x;
-              }
+              if (a.epi >= 1 && n < a.N) x += __ldg(a.bias + n);
+              if (a.epi == 2) x = fmaxf(x, 0.f);
+              if (a.epi == 3) x = 1.f / (1.f + expf(-x));
+              v[i] = x;
+            }
+            if (c_vec && col0 + c + 15 < a.N) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                reinterpret_cast<float4*>(dst)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (col0 + c + i < a.N) dst[i] = v[i];
             }
           }
         }
@@ -266,18 +317,29 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_gemm(Args a) {
       const long long m0 = it.m_tile * BM;
       const long long n0 = (long long)it.n_chunk * bn;
       for (long long kb = k0; kb < k1; kb += BK) {
-        mbar_wait(&bars->empty[stage], phase ^ 1u);
+        Frag fa[BM / 32], fb[MAX_BN / 32];  // 4 + 8 float4 in flight per thread
+        if (FORM == 0) {
+          fetch_k_contig(fa, a.A, a.lda, m0, a.M, BM, kb, k1, t, a_vec);
+          fetch_k_contig(fb, a.B, a.ldb, n0, a.N, bn, kb, k1, t, b_vec);
+        } else if (FORM == 1) {
+          fetch_k_contig(fa, a.A, a.lda, m0, a.M, BM, kb, k1, t, a_vec);
+          fetch_row_contig(fb, a.B, a.ldb, n0, a.N, bn, kb, k1, t, b_vec && (n0 & 3) == 0);
+        } else {
+          fetch_row_contig(fa, a.A, a.lda, m0, a.M, BM, kb, k1, t, a_vec && (m0 & 3) == 0);
+          fetch_row_contig(fb, a.B, a.ldb, n0, a.N, bn, kb, k1, t, b_vec && (n0 & 3) == 0);
+        }
+        mbar_wait(&bars->empty[stage], phase ^ 1u);  // the loads above are in flight while the MMAs release the stage
         unsigned char* sa = base + stage * STAGE;
         unsigned char *Ah = sa, *Al = sa + A_TILE, *Bh = sa + 2 * A_TILE, *Bl = sa + 2 * A_TILE + B_TILE;
         if (FORM == 0) {
-          load_k_contig(Ah, Al, a.A, a.lda, m0, a.M, BM, kb, k1, t, a_vec && (kb & 3) == 0);
-          load_k_contig(Bh, Bl, a.B, a.ldb, n0, a.N, bn, kb, k1, t, b_vec && (kb & 3) == 0);
+          store_k_contig(fa, Ah, Al, BM, t);
+          store_k_contig(fb, Bh, Bl, bn, t);
         } else if (FORM == 1) {
-          load_k_contig(Ah, Al, a.A, a.lda, m0, a.M, BM, kb, k1, t, a_vec && (kb & 3) == 0);
-          load_row_contig(Bh, Bl, a.B, a.ldb, n0, a.N, bn, kb, k1, t, b_vec && (n0 & 3) == 0);
+          store_k_contig(fa, Ah, Al, BM, t);
+          store_row_contig(fb, Bh, Bl, bn, t);
         } else {
-          load_row_contig(Ah, Al, a.A, a.lda, m0, a.M, BM, kb, k1, t, a_vec && (m0 & 3) == 0);
-          load_row_contig(Bh, Bl, a.B, a.ldb, n0, a.N, bn, kb, k1, t, b_vec && (n0 & 3) == 0);
+          store_row_contig(fa, Ah, Al, BM, t);
+          store_row_contig(fb, Bh, Bl, bn, t);
         }
         fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
         mbar_arrive(&bars->full[stage]);

@@ -22,8 +22,10 @@ H = W = 512
 GRID = 16          # 256 sample pixels, every 32nd pixel in x and y
 L = 96
 PRECS = ["tc", "tc_mixed", "tc_two_level"]
-GATE = {"rgb": 1e-4, "acc": 1e-4, "normal": 1e-4, "points": 1e-4, "shadow": 1e-4, "s2_rgb": 1e-4, "s2_albedo": 1e-4, "s2_normal": 1e-4,
-        "s2_vis": 1e-4, "s2_spec": 1e-4}
+# measured maxima (run 4, all precisions and weight sets): rgb 1.0e-5, acc 1.6e-5, normal 1.4e-5, points 2.1e-6, shadow 1.4e-5;
+# stage 2 on identical inputs: rgb 8e-7, albedo 6e-8, normal 1.5e-6, visibility 1.3e-7, specular 2.3e-5 (exp(lambda (h.n - 1)) with lambda = e^10)
+GATE = {"rgb": 5e-5, "acc": 5e-5, "normal": 5e-5, "points": 1e-5, "shadow": 5e-5, "s2_rgb": 1e-5, "s2_albedo": 1e-5, "s2_normal": 1e-5,
+        "s2_vis": 1e-5, "s2_spec": 1e-4}
 
 
 def _sample():
@@ -135,5 +137,5 @@ def test_relit_view_512x512x128x96L_vs_oracle(oracle_results, variant, prec):
                       ("visibility", "s2_vis"), ("sg_specular_rgb_values", "s2_spec")):
         got = gout[key][:, idx].cpu()
         util.bound(tag + name, util.max_abs(got, same[key].reshape(got.shape)), GATE[name])
-        util.bound(tag + name.replace("s2_", "s2chain_"), util.max_abs(got[:, agree], s2out[key].reshape(got.shape)[:, agree]), 2e-2)
+        util.bound(tag + name.replace("s2_", "s2chain_"), util.max_abs(got[:, agree], s2out[key].reshape(got.shape)[:, agree]), 2e-3)
     assert O.psnr(gout["sg_rgb_values"][:, idx].cpu(), same["sg_rgb_values"]) > 70.0

@@ -26,8 +26,11 @@ TOL = {"fp32": dict(rel=1e-5, abs=2e-5), "tc": dict(rel=5e-5, abs=1e-4), "tc_two
 
 
 # Gates on rendered quantities against the real reference's fixtures (all O(1) quantities, max-abs over the pixels whose discrete
-# hit / miss decision agrees).  PROVISIONAL values are replaced by <= 1e-4 / 3 x measured from the error log of the GPU run.
-GATE = {"rgb": 5e-4, "acc": 5e-4, "normal": 2e-3, "points": 2e-4, "visibility": 2e-3, "light_visibility": 5e-4}
+# hit / miss decision agrees): the north star's 1e-4 or tighter - about 3 x the largest error measured on the B200 over every case,
+# weight set and precision (profiles/r2_parity_errlog_final.jsonl: rgb 8.8e-6, acc 1.4e-5, normal 2.3e-5, points 1.2e-6, visibility
+# 1.3e-5).  Round 1 needed 5e-4 / 2e-3 here; the secant refinement and the normal output now run on the fp32 kernels under every
+# precision (csrc/api_stage1.cu accuracy policy), which took the surface points from 3.5e-5 to 1.2e-6 and everything downstream with them.
+GATE = {"rgb": 3e-5, "acc": 5e-5, "normal": 1e-4, "points": 1e-5, "visibility": 5e-5, "light_visibility": 5e-5}
 
 
 @pytest.fixture(scope="module")

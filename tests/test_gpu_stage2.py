@@ -18,6 +18,7 @@ def _precisions():
 
 PRECISIONS = _precisions()
 TOL = {"fp32": 2e-5, "tc": 1e-4}
+SHADE_GATE = 2e-5  # test_shading_vs_golden: measured on the B200 (profiles/r2_parity_errlog_final.jsonl) <= 6.1e-6 for every output, both precisions
 KEYS = ("sg_rgb_values", "sg_specular_rgb_values", "visibility", "normal_pred", "sg_diffuse_albedo_values", "sg_weight",
         "vis_train")
 
@@ -48,7 +49,7 @@ def test_shading_vs_golden(variant, case, prec):
         if key + k in g.files:
             assert tuple(out[k].shape) == g[key + k].shape, k
             util.bound("shading_golden/%s/%s/%s/%s" % (prec, variant, case, k), util.max_abs(out[k].cpu(), g[key + k]),
-                       TOL[prec] * (5 if k in ("visibility", "vis_train") else 1))
+                       SHADE_GATE)
     assert set(["points", "object_mask", "network_object_mask", "normal_values", "albedo_jitter", "rough_jitter"]) <= set(out)
 
 

@@ -87,5 +87,5 @@ def test_unisurf_vs_golden_and_tc(s1, variant, case):
     same = a["mask_pred"].cpu().numpy().reshape(-1) == g[key + "mask"].reshape(-1)
     assert same.mean() >= 0.99
     d = (a["rgb"][0].cpu().numpy() - g[key + "rgb"][0])[same]
-    util.bound("tc_mixed_unisurf_golden/%s/%s/rgb" % (variant, case), float(abs(d).max()), 5 * TOL["abs"])
+    util.bound("tc_mixed_unisurf_golden/%s/%s/rgb" % (variant, case), float(abs(d).max()), 3e-5)  # measured 8.8e-6
     assert O.psnr(a["rgb"].cpu(), torch.from_numpy(g[key + "rgb"])) > 50.0

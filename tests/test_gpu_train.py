@@ -75,7 +75,7 @@ def test_train_step_gradients_vs_oracle_autograd(shape, prec):
         got = params[n].grad
         got = torch.zeros_like(params[n]) if got is None else got
         scale = max(1.0, float(gr.abs().max()))
-        util.bound("s2_param_grad/%s/%s/%s/max_abs" % (shape[0], prec, n), util.max_abs(got.cpu(), gr) / scale, 3e-4)
+        util.bound("s2_param_grad/%s/%s/%s/max_abs" % (shape[0], prec, n), util.max_abs(got.cpu(), gr) / scale, 1e-3)
         # rel-L2 per tensor: the ReLU stacks make the gradient piecewise constant in the pre-activations; the tensor-core GEMMs
         # (tf32 x 3, ~2e-6 of truncating accumulation per layer) flip the masks of the ~60 of 2.7 M pre-activations of this case that
         # sit within 3e-6 of zero, and each flip of a deep unit moves a whole row's contribution to the layers below

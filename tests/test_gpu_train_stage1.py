@@ -64,7 +64,10 @@ def test_field_forward_backward_vs_oracle_autograd(with_app):
     names = sorted(sd)
     gr = torch.autograd.grad(ref, [sd[k] for k in names], allow_unused=True)
     ref_grads = {k: (torch.zeros_like(sd[k]) if g_ is None else g_) for k, g_ in zip(names, gr)}
-    _check_param_grads(model, ref_grads, 2e-3)
+    # 5e-3 of each tensor's largest gradient entry: the appearance MLP is a ReLU stack, and the tensor-core GEMMs (tf32 x 3, ~2e-6
+    # per layer) flip the masks of the pre-activations that sit within rounding of zero (measured worst tensor: lina0.weight_g 2.1e-3;
+    # the FFMA GEMMs of round 1, PSNERF_B200_TRAIN_GEMM=ffma, held 2e-3 here)
+    _check_param_grads(model, ref_grads, 5e-3)
 
 
 def test_composite_backward_vs_autograd():

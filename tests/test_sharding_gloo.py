@@ -203,3 +203,67 @@ def test_stage2_view_sharded_world2_gloo(case):
         for r in range(world):
             assert sorted(res[r].keys()) == sorted(keys)
             assert torch.equal(torch.from_numpy(res[r][k]), want[k].reshape(single[k].shape)), (k, r)
+
+
+class _StubRenderer(torch.nn.Module):
+    """Stage-1 Renderer stand-in for the relit-view chain: 'shape_extract' outputs as functions of the pixel positions."""
+
+    def __init__(self):
+        super().__init__()
+        self.model = torch.nn.Linear(1, 1)
+
+    def forward(self, pixels, camera_mat, world_mat, scale_mat, technique, visibility=False, light_dir=None):
+        assert technique == "shape_extract"
+        p = pixels[0].float()
+        n = p.shape[0]
+        mask = ((p[:, 0] * 7 + p[:, 1] * 3) % 5) < 2
+        pts = torch.stack([p[:, 0] * 0.01, p[:, 1] * 0.02, p.sum(-1) * 0.005], -1)
+        nrm = torch.nn.functional.normalize(pts + 0.1, dim=-1) * mask[:, None]
+        out = {"mask": mask.reshape(1, n), "points": pts.reshape(1, n, 3), "normal": nrm.reshape(1, n, 3)}
+        if visibility:
+            out["visibility"] = torch.where(mask[None], (p[:, 0] * 0.001)[None] + light_dir[:, :1], torch.ones(light_dir.shape[0], n))
+        return out
+
+
+def _relit_worker(rank, world, port, q, shadows):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from psnerf_b200 import pipeline
+    lights = torch.nn.functional.normalize(torch.randn(4, 3, generator=torch.Generator().manual_seed(5)), dim=-1)
+    shp, out = pipeline.extract_and_shade_sharded(_StubRenderer(), _StubPS(), 20, 26, torch.eye(4)[None], torch.eye(4)[None], lights, rank, world,
+                                                  light_batch=3, shadows=shadows)
+    q.put((rank, {k: v.numpy() for k, v in shp.items()}, {k: v.numpy() for k, v in out.items()}))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("shadows", [True, False])
+def test_relit_view_sharded_world2_gloo(shadows):
+    """The headline chain with the rays of one view dealt over two ranks (pipeline.extract_and_shade_sharded): packed per-pixel rows,
+    ONE all_gather, every rank ends up with the unsharded result (stub renderer / stub PSNetwork: host logic only)."""
+    from psnerf_b200 import pipeline
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_relit_worker, args=(r, world, port, q, shadows)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = {}
+    for _ in range(world):
+        r, shp, out = q.get(timeout=120)
+        res[r] = (shp, out)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    lights = torch.nn.functional.normalize(torch.randn(4, 3, generator=torch.Generator().manual_seed(5)), dim=-1)
+    shp0, out0 = pipeline.extract_and_shade(_StubRenderer(), _StubPS(), 20, 26, torch.eye(4)[None], torch.eye(4)[None], lights, light_batch=3,
+                                            shadows=shadows)
+    assert ("visibility" in shp0) == shadows
+    for r in range(world):
+        shp, out = res[r]
+        assert sorted(shp) == sorted(shp0)
+        for k in shp0:
+            assert torch.equal(torch.from_numpy(shp[k]), shp0[k].reshape(shp[k].shape)), (k, r)
+        for k in ("sg_rgb_values", "sg_specular_rgb_values", "visibility", "normal_pred", "sg_diffuse_albedo_values", "sg_weight"):
+            assert torch.equal(torch.from_numpy(out[k]), out0[k].reshape(out[k].shape)), (k, r)

@@ -12,4 +12,5 @@ import bench  # noqa: E402
 
 dev = torch.device("cuda:0")
 cfg, net, rend, conf, ps = bench.build_models(dev, "tc_two_level")
-print(json.dumps(bench.train_steps(dev, rend, ps, bench.scene(0), 1, 0)))
+for rep in range(int(os.environ.get("PROFILE_TRAIN_REPS", "1"))):  # repeated: a one-off stall (lazy module load, allocator) shows up as an outlier
+    print(json.dumps(bench.train_steps(dev, rend, ps, bench.scene(0), 1, 0)))
