@@ -419,11 +419,6 @@ def train_steps(dev, rend, ps, view, world, rank, n_px=4096, tag="", dist=None):
     lm, ln = MainLoss(1.0, "L1", 0.05, 0.01, 1.0), NormalLoss(1.0, 0.05)
     opt = torch.optim.Adam(list(ps.parameters()) + [lraw, linten], lr=1e-6)
 
-    class _Lights(torch.nn.Module):  # the light tables are reduced with the model's gradients (ADVICE: replicas must not diverge)
-        def __init__(self):
-            super().__init__()
-            self.a, self.b = lraw, linten
-
     def s2_step():
         tin["light_direction"] = torch.nn.functional.normalize(lraw, p=2, dim=-1)
         tin["light_intensity"] = linten
@@ -432,7 +427,7 @@ def train_steps(dev, rend, ps, view, world, rank, n_px=4096, tag="", dist=None):
         opt.zero_grad(set_to_none=True)
         loss.backward()
         if world > 1:
-            sharding.allreduce_gradients(torch.nn.ModuleList([ps, _Lights()]), world)
+            sharding.allreduce_gradients(ps, world, extra_params=(lraw, linten))  # the light tables are reduced with the model
         opt.step()
     ms3 = _time_dist(s2_step, 5, dev, dist)
     out["stage2_train_step%s" % tag] = {"pixels_per_rank": n_px, "lights": L_LIGHTS, "vis_train_lights": 8, "ms_fwd_bwd_adam": ms3,

@@ -75,24 +75,40 @@ def gather_pixels(local, n_rays, rank, world, tile=128, group=None):
     return full
 
 
-def allreduce_gradients(module, world, group=None, average=True):
+def allreduce_gradients(module, world, group=None, average=True, extra_params=(), weight=None):
     """Data-parallel train step: ONE all_reduce of the flattened gradients per step
     (668 K floats for the stage-2 networks; latency bound, NVLS on NVSwitch).  Parameters without a gradient contribute zeros
-    so that every rank reduces the same layout."""
+    so that every rank reduces the same layout.
+    extra_params: parameters that live outside `module` and must stay identical on every rank - the stage-2 light tables
+    (light_para / light_inten_para, stepped by their own SparseAdam, stage2/trainer.py:165); sparse gradients are densified for the
+    reduction and handed back dense.
+    weight: this rank's share of the loss normalisation, e.g. its number of masked pixels.  The reference's losses are means over
+    the masked pixels of a batch, so with unequal shards the single-GPU gradient is sum_r w_r g_r / sum_r w_r, not the plain average;
+    the weight travels as one more element of the same all_reduce."""
     if world == 1:
         return
-    params = [p for p in module.parameters() if p.requires_grad]
+    params = [p for p in module.parameters() if p.requires_grad] + [p for p in extra_params if p.requires_grad]
     if not params:
         return
-    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).float() for p in params])
+
+    def dense_grad(p):
+        if p.grad is None:
+            return torch.zeros_like(p, dtype=torch.float32)
+        g = p.grad.to_dense() if p.grad.is_sparse else p.grad
+        return g.float()
+    parts = [dense_grad(p).reshape(-1) for p in params]
+    w = None if weight is None else torch.as_tensor(float(weight), dtype=torch.float32, device=parts[0].device).reshape(1)
+    flat = torch.cat(parts if w is None else [q * w for q in parts] + [w])
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    if average:
-        flat /= world
+    if w is not None:
+        flat = flat[:-1] / flat[-1].clamp_min(1e-30)
+    elif average:
+        flat = flat / world
     off = 0
     for p in params:
         n = p.numel()
         g = flat[off:off + n].view_as(p)
-        if p.grad is None:
+        if p.grad is None or p.grad.is_sparse:
             p.grad = g.clone()
         else:
             p.grad.copy_(g)

@@ -187,6 +187,11 @@ class PSNetwork(nn.Module):
             z = noise["xyz"].to(dev) if (noise is not None and "xyz" in noise) else torch.randn(Ns, 3, device=dev)
             jp = surf + z * self.xyz_jitter_std
         lvt = input["light_vis_train"].to(dev) if ("light_vis_train" in input and Ns > 0) else None
+        if "light_vis_train" not in input and "visibility" in input:
+            # The reference's MainLoss then trains visibility_net through model_outputs['visibility'] (stage2/model/loss.py:86-87);
+            # here the L-light pass is detached (light_vis_detach), so that loss term would silently carry no gradient.
+            raise NotImplementedError("psnerf_b200 train step: a ground-truth 'visibility' input without 'light_vis_train' would train "
+                                      "visibility_net through the detached L-light pass; supply light_vis_train (trainer.py:312-330 does)")
         rgb, spec, vis, normal, albedo, sgw, aj, wj, vt = S2TrainStep.apply(self, (surf, view, pix, N), lights, inten, jp, lvt,
                                                                             *flat_params(self))
         out = {"points": input["points"], "object_mask": input["object_mask"], "network_object_mask": input["surface_mask"],

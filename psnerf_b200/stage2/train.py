@@ -51,7 +51,8 @@ class S2TrainStep(torch.autograd.Function):
             if t.numel() == 1:
                 iscalar = float(t)
             elif t.dim() == 2 and t.shape[-1] == 3:
-                ikind, iptr = 2, t
+                # [1,3] is one RGB intensity shared by all lights (renderer.py:188-190 broadcasts it): expanded like the eval path
+                ikind, iptr = 2, (t.expand(L, 3).contiguous() if t.shape[0] == 1 else t)
             else:
                 ikind, iptr = 1, t.reshape(-1)
         elif intensity is not None:
@@ -127,7 +128,8 @@ class S2TrainStep(torch.autograd.Function):
         elif ctx.ikind == 1:
             g_int = d_i[:L].reshape(ctx.int_shape)
         else:
-            g_int = d_i[:L * 3].reshape(ctx.int_shape)
+            g_int = d_i[:L * 3].reshape(L, 3)
+            g_int = g_int.sum(0, keepdim=True) if ctx.int_shape[0] == 1 else g_int.reshape(ctx.int_shape)
         flat = []
         for gw, gb in grads:
             for a, b in zip(gw, gb):

@@ -135,3 +135,36 @@ def test_optimizer_step_reduces_loss():
         opt.step()
         losses.append(float(loss))
     assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+
+
+def test_shared_rgb_intensity_broadcasts_like_the_reference():
+    """light_intensity [1,3] with L > 1 is ONE RGB intensity for all lights (renderer.py:188-190 broadcasts it): forward equals the
+    [L,3] expansion and the gradient comes back in the input's own shape, summed over the lights."""
+    conf, sds = util.stage2_state_dicts()
+    inp, lraw, _, z, g = _case(12, 10, 5, 2, seed=21)
+    ci = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in inp.items()}
+    ci["light_direction"] = torch.nn.functional.normalize(lraw, p=2, dim=-1).cuda()
+    outs, grads = [], []
+    for shape in ((1, 3), (5, 3)):
+        m = _model(conf, sds["trained"], "fp32")
+        it = torch.tensor([[1.5, 0.7, 2.0]]).expand(*shape).contiguous().cuda().requires_grad_(True)
+        ci["light_intensity"] = it
+        out = m(ci, noise={"xyz": z})
+        out["sg_rgb_values"].sum().backward()
+        outs.append(out["sg_rgb_values"].detach())
+        grads.append(it.grad)
+    assert torch.equal(outs[0], outs[1]) and grads[0].shape == (1, 3)
+    assert util.max_abs(grads[0].cpu(), grads[1].sum(0, keepdim=True).cpu()) < 1e-5 * float(grads[1].abs().max())
+
+
+def test_detached_visibility_fallback_is_refused():
+    """Without light_vis_train the reference's MainLoss trains visibility_net through model_outputs['visibility'] (loss.py:86-87);
+    the CUDA train step computes that output on the detached L-light pass, so it refuses the configuration instead of silently
+    delivering a zero gradient."""
+    conf, sds = util.stage2_state_dicts()
+    m = _model(conf, sds["init"], "fp32")
+    inp = synth.stage2_input(10, 10, 3, all_surface=False, seed=4, mask_frac=0.6)
+    ci = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in inp.items()}
+    ci["visibility"] = torch.rand(3, 100).cuda()
+    with pytest.raises(NotImplementedError, match="light_vis_train"):
+        m(ci)

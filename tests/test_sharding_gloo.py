@@ -2,6 +2,7 @@
 import os
 import socket
 
+import numpy as np
 import pytest
 import torch
 import torch.distributed as dist
@@ -267,3 +268,49 @@ def test_relit_view_sharded_world2_gloo(shadows):
             assert torch.equal(torch.from_numpy(shp[k]), shp0[k].reshape(shp[k].shape)), (k, r)
         for k in ("sg_rgb_values", "sg_specular_rgb_values", "visibility", "normal_pred", "sg_diffuse_albedo_values", "sg_weight"):
             assert torch.equal(torch.from_numpy(out[k]), out0[k].reshape(out[k].shape)), (k, r)
+
+
+def _weighted_grad_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    m = torch.nn.Linear(3, 2)
+    table = torch.nn.Embedding(6, 3, sparse=True)          # a light table outside the model, sparse gradient (trainer.py:165)
+    n = 3 if rank == 0 else 7                               # unequal shards of the masked pixels
+    x = torch.arange(n * 3, dtype=torch.float32).reshape(n, 3) / 10 + rank
+    idx = torch.tensor([rank, 4])
+    loss = m(x).pow(2).mean() + (table(idx).sum(0) * x).pow(2).mean()      # means over this rank's pixels, like the reference losses
+    loss.backward()
+    sharding.allreduce_gradients(m, world, extra_params=list(table.parameters()), weight=n)
+    q.put((rank, [p.grad.clone().numpy() for p in m.parameters()] + [table.weight.grad.clone().numpy()]))
+    dist.destroy_process_group()
+
+
+def test_allreduce_gradients_weighted_with_light_tables_gloo():
+    """Unequal shards + a sparse light table: the weighted reduction equals the gradient of ONE mean over all pixels of both ranks."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_weighted_grad_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    torch.manual_seed(0)
+    m = torch.nn.Linear(3, 2)
+    table = torch.nn.Embedding(6, 3)
+    total = 0.0
+    for rank, n in ((0, 3), (1, 7)):
+        x = torch.arange(n * 3, dtype=torch.float32).reshape(n, 3) / 10 + rank
+        idx = torch.tensor([rank, 4])
+        total = total + n * (m(x).pow(2).mean() + (table(idx).sum(0) * x).pow(2).mean())
+    (total / 10).backward()
+    want = [p.grad for p in m.parameters()] + [table.weight.grad]
+    for r in range(world):
+        assert not any(np.isnan(g).any() for g in res[r])
+        for got, w in zip(res[r], want):
+            assert torch.allclose(torch.from_numpy(got), w, atol=1e-6), r
