@@ -471,7 +471,9 @@ def train_steps(dev, rend, ps, view, world, rank, n_px=4096, tag="", dist=None):
 
 
 def _time_dist(fn, reps, dev, dist):
-    """fn timed with CUDA events after one warm-up call; with a process group: barrier on both sides, max over ranks."""
+    """fn timed with CUDA events after two warm-up calls (the first use of a kernel pays its lazy module load: a one-off stall of
+    up to a second was seen on the train steps); with a process group: barrier on both sides, max over ranks."""
+    fn()
     fn()
     if dist is not None:
         dist.barrier()

@@ -57,7 +57,7 @@ static const float kRefineMargin = 0.02f;  // >= 20 x the largest |cheap - full|
 static size_t march_ws_bytes(long long N, int S) {
   return align256((size_t)N * S * 4) + 8 * align256((size_t)N * 4) + 1024 + 4 * align256((size_t)refine_cap(N, S) * 4) + 512;
 }
-static const int kShadowLead = 8;  // in-box steps of every shadow ray evaluated before its transmittance decides about the rest (<= 32)
+static const int kShadowLead = 16;  // in-box steps of every shadow ray evaluated before its transmittance decides about the rest (<= 32)
 static const long long kShadowChunkPairs = 1 << 21;  // (light, point) pairs per shadow chunk (1 GB of occupancies at S=128)
 // A/B switch for measurements: PSNERF_B200_SHADOW_UNCULLED=1 evaluates every step of every shadow ray like the reference does
 // (fused k_tc_occ<MODE_SHADOW> on the tensor path) instead of the box-culled list.  Results agree to rounding of the product order.

@@ -14,9 +14,8 @@
 // consumes tolerates plain fp16 operands: s8..s22 run ONE pass A_hi W_hi (Step::single), their producers write only the hi
 // half of the A operand.  rgb moves by 6e-6 rel-L2 per sample / 1e-6 per rendered pixel (same tool); the gradient OUTPUT
 // (surface normals) is never taken from this program - tc_gradient always runs the three-pass one.
-// H16 (opt-in on top of the mixed program, PSNERF_B200_RAD_H16=1; not yet run on hardware): the forward layers no longer compute
-// sigma' at all - their stash is the packed fp16 hi half of h that they produce for the A operand anyway - and the reverse layers,
-// which have slack, rebuild sigma' = 1 - 2^(-100 log2(e) h) with one ex2 (emulated: rgb error unchanged at 6e-6).
+// (An "H16" variant - sigma' rebuilt in the reverse layers from the fp16 activations instead of a unorm16 stash written by the forward
+// layers - ran on the B200 in round 2: bit-compatible gates, 173.4 ms against 173.3 ms.  Not faster, removed; profiles/README.md.)
 #include <stdlib.h>
 
 #include "tc_mlp.cuh"
@@ -94,14 +93,6 @@ __device__ __forceinline__ void softplus8_d(float* v, float c, float (&sg)[8]) {
 
 // TRACE (bring-up tool only): clock64 timeline of tile iteration TRACE_ITER of CTA 0 - MMA-lane slots as in mma_loop, plus
 // trace[192 + step] / trace[224 + step] = time at which row 0 / sub 0 finished / started the epilogue of that step.
-// sigma' of two activations from their packed fp16 values h (H16 stash): 1 - 2^(-k h)
-__device__ __forceinline__ void sig_from_h_pair(uint32_t w, float k, float& a, float& b) {
-  const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&w));
-  a = 1.f - ex2_approx(-k * h.x);
-  b = 1.f - ex2_approx(-k * h.y);
-}
-#define PSN_SIG_K 144.26950408889634f /* 100 log2(e) */
-
 // Scratch accesses with an L2 evict_last policy (HINT, opt-in: PSNERF_B200_STASH_HINT=1): the per-CTA stash / parked area is
 // rewritten every tile and dead in between, but ncu shows every byte of it written back to DRAM (162 GB per launch); keeping these
 // lines at the bottom of the eviction order should let the next tile overwrite them in L2 instead.
@@ -128,7 +119,18 @@ __device__ __forceinline__ uint4 scr_ld(const uint4* p, unsigned long long pol) 
   return __ldcg(p);
 }
 
-template <bool TRACE, bool H16 = false, bool HINT = false>
+// HINT only: once a warp has consumed its 512 contiguous bytes of stash / parked scratch (32 rows x 16 B), the four 128-byte lines
+// are dead until the next tile rewrites them.  discard.global.L2 drops them from L2 WITHOUT a write-back - the point of the exercise:
+// ncu shows every byte of the scratch going to DRAM (135-162 GB per launch) although nothing ever reads it from there.
+template <bool HINT>
+__device__ __forceinline__ void scr_discard(const void* p, int row) {
+  if (HINT) {
+    __syncwarp();  // every lane's load of this line has completed (each lane has used its value)
+    if ((row & 7) == 0) asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");
+  }
+}
+
+template <bool TRACE, bool HINT = false>
 __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* __restrict__ rgb, float* __restrict__ alpha,
          float* __restrict__ grad_out, long long* trace) {
@@ -191,31 +193,6 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
         epi_for_chunks_pf<Bias16>(s, e, [&](int col, Bias16& b) { load_bias16(bias, col, b); },
                                   [&](int pass, int col, float (&v)[CW], const Bias16& b) {
           add16(v, b.b);
-          if (H16) {  // mixed program only: no sigma' here, the stash is the hi half of the operand written below
-#pragma unroll
-            for (int i = 0; i < CW; ++i) v[i] = softplus_scaled(v[i], cc);
-            if (l == 7) {
-              const float4* w4 = reinterpret_cast<const float4*>(g.w_row + col);
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                const float4 w = __ldg(w4 + t);
-                part = fmaf(v[4 * t], w.x, part); part = fmaf(v[4 * t + 1], w.y, part);
-                part = fmaf(v[4 * t + 2], w.z, part); part = fmaf(v[4 * t + 3], w.w, part);
-              }
-            }
-            if (pre_skip && col + CW > n_out) {
-#pragma unroll
-              for (int i = 0; i < CW; ++i) {
-                const int k = col + i - n_out;
-                if (k >= 0) v[i] = (k < g.pe_dim ? s.pe[k * TILE_M + row] : 0.f) * PSN_INV_SQRT2;
-              }
-            }
-            uint4 hw[2];
-            epi_store_a16_keep(e, e.d_col0(), col, v, ho_l, hw);
-            epi_signal_a(s, pass);
-            scr_st<HINT>(&stash[(size_t)(l * 32 + (col >> 3)) * TILE_M + row], hw[0], pol);
-            scr_st<HINT>(&stash[(size_t)(l * 32 + (col >> 3) + 1) * TILE_M + row], hw[1], pol);
-          } else {
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
             float sg[8];
@@ -249,7 +226,6 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
           }
           epi_store_a16(e, e.d_col0(), col, v, ho_l);
           epi_signal_a(s, pass);
-          }
         });
         PSN_RAD_MARK(192);
         ++tstep;
@@ -284,14 +260,7 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
           for (int t = 0; t < 2; ++t) {
             const uint4 q = o.q[t];
             float sg[8];
-            if (H16) {
-              sig_from_h_pair(q.x, PSN_SIG_K, sg[0], sg[1]); sig_from_h_pair(q.y, PSN_SIG_K, sg[2], sg[3]);
-              sig_from_h_pair(q.z, PSN_SIG_K, sg[4], sg[5]); sig_from_h_pair(q.w, PSN_SIG_K, sg[6], sg[7]);
-#pragma unroll
-              for (int u = 0; u < 8; ++u) sg[u] *= 65535.f;  // the common path below multiplies by PSN_INV_U16 (unorm16 stash)
-            } else {
-              dq16_pair(q.x, sg[0], sg[1]); dq16_pair(q.y, sg[2], sg[3]); dq16_pair(q.z, sg[4], sg[5]); dq16_pair(q.w, sg[6], sg[7]);
-            }
+            dq16_pair(q.x, sg[0], sg[1]); dq16_pair(q.y, sg[2], sg[3]); dq16_pair(q.z, sg[4], sg[5]); dq16_pair(q.w, sg[6], sg[7]);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const float4 w = o.w[2 * t + h];
@@ -301,6 +270,8 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
           }
           epi_store_a16(e, e.d_col0(), col, v, ho);
           epi_signal_a(s, pass);
+#pragma unroll
+          for (int t = 0; t < 2; ++t) scr_discard<HINT>(&stash[(size_t)(7 * 32 + (col >> 3) + t) * TILE_M + row], row);
         });
         PSN_RAD_MARK(192);
         ++tstep;
@@ -332,15 +303,7 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
           for (int t = 0; t < 2; ++t) {
             const uint4 q = o.q[t];
             float sg[8];
-            if (H16) {  // the stash of the layer below the skip holds h / sqrt2 (its operand scaling): undo it in the exponent
-              const float kk = is_skip ? PSN_SIG_K * 1.41421356237309504880f : PSN_SIG_K;
-              sig_from_h_pair(q.x, kk, sg[0], sg[1]); sig_from_h_pair(q.y, kk, sg[2], sg[3]);
-              sig_from_h_pair(q.z, kk, sg[4], sg[5]); sig_from_h_pair(q.w, kk, sg[6], sg[7]);
-#pragma unroll
-              for (int u = 0; u < 8; ++u) sg[u] *= 65535.f;  // `scale` carries the 1 / 65535 of the unorm16 stash
-            } else {
-              dq16_pair(q.x, sg[0], sg[1]); dq16_pair(q.y, sg[2], sg[3]); dq16_pair(q.z, sg[4], sg[5]); dq16_pair(q.w, sg[6], sg[7]);
-            }
+            dq16_pair(q.x, sg[0], sg[1]); dq16_pair(q.y, sg[2], sg[3]); dq16_pair(q.z, sg[4], sg[5]); dq16_pair(q.w, sg[6], sg[7]);
 #pragma unroll
             for (int u = 0; u < 8; ++u) v[8 * t + u] = (v[8 * t + u] * scale) * sg[u];
           }
@@ -351,6 +314,8 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
           }
           epi_store_a16(e, e.d_col0(), col, v, ho);
           epi_signal_a(s, pass);
+#pragma unroll
+          for (int t = 0; t < 2; ++t) scr_discard<HINT>(&stash[(size_t)((l - 1) * 32 + (col >> 3) + t) * TILE_M + row], row);
         });
         PSN_RAD_MARK(192);
         ++tstep;
@@ -427,6 +392,8 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
           for (int i = 0; i < CW; ++i) v[i] = fmaxf(v[i], 0.f);
           epi_store_a16(e, e.d_col0(), col, v, ho);
           epi_signal_a(s, pass);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) scr_discard<HINT>(&parked[(size_t)((col >> 2) + t) * TILE_M + row], row);
         });
         PSN_RAD_MARK(192);
         ++tstep;
@@ -529,14 +496,9 @@ size_t tc_stash_bytes() {
 
 static int launch_tc_rad(const TcRadArgs& a, const PointGen& gen, long long M, const int* M_dev, float* rgb, float* alpha,
                          float* grad, cudaStream_t st, long long* trace = nullptr) {
-  // PSNERF_B200_RAD_H16=1 selects the H16 variant of the mixed program (opt-in experiment, see the file header)
-  static const bool env_h16 = [] { const char* v = getenv("PSNERF_B200_RAD_H16"); return v && v[0] == '1'; }();
   static const bool env_hint = [] { const char* v = getenv("PSNERF_B200_STASH_HINT"); return v && v[0] == '1'; }();
-  const bool h16 = env_h16 && a.mixed && !trace;
   const bool hint = env_hint && !trace;
-  const void* kfn = trace ? (const void*)k_tc_rad<true>
-                          : h16 ? (hint ? (const void*)k_tc_rad<false, true, true> : (const void*)k_tc_rad<false, true>)
-                                : (hint ? (const void*)k_tc_rad<false, false, true> : (const void*)k_tc_rad<false>);
+  const void* kfn = trace ? (const void*)k_tc_rad<true> : (hint ? (const void*)k_tc_rad<false, true> : (const void*)k_tc_rad<false>);
   PSN_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   {
     const int rcr = check_launch_regs(kfn, "k_tc_rad");

@@ -218,8 +218,8 @@ def test_shape_extract_and_shadow_vs_golden(s1, variant, prec):
 @pytest.mark.parametrize("Ns,L", [(1, 1), (37, 7), (1000, 5)])
 def test_box_culled_shadow_pass(s1, prec, Ns, L, monkeypatch):
     """The shadow pass evaluates the occupancy MLP only at the in-box steps of every shadow ray (k_shadow_plan / GEN_SHADOW_LIST), and
-    past the first 8 of them only while the ray's transmittance is still >= 1e-7 (k_shadow_plan_b): equal to the evaluation of every
-    step (what the reference executes, PSNERF_B200_SHADOW_UNCULLED=1) up to the order of the transmittance product and the < 1e-7 of
+    past the first 16 of them only while the ray's transmittance is still >= 1e-6 (k_shadow_plan_b): equal to the evaluation of every
+    step (what the reference executes, PSNERF_B200_SHADOW_UNCULLED=1) up to the order of the transmittance product and the < 1e-6 of
     the dropped tail, and to the oracle; points outside the +-1.1 cube (no in-box step at all) give visibility exactly 1."""
     from psnerf_b200 import engine
     from psnerf_b200.stage1 import Renderer
@@ -239,17 +239,18 @@ def test_box_culled_shadow_pass(s1, prec, Ns, L, monkeypatch):
     vis_all, st_all = engine.shadow_visibility(g, surf.cuda(), lights.cuda(), precision=r.model._prec(), return_stats=True)
     monkeypatch.delenv("PSNERF_B200_SHADOW_UNCULLED")
     assert not st_all["culled"] and st_all["evaluated"] == st_all["nominal"]
-    util.bound("shadow_culled_vs_every_step/%s/%d" % (prec, Ns), util.max_abs(vis.cpu(), vis_all.cpu()), 2e-6)
+    util.bound("shadow_culled_vs_every_step/%s/%d" % (prec, Ns), util.max_abs(vis.cpu(), vis_all.cpu()), 3e-6)
     with torch.no_grad():
         ref = O.light_visibility(sds["trained"], cfg["model"], surf, lights).view(L, Ns)
     util.bound("shadow_culled_vs_oracle/%s/%d" % (prec, Ns), util.max_abs(vis.cpu(), ref), GATE["light_visibility"])
     if Ns > 2:
         assert float((vis[:, 0] - 1).abs().max()) == 0.0
-    # the in-box count is what the oracle's own box mask says
+    # never more than the oracle's own box mask admits, never less than the first 16 in-box steps of every ray
     t = torch.linspace(0, 1, 128)
     p = surf[None, :, None, :] + lights[:, None, None, :] * (0.1 * (1 - t) + 3.5 * t)[None, None, :, None]
-    inside = ((p <= 1.1) & (p >= -1.1)).all(-1).sum()
-    assert abs(st["evaluated"] - int(inside)) <= max(2, int(0.001 * int(inside)))  # a step exactly on the box face may round either way
+    inside = ((p <= 1.1) & (p >= -1.1)).all(-1)
+    slack = max(2, int(0.001 * int(inside.sum())))  # a step exactly on the box face may round either way
+    assert int(inside.sum(-1).clamp(max=16).sum()) - slack <= st["evaluated"] <= int(inside.sum()) + slack
 
 
 def test_composite_properties():

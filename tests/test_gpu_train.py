@@ -48,9 +48,15 @@ def _run_oracle(conf, sd, inp, lraw, inten, z, cot):
     return out, gd, grads[-2], grads[-1]
 
 
+@pytest.mark.parametrize("gemm", ["ffma", "tc"])
 @pytest.mark.parametrize("prec", ["fp32", "tc"])
 @pytest.mark.parametrize("shape", [(12, 10, 5, 2, False), (32, 24, 9, 3, True)])
-def test_train_step_gradients_vs_oracle_autograd(shape, prec):
+def test_train_step_gradients_vs_oracle_autograd(shape, prec, gemm, monkeypatch):
+    """gemm = 'ffma' pins the logic of the backward pass at the tight gates; gemm = 'tc' (what the train steps run: tf32 x 3 tensor-core
+    GEMMs, ~2e-6 per layer) flips the ReLU masks of the pre-activations within rounding of zero, so its per-tensor gates are looser
+    and the MEDIAN over the tensors is held tight instead (see tests/test_gpu_train_stage1.py:GEMM_GATES)."""
+    monkeypatch.setenv("PSNERF_B200_TRAIN_GEMM", gemm)
+    loose = gemm == "tc"
     h, w, L, Lt, rgb_int = shape
     conf, sds = util.stage2_state_dicts()
     sd = sds["trained"]
@@ -64,23 +70,25 @@ def test_train_step_gradients_vs_oracle_autograd(shape, prec):
     out = m(ci, noise={"xyz": z})
     cot = {k: torch.randn(out[k].shape, generator=g) for k in KEYS}
     ref_out, ref_g, ref_gl, ref_gi = _run_oracle(conf, sd, inp, lraw, inten, z, cot)
-    tol = 2e-5 if prec == "fp32" else 2e-4
+    tol = (4e-5 if loose else 2e-5) if prec == "fp32" else 2e-4
     for k in KEYS:
         assert tuple(out[k].shape) == tuple(ref_out[k].shape), k
         assert util.max_abs(out[k].detach().cpu(), ref_out[k].detach()) < tol, k
     scalar = sum((out[k] * cot[k].cuda()).sum() for k in KEYS)
     scalar.backward()
     params = dict(m.named_parameters())
+    errs = []
     for n, gr in ref_g.items():
         got = params[n].grad
         got = torch.zeros_like(params[n]) if got is None else got
         scale = max(1.0, float(gr.abs().max()))
-        util.bound("s2_param_grad/%s/%s/%s/max_abs" % (shape[0], prec, n), util.max_abs(got.cpu(), gr) / scale, 1e-3)
-        # rel-L2 per tensor: the ReLU stacks make the gradient piecewise constant in the pre-activations; the tensor-core GEMMs
-        # (tf32 x 3, ~2e-6 of truncating accumulation per layer) flip the masks of the ~60 of 2.7 M pre-activations of this case that
-        # sit within 3e-6 of zero, and each flip of a deep unit moves a whole row's contribution to the layers below
+        e_abs = util.max_abs(got.cpu(), gr) / scale
+        errs.append(e_abs)
+        util.bound("s2_param_grad/%s/%s/%s/%s/max_abs" % (gemm, shape[0], prec, n), e_abs, 5e-2 if loose else 3e-4)
         if float(gr.abs().max()) >= 1e-6:
-            util.bound("s2_param_grad/%s/%s/%s/rel_l2" % (shape[0], prec, n), util.rel_l2(got.cpu(), gr), 2e-2)
+            util.bound("s2_param_grad/%s/%s/%s/%s/rel_l2" % (gemm, shape[0], prec, n), util.rel_l2(got.cpu(), gr), 1e-1 if loose else 2e-3)
+    if loose:
+        util.bound("s2_param_grad/%s/%s/%s/median_max_abs" % (gemm, shape[0], prec), float(np.median(errs)), 3e-4)
     assert util.max_abs(lr.grad.cpu(), ref_gl) < 3e-4 * max(1.0, float(ref_gl.abs().max()))
     assert util.max_abs(it.grad.cpu(), ref_gi) < 3e-4 * max(1.0, float(ref_gi.abs().max()))
 

@@ -19,21 +19,37 @@ def _model(sd, cfg):
     return m.cuda().train()
 
 
-def _check_param_grads(model, ref_grads, rtol):
-    worst = 0.0
+def _check_param_grads(model, ref_grads, rtol, tag="ffma", median_tol=None):
+    """max |got - ref| / max |ref| per parameter tensor below rtol (and, optionally, the median over the tensors below median_tol)."""
+    errs = []
     for n, p in model.named_parameters():
         got = torch.zeros_like(p) if p.grad is None else p.grad
         ref = ref_grads[n]
         scale = max(1e-6, float(ref.abs().max()))
         err = float((got.cpu() - ref).abs().max()) / scale
-        worst = max(worst, err)
-        util.bound("s1_param_grad/" + n, err, rtol)
-    return worst
+        errs.append(err)
+        util.bound("s1_param_grad/%s/%s" % (tag, n), err, rtol)
+    if median_tol is not None:
+        util.bound("s1_param_grad/%s/median" % tag, float(np.median(errs)), median_tol)
+    return max(errs)
 
 
+# The GEMMs of the train steps run on the tensor cores (tf32 x 3, csrc/tc_gemm.cu) with ~2e-6 of error per layer (truncating
+# accumulation) against ~2e-7 for the FFMA kernel.  The appearance MLP / the stage-2 nets are ReLU stacks, so their gradient is
+# piecewise constant in the pre-activations: the units that sit within that error of zero flip, and one flip in a deep layer moves a
+# whole sample's contribution to every tensor below it - a comparison with autograd is ill-posed at those kinks, whatever the GEMM.
+# The gradient tests therefore pin the LOGIC of the backward pass with the FFMA GEMMs (PSNERF_B200_TRAIN_GEMM=ffma) at the tight
+# gate of round 1, and hold the tensor-core run to a looser per-tensor gate plus a tight gate on the MEDIAN over the tensors (a GEMM
+# that was wrong, not flipped, would move all of them); the GEMM itself is pinned at 1e-5 in tests/test_gpu_tc_gemm.py.
+GEMM_GATES = {"ffma": dict(rtol=2e-3, median=None, fwd=2e-5), "tc": dict(rtol=5e-2, median=1e-3, fwd=6e-5)}
+
+
+@pytest.mark.parametrize("gemm", ["ffma", "tc"])
 @pytest.mark.parametrize("with_app", [True, False])
-def test_field_forward_backward_vs_oracle_autograd(with_app):
+def test_field_forward_backward_vs_oracle_autograd(with_app, gemm, monkeypatch):
     """rgb / logit / grad of M = 333 samples (not a multiple of the GEMM tiles) and the gradient of every parameter."""
+    monkeypatch.setenv("PSNERF_B200_TRAIN_GEMM", gemm)
+    gates = GEMM_GATES[gemm]
     cfg, sds = util.stage1_state_dicts()
     from psnerf_b200.stage1 import train as T
     model = _model(sds["trained"], cfg)
@@ -53,21 +69,17 @@ def test_field_forward_backward_vs_oracle_autograd(with_app):
     x = O.geo_forward(sd, pts, mcfg)
     n = O.geo_gradient_analytic(sd, pts, mcfg)
     ref = (x[:, 0] * c_logit).sum() + (n[:, 0, :] * c_grad).sum()
-    # forward GEMMs on the tensor cores (tf32 x 3, csrc/tc_gemm.cu): ~2e-6 per layer from the truncating accumulation, eight layers
-    util.bound("s1_field/%s/logit" % with_app, util.max_abs(logit.detach().cpu(), x[:, 0].detach()), 6e-5)
-    util.bound("s1_field/%s/grad" % with_app, util.rel_l2(grad.detach().cpu(), n[:, 0, :].detach()), 6e-5)
+    util.bound("s1_field/%s/%s/logit" % (gemm, with_app), util.max_abs(logit.detach().cpu(), x[:, 0].detach()), gates["fwd"])
+    util.bound("s1_field/%s/%s/grad" % (gemm, with_app), util.rel_l2(grad.detach().cpu(), n[:, 0, :].detach()), gates["fwd"])
     if with_app:
         v = O.positional_encoding(views / views.norm(dim=-1, keepdim=True), mcfg["octaves_pe_views"])
         r = O.app_forward(sd, pts, n, v, x[:, 1:])
         ref = ref + (r * c_rgb).sum()
-        util.bound("s1_field/%s/rgb" % with_app, util.max_abs(rgb.detach().cpu(), r.detach()), 6e-5)
+        util.bound("s1_field/%s/%s/rgb" % (gemm, with_app), util.max_abs(rgb.detach().cpu(), r.detach()), gates["fwd"])
     names = sorted(sd)
     gr = torch.autograd.grad(ref, [sd[k] for k in names], allow_unused=True)
     ref_grads = {k: (torch.zeros_like(sd[k]) if g_ is None else g_) for k, g_ in zip(names, gr)}
-    # 5e-3 of each tensor's largest gradient entry: the appearance MLP is a ReLU stack, and the tensor-core GEMMs (tf32 x 3, ~2e-6
-    # per layer) flip the masks of the pre-activations that sit within rounding of zero (measured worst tensor: lina0.weight_g 2.1e-3;
-    # the FFMA GEMMs of round 1, PSNERF_B200_TRAIN_GEMM=ffma, held 2e-3 here)
-    _check_param_grads(model, ref_grads, 5e-3)
+    _check_param_grads(model, ref_grads, gates["rtol"], gemm, gates["median"])
 
 
 def test_composite_backward_vs_autograd():
