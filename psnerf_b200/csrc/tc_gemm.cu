@@ -37,7 +37,7 @@ constexpr int THREADS = (EPI_WARPS + 1 + LOAD_WARPS) * 32;  // 416
 constexpr int LOAD_THREADS = LOAD_WARPS * 32;
 
 struct Bars {
-  unsigned long long full[STAGES];    // loaders -> MMA (LOAD_THREADS arrivals)
+  unsigned long long full[STAGES];    // loaders -> MMA (one arrival per loader warp)
   unsigned long long empty[STAGES];   // MMA -> loaders (tcgen05.commit)
   unsigned long long acc_full[2];     // MMA -> epilogue (tcgen05.commit)
   unsigned long long acc_empty[2];    // epilogue -> MMA (EPI_WARPS arrivals)
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_gemm(Args a) {
   Bars* bars = reinterpret_cast<Bars*>(base + STAGES * STAGE);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&bars->full[s], LOAD_THREADS); mbar_init(&bars->empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&bars->full[s], LOAD_WARPS); mbar_init(&bars->empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&bars->acc_full[b], 1); mbar_init(&bars->acc_empty[b], EPI_WARPS); }
     fence_barrier_init();
   }
@@ -341,7 +341,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_gemm(Args a) {
           store_row_contig(fb, Bh, Bl, bn, t);
         }
         fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
-        mbar_arrive(&bars->full[stage]);
+        __syncwarp();              // one arrival per warp: 256 single-thread arrivals on one mbarrier serialise (~1000 cycles per K block)
+        if (lane == 0) mbar_arrive(&bars->full[stage]);
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }

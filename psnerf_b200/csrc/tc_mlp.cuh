@@ -583,30 +583,6 @@ __device__ __forceinline__ void epi_store_a16_hi(const EpiCtx& e, uint32_t col0,
   }
   tmem_st8(e.tmem_base + e.lane_addr + col0 + (uint32_t)col, r);
 }
-// Variant for the H16 radiance program: the same store (full or hi-only), and the eight packed fp16 hi words are handed back - they
-// double as the stash from which the reverse sweep rebuilds sigma'.
-__device__ __forceinline__ void epi_store_a16_keep(const EpiCtx& e, uint32_t col0, int col, const float (&v)[CW], bool hi_only,
-                                                   uint4 (&hw)[2]) {
-  uint32_t r[16];
-#pragma unroll
-  for (int u = 0; u < 8; ++u) {
-    const __half2 hh = __floats2half2_rn(v[2 * u], v[2 * u + 1]);
-    const float2 hf = __half22float2(hh);
-    const __half2 ll = __floats2half2_rn(v[2 * u] - hf.x, v[2 * u + 1] - hf.y);
-    r[u] = *reinterpret_cast<const uint32_t*>(&hh);
-    r[8 + u] = *reinterpret_cast<const uint32_t*>(&ll);
-  }
-  hw[0] = make_uint4(r[0], r[1], r[2], r[3]);
-  hw[1] = make_uint4(r[4], r[5], r[6], r[7]);
-  if (hi_only) {
-    uint32_t h8[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) h8[u] = r[u];
-    tmem_st8(e.tmem_base + e.lane_addr + col0 + (uint32_t)col, h8);
-  } else {
-    tmem_st16(e.tmem_base + e.lane_addr + col0 + (uint32_t)col, r);
-  }
-}
 __device__ __forceinline__ void epi_store_a16(const EpiCtx& e, uint32_t col0, int col, const float (&v)[CW], bool hi_only) {
   if (hi_only) epi_store_a16_hi(e, col0, col, v);
   else epi_store_a16(e, col0, col, v);
