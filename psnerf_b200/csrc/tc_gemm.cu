@@ -393,17 +393,17 @@ int tc_gemm(int form, const float* A, long long lda, const float* B, long long l
   }
   const long long total = a.m_tiles * a.n_chunks * a.k_splits;
   const int grid = (int)(total < ctas ? total : ctas);
-  count_launch();
-  if (form == 0) {
+  static bool attr_set = false;  // one device per process (num_ctas() makes the same assumption)
+  if (!attr_set) {
     PSN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_gemm<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    k_tc_gemm<0><<<grid, THREADS, SMEM, st>>>(a);
-  } else if (form == 1) {
     PSN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_gemm<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    k_tc_gemm<1><<<grid, THREADS, SMEM, st>>>(a);
-  } else {
     PSN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_gemm<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    k_tc_gemm<2><<<grid, THREADS, SMEM, st>>>(a);
+    attr_set = true;
   }
+  count_launch();
+  if (form == 0) k_tc_gemm<0><<<grid, THREADS, SMEM, st>>>(a);
+  else if (form == 1) k_tc_gemm<1><<<grid, THREADS, SMEM, st>>>(a);
+  else k_tc_gemm<2><<<grid, THREADS, SMEM, st>>>(a);
   PSN_CUDA_CHECK(cudaGetLastError());
   return PSN_OK;
 }

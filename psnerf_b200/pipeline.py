@@ -12,10 +12,18 @@
 All functions take / return torch tensors; `view` dicts carry the camera: stage 1 {camera_mat, world_mat}, stage 2
 {intrinsics, pose}.  The pixel order conventions of the reference are preserved (stage 1: x-major, undone by to_hw;
 stage 2: row-major uv)."""
+import functools
+
 import torch
 
 from . import sharding
 from .stage1.common import arange_pixels, to_hw
+
+
+@functools.lru_cache(maxsize=64)
+def _shard_pixels(h, w, rank, world, device):
+    """[1, n_local, 2] integer pixel positions of one rank's ray tiles, resident on `device` (built once per view size)."""
+    return arange_pixels((h, w))[0][:, sharding.shard_indices(h * w, rank, world)].to(device)
 
 
 @torch.no_grad()
@@ -180,9 +188,9 @@ def extract_and_shade_sharded(renderer, ps_model, h, w, camera_mat, world_mat, l
     """extract_and_shade with the rays of the view dealt over the ranks (128-ray tiles round-robin, sharding.shard_indices) and ONE
     all_gather of the packed per-pixel rows at the end: every rank returns the full view."""
     N = h * w
-    idx = sharding.shard_indices(N, rank, world)
-    p_all = arange_pixels((h, w))[0]
-    local = extract_and_shade_rows(renderer, ps_model, h, w, camera_mat, world_mat, light_dirs, p_all[:, idx], light_batch, shadows)
+    dev = next(renderer.model.parameters()).device
+    local = extract_and_shade_rows(renderer, ps_model, h, w, camera_mat, world_mat, light_dirs, _shard_pixels(h, w, rank, world, dev),
+                                   light_batch, shadows)
     full = sharding.gather_pixels(local, N, rank, world, group=group)
     return unpack_relit_rows(full, ps_model, light_dirs.shape[0], shadows)
 

@@ -3,17 +3,27 @@
 Every ray / pixel / (point, light) pair is independent and the weights (<= 3.2 MB) are replicated, so the data path
 needs no collective; the only exchange is one all_gather of the rendered pixel shards.  Backend-agnostic
 (`nccl` on GPUs, `gloo` in the CPU tests)."""
+import functools
+
 import torch
 import torch.distributed as dist
 
 
+@functools.lru_cache(maxsize=256)
 def shard_indices(n_rays, rank, world, tile=128):
-    """Ray ids owned by `rank`: tiles of `tile` consecutive rays dealt round-robin (balances sparse masks)."""
+    """Ray ids owned by `rank`: tiles of `tile` consecutive rays dealt round-robin (balances sparse masks).  Cached: the same
+    (view size, rank, world) is asked for on every view."""
     ids = torch.arange(n_rays)
     t = ids // tile
     return ids[(t % world) == rank]
 
 
+@functools.lru_cache(maxsize=256)
+def _shard_indices_on(n_rays, rank, world, tile, device):
+    return shard_indices(n_rays, rank, world, tile).to(device)
+
+
+@functools.lru_cache(maxsize=64)
 def shard_counts(n_rays, world, tile=128):
     return [int(shard_indices(n_rays, r, world, tile).numel()) for r in range(world)]
 
@@ -70,8 +80,7 @@ def gather_pixels(local, n_rays, rank, world, tile=128, group=None):
     dist.all_gather_into_tensor(out, buf, group=group)
     full = local.new_empty(n_rays, C)
     for r in range(world):
-        idx = shard_indices(n_rays, r, world, tile).to(local.device)
-        full[idx] = out[r * pad: r * pad + counts[r]]
+        full[_shard_indices_on(n_rays, r, world, tile, local.device)] = out[r * pad: r * pad + counts[r]]
     return full
 
 
