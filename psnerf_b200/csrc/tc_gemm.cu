@@ -58,7 +58,19 @@ struct Args {
   long long k_per_split; // FORM 2: multiple of BK
 };
 
-__device__ __forceinline__ uint32_t idesc_tf32(uint32_t n) { return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | (8u << 24); }
+// kind::tf32 instruction descriptor: D = F32 (bit 4), A / B format TF32 = 2 (bits 7-9 / 10-12), a_major / b_major (bits 15 / 16:
+// 0 = K-major, 1 = MN-major operand tile), N >> 3 (bits 17-22), M >> 4 (bits 24-28)
+__device__ __forceinline__ uint32_t idesc_tf32(uint32_t n, uint32_t a_mn, uint32_t b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (a_mn << 15) | (b_mn << 16) | ((n >> 3) << 17) | (8u << 24);
+}
+// MN-major SWIZZLE_128B operand tile [32 k][rows]: blocks of 32 consecutive rows (128 bytes) x 8 k (1024-byte swizzle atom, 16-byte
+// chunk index XOR k % 8); the four k groups of a block are adjacent (SBO = 1024), row blocks follow at LBO = 4096.  K step ks of an
+// MMA starts at + ks * 1024.  (Canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units, cute/atom/mma_traits_sm100.hpp.)
+constexpr uint32_t MN_LBO = 4096, MN_SBO = 1024;
+__device__ __forceinline__ uint32_t mn_off(int r, int k) {
+  return (uint32_t)(r >> 5) * MN_LBO + (uint32_t)(k >> 3) * MN_SBO + (uint32_t)(k & 7) * 128u + (((((uint32_t)r & 31u) >> 2) ^ ((uint32_t)k & 7u)) << 4);
+}
+__device__ __forceinline__ uint32_t umma_desc_lo_mn(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | ((MN_LBO >> 4) << 16); }
 __device__ __forceinline__ void umma_ss_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -188,7 +200,26 @@ __device__ __forceinline__ void store_row_contig(const Frag (&f)[NIT], unsigned 
   }
 }
 
-template <int FORM>
+// The same fragments written as an MN-major tile: the four consecutive rows of a float4 stay one 16-byte chunk - no transposition,
+// conflict-free 16-byte stores (MNMAJ kernels; the MMA reads the tile through a_major / b_major = 1).
+template <int NIT>
+__device__ __forceinline__ void store_row_contig_mn(const Frag (&f)[NIT], unsigned char* hi, unsigned char* lo, int rows, int t) {
+  const int quads = rows >> 2;
+#pragma unroll
+  for (int j = 0; j < NIT; ++j) {
+    const int idx = t + LOAD_THREADS * j;
+    if (idx >= quads * BK) break;
+    const int q = idx % quads, k = idx / quads;
+    const float4 v = f[j].v;
+    const float4 h = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+    const float4 l = make_float4(to_tf32(v.x - h.x), to_tf32(v.y - h.y), to_tf32(v.z - h.z), to_tf32(v.w - h.w));
+    const uint32_t off = mn_off(4 * q, k);
+    *reinterpret_cast<float4*>(hi + off) = h;
+    *reinterpret_cast<float4*>(lo + off) = l;
+  }
+}
+
+template <int FORM, bool MNMAJ>
 __global__ void __launch_bounds__(THREADS, 1) k_tc_gemm(Args a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -266,7 +297,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_gemm(Args a) {
     // ---- MMA issuer (whole warp converged, one elected lane issues) -----------------------------------------------------------------
     uint32_t stage = 0, phase = 0, acc_phase = 0;
     long long it_ctr = 0;
-    const uint32_t idesc = idesc_tf32((uint32_t)bn);
+    constexpr bool A_MN = MNMAJ && FORM == 2, B_MN = MNMAJ && FORM >= 1;  // operands whose contiguous dimension is not k
+    const uint32_t idesc = idesc_tf32((uint32_t)bn, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+    constexpr uint32_t a_step = A_MN ? MN_SBO : 32u, b_step = B_MN ? MN_SBO : 32u;  // bytes between the K steps (8 k) of a K block
     for (long long t = blockIdx.x; t < total; t += gridDim.x, ++it_ctr) {
       const TileIt it = tile_at<FORM>(a, t);
       long long k0, k1;
@@ -283,13 +316,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_gemm(Args a) {
         mbar_wait(&bars->full[stage], phase);
         tc_fence_after();
         const uint32_t sa = smem_u32(base + stage * STAGE);
-        const uint32_t a_hi = umma_desc_lo(sa), a_lo = umma_desc_lo(sa + A_TILE);
-        const uint32_t b_hi = umma_desc_lo(sa + 2 * A_TILE), b_lo = umma_desc_lo(sa + 2 * A_TILE + B_TILE);
+        const uint32_t a_hi = A_MN ? umma_desc_lo_mn(sa) : umma_desc_lo(sa), a_lo = A_MN ? umma_desc_lo_mn(sa + A_TILE) : umma_desc_lo(sa + A_TILE);
+        const uint32_t b_hi = B_MN ? umma_desc_lo_mn(sa + 2 * A_TILE) : umma_desc_lo(sa + 2 * A_TILE);
+        const uint32_t b_lo = B_MN ? umma_desc_lo_mn(sa + 2 * A_TILE + B_TILE) : umma_desc_lo(sa + 2 * A_TILE + B_TILE);
         if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t ah = umma_desc_at(a_hi, ks * 32), al = umma_desc_at(a_lo, ks * 32);
-            const uint64_t bh = umma_desc_at(b_hi, ks * 32), bl = umma_desc_at(b_lo, ks * 32);
+            const uint64_t ah = umma_desc_at(a_hi, ks * a_step), al = umma_desc_at(a_lo, ks * a_step);
+            const uint64_t bh = umma_desc_at(b_hi, ks * b_step), bl = umma_desc_at(b_lo, ks * b_step);
             umma_ss_tf32(d_addr, ah, bh, idesc, (first && ks == 0) ? 0u : 1u);
             umma_ss_tf32(d_addr, al, bh, idesc, 1u);
             umma_ss_tf32(d_addr, ah, bl, idesc, 1u);
@@ -335,10 +369,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_gemm(Args a) {
           store_k_contig(fb, Bh, Bl, bn, t);
         } else if (FORM == 1) {
           store_k_contig(fa, Ah, Al, BM, t);
-          store_row_contig(fb, Bh, Bl, bn, t);
+          if (MNMAJ) store_row_contig_mn(fb, Bh, Bl, bn, t); else store_row_contig(fb, Bh, Bl, bn, t);
         } else {
-          store_row_contig(fa, Ah, Al, BM, t);
-          store_row_contig(fb, Bh, Bl, bn, t);
+          if (MNMAJ) { store_row_contig_mn(fa, Ah, Al, BM, t); store_row_contig_mn(fb, Bh, Bl, bn, t); }
+          else { store_row_contig(fa, Ah, Al, BM, t); store_row_contig(fb, Bh, Bl, bn, t); }
         }
         fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
         __syncwarp();              // one arrival per warp: 256 single-thread arrivals on one mbarrier serialise (~1000 cycles per K block)
@@ -395,15 +429,21 @@ int tc_gemm(int form, const float* A, long long lda, const float* B, long long l
   const int grid = (int)(total < ctas ? total : ctas);
   static bool attr_set = false;  // one device per process (num_ctas() makes the same assumption)
   if (!attr_set) {
-    PSN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_gemm<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    PSN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_gemm<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    PSN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_gemm<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    PSN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_gemm<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    PSN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_gemm<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    PSN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_gemm<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    PSN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_gemm<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    PSN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_gemm<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_set = true;
   }
+  // Operands whose contiguous dimension is the row index (B of FORM 1, A and B of FORM 2) as MN-major tiles (a_major / b_major = 1):
+  // PSNERF_B200_GEMM_MN=0 selects the K-major tiles filled by transposing 4-byte stores instead (A/B measurements, cross-check).
+  const char* e_mn = getenv("PSNERF_B200_GEMM_MN");
+  const bool mn = !(e_mn && e_mn[0] == '0');
   count_launch();
-  if (form == 0) k_tc_gemm<0><<<grid, THREADS, SMEM, st>>>(a);
-  else if (form == 1) k_tc_gemm<1><<<grid, THREADS, SMEM, st>>>(a);
-  else k_tc_gemm<2><<<grid, THREADS, SMEM, st>>>(a);
+  if (form == 0) k_tc_gemm<0, false><<<grid, THREADS, SMEM, st>>>(a);
+  else if (form == 1) { if (mn) k_tc_gemm<1, true><<<grid, THREADS, SMEM, st>>>(a); else k_tc_gemm<1, false><<<grid, THREADS, SMEM, st>>>(a); }
+  else { if (mn) k_tc_gemm<2, true><<<grid, THREADS, SMEM, st>>>(a); else k_tc_gemm<2, false><<<grid, THREADS, SMEM, st>>>(a); }
   PSN_CUDA_CHECK(cudaGetLastError());
   return PSN_OK;
 }
