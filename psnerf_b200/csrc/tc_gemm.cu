@@ -63,14 +63,39 @@ struct Args {
 __device__ __forceinline__ uint32_t idesc_tf32(uint32_t n, uint32_t a_mn, uint32_t b_mn) {
   return (1u << 4) | (2u << 7) | (2u << 10) | (a_mn << 15) | (b_mn << 16) | ((n >> 3) << 17) | (8u << 24);
 }
-// MN-major SWIZZLE_128B operand tile [32 k][rows]: blocks of 32 consecutive rows (128 bytes) x 8 k (1024-byte swizzle atom, 16-byte
-// chunk index XOR k % 8); the four k groups of a block are adjacent (SBO = 1024), row blocks follow at LBO = 4096.  K step ks of an
-// MMA starts at + ks * 1024.  (Canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units, cute/atom/mma_traits_sm100.hpp.)
-constexpr uint32_t MN_LBO = 4096, MN_SBO = 1024;
-__device__ __forceinline__ uint32_t mn_off(int r, int k) {
-  return (uint32_t)(r >> 5) * MN_LBO + (uint32_t)(k >> 3) * MN_SBO + (uint32_t)(k & 7) * 128u + (((((uint32_t)r & 31u) >> 2) ^ ((uint32_t)k & 7u)) << 4);
+// MN-major operand tiles [32 k][rows] (operands whose contiguous dimension in memory is the row index: a float4 of 4 consecutive rows
+// stays one 16-byte chunk, no transposition).  Two candidate canonical layouts (cute/atom/mma_traits_sm100.hpp), selected by MNL:
+//  MNL 2  SWIZZLE_128B_BASE32B: blocks of 32 rows (128 bytes) x 4 k = 512-byte atoms, 32-byte chunk index XOR k % 4; the eight k
+//         groups of a block are adjacent (SBO = 512), row blocks follow at LBO = 4096; K step ks (8 k) starts at + ks * 1024.
+//  MNL 3  no swizzle ("interleave"): core matrices of 4 rows (16 bytes) x 8 k = 128 contiguous bytes; row groups at SBO = 128, k groups
+//         at LBO = rows / 4 * 128 (fixed: 4096 for A, 8192 for B); K step ks starts at + ks * LBO.
+template <int MNL> struct MnLayout;
+template <> struct MnLayout<2> {
+  static constexpr uint32_t TYPE = 1;  // UMMA::LayoutType::SWIZZLE_128B_BASE32B
+  __device__ static uint32_t lbo(bool) { return 4096; }
+  __device__ static uint32_t sbo(bool) { return 512; }
+  __device__ static uint32_t kstep(bool) { return 1024; }
+  __device__ static uint32_t off(int r, int k, bool) {
+    return (uint32_t)(r >> 5) * 4096u + (uint32_t)(k >> 2) * 512u + (uint32_t)(k & 3) * 128u +
+           (((((uint32_t)r & 31u) >> 3) ^ ((uint32_t)k & 3u)) << 5) + ((uint32_t)r & 7u) * 4u;
+  }
+};
+template <> struct MnLayout<3> {
+  static constexpr uint32_t TYPE = 0;  // UMMA::LayoutType::SWIZZLE_NONE
+  __device__ static uint32_t lbo(bool is_b) { return is_b ? 8192u : 4096u; }
+  __device__ static uint32_t sbo(bool) { return 128; }
+  __device__ static uint32_t kstep(bool is_b) { return lbo(is_b); }
+  __device__ static uint32_t off(int r, int k, bool is_b) {
+    return (uint32_t)(r >> 2) * 128u + (uint32_t)(k >> 3) * lbo(is_b) + (uint32_t)(k & 7) * 16u + ((uint32_t)r & 3u) * 4u;
+  }
+};
+// descriptor: start address >> 4 | LBO >> 4 << 16 | SBO >> 4 << 32 | version 1 << 46 | layout type << 61
+template <int MNL>
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, bool is_b) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(MnLayout<MNL>::lbo(is_b) >> 4) << 16) | ((uint64_t)(MnLayout<MNL>::sbo(is_b) >> 4) << 32) |
+         (1ull << 46) | ((uint64_t)MnLayout<MNL>::TYPE << 61);
 }
-__device__ __forceinline__ uint32_t umma_desc_lo_mn(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | ((MN_LBO >> 4) << 16); }
+
 __device__ __forceinline__ void umma_ss_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -200,10 +225,9 @@ __device__ __forceinline__ void store_row_contig(const Frag (&f)[NIT], unsigned 
   }
 }
 
-// The same fragments written as an MN-major tile: the four consecutive rows of a float4 stay one 16-byte chunk - no transposition,
-// conflict-free 16-byte stores (MNMAJ kernels; the MMA reads the tile through a_major / b_major = 1).
-template <int NIT>
-__device__ __forceinline__ void store_row_contig_mn(const Frag (&f)[NIT], unsigned char* hi, unsigned char* lo, int rows, int t) {
+// The same fragments written as an MN-major tile: the four consecutive rows of a float4 stay one 16-byte chunk.
+template <int MNL, int NIT>
+__device__ __forceinline__ void store_row_contig_mn(const Frag (&f)[NIT], unsigned char* hi, unsigned char* lo, int rows, int t, bool is_b) {
   const int quads = rows >> 2;
 #pragma unroll
   for (int j = 0; j < NIT; ++j) {
@@ -213,13 +237,14 @@ __device__ __forceinline__ void store_row_contig_mn(const Frag (&f)[NIT], unsign
     const float4 v = f[j].v;
     const float4 h = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
     const float4 l = make_float4(to_tf32(v.x - h.x), to_tf32(v.y - h.y), to_tf32(v.z - h.z), to_tf32(v.w - h.w));
-    const uint32_t off = mn_off(4 * q, k);
+    const uint32_t off = MnLayout<MNL>::off(4 * q, k, is_b);
     *reinterpret_cast<float4*>(hi + off) = h;
     *reinterpret_cast<float4*>(lo + off) = l;
   }
 }
 
-template <int FORM, bool MNMAJ>
+// MNL: 0 = every operand tile K-major (row-contiguous operands are transposed by the loaders), 2 / 3 = MN-major tiles (MnLayout)
+template <int FORM, int MNL>
 __global__ void __launch_bounds__(THREADS, 1) k_tc_gemm(Args a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -297,9 +322,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_gemm(Args a) {
     // ---- MMA issuer (whole warp converged, one elected lane issues) -----------------------------------------------------------------
     uint32_t stage = 0, phase = 0, acc_phase = 0;
     long long it_ctr = 0;
-    constexpr bool A_MN = MNMAJ && FORM == 2, B_MN = MNMAJ && FORM >= 1;  // operands whose contiguous dimension is not k
+    constexpr bool A_MN = MNL != 0 && FORM == 2, B_MN = MNL != 0 && FORM >= 1;  // operands whose contiguous dimension is not k
+    constexpr int ML = MNL == 0 ? 2 : MNL;  // (any valid MnLayout for the dead branches)
     const uint32_t idesc = idesc_tf32((uint32_t)bn, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
-    constexpr uint32_t a_step = A_MN ? MN_SBO : 32u, b_step = B_MN ? MN_SBO : 32u;  // bytes between the K steps (8 k) of a K block
     for (long long t = blockIdx.x; t < total; t += gridDim.x, ++it_ctr) {
       const TileIt it = tile_at<FORM>(a, t);
       long long k0, k1;
@@ -316,14 +341,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_gemm(Args a) {
         mbar_wait(&bars->full[stage], phase);
         tc_fence_after();
         const uint32_t sa = smem_u32(base + stage * STAGE);
-        const uint32_t a_hi = A_MN ? umma_desc_lo_mn(sa) : umma_desc_lo(sa), a_lo = A_MN ? umma_desc_lo_mn(sa + A_TILE) : umma_desc_lo(sa + A_TILE);
-        const uint32_t b_hi = B_MN ? umma_desc_lo_mn(sa + 2 * A_TILE) : umma_desc_lo(sa + 2 * A_TILE);
-        const uint32_t b_lo = B_MN ? umma_desc_lo_mn(sa + 2 * A_TILE + B_TILE) : umma_desc_lo(sa + 2 * A_TILE + B_TILE);
+        const uint32_t sA[2] = {sa, sa + A_TILE}, sB[2] = {sa + 2 * A_TILE, sa + 2 * A_TILE + B_TILE};  // hi, lo
+        uint64_t dA[2], dB[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          dA[h] = A_MN ? umma_desc_mn<ML>(sA[h], false) : (UMMA_DESC_HI | (uint64_t)umma_desc_lo(sA[h]));
+          dB[h] = B_MN ? umma_desc_mn<ML>(sB[h], true) : (UMMA_DESC_HI | (uint64_t)umma_desc_lo(sB[h]));
+        }
+        const uint32_t a_step = A_MN ? MnLayout<ML>::kstep(false) : 32u, b_step = B_MN ? MnLayout<ML>::kstep(true) : 32u;
         if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t ah = umma_desc_at(a_hi, ks * a_step), al = umma_desc_at(a_lo, ks * a_step);
-            const uint64_t bh = umma_desc_at(b_hi, ks * b_step), bl = umma_desc_at(b_lo, ks * b_step);
+            const uint64_t ah = dA[0] + ((ks * a_step) >> 4), al = dA[1] + ((ks * a_step) >> 4);  // advances the start-address field
+            const uint64_t bh = dB[0] + ((ks * b_step) >> 4), bl = dB[1] + ((ks * b_step) >> 4);
             umma_ss_tf32(d_addr, ah, bh, idesc, (first && ks == 0) ? 0u : 1u);
             umma_ss_tf32(d_addr, al, bh, idesc, 1u);
             umma_ss_tf32(d_addr, ah, bl, idesc, 1u);
@@ -369,9 +399,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_gemm(Args a) {
           store_k_contig(fb, Bh, Bl, bn, t);
         } else if (FORM == 1) {
           store_k_contig(fa, Ah, Al, BM, t);
-          if (MNMAJ) store_row_contig_mn(fb, Bh, Bl, bn, t); else store_row_contig(fb, Bh, Bl, bn, t);
+          if (MNL != 0) store_row_contig_mn<MNL == 0 ? 2 : MNL>(fb, Bh, Bl, bn, t, true); else store_row_contig(fb, Bh, Bl, bn, t);
         } else {
-          if (MNMAJ) { store_row_contig_mn(fa, Ah, Al, BM, t); store_row_contig_mn(fb, Bh, Bl, bn, t); }
+          if (MNL != 0) { store_row_contig_mn<MNL == 0 ? 2 : MNL>(fa, Ah, Al, BM, t, false); store_row_contig_mn<MNL == 0 ? 2 : MNL>(fb, Bh, Bl, bn, t, true); }
           else { store_row_contig(fa, Ah, Al, BM, t); store_row_contig(fb, Bh, Bl, bn, t); }
         }
         fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
@@ -429,21 +459,30 @@ int tc_gemm(int form, const float* A, long long lda, const float* B, long long l
   const int grid = (int)(total < ctas ? total : ctas);
   static bool attr_set = false;  // one device per process (num_ctas() makes the same assumption)
   if (!attr_set) {
-    PSN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_gemm<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    PSN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_gemm<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    PSN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_gemm<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    PSN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_gemm<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    PSN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_gemm<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    PSN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_gemm<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    PSN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_gemm<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    PSN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_gemm<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    PSN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_gemm<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    PSN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_gemm<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    PSN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_gemm<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    PSN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_gemm<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_set = true;
   }
-  // Operands whose contiguous dimension is the row index (B of FORM 1, A and B of FORM 2) as MN-major tiles (a_major / b_major = 1):
-  // PSNERF_B200_GEMM_MN=0 selects the K-major tiles filled by transposing 4-byte stores instead (A/B measurements, cross-check).
+  // Operand tiles of the row-contiguous operands (B of FORM 1, A and B of FORM 2): PSNERF_B200_GEMM_MN = 0 K-major tiles filled by
+  // transposing 4-byte stores (default, verified), 2 / 3 = MN-major tiles (bring-up: SWIZZLE_128B_BASE32B / no swizzle).
   const char* e_mn = getenv("PSNERF_B200_GEMM_MN");
-  const bool mn = !(e_mn && e_mn[0] == '0');
+  const int mn = e_mn ? atoi(e_mn) : 0;
   count_launch();
-  if (form == 0) k_tc_gemm<0, false><<<grid, THREADS, SMEM, st>>>(a);
-  else if (form == 1) { if (mn) k_tc_gemm<1, true><<<grid, THREADS, SMEM, st>>>(a); else k_tc_gemm<1, false><<<grid, THREADS, SMEM, st>>>(a); }
-  else { if (mn) k_tc_gemm<2, true><<<grid, THREADS, SMEM, st>>>(a); else k_tc_gemm<2, false><<<grid, THREADS, SMEM, st>>>(a); }
+  if (form == 0) k_tc_gemm<0, 0><<<grid, THREADS, SMEM, st>>>(a);
+  else if (form == 1) {
+    if (mn == 2) k_tc_gemm<1, 2><<<grid, THREADS, SMEM, st>>>(a);
+    else if (mn == 3) k_tc_gemm<1, 3><<<grid, THREADS, SMEM, st>>>(a);
+    else k_tc_gemm<1, 0><<<grid, THREADS, SMEM, st>>>(a);
+  } else {
+    if (mn == 2) k_tc_gemm<2, 2><<<grid, THREADS, SMEM, st>>>(a);
+    else if (mn == 3) k_tc_gemm<2, 3><<<grid, THREADS, SMEM, st>>>(a);
+    else k_tc_gemm<2, 0><<<grid, THREADS, SMEM, st>>>(a);
+  }
   PSN_CUDA_CHECK(cudaGetLastError());
   return PSN_OK;
 }
