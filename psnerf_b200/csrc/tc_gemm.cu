@@ -63,12 +63,12 @@ struct Args {
 __device__ __forceinline__ uint32_t idesc_tf32(uint32_t n, uint32_t a_mn, uint32_t b_mn) {
   return (1u << 4) | (2u << 7) | (2u << 10) | (a_mn << 15) | (b_mn << 16) | ((n >> 3) << 17) | (8u << 24);
 }
-// MN-major operand tiles [32 k][rows] (operands whose contiguous dimension in memory is the row index: a float4 of 4 consecutive rows
-// stays one 16-byte chunk, no transposition).  Two candidate canonical layouts (cute/atom/mma_traits_sm100.hpp), selected by MNL:
-//  MNL 2  SWIZZLE_128B_BASE32B: blocks of 32 rows (128 bytes) x 4 k = 512-byte atoms, 32-byte chunk index XOR k % 4; the eight k
-//         groups of a block are adjacent (SBO = 512), row blocks follow at LBO = 4096; K step ks (8 k) starts at + ks * 1024.
-//  MNL 3  no swizzle ("interleave"): core matrices of 4 rows (16 bytes) x 8 k = 128 contiguous bytes; row groups at SBO = 128, k groups
-//         at LBO = rows / 4 * 128 (fixed: 4096 for A, 8192 for B); K step ks starts at + ks * LBO.
+// MN-major operand tiles [32 k][rows] for the operands whose contiguous dimension in memory is the row index (B of FORM 1, A and B of
+// FORM 2): a float4 of 4 consecutive rows stays one 16-byte chunk, the loaders never transpose.  For 32-bit operands the MN-major
+// canonical layout is SWIZZLE_128B_BASE32B (cute/atom/mma_traits_sm100.hpp): blocks of 32 rows (128 bytes) x 4 k = 512-byte atoms with
+// the 32-byte chunk index XOR k % 4; the eight k groups of a block are adjacent (SBO = 512), row blocks follow at LBO = 4096; K step
+// ks (8 k) of an MMA starts at + ks * 1024; a_major / b_major = 1 in the instruction descriptor.  (Bring-up, r2: the plain SWIZZLE_128B
+// and the unswizzled MN-major layouts make the MMA return zeros for tf32; this one passes tests/test_gpu_tc_gemm.py, 47 cases.)
 template <int MNL> struct MnLayout;
 template <> struct MnLayout<2> {
   static constexpr uint32_t TYPE = 1;  // UMMA::LayoutType::SWIZZLE_128B_BASE32B
@@ -78,15 +78,6 @@ template <> struct MnLayout<2> {
   __device__ static uint32_t off(int r, int k, bool) {
     return (uint32_t)(r >> 5) * 4096u + (uint32_t)(k >> 2) * 512u + (uint32_t)(k & 3) * 128u +
            (((((uint32_t)r & 31u) >> 3) ^ ((uint32_t)k & 3u)) << 5) + ((uint32_t)r & 7u) * 4u;
-  }
-};
-template <> struct MnLayout<3> {
-  static constexpr uint32_t TYPE = 0;  // UMMA::LayoutType::SWIZZLE_NONE
-  __device__ static uint32_t lbo(bool is_b) { return is_b ? 8192u : 4096u; }
-  __device__ static uint32_t sbo(bool) { return 128; }
-  __device__ static uint32_t kstep(bool is_b) { return lbo(is_b); }
-  __device__ static uint32_t off(int r, int k, bool is_b) {
-    return (uint32_t)(r >> 2) * 128u + (uint32_t)(k >> 3) * lbo(is_b) + (uint32_t)(k & 7) * 16u + ((uint32_t)r & 3u) * 4u;
   }
 };
 // descriptor: start address >> 4 | LBO >> 4 << 16 | SBO >> 4 << 32 | version 1 << 46 | layout type << 61
@@ -243,7 +234,7 @@ __device__ __forceinline__ void store_row_contig_mn(const Frag (&f)[NIT], unsign
   }
 }
 
-// MNL: 0 = every operand tile K-major (row-contiguous operands are transposed by the loaders), 2 / 3 = MN-major tiles (MnLayout)
+// MNL: 0 = every operand tile K-major (row-contiguous operands are transposed by the loaders), 2 = MN-major tiles (MnLayout<2>)
 template <int FORM, int MNL>
 __global__ void __launch_bounds__(THREADS, 1) k_tc_gemm(Args a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -464,25 +455,16 @@ int tc_gemm(int form, const float* A, long long lda, const float* B, long long l
     PSN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_gemm<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     PSN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_gemm<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     PSN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_gemm<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    PSN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_gemm<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    PSN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_gemm<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_set = true;
   }
-  // Operand tiles of the row-contiguous operands (B of FORM 1, A and B of FORM 2): PSNERF_B200_GEMM_MN = 0 K-major tiles filled by
-  // transposing 4-byte stores (default, verified), 2 / 3 = MN-major tiles (bring-up: SWIZZLE_128B_BASE32B / no swizzle).
+  // Row-contiguous operands (B of FORM 1, A and B of FORM 2) as MN-major tiles; PSNERF_B200_GEMM_MN=0 selects K-major tiles filled by
+  // transposing 4-byte stores instead (the first verified version: cross-check / A/B; stage-1 train step 136 -> 107 ms with MN-major).
   const char* e_mn = getenv("PSNERF_B200_GEMM_MN");
-  const int mn = e_mn ? atoi(e_mn) : 0;
+  const bool mn = !(e_mn && e_mn[0] == '0');
   count_launch();
   if (form == 0) k_tc_gemm<0, 0><<<grid, THREADS, SMEM, st>>>(a);
-  else if (form == 1) {
-    if (mn == 2) k_tc_gemm<1, 2><<<grid, THREADS, SMEM, st>>>(a);
-    else if (mn == 3) k_tc_gemm<1, 3><<<grid, THREADS, SMEM, st>>>(a);
-    else k_tc_gemm<1, 0><<<grid, THREADS, SMEM, st>>>(a);
-  } else {
-    if (mn == 2) k_tc_gemm<2, 2><<<grid, THREADS, SMEM, st>>>(a);
-    else if (mn == 3) k_tc_gemm<2, 3><<<grid, THREADS, SMEM, st>>>(a);
-    else k_tc_gemm<2, 0><<<grid, THREADS, SMEM, st>>>(a);
-  }
+  else if (form == 1) { if (mn) k_tc_gemm<1, 2><<<grid, THREADS, SMEM, st>>>(a); else k_tc_gemm<1, 0><<<grid, THREADS, SMEM, st>>>(a); }
+  else { if (mn) k_tc_gemm<2, 2><<<grid, THREADS, SMEM, st>>>(a); else k_tc_gemm<2, 0><<<grid, THREADS, SMEM, st>>>(a); }
   PSN_CUDA_CHECK(cudaGetLastError());
   return PSN_OK;
 }
