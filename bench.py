@@ -557,6 +557,7 @@ def main():
     ap.add_argument("--sample-grid", type=int, default=SAMPLE_GRID, help="side of the strided pixel sub-grid the CPU legs run on")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="headline steps only (launch lists / profiles of the headline)")
     args = ap.parse_args()
     globals()["SAMPLE_GRID"] = args.sample_grid
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
@@ -701,7 +702,7 @@ def main():
                 "roofline": roof, "kernels": kern}
         if mg is not None:
             line["multi_gpu"] = mg
-        if world == 1:
+        if world == 1 and not args.no_secondary:
             K, pose = views[0]
             sec, gpu_render = secondary_stage1_render(lib, dev, rend, precision, views[0], peaks, 3)
             line["secondary"] = {"stage1_unisurf_512x512x128spp": sec}

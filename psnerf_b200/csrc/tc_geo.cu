@@ -29,6 +29,9 @@ struct TcGeoArgs {
   float rescale;
 };
 
+#ifndef PSN_CHEAP_PREFETCH
+#define PSN_CHEAP_PREFETCH 1  // TMEM-load prefetch in the epilogue of the single-pass program (epi_for_chunks_pf_ld)
+#endif
 constexpr int MODE_OUT = 0, MODE_SHADOW = 1, MODE_DEBUG = 2, MODE_FEAT = 3;  // MODE_DEBUG = MODE_OUT + layer dump / clock64 trace hooks
 
 template <int MODE, bool CHEAP = false>
@@ -81,8 +84,8 @@ k_tc_occ(TcGeoArgs g, PointGen gen, long long M_host, const int* M_dev, int out_
         const bool pre_skip = (l + 1 == g.skip);
         const int n_out = g.n_out[l];
         const float cc = pre_skip ? PSN_SOFTPLUS_C * 0.70710678118654752440f : PSN_SOFTPLUS_C;
-        epi_for_chunks_pf<Bias16>(s, e, [&](int col, Bias16& b) { load_bias16(bias, col, b); },
-                                  [&](int pass, int col, float (&v)[CW], const Bias16& b) {
+        auto pre_bias = [&](int col, Bias16& b) { load_bias16(bias, col, b); };
+        auto chunk = [&](int pass, int col, float (&v)[CW], const Bias16& b) {
           if (tr && pass == 0) trace[64 + sub * 40 + l * 5] = clock64();
           add16(v, b.b);
           if (CHEAP && l < 7 && !(pre_skip && col + CW > n_out)) {
@@ -133,7 +136,9 @@ k_tc_occ(TcGeoArgs g, PointGen gen, long long M_host, const int* M_dev, int out_
               part = fmaf(v[4 * t + 2], w.z, part); part = fmaf(v[4 * t + 3], w.w, part);
             }
           }
-        });
+        };
+        if (CHEAP && PSN_CHEAP_PREFETCH) epi_for_chunks_pf_ld<Bias16>(s, e, pre_bias, chunk);
+        else epi_for_chunks_pf<Bias16>(s, e, pre_bias, chunk);
         e.step_ctr++;
       }
       if (MODE == MODE_FEAT) {  // step 8: feature head, no activation (network.py:95 returns the raw last Linear)

@@ -541,6 +541,44 @@ __device__ __forceinline__ void epi_for_chunks_pf(const Smem& s, const EpiCtx& e
     f(pass, col, v, cur);
   }
 }
+// Same walk with the TMEM chunk of pass p + 1 requested BEFORE pass p is processed (passes 1..3: their columns are complete once
+// d_q[.][1] has fired), so the tcgen05.ld latency of every pass but the first two hides under the arithmetic of its predecessor.
+// Costs one more 16-register buffer: only the single-pass (CHEAP) occupancy program, whose packed-fp16 epilogue is short on registers
+// to spare, uses it - the full epilogue spills with it (profiles/README.md item 11).
+template <class Buf, class Pre, class F>
+__device__ __forceinline__ void epi_for_chunks_pf_ld(const Smem& s, const EpiCtx& e, Pre&& pre, F&& f) {
+  const uint32_t base = e.tmem_base + e.lane_addr + e.d_col0() + (uint32_t)(CW * e.sub);
+  Buf nxt;
+  pre(CW * e.sub, nxt);
+  uint32_t r0[CW], r1[CW];
+  epi_wait_q(s, e, 0);
+  tmem_ld16_issue(base, r0);
+  {  // pass 0 (the remaining columns may still be accumulating: nothing to prefetch yet)
+    const Buf cur = nxt;
+    pre(CW * e.sub + 64, nxt);
+    tmem_ld16_wait(r0);
+    float v[CW];
+#pragma unroll
+    for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(r0[i]);
+    f(0, CW * e.sub, v, cur);
+  }
+  epi_wait_q(s, e, 1);
+  tmem_ld16_issue(base + 64u, r1);
+#pragma unroll
+  for (int pass = 1; pass < 4; ++pass) {
+    const Buf cur = nxt;
+    const int col = 64 * pass + CW * e.sub;
+    if (pass < 3) pre(col + 64, nxt);
+    uint32_t (&rc)[CW] = (pass & 1) ? r1 : r0;
+    uint32_t (&rn)[CW] = (pass & 1) ? r0 : r1;
+    tmem_ld16_wait(rc);
+    if (pass < 3) tmem_ld16_issue(base + 64u * (uint32_t)(pass + 1), rn);
+    float v[CW];
+#pragma unroll
+    for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(rc[i]);
+    f(pass, col, v, cur);
+  }
+}
 struct Bias16 { float4 b[4]; };
 __device__ __forceinline__ void load_bias16(const float* __restrict__ bias, int col, Bias16& o) {
   const float4* b4 = reinterpret_cast<const float4*>(bias + col);

@@ -4,12 +4,13 @@ mkdir -p gpurun_out
 for d in psnerf_b200/lib psnerf_b200/lib_*; do
   [ -f $d/libpsnerf_b200.so ] || continue
   n=$(basename $d)
-  PSNERF_B200_LIB=$PWD/$d/libpsnerf_b200.so timeout 300 python bench.py --no-cpu-baseline --steps 4 --warmup 3 > gpurun_out/ab_$n.json 2> gpurun_out/ab_$n.err
+  PSNERF_B200_LIB=$PWD/$d/libpsnerf_b200.so timeout 300 python bench.py --no-cpu-baseline --no-extras --steps 4 --warmup 3 > gpurun_out/ab_$n.json 2> gpurun_out/ab_$n.err
   python - <<PY
 import json
 d=json.load(open("gpurun_out/ab_$n.json"))
 k=d["kernels"]; o=d.get("other_workloads",{})
-print("$n", "step %.1f ms"%d["ms_per_step"], "march %.1f"%k["occ_march"]["ms_per_launch"], "rad %.1f"%k["radiance"]["ms_per_launch"], "clk", d["clocks"]["sm_mhz"],
-      "| s2 %.1f ms"%o.get("stage2_shade_512x512x96L",{}).get("ms",-1), "shadow %.0f ms"%o.get("shadow_visibility_96L_x128",{}).get("ms",-1))
+s=d.get("secondary",{}).get("stage1_unisurf_512x512x128spp",{})
+print("$n", "relit step %.1f ms"%d["ms_per_step"], "march %.1f"%k["occ_march"]["ms_per_step"], "shadow %.1f"%k["shadow"]["ms_per_step"], "clk", d["clocks"]["sm_mhz"],
+      "| stage-1 render %.1f ms"%s.get("ms_per_step",-1), "march %.1f"%s.get("kernels",{}).get("occ_march",{}).get("ms_per_step",-1))
 PY
 done
