@@ -473,7 +473,7 @@ extern "C" int psn_s1_train_backward(const psn_train_net* geo, const psn_train_n
       const int K = app->in_dims[l], N = app->out_dims[l];
       if ((rc = gemm(2, dz, lddz, x, K, app->dW[l], K, nullptr, N, K, M, 0, st))) return rc;
       count_launch();
-      k_colsum<<<dim3((N + 255) / 256, (unsigned)((M + 1023) / 1024)), 256, 0, st>>>(dz, lddz, M, N, app->db[l]);
+      colsum(dz, lddz, M, N, app->db[l], st);
       float* dx = l == 0 ? UB : T2;
       if ((rc = gemm(1, dz, lddz, app->W[l], K, dx, K, nullptr, M, K, N, 0, st))) return rc;
       if (l > 0) {  // relu'
@@ -526,7 +526,7 @@ extern "C" int psn_s1_train_backward(const psn_train_net* geo, const psn_train_n
     k_s1_outbar<<<nblk(M * No), 256, 0, st>>>(g_logit, have_u ? UB : nullptr, sh.app_in, gcol + 3, sh.feat, M, OB);
     if ((rc = gemm(2, OB, No, t.h[nh - 1], Ko, geo->dW[nh], Ko, nullptr, No, Ko, M, 0, st))) return rc;
     count_launch();
-    k_colsum<<<dim3((No + 255) / 256, (unsigned)((M + 1023) / 1024)), 256, 0, st>>>(OB, No, M, No, geo->db[nh]);
+    colsum(OB, No, M, No, geo->db[nh], st);
     if ((rc = gemm(1, OB, No, geo->W[nh], Ko, A0, Ko, nullptr, M, Ko, No, 0, st))) return rc;
     hbar = A0;
     ldh = Ko;
@@ -539,7 +539,7 @@ extern "C" int psn_s1_train_backward(const psn_train_net* geo, const psn_train_n
     const float* x = (l == 0) ? t.pe : (l == sh.skip ? t.x_skip : t.h[l - 1]);
     if ((rc = gemm(2, T1, N, x, K, geo->dW[l], K, nullptr, N, K, M, 0, st))) return rc;
     count_launch();
-    k_colsum<<<dim3((N + 255) / 256, (unsigned)((M + 1023) / 1024)), 256, 0, st>>>(T1, N, M, N, geo->db[l]);
+    colsum(T1, N, M, N, geo->db[l], st);
     if (l > 0) {
       float* xb = (hbar == A0) ? A1 : A0;
       if ((rc = gemm(1, T1, N, geo->W[l], K, xb, K, nullptr, M, K, N, 0, st))) return rc;

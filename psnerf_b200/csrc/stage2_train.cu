@@ -220,7 +220,7 @@ static int mlp_backward(const psn_train_net* n, const MlpTape* t, const float* d
     int rc;
     if ((rc = gemm(2, dz, lddz, xin, ldx, n->dW[l], n->in_dims[l], nullptr, n->out_dims[l], n->in_dims[l], rows, 0, st))) return rc;
     count_launch();
-    k_colsum<<<dim3((n->out_dims[l] + 127) / 128, (unsigned)((rows + 1023) / 1024)), 128, 0, st>>>(dz, lddz, rows, n->out_dims[l], n->db[l]);
+    colsum(dz, lddz, rows, n->out_dims[l], n->db[l], st);
     if (l == 0) break;
     if ((rc = gemm(1, dz, lddz, n->W[l], n->in_dims[l], s1, n->in_dims[l], nullptr, rows, n->in_dims[l], n->out_dims[l], 0, st))) return rc;
     // only the first out_{l-1} columns flow on (the appended skip input carries no gradient: points / detached lights)

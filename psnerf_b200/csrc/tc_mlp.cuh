@@ -505,6 +505,36 @@ __device__ __forceinline__ void epi_wait_q(const Smem& s, const EpiCtx& e, int q
   mbar_wait(&s.c->d_q[e.step_ctr & 1u][q], (e.step_ctr >> 1) & 1u);
   tc_fence_after();
 }
+// PSN_EPI_SKEW (cycles per sub; 0 = off): the four epilogue warps of a scheduler leave the accumulator wait of pass 0 in the same
+// cycle and then walk ld -> MUFU burst -> ALU / convert -> st in lock-step, so the XU pipe is oversubscribed in one phase and idle
+// in the next.  When the wait actually blocked (epilogue-bound regime), sub s starts s * PSN_EPI_SKEW cycles late: the bursts of the
+// four warps then interleave instead of colliding.  Nothing re-synchronises the warps until the next step's pass 0.
+#ifndef PSN_EPI_SKEW
+#define PSN_EPI_SKEW 0
+#endif
+#ifndef PSN_EPI_UNROLL
+#define PSN_EPI_UNROLL 1  // the four passes of epi_for_chunks_pf fully unrolled: no register copies of the prefetched side loads (16 moves per pass);
+                          // r2 A/B on the relit view: shadow pass 334.2 -> 320.9 ms.  0 = rolled loop (the round-1 form)
+#endif
+__device__ __forceinline__ void epi_wait_q0_skewed(const Smem& s, const EpiCtx& e) {
+  void* bar = &s.c->d_q[e.step_ctr & 1u][0];
+  const uint32_t par = (e.step_ctr >> 1) & 1u;
+  if (PSN_EPI_SKEW > 0) {
+    uint32_t done;  // test_wait: non-blocking (try_wait suspends in hardware and would report "not blocked" after sleeping)
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(par) : "memory");
+    if (!done) {
+      mbar_wait(bar, par);
+      const unsigned d = (unsigned)e.sub * (unsigned)PSN_EPI_SKEW;
+      const unsigned t0 = (unsigned)clock();
+      while ((unsigned)clock() - t0 < d) {
+      }
+    }
+  } else {
+    mbar_wait(bar, par);
+  }
+  tc_fence_after();
+}
 // wait for the whole accumulator of the current step
 __device__ __forceinline__ void epi_wait_d(const Smem& s, const EpiCtx& e) {
   mbar_wait(&s.c->d_q[e.step_ctr & 1u][0], (e.step_ctr >> 1) & 1u);
@@ -526,10 +556,15 @@ __device__ __forceinline__ void epi_for_chunks_pf(const Smem& s, const EpiCtx& e
   const uint32_t base = e.tmem_base + e.lane_addr + e.d_col0();
   Buf nxt;
   pre(CW * e.sub, nxt);
+#if PSN_EPI_UNROLL
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
   for (int pass = 0; pass < 4; ++pass) {
     const Buf cur = nxt;
-    if (pass < 2) epi_wait_q(s, e, pass);
+    if (pass == 0) epi_wait_q0_skewed(s, e);
+    else if (pass == 1) epi_wait_q(s, e, 1);
     const int col = 64 * pass + CW * e.sub;
     uint32_t r[CW];
     tmem_ld16_issue(base + (uint32_t)col, r);

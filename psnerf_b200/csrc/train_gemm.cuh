@@ -89,13 +89,33 @@ static __global__ void k_act_bwd(const float* __restrict__ dY, int lddy, const f
   const float g = dY[r * lddy + c], y = Y[r * ldy + c];
   dZ[r * lddz + c] = kind == 2 ? (y > 0.f ? g : 0.f) : kind == 3 ? g * y * (1.f - y) : g;
 }
-static __global__ void k_colsum(const float* __restrict__ dZ, int ld, long long rows, int ncols, float* __restrict__ db) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= ncols) return;
-  const long long r0 = (long long)blockIdx.y * 1024, r1 = min(rows, r0 + 1024);
-  float s = 0.f;
-  for (long long r = r0; r < r1; ++r) s += dZ[r * ld + c];
-  atomicAdd(&db[c], s);
+// Bias gradient db[c] += sum_r dZ[r, c].  A block sums COLSUM_ROWS rows of a 64-column strip: thread (tx, ty) walks rows ty, ty + 4,
+// ... with eight independent accumulators (the round-1 version walked 1024 rows per thread in one dependent chain on 32 blocks:
+// 58 us for a 32768 x 256 matrix, longer than the weight-gradient GEMM next to it), the four row lanes are combined in shared memory
+// and every column costs one atomic per block.
+constexpr int COLSUM_ROWS = 256;
+static __global__ void __launch_bounds__(256) k_colsum(const float* __restrict__ dZ, int ld, long long rows, int ncols, float* __restrict__ db) {
+  __shared__ float part[4][64];
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const int c = blockIdx.x * 64 + tx;
+  const long long r0 = (long long)blockIdx.y * COLSUM_ROWS, r1 = min(rows, r0 + COLSUM_ROWS);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (c < ncols) {
+    const float* src = dZ + c;
+    long long r = r0 + ty;
+    for (; r + 28 < r1; r += 32) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc[u] += __ldg(src + (r + 4 * u) * ld);
+    }
+    for (; r < r1; r += 4) acc[0] += __ldg(src + r * ld);
+  }
+  part[ty][tx] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+  __syncthreads();
+  if (ty == 0 && c < ncols) atomicAdd(&db[c], (part[0][tx] + part[1][tx]) + (part[2][tx] + part[3][tx]));
+}
+static inline void colsum(const float* dZ, int ld, long long rows, int ncols, float* db, cudaStream_t st) {
+  if (rows <= 0 || ncols <= 0) return;
+  k_colsum<<<dim3((unsigned)((ncols + 63) / 64), (unsigned)((rows + COLSUM_ROWS - 1) / COLSUM_ROWS)), 256, 0, st>>>(dZ, ld, rows, ncols, db);
 }
 static inline unsigned nblk(long long n, int t = 256) { return (unsigned)((n + t - 1) / t); }
 

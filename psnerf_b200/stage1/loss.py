@@ -10,7 +10,6 @@ class Loss(nn.Module):
         self.full_weight, self.grad_weight = full_weight, grad_weight
         self.norm_weight, self.mask_weight = norm_weight, mask_weight
         self.l1_loss = nn.L1Loss(reduction="sum")
-        self.mask_loss = nn.BCELoss(reduction="mean")
         self.device = device
 
     def forward(self, out_dict, rgb_gt, normal_gt=None, norm_mask=None, mask=None, mask_gt=None, mask_valid=None):
@@ -22,12 +21,17 @@ class Loss(nn.Module):
         grad_loss = diff_norm.mean() if (diff_norm is not None and diff_norm.shape[0] > 0 and self.grad_weight != 0.0) else zero
         loss = self.full_weight * rgb_full + self.grad_weight * grad_loss
         terms = {"fullrgb_loss": rgb_full, "grad_loss": grad_loss}
-        if normal is not None and normal_gt is not None and norm_mask.sum() > 0:
-            nl = self.l1_loss(normal[norm_mask], normal_gt.to(dev)[norm_mask]) / float(normal[norm_mask].shape[0])
+        # Masked terms as where-sums over their counts instead of boolean gathers: no device -> host synchronisation per step (the
+        # reference's `norm_mask.sum() > 0` and `x[mask]` cost one each); an empty mask contributes 0 with zero gradients.
+        if normal is not None and normal_gt is not None:
+            nm = norm_mask.to(dev).unsqueeze(-1)
+            nl = torch.where(nm, (normal - normal_gt.to(dev)).abs(), zero).sum() / nm.sum().clamp_min(1).to(normal.dtype)
             loss = loss + self.norm_weight * nl
             terms["normal_loss"] = nl
         if mask is not None and mask_gt is not None:
-            lm = self.mask_loss(mask[mask_valid].clamp(0, 1), mask_gt.to(dev)[mask_valid])
+            mv = mask_valid.to(dev)
+            bce = torch.nn.functional.binary_cross_entropy(mask.clamp(0, 1), mask_gt.to(dev).to(mask.dtype), reduction="none")
+            lm = torch.where(mv, bce, zero).sum() / mv.sum().clamp_min(1).to(bce.dtype)
             loss = loss + self.mask_weight * lm
             terms["mask_loss"] = lm
         terms["loss"] = loss

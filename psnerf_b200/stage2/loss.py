@@ -16,12 +16,16 @@ class MainLoss(nn.Module):
         self.smooth_loss = nn.L1Loss(reduction="mean")
 
     def _masked(self, fn, a, b, mask, last=None):
-        if mask.sum() == 0:
-            return torch.zeros((), device=a.device)
+        """fn(a[m], b[m]) (mean reduction) without the boolean gather: sum of the masked element losses / their count.  No
+        device -> host synchronisation (the reference's `mask.sum() == 0` test and `a[m]` each cost one per term and step); an empty
+        mask gives 0 with zero gradients, like the reference's early return."""
         m = mask.expand(a.shape[0], -1)
-        if last is None:
-            return fn(a[m], b[m])
-        return fn(a[m].reshape(last), b[m].reshape(last))
+        d = a - b.to(a.dtype)
+        e = d.abs() if isinstance(fn, nn.L1Loss) else d * d
+        per = 1
+        if e.dim() == m.dim() + 1:
+            m, per = m.unsqueeze(-1), e.shape[-1]
+        return torch.where(m, e, torch.zeros((), device=e.device, dtype=e.dtype)).sum() / (m.sum() * per).clamp_min(1).to(e.dtype)
 
     def forward(self, model_outputs, ground_truth, model_input=None):
         dev = model_outputs["sg_rgb_values"].device
@@ -59,13 +63,14 @@ class NormalLoss(nn.Module):
         dev = model_outputs["normal_pred"].device
         gt = F.normalize(model_outputs["normal_values"].to(dev), dim=-1)
         mask = model_outputs["network_object_mask"].to(dev) & model_outputs["object_mask"].to(dev)
-        if mask.sum() == 0:
-            z = torch.zeros((), device=dev)
-            return {"loss": z, "normal_loss": z, "normal_smooth_loss": None}
-        norm_loss = F.mse_loss(model_outputs["normal_pred"][mask].reshape(-1, 3), gt[mask].reshape(-1, 3))
+        m3 = mask.unsqueeze(-1)
+        cnt = (mask.sum() * 3).clamp_min(1).to(gt.dtype)
+        zero = torch.zeros((), device=dev, dtype=gt.dtype)
+        d = model_outputs["normal_pred"] - gt
+        norm_loss = torch.where(m3, d * d, zero).sum() / cnt   # = F.mse_loss(pred[mask], gt[mask]) without the gather / host sync
         loss = self.normal_weight * norm_loss
         smooth = None
         if "normal_jitter" in model_outputs and self.normal_smooth_weight > 0:
-            smooth = F.l1_loss(model_outputs["normal_pred"][mask], model_outputs["normal_jitter"][mask])
+            smooth = torch.where(m3, (model_outputs["normal_pred"] - model_outputs["normal_jitter"]).abs(), zero).sum() / cnt
             loss = loss + self.normal_smooth_weight * smooth
         return {"loss": loss, "normal_loss": norm_loss, "normal_smooth_loss": smooth}
