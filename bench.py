@@ -429,7 +429,7 @@ def train_steps(dev, rend, ps, view, world, rank, n_px=4096, tag="", dist=None):
         if world > 1:
             sharding.allreduce_gradients(ps, world, extra_params=(lraw, linten))  # the light tables are reduced with the model
         opt.step()
-    ms3 = _time_dist(s2_step, 5, dev, dist)
+    ms3 = _time_dist(s2_step, 7, dev, dist)
     out["stage2_train_step%s" % tag] = {"pixels_per_rank": n_px, "lights": L_LIGHTS, "vis_train_lights": 8, "ms_fwd_bwd_adam": ms3,
                                         "Mpairs_per_s": world * n_px * L_LIGHTS / ms3 / 1e3}
     ps.eval()
@@ -459,7 +459,7 @@ def train_steps(dev, rend, ps, view, world, rank, n_px=4096, tag="", dist=None):
             if world > 1:
                 sharding.allreduce_gradients(net, world)
             opt1.step()
-        ms4 = _time_dist(s1_step, 3, dev, dist)
+        ms4 = _time_dist(s1_step, 5, dev, dist)
         out["stage1_train_step%s" % tag] = {"rays_per_rank": n_px, "samples_per_ray": S_IN + S_OUT, "ms_fwd_bwd_adam": ms4,
                                             "Msamples_per_s": world * n_px * (S_IN + S_OUT) / ms4 / 1e3}
         net.eval()
@@ -471,22 +471,26 @@ def train_steps(dev, rend, ps, view, world, rank, n_px=4096, tag="", dist=None):
 
 
 def _time_dist(fn, reps, dev, dist):
-    """fn timed with CUDA events after two warm-up calls (the first use of a kernel pays its lazy module load: a one-off stall of
-    up to a second was seen on the train steps); with a process group: barrier on both sides, max over ranks."""
+    """fn timed with CUDA events after two warm-up calls (the first use of a kernel pays its lazy module load).  Every repetition has
+    its own event pair and the MEDIAN is reported: the train steps allocate a multi-GB activation tape per step, and a one-off
+    allocator stall (cudaMalloc / cudaFree of that block, 200-300 ms) inside one of three repetitions otherwise triples the mean
+    (r2: 83 / 93 / 373 ms in one process).  With a process group: barrier on both sides, max over ranks."""
     fn()
     fn()
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(reps):
+    reps = max(int(reps), 3)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+    ev[0].record()
+    for i in range(reps):
         fn()
-    b.record()
+        ev[i + 1].record()
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
-    ms = a.elapsed_time(b) / reps
+    per = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(reps))
+    ms = per[len(per) // 2]
     if dist is not None:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -206,6 +206,12 @@ int psn_tc_debug_trace_rad(const psn_mlp* geo, const psn_mlp* app, const float* 
  * form 2: C[M,N] += A[K,M]^T B[K,N].  Row-major fp32 device matrices with leading dimensions lda / ldb / ldc. */
 int psn_tc_gemm_debug(int form, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, const float* bias,
                       int64_t M, int N, int64_t K, int epi, void* stream);
+/* Same with the fused element-wise epilogues of the stage-1 train step (form 0 / 1; C2 / E1 / E2 are [M,N] with leading dimension lde):
+ * epi 4: C = softplus_100(acc + bias), C2 = sigmoid(100 (acc + bias));  5: C = acc E1, E2 := acc E2 100 E1 (1 - E1);
+ * 6: C = acc scale E1 + E2;  7: C = acc, C2 = acc E1.  (stage1/model/network.py:88-92,108-120 forward / double backward pieces) */
+int psn_tc_gemm_debug_fused(int form, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, const float* bias,
+                            int64_t M, int N, int64_t K, int epi, float* C2, const float* E1, float* E2, int64_t lde, float scale,
+                            void* stream);
 
 /* ---- stage-2 train step (BASELINE config 5): PSNetwork.forward + backward, stage2/trainer.py:394-410 ------------------------
  * Gradient-carrying parts (renderer.py:193-199,211-231,251-262 with light_vis_detach = vis_rgb_detach = True): the per-point nets

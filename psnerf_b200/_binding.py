@@ -104,6 +104,7 @@ def load():
     lib.psn_tc_debug_trace_q.argtypes = [vp, vp, i64, vp, vp, i32, vp]
     lib.psn_tc_debug_trace_rad.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp, vp, i32, vp]
     lib.psn_tc_gemm_debug.argtypes = [i32, vp, i64, vp, i64, vp, i64, vp, i64, i32, i64, i32, vp]
+    lib.psn_tc_gemm_debug_fused.argtypes = [i32, vp, i64, vp, i64, vp, i64, vp, i64, i32, i64, i32, vp, vp, vp, i64, f32, vp]
     tn = C.POINTER(TrainNet)
     lib.psn_s1_train_tape_bytes.argtypes = [tn, tn, i32, i32, i64]
     lib.psn_s1_train_tape_bytes.restype = i64

@@ -33,6 +33,9 @@ void count_launch();  // every kernel launch of this library is counted (psn_lau
 
 inline int pad_to(int x, int m) { return (x + m - 1) / m * m; }
 
+// operands of the fused element-wise epilogues of the train-step GEMM (train_gemm.cuh / tc_gemm.cu): [M, N] matrices, leading dimension lde
+struct GemmFuse { float* C2; const float* E1; float* E2; long long lde; float scale; };
+
 // One Linear layer packed for the SIMT fp32 path: wt is [K_pad][N_pad] (k-major, i.e. the transpose of
 // torch's [out,in] weight), zero padded; bias is [N_pad].
 struct SimtLayer {

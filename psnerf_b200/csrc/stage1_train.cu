@@ -361,18 +361,25 @@ extern "C" int psn_s1_train_forward(const psn_train_net* geo, const psn_train_ne
   for (int l = 0; l < sh.nh; ++l) wmax = sh.in[l] > wmax ? sh.in[l] : wmax;
   float* T1 = w.take<float>((size_t)M * wmax);
   float* T2 = w.take<float>((size_t)M * wmax);
+  float* T3 = w.take<float>((size_t)M * wmax);
   float* gpe = w.take<float>((size_t)M * sh.pe_dim);
   float* pre = w.take<float>((size_t)M * 4);
   PSN_REQUIRE(w.ok, PSN_ERR_WORKSPACE, "psn_s1_train_forward: workspace too small (need %zu bytes, have %lld)", w.used, (long long)ws_bytes);
   const int nh = sh.nh;
+  const bool fused = train_gemm_fused();  // element-wise passes inside the GEMM epilogues (tc_gemm.cu, EPI 4-7)
   // ---- forward stack ----------------------------------------------------------------------------------------------------
   count_launch();
   k_s1_pe<<<nblk(M), 256, 0, st>>>(pts, M, octaves, rescale, t.pe, sh.pe_dim);
   for (int l = 0; l < nh; ++l) {
     const float* x = (l == 0) ? t.pe : (l == sh.skip ? t.x_skip : t.h[l - 1]);
-    if ((rc = gemm(0, x, sh.in[l], geo->W[l], sh.in[l], t.h[l], sh.out[l], geo->b[l], M, sh.out[l], sh.in[l], 1, st))) return rc;
-    count_launch();
-    k_s1_softplus<<<nblk(M * sh.out[l]), 256, 0, st>>>(t.h[l], t.s[l], M * sh.out[l]);
+    if (fused) {  // h_l = softplus(z_l) and s_l = sigmoid(100 z_l) written by the GEMM epilogue
+      const GemmFuse fz = {t.s[l], nullptr, nullptr, sh.out[l], 0.f};
+      if ((rc = gemm(0, x, sh.in[l], geo->W[l], sh.in[l], t.h[l], sh.out[l], geo->b[l], M, sh.out[l], sh.in[l], 4, st, &fz))) return rc;
+    } else {
+      if ((rc = gemm(0, x, sh.in[l], geo->W[l], sh.in[l], t.h[l], sh.out[l], geo->b[l], M, sh.out[l], sh.in[l], 1, st))) return rc;
+      count_launch();
+      k_s1_softplus<<<nblk(M * sh.out[l]), 256, 0, st>>>(t.h[l], t.s[l], M * sh.out[l]);
+    }
     if (l + 1 == sh.skip) {
       count_launch();
       k_s1_skip_cat<<<nblk(M * sh.in[sh.skip]), 256, 0, st>>>(t.h[l], sh.out[l], t.pe, sh.pe_dim, M, t.x_skip);
@@ -396,17 +403,29 @@ extern "C" int psn_s1_train_forward(const psn_train_net* geo, const psn_train_ne
   // ---- analytic normal: reverse sweep ------------------------------------------------------------------------------------------
   count_launch();
   k_s1_bcast_row<<<nblk(M * sh.out[nh - 1]), 256, 0, st>>>(geo->W[nh], sh.out[nh - 1], M, t.ap[nh - 1]);  // row 0 of the last layer
+  count_launch();
+  k_s1_mul<<<nblk(M * sh.out[nh - 1]), 256, 0, st>>>(t.ap[nh - 1], t.s[nh - 1], M * sh.out[nh - 1], T1);  // dz of the last hidden layer
+  float *dz = T1, *dz_next = T3;
   for (int l = nh - 1; l >= 0; --l) {
-    count_launch();
-    k_s1_mul<<<nblk(M * sh.out[l]), 256, 0, st>>>(t.ap[l], t.s[l], M * sh.out[l], T1);  // dz_l
     float* dst = (l == 0 || l == sh.skip) ? T2 : t.ap[l - 1];
-    if ((rc = gemm(1, T1, sh.out[l], geo->W[l], sh.in[l], dst, sh.in[l], nullptr, M, sh.in[l], sh.out[l], 0, st))) return rc;
+    if (fused && l > 0 && l != sh.skip) {
+      // a'_{l-1} = dz_l W_l and, in the same epilogue, dz_{l-1} = a'_{l-1} * s_{l-1} (the next iteration's operand)
+      const GemmFuse fz = {dz_next, t.s[l - 1], nullptr, sh.in[l], 0.f};
+      if ((rc = gemm(1, dz, sh.out[l], geo->W[l], sh.in[l], dst, sh.in[l], nullptr, M, sh.in[l], sh.out[l], 7, st, &fz))) return rc;
+      float* sw = dz; dz = dz_next; dz_next = sw;
+      continue;
+    }
+    if ((rc = gemm(1, dz, sh.out[l], geo->W[l], sh.in[l], dst, sh.in[l], nullptr, M, sh.in[l], sh.out[l], 0, st))) return rc;
     if (l == sh.skip) {
       count_launch();
       k_s1_skip_split<<<nblk(M * sh.in[l]), 256, 0, st>>>(T2, sh.out[l - 1], sh.pe_dim, M, t.ap[l - 1], gpe);
     } else if (l == 0) {
       count_launch();
       k_s1_axpy<<<nblk(M * sh.pe_dim), 256, 0, st>>>(T2, M * sh.pe_dim, sh.skip > 0 ? 1 : 0, gpe);
+    }
+    if (l > 0) {
+      count_launch();
+      k_s1_mul<<<nblk(M * sh.out[l - 1]), 256, 0, st>>>(t.ap[l - 1], t.s[l - 1], M * sh.out[l - 1], dz);  // dz_{l-1} (its reader has run)
     }
   }
   count_launch();
@@ -461,6 +480,7 @@ extern "C" int psn_s1_train_backward(const psn_train_net* geo, const psn_train_n
   PSN_REQUIRE(w.ok, PSN_ERR_WORKSPACE, "psn_s1_train_backward: workspace too small (need %zu bytes, have %lld)", w.used, (long long)ws_bytes);
   const int nh = sh.nh;
   const bool have_u = app && g_rgb;
+  const bool fused = train_gemm_fused();  // element-wise passes inside the GEMM epilogues (tc_gemm.cu, EPI 4-7)
   // ---- A. appearance MLP backward -----------------------------------------------------------------------------------------------
   if (have_u) {
     const int na = app->n_layers;
@@ -500,10 +520,15 @@ extern "C" int psn_s1_train_backward(const psn_train_net* geo, const psn_train_n
       count_launch();
       k_s1_mul<<<nblk(M * N), 256, 0, st>>>(t.ap[l], t.s[l], M * N, T1);                        // dz_l
       if ((rc = gemm(2, T1, N, abar, K, geo->dW[l], K, nullptr, N, K, M, 0, st))) return rc;    // Wbar_l += dz_l^T abar_l
-      if ((rc = gemm(0, abar, K, geo->W[l], K, T2, N, nullptr, M, N, K, 0, st))) return rc;     // dzbar = abar_l W_l^T
       float* an = (abar == A0) ? A1 : A0;
-      count_launch();
-      k_s1_second<<<nblk(M * N), 256, 0, st>>>(T2, t.ap[l], t.s[l], M * N, l + 1 == sh.skip ? T1 : an);
+      if (fused) {  // dzbar = abar_l W_l^T with k_s1_second as its epilogue: abar' = dzbar s_l, ap_l := zbar2_l
+        const GemmFuse fz = {nullptr, t.s[l], t.ap[l], N, 0.f};
+        if ((rc = gemm(0, abar, K, geo->W[l], K, l + 1 == sh.skip ? T1 : an, N, nullptr, M, N, K, 5, st, &fz))) return rc;
+      } else {
+        if ((rc = gemm(0, abar, K, geo->W[l], K, T2, N, nullptr, M, N, K, 0, st))) return rc;     // dzbar = abar_l W_l^T
+        count_launch();
+        k_s1_second<<<nblk(M * N), 256, 0, st>>>(T2, t.ap[l], t.s[l], M * N, l + 1 == sh.skip ? T1 : an);
+      }
       if (l + 1 == sh.skip) {
         count_launch();
         k_s1_skip_merge<<<nblk(M * sh.in[sh.skip]), 256, 0, st>>>(T1, N, gpe_bar, sh.pe_dim, M, an);
@@ -520,6 +545,7 @@ extern "C" int psn_s1_train_backward(const psn_train_net* geo, const psn_train_n
   const float* hbar = nullptr;
   int ldh = 0;
   float hscale = 1.f;
+  const float* zfused = nullptr;  // fused path: zbar of the layer about to be visited (produced by the previous GEMM's epilogue)
   if (have_out) {
     const int No = sh.out[nh], Ko = sh.in[nh];
     count_launch();
@@ -527,11 +553,38 @@ extern "C" int psn_s1_train_backward(const psn_train_net* geo, const psn_train_n
     if ((rc = gemm(2, OB, No, t.h[nh - 1], Ko, geo->dW[nh], Ko, nullptr, No, Ko, M, 0, st))) return rc;
     count_launch();
     colsum(OB, No, M, No, geo->db[nh], st);
-    if ((rc = gemm(1, OB, No, geo->W[nh], Ko, A0, Ko, nullptr, M, Ko, No, 0, st))) return rc;
-    hbar = A0;
-    ldh = Ko;
+    if (fused) {  // hbar = OB W_last and zbar_{nh-1} = hbar s + zbar2 in one launch
+      const GemmFuse fz = {nullptr, t.s[nh - 1], t.ap[nh - 1], Ko, 1.f};
+      if ((rc = gemm(1, OB, No, geo->W[nh], Ko, A0, Ko, nullptr, M, Ko, No, 6, st, &fz))) return rc;
+      zfused = A0;
+    } else {
+      if ((rc = gemm(1, OB, No, geo->W[nh], Ko, A0, Ko, nullptr, M, Ko, No, 0, st))) return rc;
+      hbar = A0;
+      ldh = Ko;
+    }
+  } else if (fused) {
+    zfused = t.ap[nh - 1];  // no cotangent on the outputs: zbar = zbar2
   }
   if (!have_out && !have_g) return PSN_OK;
+  if (fused) {
+    for (int l = nh - 1; l >= 0; --l) {
+      const int K = sh.in[l], N = sh.out[l];
+      const float* x = (l == 0) ? t.pe : (l == sh.skip ? t.x_skip : t.h[l - 1]);
+      if ((rc = gemm(2, zfused, N, x, K, geo->dW[l], K, nullptr, N, K, M, 0, st))) return rc;
+      count_launch();
+      colsum(zfused, N, M, N, geo->db[l], st);
+      if (l > 0) {
+        // zbar_{l-1} = (zbar_l W_l)[:, :out_{l-1}] * hscale * s_{l-1} + zbar2_{l-1}   (x_skip = cat[h, pe] / sqrt2: only h's share)
+        const int Np = sh.out[l - 1];
+        float* zn = (zfused == A0) ? A1 : A0;
+        const GemmFuse fz = {nullptr, t.s[l - 1], t.ap[l - 1], Np, (l == sh.skip) ? PSN_S1_INV_SQRT2 : 1.f};
+        if ((rc = gemm(1, zfused, N, geo->W[l], K, zn, Np, nullptr, M, Np, N, 6, st, &fz))) return rc;
+        zfused = zn;
+      }
+    }
+    PSN_CUDA_CHECK(cudaGetLastError());
+    return PSN_OK;
+  }
   for (int l = nh - 1; l >= 0; --l) {
     const int K = sh.in[l], N = sh.out[l];
     count_launch();

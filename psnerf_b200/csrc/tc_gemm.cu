@@ -5,16 +5,21 @@
 //   FORM 1 (NN): C[m,n]  = sum_k A[m,k] B[k,n]   input gradient    (A = dZ [M,K], B = W [K,N])
 //   FORM 2 (TN): C[m,n] += sum_k A[k,m] B[k,n]   weight gradient   (A = dZ [K,M], B = X [K,N]), K = samples, split over CTAs
 // Gradients span many binades (1e-9 ... 1), so the fp16 hi/lo split of the inference kernels (tc_mlp.cuh) is not usable here; TF32
-// keeps the fp32 exponent.  Every operand value x is split as x = hi + lo with hi = tf32(x), lo = tf32(x - hi) and a product is
-// three kind::tf32 MMAs  hi hi + lo hi + hi lo  accumulated in fp32 (TMEM): per-product error ~2^-21, i.e. an fp32-class GEMM at a
-// sixth of the fp16 tensor rate - still ~9 x the FFMA GEMM it replaces (train_gemm.cuh:k_gemm, 26 TFLOP/s measured).
+// keeps the fp32 exponent.  Every operand value x is split as x = hi + lo and a product is three kind::tf32 MMAs  hi hi + lo hi + hi lo
+// accumulated in fp32 (TMEM): per-product error ~2^-21, i.e. an fp32-class GEMM at a sixth of the fp16 tensor rate.  kind::tf32 reads the
+// upper 19 bits of each 32-bit operand element, so hi is simply the raw value (truncated by the hardware) and lo = rn_tf32(x - trunc(x)).
 //
 // One CTA = one 128-row tile of C x up to 256 columns, persistent over tiles.  Warps 0-3: epilogue (TMEM lane quadrant = warp),
 // warp 4: MMA issuer, warps 5-12: loaders.  The loaders read fp32 from global (coalesced along the contiguous dimension of the
-// operand), split, and write the hi and lo tiles [rows][32 k] straight into the K-major SWIZZLE_128B layout the MMA reads (a
-// transposing write for the operands whose contiguous dimension is not k) - no pre-pass over HBM, no extra copy of any matrix.
+// operand), split, and write the hi and lo tiles [rows][32 k] straight into the layout the MMA reads - K-major SWIZZLE_128B for the
+// operands whose contiguous dimension is k, MN-major tiles for the others - no pre-pass over HBM, no extra copy of any matrix.
 // K block = 32 elements (one 128-byte swizzle row); stage = A_hi, A_lo (16 KB each) + B_hi, B_lo (32 KB each) = 96 KB, two stages.
 // The fp32 accumulator is double-buffered in TMEM (2 x 256 columns) so that the epilogue of tile i runs under the MMAs of tile i+1.
+// Epilogues: row-per-thread stores for 16-byte-aligned outputs, a transposed (coalescing) one for ragged leading dimensions and the
+// split-K reductions; EPI 4-7 fuse the element-wise passes of the stage-1 train step (train_gemm.cuh).
+// What was measured and dropped in r2 (profiles/r2_time_gemm_variants.json, r2_ncu_train_gemm_gen*_nt.json): a second register buffer in
+// the loaders (spills, slower), and a second-generation kernel that staged raw tiles with cp.async and derived the lo tiles with
+// converter warps (correct on the first run, tensor pipe 18 % against 36 %: three more mbarrier hand-offs per K block).
 #include <stdlib.h>
 
 #include "tc_mlp.cuh"
@@ -43,7 +48,8 @@ struct Bars {
   unsigned long long acc_empty[2];    // epilogue -> MMA (EPI_WARPS arrivals)
   unsigned int tmem_base;
 };
-constexpr int SMEM = STAGES * STAGE + (int)sizeof(Bars) + 1024;
+constexpr int BARS_BYTES = ((int)sizeof(Bars) + 127) / 128 * 128;
+constexpr int SMEM = STAGES * STAGE + BARS_BYTES + EPI_WARPS * 32 * 128 + 1024;  // + the epilogue warps' transpose buffers (epilogue_tile)
 
 struct Args {
   const float* A; const float* B; float* C; const float* bias;
@@ -56,6 +62,8 @@ struct Args {
   long long m_tiles;
   int k_splits;          // FORM 2: CTAs sharing one C tile (atomicAdd epilogue)
   long long k_per_split; // FORM 2: multiple of BK
+  // fused element-wise epilogues of the second-generation kernel (epi 4-7, FORM 0 / 1): [M, N] matrices with leading dimension lde
+  float* C2; const float* E1; float* E2; long long lde; float scale;
 };
 
 // kind::tf32 instruction descriptor: D = F32 (bit 4), A / B format TF32 = 2 (bits 7-9 / 10-12), a_major / b_major (bits 15 / 16:
@@ -100,6 +108,12 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 // instruction issues on the quarter-rate XU pipe, and a K block needs 24 576 of them per CTA - as many XU cycles as the twelve MMAs
 // of the block take on the tensor pipe.  (Inf / NaN inputs are not rounded correctly; the train steps never produce them.)
 __device__ __forceinline__ float to_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x00001000u) & 0xFFFFE000u); }
+// The split the loaders store (r2): kind::tf32 reads the upper 19 bits of every 32-bit operand element, so the raw fp32 value IS
+// hi = x truncated to TF32 (no instruction), and lo = x - trunc(x) is exact in fp32; adding half a TF32 ulp to its bit pattern makes
+// the hardware truncation of lo a round-to-nearest.  Three integer / fp ops per element instead of five (verified by the second-
+// generation kernel, which takes hi straight from the cp.async'ed raw tile: tests/test_gpu_tc_gemm.py).
+__device__ __forceinline__ float lo_of(float x) { return __uint_as_float(__float_as_uint(x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u)) + 0x1000u); }
+__device__ __forceinline__ float4 lo_of4(const float4& v) { return make_float4(lo_of(v.x), lo_of(v.y), lo_of(v.z), lo_of(v.w)); }
 // byte offset of element (row r, k) of a [rows][32] tf32 tile in the K-major SWIZZLE_128B layout
 __device__ __forceinline__ uint32_t sw_off(int r, int k) { return (uint32_t)r * 128u + ((((uint32_t)k >> 2) ^ ((uint32_t)r & 7u)) << 4) + ((uint32_t)k & 3u) * 4u; }
 
@@ -123,6 +137,252 @@ __device__ __forceinline__ void k_range(const Args& a, const TileIt& it, long lo
     *k0 = (long long)it.split * a.k_per_split;
     *k1 = *k0 + a.k_per_split < a.K ? *k0 + a.k_per_split : a.K;
   } else { *k0 = 0; *k1 = a.K; }
+}
+
+// Flattened (tile, K block) sequence of one CTA - every role of a kernel walks the same one.
+template <int FORM>
+struct BlockSeq {
+  const Args* a;
+  long long t, total, k0, k1, kb;
+  TileIt it;
+  __device__ explicit BlockSeq(const Args& a_) : a(&a_), t(blockIdx.x), total(n_tiles_total<FORM>(a_)), k0(0), k1(0), kb(0) {
+    if (t < total) { it = tile_at<FORM>(*a, t); k_range<FORM>(*a, it, &k0, &k1); kb = k0; }
+  }
+  __device__ bool valid() const { return t < total; }
+  __device__ bool first_of_tile() const { return kb == k0; }
+  __device__ bool last_of_tile() const { return kb + BK >= k1; }
+  __device__ void next() {
+    kb += BK;
+    if (kb >= k1) {
+      t += gridDim.x;
+      if (t < total) { it = tile_at<FORM>(*a, t); k_range<FORM>(*a, it, &k0, &k1); kb = k0; }
+    }
+  }
+};
+
+// ---- epilogue of one accumulator tile, by one warp (its 32 TMEM lanes = 32 rows of C) ----------------------------------------------------
+// A thread that reads TMEM owns ONE ROW, so storing straight from the tcgen05.ld registers makes every STG of a warp touch 32
+// different 128-byte lines, 16 bytes each: r2 measurements showed the forward / input-gradient forms bound by exactly that (the time of
+// a 524288-row product did not depend on K; ncu: l1tex 60 % busy at 36 % tensor activity).  Each 32-column group therefore goes
+// through a 4 KB per-warp transpose buffer (16-byte chunks XOR-swizzled by row & 7: conflict-free both ways) and leaves as full
+// 128-byte row segments: lane l stores columns 4 (l & 7) .. +3 of rows 4 i + (l >> 3).  The saved matrices of the fused modes
+// (EPI 4-7, train_gemm.cuh) are read / written in the same pattern.
+constexpr int EPI_STG_BYTES = 32 * 128;
+template <int FORM>
+__device__ __forceinline__ void epilogue_tile(const Args& a, uint32_t taddr, unsigned char* stg, long long row0, int col0, int bn, int lane) {
+  const bool c_vec = ((reinterpret_cast<uintptr_t>(a.C) | (uintptr_t)(a.ldc * 4)) & 15u) == 0;
+  const bool e_vec = ((reinterpret_cast<uintptr_t>(a.C2) | reinterpret_cast<uintptr_t>(a.E1) | reinterpret_cast<uintptr_t>(a.E2) |
+                       (uintptr_t)(a.lde * 4)) & 15u) == 0;
+  const int j = lane & 7, rsub = lane >> 3;
+  const int epi = a.epi;
+  for (int c = 0; c < bn; c += 32) {
+    {
+      float v[16];
+      tmem_ld16(taddr + (uint32_t)c, v);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<float4*>(stg + lane * 128 + ((q ^ (lane & 7)) << 4)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      if (c + 16 < bn) {
+        tmem_ld16(taddr + (uint32_t)c + 16u, v);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<float4*>(stg + lane * 128 + (((q + 4) ^ (lane & 7)) << 4)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      }
+    }
+    __syncwarp();
+    const int n = col0 + c + 4 * j;                       // first of this lane's four columns
+    const int nv = (c + 4 * j < bn) ? (a.N - n < 4 ? a.N - n : 4) : 0;  // valid ones (<= 0: none)
+    float bias[4] = {0.f, 0.f, 0.f, 0.f};
+    if (FORM != 2 && epi >= 1 && epi <= 4) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (e < nv) bias[e] = __ldg(a.bias + n + e);
+    }
+    if (nv > 0) {
+#pragma unroll 2
+      for (int i = 0; i < 8; ++i) {
+        const int r = 4 * i + rsub;
+        const long long row = row0 + r;
+        if (row >= a.M) break;  // rows ascend with i
+        const float4 xv = *reinterpret_cast<const float4*>(stg + r * 128 + ((j ^ (r & 7)) << 4));
+        float x[4] = {xv.x, xv.y, xv.z, xv.w};
+        float* dst = a.C + row * a.ldc + n;
+        if (FORM == 2) {
+          if (c_vec && nv == 4) atomicAdd(reinterpret_cast<float4*>(dst), xv);  // 16-byte reduction (sm_90+)
+          else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (e < nv) atomicAdd(dst + e, x[e]);
+          }
+          continue;
+        }
+        float w[4] = {0.f, 0.f, 0.f, 0.f};        // second output of the fused modes
+        const long long eoff = row * a.lde + n;
+        float e1[4] = {0.f, 0.f, 0.f, 0.f}, e2[4] = {0.f, 0.f, 0.f, 0.f};
+        if (epi >= 5) {
+          if (e_vec && nv == 4) {
+            const float4 t1 = __ldg(reinterpret_cast<const float4*>(a.E1 + eoff));
+            e1[0] = t1.x; e1[1] = t1.y; e1[2] = t1.z; e1[3] = t1.w;
+            if (epi != 7) {
+              const float4 t2 = *reinterpret_cast<const float4*>(a.E2 + eoff);
+              e2[0] = t2.x; e2[1] = t2.y; e2[2] = t2.z; e2[3] = t2.w;
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (e < nv) { e1[e] = __ldg(a.E1 + eoff + e); if (epi != 7) e2[e] = a.E2[eoff + e]; }
+          }
+        }
+        switch (epi) {
+          case 1:
+#pragma unroll
+            for (int e = 0; e < 4; ++e) x[e] += bias[e];
+            break;
+          case 2:
+#pragma unroll
+            for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e] + bias[e], 0.f);
+            break;
+          case 3:
+#pragma unroll
+            for (int e = 0; e < 4; ++e) x[e] = 1.f / (1.f + expf(-(x[e] + bias[e])));
+            break;
+          case 4:  // softplus_100 + its derivative (k_s1_softplus)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float z = x[e] + bias[e], tt = 100.f * z;
+              w[e] = 1.f / (1.f + expf(-tt));
+              x[e] = tt > 20.f ? z : log1pf(expf(tt)) / 100.f;
+            }
+            break;
+          case 5:  // second-order pass (k_s1_second): C = d s ; E2 := d E2 100 s (1 - s)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              w[e] = x[e] * e2[e] * (100.f * e1[e] * (1.f - e1[e]));
+              x[e] = x[e] * e1[e];
+            }
+            break;
+          case 6:  // zbar (k_s1_zbar): C = acc scale E1 + E2
+#pragma unroll
+            for (int e = 0; e < 4; ++e) x[e] = x[e] * a.scale * e1[e] + e2[e];
+            break;
+          case 7:  // C = acc ; C2 = acc E1
+#pragma unroll
+            for (int e = 0; e < 4; ++e) w[e] = x[e] * e1[e];
+            break;
+          default: break;
+        }
+        if (c_vec && nv == 4) *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
+        else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (e < nv) dst[e] = x[e];
+        }
+        if (epi == 4 || epi == 5 || epi == 7) {
+          float* d2 = (epi == 5 ? a.E2 : a.C2) + eoff;
+          if (e_vec && nv == 4) *reinterpret_cast<float4*>(d2) = make_float4(w[0], w[1], w[2], w[3]);
+          else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (e < nv) d2[e] = w[e];
+          }
+        }
+      }
+    }
+    __syncwarp();  // every lane has read the group before the next one overwrites the buffer
+  }
+}
+
+// Row-per-thread epilogue: every thread stores its own row straight from the tcgen05.ld registers (16-byte pieces of 32 different
+// lines per warp instruction).  Shorter dependent chain than epilogue_tile, which wins whenever the 16-byte accesses are possible
+// (aligned C): the kernel picks per call.
+template <int FORM>
+__device__ __forceinline__ void epilogue_rows(const Args& a, uint32_t taddr, long long row, int col0, int bn) {
+  const bool c_vec = ((reinterpret_cast<uintptr_t>(a.C) | (uintptr_t)(a.ldc * 4)) & 15u) == 0;
+  const bool e_vec = ((reinterpret_cast<uintptr_t>(a.C2) | reinterpret_cast<uintptr_t>(a.E1) | reinterpret_cast<uintptr_t>(a.E2) |
+                       (uintptr_t)(a.lde * 4)) & 15u) == 0;
+  const int epi = a.epi;
+  for (int c = 0; c < bn; c += 16) {
+    float v[16], w[16];
+    tmem_ld16(taddr + (uint32_t)c, v);
+    if (row >= a.M) continue;
+    float* dst = a.C + row * a.ldc + col0 + c;
+    const bool full = col0 + c + 15 < a.N;
+    if (FORM == 2) {
+      if (c_vec && full) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) atomicAdd(reinterpret_cast<float4*>(dst) + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (col0 + c + i < a.N) atomicAdd(dst + i, v[i]);
+      }
+      continue;
+    }
+    const long long eoff = row * a.lde + col0 + c;
+    if (epi >= 1 && epi <= 4) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (col0 + c + i < a.N) v[i] += __ldg(a.bias + col0 + c + i);
+    }
+    if (epi == 2) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+    } else if (epi == 3) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = 1.f / (1.f + expf(-v[i]));
+    } else if (epi == 4) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float tt = 100.f * v[i];
+        w[i] = 1.f / (1.f + expf(-tt));
+        v[i] = tt > 20.f ? v[i] : log1pf(expf(tt)) / 100.f;
+      }
+    } else if (epi >= 5) {
+      float e1[16], e2[16];
+      if (e_vec && full) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 t1 = __ldg(reinterpret_cast<const float4*>(a.E1 + eoff) + q);
+          e1[4 * q] = t1.x; e1[4 * q + 1] = t1.y; e1[4 * q + 2] = t1.z; e1[4 * q + 3] = t1.w;
+          if (epi != 7) {
+            const float4 t2 = reinterpret_cast<const float4*>(a.E2 + eoff)[q];
+            e2[4 * q] = t2.x; e2[4 * q + 1] = t2.y; e2[4 * q + 2] = t2.z; e2[4 * q + 3] = t2.w;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          e1[i] = e2[i] = 0.f;
+          if (col0 + c + i < a.N) { e1[i] = __ldg(a.E1 + eoff + i); if (epi != 7) e2[i] = a.E2[eoff + i]; }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        if (epi == 5) { w[i] = v[i] * e2[i] * (100.f * e1[i] * (1.f - e1[i])); v[i] *= e1[i]; }
+        else if (epi == 6) v[i] = v[i] * a.scale * e1[i] + e2[i];
+        else w[i] = v[i] * e1[i];
+      }
+    }
+    if (c_vec && full) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) reinterpret_cast<float4*>(dst)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (col0 + c + i < a.N) dst[i] = v[i];
+    }
+    if (epi == 4 || epi == 5 || epi == 7) {
+      float* d2 = (epi == 5 ? a.E2 : a.C2) + eoff;
+      if (e_vec && full) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) reinterpret_cast<float4*>(d2)[q] = make_float4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (col0 + c + i < a.N) d2[i] = w[i];
+      }
+    }
+  }
 }
 
 // ---- loaders: 256 threads fill one stage (A_hi, A_lo, B_hi, B_lo) for K block [kb, kb + 32) ----------------------------------------
@@ -162,8 +422,8 @@ __device__ __forceinline__ void store_k_contig(const Frag (&f)[NIT], unsigned ch
     const int r = (t >> 3) + 32 * j;
     if (r >= rows) break;
     const float4 v = f[j].v;
-    const float4 h = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
-    const float4 l = make_float4(to_tf32(v.x - h.x), to_tf32(v.y - h.y), to_tf32(v.z - h.z), to_tf32(v.w - h.w));
+    const float4 h = v;
+    const float4 l = lo_of4(v);
     const uint32_t off = (uint32_t)r * 128u + (((uint32_t)c ^ ((uint32_t)r & 7u)) << 4);
     *reinterpret_cast<float4*>(hi + off) = h;
     *reinterpret_cast<float4*>(lo + off) = l;
@@ -176,12 +436,14 @@ template <int NIT>
 __device__ __forceinline__ void fetch_row_contig(Frag (&f)[NIT], const float* __restrict__ P, long long ld, long long row0, long long n_rows_valid,
                                                  int rows, long long kb, long long k_end, int t, bool vec_ok) {
   const int quads = rows >> 2;
+  const bool pow2 = (quads & (quads - 1)) == 0;  // 128- and 256-row tiles: shifts instead of two integer divisions per 16-byte item
+  const int qsh = 31 - __clz(quads);
 #pragma unroll
   for (int j = 0; j < NIT; ++j) {
     const int idx = t + LOAD_THREADS * j;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (idx < quads * BK) {
-      const int q = idx % quads, k = idx / quads;
+      const int q = pow2 ? (idx & (quads - 1)) : idx % quads, k = pow2 ? (idx >> qsh) : idx / quads;
       const long long gk = kb + k, gr = row0 + 4 * q;
       if (gk < k_end && gr < n_rows_valid) {
         const float* src = P + gk * ld + gr;
@@ -200,18 +462,19 @@ __device__ __forceinline__ void fetch_row_contig(Frag (&f)[NIT], const float* __
 template <int NIT>
 __device__ __forceinline__ void store_row_contig(const Frag (&f)[NIT], unsigned char* hi, unsigned char* lo, int rows, int t) {
   const int quads = rows >> 2;
+  const bool pow2 = (quads & (quads - 1)) == 0;  // 128- and 256-row tiles: shifts instead of two integer divisions per 16-byte item
+  const int qsh = 31 - __clz(quads);
 #pragma unroll
   for (int j = 0; j < NIT; ++j) {
     const int idx = t + LOAD_THREADS * j;
     if (idx >= quads * BK) break;
-    const int q = idx % quads, k = idx / quads;
+    const int q = pow2 ? (idx & (quads - 1)) : idx % quads, k = pow2 ? (idx >> qsh) : idx / quads;
     const float v[4] = {f[j].v.x, f[j].v.y, f[j].v.z, f[j].v.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float h = to_tf32(v[i]);
       const uint32_t off = sw_off(4 * q + i, k);
-      *reinterpret_cast<float*>(hi + off) = h;
-      *reinterpret_cast<float*>(lo + off) = to_tf32(v[i] - h);
+      *reinterpret_cast<float*>(hi + off) = v[i];
+      *reinterpret_cast<float*>(lo + off) = lo_of(v[i]);
     }
   }
 }
@@ -220,14 +483,16 @@ __device__ __forceinline__ void store_row_contig(const Frag (&f)[NIT], unsigned 
 template <int MNL, int NIT>
 __device__ __forceinline__ void store_row_contig_mn(const Frag (&f)[NIT], unsigned char* hi, unsigned char* lo, int rows, int t, bool is_b) {
   const int quads = rows >> 2;
+  const bool pow2 = (quads & (quads - 1)) == 0;  // 128- and 256-row tiles: shifts instead of two integer divisions per 16-byte item
+  const int qsh = 31 - __clz(quads);
 #pragma unroll
   for (int j = 0; j < NIT; ++j) {
     const int idx = t + LOAD_THREADS * j;
     if (idx >= quads * BK) break;
-    const int q = idx % quads, k = idx / quads;
+    const int q = pow2 ? (idx & (quads - 1)) : idx % quads, k = pow2 ? (idx >> qsh) : idx / quads;
     const float4 v = f[j].v;
-    const float4 h = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
-    const float4 l = make_float4(to_tf32(v.x - h.x), to_tf32(v.y - h.y), to_tf32(v.z - h.z), to_tf32(v.w - h.w));
+    const float4 h = v;
+    const float4 l = lo_of4(v);
     const uint32_t off = MnLayout<MNL>::off(4 * q, k, is_b);
     *reinterpret_cast<float4*>(hi + off) = h;
     *reinterpret_cast<float4*>(lo + off) = l;
@@ -240,6 +505,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_gemm(Args a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   Bars* bars = reinterpret_cast<Bars*>(base + STAGES * STAGE);
+  unsigned char* epi_stg = base + STAGES * STAGE + BARS_BYTES;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&bars->full[s], LOAD_WARPS); mbar_init(&bars->empty[s], 1); }
@@ -258,53 +524,20 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_gemm(Args a) {
     // ---- epilogue: TMEM lanes 32 warp .. +31 = tile rows; 16 columns at a time ----------------------------------------------------
     uint32_t acc_phase = 0;  // bit b = parity to wait for on acc_full[b]
     long long it_ctr = 0;
-    const bool c_vec = ((reinterpret_cast<uintptr_t>(a.C) | (uintptr_t)(a.ldc * 4)) & 15u) == 0;  // 16-byte stores (bn is a multiple of 16)
+    const bool c_rows = ((reinterpret_cast<uintptr_t>(a.C) | (uintptr_t)(a.ldc * 4)) & 15u) == 0;
     for (long long t = blockIdx.x; t < total; t += gridDim.x, ++it_ctr) {
       const TileIt it = tile_at<FORM>(a, t);
       const uint32_t buf = (uint32_t)(it_ctr & 1);
       mbar_wait(&bars->acc_full[buf], (acc_phase >> buf) & 1u);
       acc_phase ^= (1u << buf);
       tc_fence_after();
-      const long long row = it.m_tile * BM + warp * 32 + lane;
-      const int col0 = it.n_chunk * bn;
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * 256u;
-      for (int c = 0; c < bn; c += 16) {
-        float v[16];
-        tmem_ld16(taddr + (uint32_t)c, v);
-        if (row < a.M) {
-          float* dst = a.C + row * a.ldc + col0 + c;
-          if (FORM == 2) {
-            if (c_vec && col0 + c + 15 < a.N) {  // 16-byte reductions (sm_90+): a quarter of the atomic traffic of the split-K sum
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                atomicAdd(reinterpret_cast<float4*>(dst) + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (col0 + c + i < a.N) atomicAdd(dst + i, v[i]);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int n = col0 + c + i;
-              float x = v[i];
-              if (a.epi >= 1 && n < a.N) x += __ldg(a.bias + n);
-              if (a.epi == 2) x = fmaxf(x, 0.f);
-              if (a.epi == 3) x = 1.f / (1.f + expf(-x));
-              v[i] = x;
-            }
-            if (c_vec && col0 + c + 15 < a.N) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                reinterpret_cast<float4*>(dst)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (col0 + c + i < a.N) dst[i] = v[i];
-            }
-          }
-        }
-      }
+      // aligned forward / input-gradient outputs: row-per-thread stores; ragged leading dimensions and the split-K reductions: the
+      // transposed epilogue (r2 A/B: 0.25 vs 0.47 ms on an epilogue-bound aligned product, 0.81 vs 0.57 ms with ldc = 217)
+      if (FORM != 2 && c_rows)
+        epilogue_rows<FORM>(a, tmem_base + ((uint32_t)(warp * 32) << 16) + buf * 256u, it.m_tile * BM + warp * 32 + lane, it.n_chunk * bn, bn);
+      else
+        epilogue_tile<FORM>(a, tmem_base + ((uint32_t)(warp * 32) << 16) + buf * 256u, epi_stg + warp * EPI_STG_BYTES, it.m_tile * BM + warp * 32,
+                            it.n_chunk * bn, bn, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->acc_empty[buf]);
@@ -364,42 +597,45 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_gemm(Args a) {
     uint32_t stage = 0, phase = 0;
     const bool a_vec = ((reinterpret_cast<uintptr_t>(a.A) | (uintptr_t)(a.lda * 4)) & 15u) == 0;
     const bool b_vec = ((reinterpret_cast<uintptr_t>(a.B) | (uintptr_t)(a.ldb * 4)) & 15u) == 0;
-    for (long long tt = blockIdx.x; tt < total; tt += gridDim.x) {
-      const TileIt it = tile_at<FORM>(a, tt);
-      long long k0, k1;
-      k_range<FORM>(a, it, &k0, &k1);
-      const long long m0 = it.m_tile * BM;
-      const long long n0 = (long long)it.n_chunk * bn;
-      for (long long kb = k0; kb < k1; kb += BK) {
-        Frag fa[BM / 32], fb[MAX_BN / 32];  // 4 + 8 float4 in flight per thread
-        if (FORM == 0) {
-          fetch_k_contig(fa, a.A, a.lda, m0, a.M, BM, kb, k1, t, a_vec);
-          fetch_k_contig(fb, a.B, a.ldb, n0, a.N, bn, kb, k1, t, b_vec);
-        } else if (FORM == 1) {
-          fetch_k_contig(fa, a.A, a.lda, m0, a.M, BM, kb, k1, t, a_vec);
-          fetch_row_contig(fb, a.B, a.ldb, n0, a.N, bn, kb, k1, t, b_vec && (n0 & 3) == 0);
-        } else {
-          fetch_row_contig(fa, a.A, a.lda, m0, a.M, BM, kb, k1, t, a_vec && (m0 & 3) == 0);
-          fetch_row_contig(fb, a.B, a.ldb, n0, a.N, bn, kb, k1, t, b_vec && (n0 & 3) == 0);
-        }
-        mbar_wait(&bars->empty[stage], phase ^ 1u);  // the loads above are in flight while the MMAs release the stage
-        unsigned char* sa = base + stage * STAGE;
-        unsigned char *Ah = sa, *Al = sa + A_TILE, *Bh = sa + 2 * A_TILE, *Bl = sa + 2 * A_TILE + B_TILE;
-        if (FORM == 0) {
-          store_k_contig(fa, Ah, Al, BM, t);
-          store_k_contig(fb, Bh, Bl, bn, t);
-        } else if (FORM == 1) {
-          store_k_contig(fa, Ah, Al, BM, t);
-          if (MNL != 0) store_row_contig_mn<MNL == 0 ? 2 : MNL>(fb, Bh, Bl, bn, t, true); else store_row_contig(fb, Bh, Bl, bn, t);
-        } else {
-          if (MNL != 0) { store_row_contig_mn<MNL == 0 ? 2 : MNL>(fa, Ah, Al, BM, t, false); store_row_contig_mn<MNL == 0 ? 2 : MNL>(fb, Bh, Bl, bn, t, true); }
-          else { store_row_contig(fa, Ah, Al, BM, t); store_row_contig(fb, Bh, Bl, bn, t); }
-        }
-        fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
-        __syncwarp();              // one arrival per warp: 256 single-thread arrivals on one mbarrier serialise (~1000 cycles per K block)
-        if (lane == 0) mbar_arrive(&bars->full[stage]);
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+    auto fetch = [&](Frag (&fa)[BM / 32], Frag (&fb)[MAX_BN / 32], const BlockSeq<FORM>& q) {
+      const long long m0 = q.it.m_tile * BM, n0 = (long long)q.it.n_chunk * bn;
+      if (FORM == 0) {
+        fetch_k_contig(fa, a.A, a.lda, m0, a.M, BM, q.kb, q.k1, t, a_vec);
+        fetch_k_contig(fb, a.B, a.ldb, n0, a.N, bn, q.kb, q.k1, t, b_vec);
+      } else if (FORM == 1) {
+        fetch_k_contig(fa, a.A, a.lda, m0, a.M, BM, q.kb, q.k1, t, a_vec);
+        fetch_row_contig(fb, a.B, a.ldb, n0, a.N, bn, q.kb, q.k1, t, b_vec && (n0 & 3) == 0);
+      } else {
+        fetch_row_contig(fa, a.A, a.lda, m0, a.M, BM, q.kb, q.k1, t, a_vec && (m0 & 3) == 0);
+        fetch_row_contig(fb, a.B, a.ldb, n0, a.N, bn, q.kb, q.k1, t, b_vec && (n0 & 3) == 0);
       }
+    };
+    auto store = [&](const Frag (&fa)[BM / 32], const Frag (&fb)[MAX_BN / 32]) {
+      mbar_wait(&bars->empty[stage], phase ^ 1u);
+      unsigned char* sa = base + stage * STAGE;
+      unsigned char *Ah = sa, *Al = sa + A_TILE, *Bh = sa + 2 * A_TILE, *Bl = sa + 2 * A_TILE + B_TILE;
+      if (FORM == 0) {
+        store_k_contig(fa, Ah, Al, BM, t);
+        store_k_contig(fb, Bh, Bl, bn, t);
+      } else if (FORM == 1) {
+        store_k_contig(fa, Ah, Al, BM, t);
+        if (MNL != 0) store_row_contig_mn<MNL == 0 ? 2 : MNL>(fb, Bh, Bl, bn, t, true); else store_row_contig(fb, Bh, Bl, bn, t);
+      } else {
+        if (MNL != 0) { store_row_contig_mn<MNL == 0 ? 2 : MNL>(fa, Ah, Al, BM, t, false); store_row_contig_mn<MNL == 0 ? 2 : MNL>(fb, Bh, Bl, bn, t, true); }
+        else { store_row_contig(fa, Ah, Al, BM, t); store_row_contig(fb, Bh, Bl, bn, t); }
+      }
+      fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+      __syncwarp();              // one arrival per warp: 256 single-thread arrivals on one mbarrier serialise (~1000 cycles per K block)
+      if (lane == 0) mbar_arrive(&bars->full[stage]);
+      if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+    };
+    // One register buffer per thread.  (r2 A/B, profiles/r2_time_gemm_variants.json: a second buffer - loads of block i + 1 issued before
+    // block i is split and stored - needs 96 live registers for the fragments alone, spills under the 128-register cap of this
+    // 416-thread CTA and was 10-50 % SLOWER in every form; so was staging raw tiles with cp.async plus converter warps.)
+    Frag fa0[BM / 32], fb0[MAX_BN / 32];
+    for (BlockSeq<FORM> q(a); q.valid(); q.next()) {
+      fetch(fa0, fb0, q);
+      store(fa0, fb0);
     }
   }
   tc_fence_before();
@@ -409,6 +645,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_gemm(Args a) {
 
 }  // namespace gemm_tc
 
+
 // PSNERF_B200_TRAIN_GEMM=ffma keeps the fp32 FFMA GEMM (train_gemm.cuh) for A/B measurements and as the cross-check path of the
 // gradient tests (read on every call: a getenv against GEMMs of >= 30 us).
 bool train_gemm_use_tc() {
@@ -416,8 +653,15 @@ bool train_gemm_use_tc() {
   return !(e && !strcmp(e, "ffma"));
 }
 
+// PSNERF_B200_TRAIN_FUSED=1 runs the element-wise passes of the stage-1 train step inside the GEMM epilogues (EPI 4-7); the default is
+// decided by measurement.
+bool train_gemm_fused() {
+  const char* e = getenv("PSNERF_B200_TRAIN_FUSED");
+  return train_gemm_use_tc() && !(e && e[0] == '0');
+}
+
 int tc_gemm(int form, const float* A, long long lda, const float* B, long long ldb, float* C, long long ldc, const float* bias, long long M,
-            int N, long long K, int epi, cudaStream_t st) {
+            int N, long long K, int epi, cudaStream_t st, const GemmFuse* fz) {
   using namespace gemm_tc;
   if (M == 0 || N == 0 || K == 0) return PSN_OK;
   Args a;
@@ -425,6 +669,8 @@ int tc_gemm(int form, const float* A, long long lda, const float* B, long long l
   a.A = A; a.B = B; a.C = C; a.bias = bias;
   a.lda = lda; a.ldb = ldb; a.ldc = ldc;
   a.M = M; a.K = K; a.N = N; a.epi = epi;
+  PSN_REQUIRE(epi <= 3 || (fz && form != 2), PSN_ERR_ARG, "tc_gemm: fused epilogue %d without its operands", epi);
+  if (fz) { a.C2 = fz->C2; a.E1 = fz->E1; a.E2 = fz->E2; a.lde = fz->lde; a.scale = fz->scale; }
   // columns per tile: the whole N when it fits one MMA, else equal chunks; multiples of 16 (UMMA N at M = 128)
   a.n_chunks = (N + MAX_BN - 1) / MAX_BN;
   a.bn = ((N + a.n_chunks - 1) / a.n_chunks + 15) / 16 * 16;
@@ -457,11 +703,11 @@ int tc_gemm(int form, const float* A, long long lda, const float* B, long long l
     PSN_CUDA_CHECK(cudaFuncSetAttribute(k_tc_gemm<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_set = true;
   }
-  // Row-contiguous operands (B of FORM 1, A and B of FORM 2) as MN-major tiles; PSNERF_B200_GEMM_MN=0 selects K-major tiles filled by
-  // transposing 4-byte stores instead (the first verified version: cross-check / A/B; stage-1 train step 136 -> 107 ms with MN-major).
+  count_launch();
+  // Row-contiguous operands (B of FORM 1, A and B of FORM 2) as MN-major tiles; PSNERF_B200_GEMM_MN=0 selects K-major
+  // tiles filled by transposing 4-byte stores instead (the first verified version; stage-1 train step 136 -> 107 ms with MN-major).
   const char* e_mn = getenv("PSNERF_B200_GEMM_MN");
   const bool mn = !(e_mn && e_mn[0] == '0');
-  count_launch();
   if (form == 0) k_tc_gemm<0, 0><<<grid, THREADS, SMEM, st>>>(a);
   else if (form == 1) { if (mn) k_tc_gemm<1, 2><<<grid, THREADS, SMEM, st>>>(a); else k_tc_gemm<1, 0><<<grid, THREADS, SMEM, st>>>(a); }
   else { if (mn) k_tc_gemm<2, 2><<<grid, THREADS, SMEM, st>>>(a); else k_tc_gemm<2, 0><<<grid, THREADS, SMEM, st>>>(a); }
@@ -471,9 +717,20 @@ int tc_gemm(int form, const float* A, long long lda, const float* B, long long l
 
 }  // namespace psn
 
-// Test hook: one GEMM through the tcgen05 kernel (tests/test_gpu_tc_gemm.py).  form / epi as in train_gemm.cuh.
+// Test hooks: one GEMM through the tcgen05 kernel (tests/test_gpu_tc_gemm.py).  form / epi as in train_gemm.cuh; the _fused variant
+// takes the operands of the fused epilogues 4-7 (second-generation kernel): C2 / E1 / E2 are [M, N] with leading dimension lde.
 extern "C" int psn_tc_gemm_debug(int form, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
                                  const float* bias, int64_t M, int N, int64_t K, int epi, void* stream) {
-  PSN_REQUIRE(form >= 0 && form <= 2 && A && B && C && (epi == 0 || bias), PSN_ERR_ARG, "psn_tc_gemm_debug: bad argument");
-  return psn::tc_gemm(form, A, lda, B, ldb, C, ldc, bias, M, N, K, epi, (cudaStream_t)stream);
+  PSN_REQUIRE(form >= 0 && form <= 2 && A && B && C && (epi == 0 || bias) && epi <= 3, PSN_ERR_ARG, "psn_tc_gemm_debug: bad argument");
+  return psn::tc_gemm(form, A, lda, B, ldb, C, ldc, bias, M, N, K, epi, (cudaStream_t)stream, nullptr);
+}
+extern "C" int psn_tc_gemm_debug_fused(int form, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                                       const float* bias, int64_t M, int N, int64_t K, int epi, float* C2, const float* E1, float* E2,
+                                       int64_t lde, float scale, void* stream) {
+  PSN_REQUIRE((form == 0 || form == 1) && A && B && C && epi >= 4 && epi <= 7, PSN_ERR_ARG, "psn_tc_gemm_debug_fused: bad argument");
+  PSN_REQUIRE((epi != 4 || (bias && C2)) && (epi != 5 || (E1 && E2)) && (epi != 6 || (E1 && E2)) && (epi != 7 || (E1 && C2)), PSN_ERR_ARG,
+              "psn_tc_gemm_debug_fused: missing operand of epilogue %d", epi);
+  psn::GemmFuse fz;
+  fz.C2 = C2; fz.E1 = E1; fz.E2 = E2; fz.lde = lde; fz.scale = scale;
+  return psn::tc_gemm(form, A, lda, B, ldb, C, ldc, bias, M, N, K, epi, (cudaStream_t)stream, &fz);
 }

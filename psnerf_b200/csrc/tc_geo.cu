@@ -32,6 +32,9 @@ struct TcGeoArgs {
 #ifndef PSN_CHEAP_PREFETCH
 #define PSN_CHEAP_PREFETCH 1  // TMEM-load prefetch in the epilogue of the single-pass program (epi_for_chunks_pf_ld)
 #endif
+#ifndef PSN_FULL_PREFETCH
+#define PSN_FULL_PREFETCH 0   // the same TMEM-load prefetch in the three-pass program, paid for with un-prefetched (L1-resident) bias loads
+#endif
 constexpr int MODE_OUT = 0, MODE_SHADOW = 1, MODE_DEBUG = 2, MODE_FEAT = 3;  // MODE_DEBUG = MODE_OUT + layer dump / clock64 trace hooks
 
 template <int MODE, bool CHEAP = false>
@@ -84,10 +87,18 @@ k_tc_occ(TcGeoArgs g, PointGen gen, long long M_host, const int* M_dev, int out_
         const bool pre_skip = (l + 1 == g.skip);
         const int n_out = g.n_out[l];
         const float cc = pre_skip ? PSN_SOFTPLUS_C * 0.70710678118654752440f : PSN_SOFTPLUS_C;
-        auto pre_bias = [&](int col, Bias16& b) { load_bias16(bias, col, b); };
+        auto pre_bias = [&](int col, Bias16& b) {
+          if (!(PSN_FULL_PREFETCH && !CHEAP)) load_bias16(bias, col, b);
+        };
         auto chunk = [&](int pass, int col, float (&v)[CW], const Bias16& b) {
           if (tr && pass == 0) trace[64 + sub * 40 + l * 5] = clock64();
-          add16(v, b.b);
+          if (PSN_FULL_PREFETCH && !CHEAP) {  // bias straight from L1 at its use: the registers of the two prefetched copies hold the TMEM chunk of the next pass instead
+            Bias16 bl;
+            load_bias16(bias, col, bl);
+            add16(v, bl.b);
+          } else {
+            add16(v, b.b);
+          }
           if (CHEAP && l < 7 && !(pre_skip && col + CW > n_out)) {
             // level-1 march program, ordinary chunk: activation in packed fp16, result = the hi-only operand columns
             const __half2 c2 = __float2half2_rn(cc);
@@ -137,7 +148,7 @@ k_tc_occ(TcGeoArgs g, PointGen gen, long long M_host, const int* M_dev, int out_
             }
           }
         };
-        if (CHEAP && PSN_CHEAP_PREFETCH) epi_for_chunks_pf_ld<Bias16>(s, e, pre_bias, chunk);
+        if ((CHEAP && PSN_CHEAP_PREFETCH) || (!CHEAP && PSN_FULL_PREFETCH)) epi_for_chunks_pf_ld<Bias16>(s, e, pre_bias, chunk);
         else epi_for_chunks_pf<Bias16>(s, e, pre_bias, chunk);
         e.step_ctr++;
       }

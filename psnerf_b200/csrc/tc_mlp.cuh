@@ -79,6 +79,9 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(void* bar, uint32_t bytes)
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
+#ifndef PSN_MBAR_HINT_NS
+#define PSN_MBAR_HINT_NS 2000
+#endif
 __device__ __forceinline__ bool mbar_try_wait(void* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -86,7 +89,7 @@ __device__ __forceinline__ bool mbar_try_wait(void* bar, uint32_t parity) {
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(2000u)  // suspend-time hint (ns): sleep in hardware instead of spinning
+      : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)PSN_MBAR_HINT_NS)  // suspend-time hint (ns): sleep in hardware instead of spinning
       : "memory");
   return ok != 0;
 }

@@ -121,14 +121,21 @@ static inline unsigned nblk(long long n, int t = 256) { return (unsigned)((n + t
 
 // tc_gemm.cu: the same three products on the tensor cores (tcgen05 kind::tf32, x = hi + lo split, three passes, fp32 accumulate).
 // It is what the train steps run; PSNERF_B200_TRAIN_GEMM=ffma selects the FFMA kernel above (A/B measurements, cross-check).
+// Fused element-wise epilogues of the tensor-core kernel (FORM 0 / 1; all matrices [M, N] with leading dimension lde):
+//   EPI 4  C = softplus_100(acc + bias), C2 = sigmoid(100 (acc + bias))                       (k_s1_softplus)
+//   EPI 5  C = acc * E1, E2 := acc * E2 * 100 E1 (1 - E1)                                     (k_s1_second)
+//   EPI 6  C = acc * scale * E1 + E2                                                          (k_s1_zbar)
+//   EPI 7  C = acc, C2 = acc * E1                                                             (k_s1_mul on the GEMM's own output)
 int tc_gemm(int form, const float* A, long long lda, const float* B, long long ldb, float* C, long long ldc, const float* bias, long long M,
-            int N, long long K, int epi, cudaStream_t st);
+            int N, long long K, int epi, cudaStream_t st, const GemmFuse* fz);
 bool train_gemm_use_tc();
+bool train_gemm_fused();  // the fused epilogues are available (tensor-core GEMM, second generation)
 
 static int gemm(int form, const float* A, int lda, const float* B, int ldb, float* C, int ldc, const float* bias, long long M, int N,
-                long long K, int epi, cudaStream_t st) {
+                long long K, int epi, cudaStream_t st, const GemmFuse* fz = nullptr) {
   if (M == 0 || N == 0 || K == 0) return PSN_OK;
-  if (train_gemm_use_tc()) return tc_gemm(form, A, lda, B, ldb, C, ldc, bias, M, N, K, epi, st);
+  if (train_gemm_use_tc()) return tc_gemm(form, A, lda, B, ldb, C, ldc, bias, M, N, K, epi, st, fz);
+  PSN_REQUIRE(epi <= 3, PSN_ERR_ARG, "gemm: fused epilogue %d on the FFMA path", epi);
   count_launch();
   if (form == 0) {
     dim3 g((N + 63) / 64, (unsigned)((M + 63) / 64));

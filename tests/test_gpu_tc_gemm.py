@@ -95,6 +95,56 @@ def test_weight_gradient_form_tn_accumulates(Kc, M, N):
     assert err < 3 * GATE, err   # K = samples: thousands of accumulating MMAs per tile; split-K partial sums are combined with fp32 atomics
 
 
+def _gemm_fused(form, A, B_, Cm, bias, M, N, K, epi, C2=None, E1=None, E2=None, lde=0, scale=1.0):
+    lib = B.load()
+    B.require_device()
+    P = lambda t: C.c_void_p(0 if t is None else t.data_ptr())
+    B.check(lib.psn_tc_gemm_debug_fused(form, P(A), A.stride(0), P(B_), B_.stride(0), P(Cm), Cm.stride(0), P(bias), M, N, K, epi, P(C2), P(E1),
+                                        P(E2), lde, scale, C.c_void_p(torch.cuda.current_stream().cuda_stream)), "psn_tc_gemm_debug_fused")
+
+
+@pytest.mark.parametrize("M,N,K", [(127, 256, 256), (4133, 217, 256), (300, 256, 39), (1000, 257, 256)])
+def test_fused_softplus_epilogue(M, N, K):
+    """EPI 4 (forward layer of the stage-1 train step): h = softplus_100(x W^T + b), s = sigmoid(100 (x W^T + b))."""
+    gen = torch.Generator().manual_seed(M + N + K)
+    A = _view(M, K, gen, pad=(4 - K % 4) % 4)
+    W = _view(N, K, gen) * 0.05
+    bias = _rand((N,), gen) * 0.01
+    h = torch.zeros(M, N, device="cuda")
+    sg = torch.zeros(M, N, device="cuda")
+    _gemm_fused(0, A, W, h, bias, M, N, K, 4, C2=sg, lde=N)
+    z = A.double() @ W.double().t() + bias.double()
+    assert float((h.double() - torch.nn.functional.softplus(z, beta=100)).abs().max()) < GATE * float(z.abs().max())
+    assert float((sg.double() - torch.sigmoid(100 * z)).abs().max()) < 2e-3  # 100 x the 1e-5 of z
+
+
+@pytest.mark.parametrize("form", [0, 1])
+@pytest.mark.parametrize("M,N,K", [(129, 256, 256), (2000, 217, 256), (4133, 256, 217)])
+def test_fused_elementwise_epilogues(form, M, N, K):
+    """EPI 5 / 6 / 7 of the stage-1 backward: products of the accumulator with saved [M, N] matrices, one of them updated in place."""
+    gen = torch.Generator().manual_seed(7 * M + N + K + form)
+    A = _view(M, K, gen, spread=3.0)
+    Bm = _view(N, K, gen) if form == 0 else _view(K, N, gen)
+    ref = A.double() @ (Bm.double().t() if form == 0 else Bm.double())
+    mx = float(ref.abs().max())
+    E1 = torch.rand(M, N, generator=gen).cuda()
+    E2 = _rand((M, N), gen)
+    # 7: C = acc, C2 = acc E1
+    Cm, C2 = torch.zeros(M, N, device="cuda"), torch.zeros(M, N, device="cuda")
+    _gemm_fused(form, A, Bm, Cm, None, M, N, K, 7, C2=C2, E1=E1, lde=N)
+    assert float((Cm.double() - ref).abs().max()) < GATE * mx
+    assert float((C2.double() - ref * E1.double()).abs().max()) < GATE * mx
+    # 6: C = acc scale E1 + E2
+    _gemm_fused(form, A, Bm, Cm, None, M, N, K, 6, E1=E1, E2=E2, lde=N, scale=0.70710678)
+    assert float((Cm.double() - (ref * 0.70710678 * E1.double() + E2.double())).abs().max()) < GATE * max(mx, 1.0)
+    # 5: C = acc E1 ; E2 := acc E2 100 E1 (1 - E1)
+    E2w = E2.clone()
+    _gemm_fused(form, A, Bm, Cm, None, M, N, K, 5, E1=E1, E2=E2w, lde=N)
+    assert float((Cm.double() - ref * E1.double()).abs().max()) < GATE * mx
+    want = ref * E2.double() * (100 * E1.double() * (1 - E1.double()))
+    assert float((E2w.double() - want).abs().max()) < GATE * float(want.abs().max())
+
+
 def test_train_steps_use_the_tensor_gemm(monkeypatch):
     """The switch the train steps read: tensor-core GEMM unless PSNERF_B200_TRAIN_GEMM=ffma (evaluated once per process)."""
     import os
