@@ -221,7 +221,7 @@ int tc_grid(const void* kernel, long long tiles) {
   if (!max_ctas) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)(num_ctas() & ~1));
+    cfg.gridDim = dim3((unsigned)(num_ctas() / CLUSTER * CLUSTER));
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = SMEM_BYTES;
     cudaLaunchAttribute at;
@@ -232,14 +232,14 @@ int tc_grid(const void* kernel, long long tiles) {
     cfg.numAttrs = 1;
     int n = 0;
     if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) == cudaSuccess && n > 0) {
-      max_ctas = CLUSTER * n < (num_ctas() & ~1) ? CLUSTER * n : (num_ctas() & ~1);
+      max_ctas = CLUSTER * n < num_ctas() / CLUSTER * CLUSTER ? CLUSTER * n : num_ctas() / CLUSTER * CLUSTER;
     } else {
       (void)cudaGetLastError();
-      max_ctas = num_ctas() & ~1;
+      max_ctas = num_ctas() / CLUSTER * CLUSTER;
     }
   }
   long long g = tiles < max_ctas ? tiles : max_ctas;
-  g = (g + 1) & ~1LL;
+  g = (g + CLUSTER - 1) / CLUSTER * CLUSTER;
   return (int)(g < CLUSTER ? CLUSTER : g);
 }
 }  // namespace tc

@@ -49,7 +49,10 @@ constexpr int EPI_WARP0 = 4;
 constexpr int EPI_THREADS = 512;
 constexpr int EPI_SUBS = 4;       // epilogue warps per TMEM lane quadrant
 constexpr int CW = 16;            // columns per epilogue chunk: in pass p sub s owns columns [64 p + 16 s, +16)
-constexpr int CLUSTER = 2;             // CTAs per cluster sharing one weight stream (multicast)
+#ifndef PSN_CLUSTER
+#define PSN_CLUSTER 2
+#endif
+constexpr int CLUSTER = PSN_CLUSTER;   // CTAs per cluster sharing one weight stream (multicast); 2 = one TPC (r2 A/B of 4: see profiles/README.md)
 constexpr int A_READY_ARRIVALS = 16;   // a K block (64 columns) is written by the 16 epilogue warps in ONE pass; lane 0 of each arrives
 
 // ---- shared-memory control block (after the 1024-aligned A and W regions) ---------------------------------
@@ -229,7 +232,7 @@ inline int check_launch_regs(const void* kernel, const char* name) {
 // Both CTAs of a pair must run the same number of tile iterations (they share every weight stage): the pair uses the count of
 // its even CTA, the odd one may get one masked dummy tile.  Round-robin tile assignment: tile = blockIdx.x + it * gridDim.x.
 __device__ __forceinline__ long long pair_iters(long long n_tiles) {
-  const long long b0 = (long long)(blockIdx.x & ~1u);
+  const long long b0 = (long long)(blockIdx.x - blockIdx.x % CLUSTER);
   return n_tiles > b0 ? (n_tiles - b0 + gridDim.x - 1) / gridDim.x : 0;
 }
 // persistent grid: an even number of CTAs, at most 2 x the clusters the device can hold at once
@@ -308,7 +311,7 @@ template <bool ALLOW_SINGLE = true>
 __device__ __forceinline__ void producer_loop(const Smem& s, const Program& prog, long long iters) {
   uint32_t stage = 0, phase = 0;
   const uint32_t rank = cluster_ctarank();
-  uint32_t t_parity = 0;
+  uint32_t t_parity = 0;  // tile counter modulo CLUSTER: CTA `rank` issues the tiles with counter == rank
   for (long long it = 0; it < iters; ++it) {
     for (int st = 0; st < prog.n_steps; ++st) {
       const typename StepView<ALLOW_SINGLE>::type sp = reinterpret_cast<const typename StepView<ALLOW_SINGLE>::type&>(prog.step[st]);
@@ -316,7 +319,7 @@ __device__ __forceinline__ void producer_loop(const Smem& s, const Program& prog
       const unsigned char* src = prog.blob[st] + sp.w_off;
       const bool single = ALLOW_SINGLE && step_is_single(sp);
       const int n_tiles = single ? sp.nkb : 2 * sp.nkb;
-      for (int t = 0; t < n_tiles; ++t, t_parity ^= 1u) {
+      for (int t = 0; t < n_tiles; ++t, t_parity = (t_parity + 1u == CLUSTER ? 0u : t_parity + 1u)) {
         mbar_wait_cluster_relaxed(&s.c->w_empty[stage], phase ^ 1u);     // released by the MMA warps of both CTAs
         mbar_arrive_expect_tx(&s.c->w_full[stage], tile_bytes);          // this CTA's copy of the tile
         const int blob_tile = single ? 2 * t : (t ^ 1);  // ring order per K block: lo tile, then hi tile (blob: hi, lo); single: hi only
