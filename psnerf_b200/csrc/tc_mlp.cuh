@@ -557,17 +557,15 @@ __device__ __forceinline__ void epi_load16(const EpiCtx& e, int col, float (&v)[
 // sigma', parked partials, per-point tables) into a register struct; it runs for pass 0 BEFORE the accumulator wait and for pass
 // p+1 between the issue and the wait of pass p's TMEM load, so the ~700-cycle L2 latency of those loads is off the critical
 // path of every pass (with four epilogue warps per scheduler it used to be exposed four times per layer).
-template <class Buf, class Pre, class F>
+// UNROLL: the four passes fully unrolled (no register copies of the prefetched side loads: 16 moves per pass; r2: shadow pass 334 -> 321
+// ms) - the default of the occupancy / visibility kernels.  The radiance kernel keeps the rolled loop: unrolled it is no faster and the
+// write-backs of its dead scratch lines rose from 9.8 to 37 GB per launch (the discards land later relative to the evictions).
+template <class Buf, bool UNROLL = (PSN_EPI_UNROLL != 0), class Pre, class F>
 __device__ __forceinline__ void epi_for_chunks_pf(const Smem& s, const EpiCtx& e, Pre&& pre, F&& f) {
   const uint32_t base = e.tmem_base + e.lane_addr + e.d_col0();
   Buf nxt;
   pre(CW * e.sub, nxt);
-#if PSN_EPI_UNROLL
-#pragma unroll
-#else
-#pragma unroll 1
-#endif
-  for (int pass = 0; pass < 4; ++pass) {
+  auto body = [&](int pass) {
     const Buf cur = nxt;
     if (pass == 0) epi_wait_q0_skewed(s, e);
     else if (pass == 1) epi_wait_q(s, e, 1);
@@ -580,6 +578,13 @@ __device__ __forceinline__ void epi_for_chunks_pf(const Smem& s, const EpiCtx& e
 #pragma unroll
     for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(r[i]);
     f(pass, col, v, cur);
+  };
+  if (UNROLL) {
+#pragma unroll
+    for (int pass = 0; pass < 4; ++pass) body(pass);
+  } else {
+#pragma unroll 1
+    for (int pass = 0; pass < 4; ++pass) body(pass);
   }
 }
 // Same walk with the TMEM chunk of pass p + 1 requested BEFORE pass p is processed (passes 1..3: their columns are complete once

@@ -190,7 +190,7 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
         const int n_out = g.n_out[l];
         const float cc = pre_skip ? PSN_SOFTPLUS_C * PSN_INV_SQRT2 : PSN_SOFTPLUS_C;
         const bool ho_l = ho && l == 7;  // h_7 feeds the (single-pass) feature head s8
-        epi_for_chunks_pf<Bias16>(s, e, [&](int col, Bias16& b) { load_bias16(bias, col, b); },
+        epi_for_chunks_pf<Bias16, false>(s, e, [&](int col, Bias16& b) { load_bias16(bias, col, b); },
                                   [&](int pass, int col, float (&v)[CW], const Bias16& b) {
           add16(v, b.b);
 #pragma unroll
@@ -234,7 +234,7 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
       float g_acc[3] = {0.f, 0.f, 0.f};  // this thread's share of J_pe^T (d logit / d pe)
       if (g.with_app) {
         // ---- s8: feature head -> A (no activation) ---------------------------------------------------------------------
-        epi_for_chunks_pf<Bias16>(s, e, [&](int col, Bias16& b) { load_bias16(g.bias_feat, col, b); },
+        epi_for_chunks_pf<Bias16, false>(s, e, [&](int col, Bias16& b) { load_bias16(g.bias_feat, col, b); },
                                   [&](int pass, int col, float (&v)[CW], const Bias16& b) {
           add16(v, b.b);
           epi_store_a16(e, e.d_col0(), col, v, ho);
@@ -245,7 +245,7 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
         e.step_ctr++;
         // ---- s9: appearance layer 0, feature part -> parked; then the reverse seed dz_7 -> A -------------------------------
         struct Seed { uint4 q[2]; float4 w[4]; };
-        epi_for_chunks_pf<Seed>(s, e, [&](int col, Seed& o) {
+        epi_for_chunks_pf<Seed, false>(s, e, [&](int col, Seed& o) {
 #pragma unroll
           for (int t = 0; t < 2; ++t) o.q[t] = scr_ld<HINT>(&stash[(size_t)(7 * 32 + (col >> 3) + t) * TILE_M + row], pol);
 #pragma unroll
@@ -284,7 +284,7 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
         const int nprev = g.n_out[l - 1];
         const float scale = is_skip ? PSN_INV_SQRT2 * PSN_INV_U16 : PSN_INV_U16;
         struct Sig { uint4 q[2]; };
-        epi_for_chunks_pf<Sig>(s, e, [&](int col, Sig& o) {
+        epi_for_chunks_pf<Sig, false>(s, e, [&](int col, Sig& o) {
 #pragma unroll
           for (int t = 0; t < 2; ++t) o.q[t] = scr_ld<HINT>(&stash[(size_t)((l - 1) * 32 + (col >> 3) + t) * TILE_M + row], pol);
         }, [&](int pass, int col, float (&v)[CW], const Sig& o) {
@@ -376,7 +376,7 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
         }
         // ---- s18: appearance layer 0 (rest) + parked + bias, ReLU ------------------------------------------------------------
         struct Park { float4 pk[4], b[4]; };
-        epi_for_chunks_pf<Park>(s, e, [&](int col, Park& o) {
+        epi_for_chunks_pf<Park, false>(s, e, [&](int col, Park& o) {
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             {
@@ -402,7 +402,7 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
 #pragma unroll 1
         for (int l = 1; l <= 3; ++l) {
           const float* bias = g.abias[l];
-          epi_for_chunks_pf<Bias16>(s, e, [&](int col, Bias16& b) { load_bias16(bias, col, b); },
+          epi_for_chunks_pf<Bias16, false>(s, e, [&](int col, Bias16& b) { load_bias16(bias, col, b); },
                                     [&](int pass, int col, float (&v)[CW], const Bias16& b) {
             add16(v, b.b);
 #pragma unroll

@@ -82,6 +82,40 @@ def test_field_forward_backward_vs_oracle_autograd(with_app, gemm, monkeypatch):
     _check_param_grads(model, ref_grads, gates["rtol"], gemm, gates["median"])
 
 
+@pytest.mark.parametrize("with_app", [True, False])
+def test_fused_gemm_epilogues_equal_the_separate_kernels(with_app, monkeypatch):
+    """The stage-1 step with its element-wise passes inside the GEMM epilogues (EPI 4-7, the default) against the same step with the
+    separate kernels (PSNERF_B200_TRAIN_FUSED=0): the GEMM kernel and the element-wise formulas are the same, so outputs and every
+    parameter gradient agree to rounding (FMA contraction of the z-bar update) - a sharp check that does not suffer from the
+    ReLU-kink ambiguity of the comparison with autograd.  M = 1777 is ragged against the 128-row tiles; layer 3 has ldc = 217."""
+    cfg, sds = util.stage1_state_dicts()
+    from psnerf_b200.stage1 import train as T
+    gen = torch.Generator().manual_seed(11)
+    M = 1777
+    pts = (torch.rand(M, 3, generator=gen) * 2.0 - 1.0).cuda()
+    views = torch.randn(M, 3, generator=gen).cuda()
+    c_rgb, c_logit, c_grad = torch.randn(M, 3, generator=gen).cuda(), torch.randn(M, generator=gen).cuda(), torch.randn(M, 3, generator=gen).cuda()
+    res = {}
+    for fused in ("1", "0"):
+        monkeypatch.setenv("PSNERF_B200_TRAIN_FUSED", fused)
+        model = _model(sds["trained"], cfg)
+        rgb, logit, grad = T.field(model, pts, views if with_app else None)
+        loss = (logit * c_logit).sum() + (grad * c_grad).sum()
+        if with_app:
+            loss = loss + (rgb * c_rgb).sum()
+        loss.backward()
+        res[fused] = (logit.detach(), grad.detach(), rgb.detach() if with_app else None, {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None})
+    a, b = res["1"], res["0"]
+    assert util.max_abs(a[0].cpu(), b[0].cpu()) < 1e-6 and util.rel_l2(a[1].cpu(), b[1].cpu()) < 1e-6
+    if with_app:
+        assert util.max_abs(a[2].cpu(), b[2].cpu()) < 1e-6
+    assert set(a[3]) == set(b[3])
+    for n in a[3]:
+        scale = max(float(b[3][n].abs().max()), 1e-12)
+        err = float((a[3][n] - b[3][n]).abs().max()) / scale
+        util.bound("s1_fused_vs_separate/%s/%s" % (with_app, n), err, 2e-5)
+
+
 def test_composite_backward_vs_autograd():
     from psnerf_b200.stage1 import train as T
     gen = torch.Generator().manual_seed(4)
