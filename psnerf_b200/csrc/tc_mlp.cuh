@@ -682,8 +682,34 @@ __device__ __forceinline__ void epi_signal_a(const Smem& s, int kb) {
 // Point encoding [x, sin(2^0 x), cos(2^0 x), ...] (network.py:141-150) of this thread's row into the smem table pe[k][row]:
 // sub s evaluates the sincos pairs m = s, s+4, ... (m = 3*octave + coordinate).  Callers follow with a barrier over the
 // epilogue threads; the table then serves the layer-0 operand, the skip-layer concat and the encoding Jacobian.
+#ifndef PSN_PE_DOUBLING
+#define PSN_PE_DOUBLING 1  // octaves 1, 2 and 4, 5 from octaves 0 and 3 by angle doubling: 2 sincosf per thread and tile instead of up to 5 (the tensor pipe idles
+                           // during the encoding).  r2 A/B: march 157.1 -> 153.7 ms, relit step 518.2 -> 513.2 ms; every measured parity error unchanged
+                           // (117 tests, profiles/r2_parity_errlog_pe_doubling.jsonl).  0 = one sincosf per octave and coordinate
+#endif
 __device__ __forceinline__ void epi_write_pe(const Smem& s, int row, int sub, const float (&x)[3], int octaves) {
   if (sub == 0) { s.pe[row] = x[0]; s.pe[TILE_M + row] = x[1]; s.pe[2 * TILE_M + row] = x[2]; }
+  if (PSN_PE_DOUBLING && octaves == 6) {
+    // sub c (0..2) owns coordinate c: sincosf at octaves 0 and 3 (their arguments 2^k x are exact in fp32), the two octaves above
+    // each by  sin 2a = 2 sin a cos a,  cos 2a = 1 - 2 sin^2 a  (|error| <= ~4 ulp of the base value after two doublings)
+    if (sub < 3) {
+      const float xc = sub == 0 ? x[0] : (sub == 1 ? x[1] : x[2]);
+#pragma unroll
+      for (int base = 0; base < 6; base += 3) {
+        float sn, cs;
+        sincosf((float)(1 << base) * xc, &sn, &cs);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const int oct = base + d;
+          s.pe[(3 + 6 * oct + sub) * TILE_M + row] = sn;
+          s.pe[(6 + 6 * oct + sub) * TILE_M + row] = cs;
+          const float s2 = 2.f * sn * cs, c2 = fmaf(-2.f * sn, sn, 1.f);
+          sn = s2; cs = c2;
+        }
+      }
+    }
+    return;
+  }
 #pragma unroll 1
   for (int m = sub; m < 3 * octaves; m += EPI_SUBS) {
     const int oct = m / 3, c = m - 3 * oct;
