@@ -78,6 +78,7 @@ struct psn_mlp {
   psn::TcStepW tc_step[psn::kMaxTcSteps];
   const unsigned char* tc_blob;
   const float* tc_bias_scaled[8];  // GEO: biases of the softplus layers times 100*log2(e)
+  const float* tc_w_logit_row_scaled;  // GEO: w_logit_row / (100 log2 e): the logit dot over the scaled activations of the tensor path
   // stage-2 visibility net restructuring (tc path): layer 0 and the skip layer are split into per-point and
   // per-light partial products; vis_aux = {W0 point part, W0 light part, Wskip point part, Wskip light part}
   psn::SimtLayer vis_aux[4];

@@ -86,7 +86,6 @@ k_tc_occ(TcGeoArgs g, PointGen gen, long long M_host, const int* M_dev, int out_
         const float* bias = g.bias[l];
         const bool pre_skip = (l + 1 == g.skip);
         const int n_out = g.n_out[l];
-        const float cc = pre_skip ? PSN_SOFTPLUS_C * 0.70710678118654752440f : PSN_SOFTPLUS_C;
         auto pre_bias = [&](int col, Bias16& b) {
           if (!(PSN_FULL_PREFETCH && !CHEAP)) load_bias16(bias, col, b);
         };
@@ -101,20 +100,19 @@ k_tc_occ(TcGeoArgs g, PointGen gen, long long M_host, const int* M_dev, int out_
           }
           if (CHEAP && l < 7 && !(pre_skip && col + CW > n_out)) {
             // level-1 march program, ordinary chunk: activation in packed fp16, result = the hi-only operand columns
-            const __half2 c2 = __float2half2_rn(cc);
             uint32_t r8[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) r8[u] = softplus_scaled_cheap_h2(v[2 * u], v[2 * u + 1], c2);
+            for (int u = 0; u < 8; ++u) r8[u] = softplus_scaled_cheap_h2(v[2 * u], v[2 * u + 1]);
             tmem_st8(e.tmem_base + e.lane_addr + e.d_col0() + (uint32_t)col, r8);
             epi_signal_a(s, pass);
             return;
           }
 #pragma unroll
-          for (int i = 0; i < CW; ++i) v[i] = CHEAP ? softplus_scaled_cheap(v[i], cc) : softplus_scaled(v[i], cc);
+          for (int i = 0; i < CW; ++i) v[i] = CHEAP ? softplus_scaled_cheap(v[i]) : softplus_scaled(v[i]);  // s = P h (scaled domain, tc_pack.cu)
           if (MODE == MODE_DEBUG) {
             if (dump && dump_layer == l && idx < M) {  // bring-up hook: the MMA-produced columns only
 #pragma unroll
-              for (int i = 0; i < CW; ++i) dump[idx * 256 + col + i] = v[i];
+              for (int i = 0; i < CW; ++i) dump[idx * 256 + col + i] = v[i] * (pre_skip ? PSN_SOFTPLUS_C * 0.70710678118654752440f : PSN_SOFTPLUS_C);  // h (/ sqrt2)
             }
           }
           if (MODE == MODE_FEAT && l == 7) {  // h_7 feeds both the fp32 logit row and the feature-head step
@@ -132,7 +130,7 @@ k_tc_occ(TcGeoArgs g, PointGen gen, long long M_host, const int* M_dev, int out_
 #pragma unroll
               for (int i = 0; i < CW; ++i) {
                 const int k = col + i - n_out;
-                if (k >= 0) v[i] = (k < g.pe_dim ? s.pe[k * TILE_M + row] : 0.f) * 0.70710678118654752440f;
+                if (k >= 0) v[i] = k < g.pe_dim ? s.pe[k * TILE_M + row] : 0.f;  // the 1 / sqrt2 (and P) sit in the packed skip-layer columns
               }
             }
             epi_store_a16(e, e.d_col0(), col, v, CHEAP);
@@ -156,7 +154,7 @@ k_tc_occ(TcGeoArgs g, PointGen gen, long long M_host, const int* M_dev, int out_
         const int stride = 1 + g.n_feat;
         epi_for_chunks_pf<Bias16>(s, e, [&](int col, Bias16& b) { load_bias16(g.bias_feat, col, b); },
                                   [&](int pass, int col, float (&v)[CW], const Bias16& b) {
-          add16(v, b.b);
+          fma16(v, PSN_SOFTPLUS_C, b.b);  // accumulator = W_feat s_7 = P W_feat h_7
           if (idx < M) {
 #pragma unroll
             for (int i = 0; i < CW; ++i)
@@ -258,7 +256,7 @@ static int make_tc_geo(const psn_mlp* geo, TcGeoArgs* a) {
     a->bias[l] = geo->tc_bias_scaled[l];
     a->n_out[l] = geo->fwd[l].N;
   }
-  a->w_row = geo->w_logit_row;
+  a->w_row = geo->tc_w_logit_row_scaled;  // the logit dot runs over s_7 = P h_7
   a->b_logit = geo->logit_head.bias;
   a->skip = geo->desc.skip;
   a->octaves = geo->desc.octaves;

@@ -631,6 +631,14 @@ __device__ __forceinline__ void load_bias16(const float* __restrict__ bias, int 
 #pragma unroll
   for (int t = 0; t < 4; ++t) o.b[t] = __ldg(b4 + t);
 }
+// v <- v * c + b (feature head of the geo net: its input is the scaled activation s_7 = P h_7, c = 1 / P)
+__device__ __forceinline__ void fma16(float (&v)[CW], float c, const float4 (&b)[4]) {
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    v[4 * t] = fmaf(v[4 * t], c, b[t].x); v[4 * t + 1] = fmaf(v[4 * t + 1], c, b[t].y);
+    v[4 * t + 2] = fmaf(v[4 * t + 2], c, b[t].z); v[4 * t + 3] = fmaf(v[4 * t + 3], c, b[t].w);
+  }
+}
 __device__ __forceinline__ void add16(float (&v)[CW], const float4 (&b)[4]) {
 #pragma unroll
   for (int t = 0; t < 4; ++t) { v[4 * t] += b[t].x; v[4 * t + 1] += b[t].y; v[4 * t + 2] += b[t].z; v[4 * t + 3] += b[t].w; }
@@ -729,33 +737,34 @@ __device__ __forceinline__ float pe_jac_tab(const Smem& s, int row, int k, int* 
   return -f * s.pe[(k - 3) * TILE_M + row];
 }
 
-// softplus(beta=100) on pre-scaled accumulators: zs = 100*log2(e)*z  ->  softplus(z) = c * max(zs, lg2(1 + 2^min(zs,40))),
-// c = ln2/100 (times any layer constant).  2 MUFU + 4 ALU ops; for zs > ~25 the lg2 term equals zs in fp32, so the max
-// reproduces PyTorch's linear branch (threshold 20) to <1e-9 without a compare/select.
+// softplus(beta=100) in the scaled domain (tc_pack.cu): zs = P z with P = 100 log2(e) is the accumulator, the activation handed on is
+// s = P softplus(z) = max(zs, lg2(1 + 2^min(zs, 40))).  2 MUFU + 3 ALU ops and no multiplication by ln2 / 100 (it is folded into the
+// packed weights of whatever consumes s); for zs > ~25 the lg2 term equals zs in fp32, so the max reproduces PyTorch's linear branch
+// (threshold 20) to <1e-9 without a compare/select.
 // (Measured alternatives, profiles/README.md: one MUFU + a degree-6 FMA-pipe polynomial for lg2(1 + u) halves the XU load but
 // costs five more issue slots per activation - the march kernel got 8 % slower; applying it to every 2nd / 4th element was
 // within run-to-run noise of this form, so the two-MUFU form stays.)
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-#define PSN_SOFTPLUS_C 0.0069314718055994531f  /* ln2 / 100 */
-__device__ __forceinline__ float softplus_scaled(float zs, float c) {
+#define PSN_SOFTPLUS_C 0.0069314718055994531f  /* ln2 / 100 = 1 / P: s -> h (bring-up dumps only) */
+__device__ __forceinline__ float softplus_scaled(float zs) {
   const float e = ex2_approx(fminf(zs, 40.f));
-  return c * fmaxf(zs, lg2_approx(1.f + e));
+  return fmaxf(zs, lg2_approx(1.f + e));
 }
-// First level of the two-level march only (k_tc_occ<.., CHEAP>): softplus = c (max(zs, 0) + lg2(1 + u)), u = 2^-|zs| in (0, 1], with
-// lg2(1 + u) ~ u (C1 + C2 u + C3 u^2) (no constant term; max error 7.7e-4, i.e. 5e-6 on the activation): ONE MUFU and the same six
-// issue slots as the two-MUFU form.  The values this produces are only trusted away from the occupancy threshold
+// First level of the two-level march only (k_tc_occ<.., CHEAP>): s = max(zs, 0) + lg2(1 + u), u = 2^-|zs| in (0, 1], with
+// lg2(1 + u) ~ u (C1 + C2 u + C3 u^2) (no constant term; max error 7.7e-4, i.e. 5e-6 on the activation): ONE MUFU.
+// The values this produces are only trusted away from the occupancy threshold
 // (tests/precision_study.py: max |cheap - full| = 1e-3 on alpha against a refine margin of 0.02).
-__device__ __forceinline__ float softplus_scaled_cheap(float zs, float c) {
+__device__ __forceinline__ float softplus_scaled_cheap(float zs) {
   const float u = ex2_approx(-fabsf(zs));
   const float q = fmaf(fmaf(0.165381165f, u, -0.589203729f), u, 1.42459315f);
-  return c * fmaf(q, u, fmaxf(zs, 0.f));
+  return fmaf(q, u, fmaxf(zs, 0.f));
 }
-// The same activation for TWO pre-scaled accumulators entirely in packed fp16 arithmetic (ex2.approx.f16x2, HFMA2, HMNMX2): the result
+// The same activation for TWO accumulators entirely in packed fp16 arithmetic (ex2.approx.f16x2, HFMA2, HMNMX2): the result
 // is directly one 32-bit column of the single-pass A operand, so neither a second MUFU nor a conversion follows.  An fp16 epilogue
 // adds about as much error as the fp16 operands themselves (emulated: max |cheap - full| = 1.5e-3 on alpha, margin 0.02).
-__device__ __forceinline__ uint32_t softplus_scaled_cheap_h2(float zs0, float zs1, __half2 c2) {
+__device__ __forceinline__ uint32_t softplus_scaled_cheap_h2(float zs0, float zs1) {
   const __half2 zs = __floats2half2_rn(zs0, zs1);
   const __half2 na = __hneg2(__habs2(zs));
   uint32_t ub;
@@ -763,15 +772,8 @@ __device__ __forceinline__ uint32_t softplus_scaled_cheap_h2(float zs0, float zs
   const __half2 u = *reinterpret_cast<const __half2*>(&ub);
   __half2 q = __hfma2(__float2half2_rn(0.165381165f), u, __float2half2_rn(-0.589203729f));
   q = __hfma2(q, u, __float2half2_rn(1.42459315f));
-  const __half2 r = __hmul2(__hfma2(q, u, __hmax2(zs, __float2half2_rn(0.f))), c2);
+  const __half2 r = __hfma2(q, u, __hmax2(zs, __float2half2_rn(0.f)));
   return *reinterpret_cast<const uint32_t*>(&r);
-}
-// same, also returning sigma'(z) = sigmoid(100 z) = e / (1 + e)
-__device__ __forceinline__ float softplus_scaled_d(float zs, float c, float* dsig) {
-  const float e = ex2_approx(fminf(zs, 40.f));
-  const float t = 1.f + e;
-  *dsig = e * rcp_approx(t);
-  return c * fmaxf(zs, lg2_approx(t));
 }
 
 }  // namespace tc

@@ -50,7 +50,8 @@ struct TcRadArgs {
   Program prog;
   const float* gbias[8];
   const float* bias_feat;
-  const float* w_row;
+  const float* w_row;     // row 0 of the last geo layer (reverse seed dz_7 = row * sigma')
+  const float* w_row_s;   // the same row / P for the fp32 logit dot over the scaled activations s_7 = P h_7
   const float* b_logit;
   int n_out[8];
   int skip, octaves, pe_dim;
@@ -64,13 +65,13 @@ struct TcRadArgs {
 
 #define PSN_INV_SQRT2 0.70710678118654752440f
 
-// Eight softplus activations with their derivatives: v <- c max(z, lg2(1 + e)), sg <- sigma' = e / (1 + e), e = 2^min(z, 30).
+// Eight softplus activations (scaled domain, tc_pack.cu) with their derivatives: v <- max(z, lg2(1 + e)), sg <- sigma' = e / (1 + e), e = 2^min(z, 30).
 // The forward layers of this kernel are bound by the XU pipe (three MUFUs per activation: ex2, lg2, rcp - clock64: 10 200 cycles per
 // layer against 8000 for layers without the derivative), so the reciprocals are batched four at a time: ONE MUFU.RCP of the product
 // t1 t2 t3 t4 and nine FMULs give the four 1 / t_i (t <= 2^30 + 1 keeps the product below 2^121; sigma' only has to be good to the
 // 7.6e-6 of its unorm16 stash, the three extra roundings cost 2e-7).  Clamping at 30 instead of 40 changes nothing: for z > 30 the
 // lg2 term is below z and sigma' rounds to 65535 / 65535 either way.
-__device__ __forceinline__ void softplus8_d(float* v, float c, float (&sg)[8]) {
+__device__ __forceinline__ void softplus8_d(float* v, float (&sg)[8]) {
   float e[8], t[8];
 #pragma unroll
   for (int u = 0; u < 8; ++u) {
@@ -88,7 +89,7 @@ __device__ __forceinline__ void softplus8_d(float* v, float c, float (&sg)[8]) {
     sg[4 * q + 3] = e[4 * q + 3] * (r23 * t[4 * q + 2]);
   }
 #pragma unroll
-  for (int u = 0; u < 8; ++u) v[u] = c * fmaxf(v[u], lg2_approx(t[u]));
+  for (int u = 0; u < 8; ++u) v[u] = fmaxf(v[u], lg2_approx(t[u]));
 }
 
 // TRACE (bring-up tool only): clock64 timeline of tile iteration TRACE_ITER of CTA 0 - MMA-lane slots as in mma_loop, plus
@@ -188,7 +189,6 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
         const float* bias = g.gbias[l];
         const bool pre_skip = (l + 1 == g.skip);
         const int n_out = g.n_out[l];
-        const float cc = pre_skip ? PSN_SOFTPLUS_C * PSN_INV_SQRT2 : PSN_SOFTPLUS_C;
         const bool ho_l = ho && l == 7;  // h_7 feeds the (single-pass) feature head s8
         epi_for_chunks_pf<Bias16, false>(s, e, [&](int col, Bias16& b) { load_bias16(bias, col, b); },
                                   [&](int pass, int col, float (&v)[CW], const Bias16& b) {
@@ -196,7 +196,7 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
             float sg[8];
-            softplus8_d(&v[8 * t], cc, sg);
+            softplus8_d(&v[8 * t], sg);
             scr_st<HINT>(&stash[(size_t)(l * 32 + (col >> 3) + t) * TILE_M + row],
                          make_uint4(q16_pair(sg[0], sg[1]), q16_pair(sg[2], sg[3]), q16_pair(sg[4], sg[5]), q16_pair(sg[6], sg[7])), pol);
             if (l == 7 && !g.with_app) {  // gradient only: seed dz_7 = W_last[0,:] * sigma'(z_7) directly
@@ -209,7 +209,7 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
             }
           }
           if (l == 7 && g.with_app) {
-            const float4* w4 = reinterpret_cast<const float4*>(g.w_row + col);
+            const float4* w4 = reinterpret_cast<const float4*>(g.w_row_s + col);  // row / P: the dot runs over s_7 = P h_7
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
               const float4 w = __ldg(w4 + t);
@@ -221,7 +221,7 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
 #pragma unroll
             for (int i = 0; i < CW; ++i) {
               const int k = col + i - n_out;
-              if (k >= 0) v[i] = (k < g.pe_dim ? s.pe[k * TILE_M + row] : 0.f) * PSN_INV_SQRT2;
+              if (k >= 0) v[i] = k < g.pe_dim ? s.pe[k * TILE_M + row] : 0.f;  // 1 / sqrt2 and P sit in the packed skip-layer columns
             }
           }
           epi_store_a16(e, e.d_col0(), col, v, ho_l);
@@ -236,7 +236,7 @@ k_tc_rad(TcRadArgs g, PointGen gen, long long M_host, const int* M_dev, float* _
         // ---- s8: feature head -> A (no activation) ---------------------------------------------------------------------
         epi_for_chunks_pf<Bias16, false>(s, e, [&](int col, Bias16& b) { load_bias16(g.bias_feat, col, b); },
                                   [&](int pass, int col, float (&v)[CW], const Bias16& b) {
-          add16(v, b.b);
+          fma16(v, PSN_SOFTPLUS_C, b.b);  // accumulator = W_feat s_7 = P W_feat h_7
           epi_store_a16(e, e.d_col0(), col, v, ho);
           epi_signal_a(s, pass);
         });
@@ -477,6 +477,7 @@ static int make_tc_rad(const psn_mlp* geo, const psn_mlp* app, void* scratch, Tc
     for (int i = 8; i < n; ++i) a->prog.step[i].single = 1;  // s8.. : feature head, reverse sweep, appearance MLP
   a->bias_feat = geo->fwd[8].bias;
   a->w_row = geo->w_logit_row;
+  a->w_row_s = geo->tc_w_logit_row_scaled;
   a->b_logit = geo->logit_head.bias;
   a->skip = geo->desc.skip;
   a->octaves = geo->desc.octaves;
