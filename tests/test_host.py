@@ -277,3 +277,68 @@ def test_bench_reference_arm_prints_one_json_line():
         assert k in d, k
     assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_sync_free_losses_equal_the_boolean_gather_formulation():
+    """psnerf_b200.stage{1,2} losses compute their masked means as where-sums over counts (no `mask.sum() == 0` / `x[mask]` host
+    synchronisation per term).  Against the reference's own formulation - boolean gathers + nn.L1Loss / mse / BCELoss (stage1/model/
+    losses.py:24-66, stage2/model/loss.py:24-104) - on random data: same values, same gradients, and an EMPTY mask gives a zero term with
+    zero gradients instead of a NaN."""
+    import torch.nn.functional as F
+    from psnerf_b200.stage1 import Loss
+    from psnerf_b200.stage2.loss import MainLoss, NormalLoss
+    gen = torch.Generator().manual_seed(21)
+    L, N = 5, 97
+    # ---- stage 2
+    def s2_case(mask):
+        out = {"sg_rgb_values": torch.rand(L, N, 3, generator=gen).requires_grad_(True), "network_object_mask": mask, "object_mask": torch.ones_like(mask),
+               "albedo_values": torch.rand(1, N, 3, generator=gen).requires_grad_(True), "albedo_jitter": torch.rand(1, N, 3, generator=gen),
+               "rough_values": torch.rand(1, N, 9, generator=gen).requires_grad_(True), "rough_jitter": torch.rand(1, N, 9, generator=gen),
+               "vis_train": torch.rand(2, N, 3, generator=gen).requires_grad_(True), "visibility": torch.rand(L, N, 3, generator=gen),
+               "normal_pred": torch.randn(1, N, 3, generator=gen).requires_grad_(True), "normal_values": torch.randn(1, N, 3, generator=gen)}
+        inp = {"visibility": torch.rand(L, N, generator=gen), "vis_train_gt": torch.rand(2, N, generator=gen), "light_vis_train": torch.rand(2, 3, generator=gen)}
+        gt = {"rgb": torch.rand(L, N, 3, generator=gen)}
+        return out, inp, gt
+    mask = torch.rand(1, N, generator=gen) > 0.4
+    out, inp, gt = s2_case(mask)
+    terms = MainLoss(1.0, "L1", 0.05, 0.01, 1.0)(out, gt, inp)
+    nterms = NormalLoss(1.0, 0.0)(out)
+    m = mask.expand(L, -1)
+    ref_rgb = F.l1_loss(out["sg_rgb_values"][m].reshape(-1, 3), gt["rgb"][m].reshape(-1, 3))
+    ref_alb = F.l1_loss(out["albedo_values"][mask], out["albedo_jitter"][mask])
+    ref_rough = F.l1_loss(out["rough_values"][mask], out["rough_jitter"][mask])
+    ref_vis = F.l1_loss(out["vis_train"][..., 0][mask.expand(2, -1)].reshape(-1), inp["vis_train_gt"][mask.expand(2, -1)].reshape(-1))
+    ref_n = F.mse_loss(out["normal_pred"][mask].reshape(-1, 3), F.normalize(out["normal_values"], dim=-1)[mask].reshape(-1, 3))
+    for got, ref in ((terms["sg_rgb_loss"], ref_rgb), (terms["albedo_smooth_loss"], ref_alb), (terms["rough_smooth_loss"], ref_rough),
+                     (terms["vis_loss"], ref_vis), (nterms["normal_loss"], ref_n)):
+        assert abs(float(got) - float(ref)) < 1e-6 * max(1.0, abs(float(ref)))
+    total = terms["loss"] + nterms["loss"]
+    ref_total = ref_rgb + 0.05 * ref_alb + 0.01 * ref_rough + ref_vis + ref_n
+    leaves = [out["sg_rgb_values"], out["albedo_values"], out["rough_values"], out["vis_train"], out["normal_pred"]]
+    g1 = torch.autograd.grad(total, leaves, retain_graph=True)
+    g2 = torch.autograd.grad(ref_total, leaves)
+    for a, b in zip(g1, g2):
+        assert float((a - b).abs().max()) < 1e-7
+    out, inp, gt = s2_case(torch.zeros(1, N, dtype=torch.bool))
+    t0 = MainLoss(1.0, "L1", 0.05, 0.01, 1.0)(out, gt, inp)["loss"] + NormalLoss(1.0, 0.0)(out)["loss"]
+    assert float(t0) == 0.0
+    for gz in torch.autograd.grad(t0, [out["sg_rgb_values"], out["normal_pred"]], allow_unused=True):
+        assert gz is None or float(gz.abs().max()) == 0.0
+    # ---- stage 1
+    n = 61
+    o1 = {"rgb": torch.rand(1, n, 3, generator=gen).requires_grad_(True), "diff_norm": torch.rand(n, generator=gen).requires_grad_(True),
+          "normal_pred": torch.randn(1, n, 3, generator=gen).requires_grad_(True)}
+    acc = torch.rand(1, n, generator=gen).requires_grad_(True)
+    rgb_gt, n_gt = torch.rand(1, n, 3, generator=gen), torch.randn(1, n, 3, generator=gen)
+    n_mask, m_valid = torch.rand(1, n, generator=gen) > 0.5, torch.rand(1, n, generator=gen) > 0.2
+    m_gt = (torch.rand(1, n, generator=gen) > 0.5).float()
+    t1 = Loss(1.0, 0.01, 0.05, 0.1)(o1, rgb_gt, n_gt, n_mask, acc, m_gt, m_valid)
+    ref1 = (F.l1_loss(o1["rgb"], rgb_gt, reduction="sum") / n + 0.01 * o1["diff_norm"].mean()
+            + 0.05 * F.l1_loss(o1["normal_pred"][n_mask], n_gt[n_mask], reduction="sum") / float(n_mask.sum())
+            + 0.1 * F.binary_cross_entropy(acc[m_valid].clamp(0, 1), m_gt[m_valid]))
+    assert abs(float(t1["loss"]) - float(ref1)) < 1e-6 * max(1.0, abs(float(ref1)))
+    for a, b in zip(torch.autograd.grad(t1["loss"], [o1["rgb"], o1["normal_pred"], acc], retain_graph=True),
+                    torch.autograd.grad(ref1, [o1["rgb"], o1["normal_pred"], acc])):
+        assert float((a - b).abs().max()) < 1e-7
+    t2 = Loss(1.0, 0.01, 0.05, 0.1)(o1, rgb_gt, n_gt, torch.zeros(1, n, dtype=torch.bool), acc, m_gt, torch.zeros(1, n, dtype=torch.bool))
+    assert torch.isfinite(t2["loss"]) and float(t2["normal_loss"]) == 0.0 and float(t2["mask_loss"]) == 0.0
